@@ -1,0 +1,103 @@
+"""ctypes binding of libcmr_b200.so (include/cmr_b200.h).
+
+There is no CPU fallback: if the shared library is missing, or a call is made
+without a CUDA device, this module raises.  PyTorch supplies device memory and
+the current stream only.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcmr_b200.so")
+
+_c_int = ctypes.c_int
+_c_vp = ctypes.c_void_p
+_c_f = ctypes.c_float
+_c_sz = ctypes.c_size_t
+
+# name -> (restype, argtypes); mirrors include/cmr_b200.h one to one
+SIGNATURES = {
+    "cmr_abi_version": (_c_int, []),
+    "cmr_error_string": (ctypes.c_char_p, [_c_int]),
+    "cmr_launch_count": (ctypes.c_ulonglong, []),
+    "cmr_take_fault": (_c_int, [_c_vp]),
+    "cmr_workspace_bytes": (_c_sz, [_c_int] * 4),
+    "cmr_cloud_mean": (_c_int, [_c_vp, _c_int, _c_int, _c_vp, _c_vp]),
+    "cmr_episode_prepare": (_c_int, [_c_vp, _c_vp, _c_int, _c_int, _c_int, _c_vp, _c_vp]),
+    "cmr_observe": (_c_int, [_c_vp] * 7 + [_c_int] * 5 + [_c_vp] * 5),
+    "cmr_project": (_c_int, [_c_vp] * 6 + [_c_int] * 5 + [_c_vp] * 4),
+    "cmr_tile_scatter": (_c_int, [_c_vp] * 2 + [_c_int] * 5 + [_c_vp] * 2),
+    "cmr_to_disentangled": (_c_int, [_c_vp, _c_vp, _c_int, _c_vp]),
+    "cmr_step": (_c_int, [_c_vp] * 5 + [_c_int] * 3 + [_c_vp]),
+    "cmr_reward_scratch_bytes": (_c_sz, [_c_int]),
+    "cmr_reward": (_c_int, [_c_vp] * 6 + [_c_int] * 3 + [_c_vp] * 4),
+    "cmr_square_distance": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_vp, _c_vp]),
+    "cmr_index_points": (_c_int, [_c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp]),
+    "cmr_index_points_backward": (_c_int, [_c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp]),
+    "cmr_farthest_point_sample": (_c_int, [_c_vp, _c_vp, _c_int, _c_int, _c_int, _c_vp, _c_vp]),
+    "cmr_knn": (_c_int, [_c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp]),
+    "cmr_query_ball_point": (_c_int, [_c_vp, _c_vp, _c_f, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp]),
+    "cmr_group_points": (_c_int, [_c_vp] * 4 + [_c_int] * 5 + [_c_vp, _c_vp]),
+}
+
+_lib = None
+
+
+class CmrError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libcmr_b200.so (once).  Raises if it has not been built - never falls back."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise CmrError(
+                f"{LIB_PATH} is missing: build it with `python -m cmr_agent_b200.build` "
+                "(or __graft_entry__.build()); cmr_agent_b200 has no CPU or PyTorch fallback")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        if lib.cmr_abi_version() != 1:
+            raise CmrError("libcmr_b200.so ABI version mismatch; rebuild it")
+        _lib = lib
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().cmr_error_string(rc).decode()
+        raise CmrError(f"{what} failed: {msg} (code {rc})")
+
+
+def stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def require_cuda(t, name, dtype=None):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise CmrError(f"{name} must be a CUDA tensor: cmr_agent_b200 has no CPU fallback")
+    if dtype is not None and t.dtype != dtype:
+        raise CmrError(f"{name} must be {dtype}, got {t.dtype}")
+    return t
+
+
+def call(name, *args):
+    check(getattr(load(), name)(*args), name)
+
+
+def launch_count():
+    return int(load().cmr_launch_count())
+
+
+def take_fault():
+    """Read-and-clear the sticky device fault flag (synchronises the current stream)."""
+    return int(load().cmr_take_fault(stream()))

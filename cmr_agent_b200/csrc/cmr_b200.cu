@@ -1,0 +1,341 @@
+// cmr_b200.cu - the C ABI of libcmr_b200.so (see include/cmr_b200.h).  Single translation unit:
+// argument checks + launch configuration here, kernels in env_kernels.cuh / pointnet_kernels.cuh.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+
+#include "env_kernels.cuh"
+#include "pointnet_kernels.cuh"
+
+namespace cmr {
+
+static inline cudaStream_t S_(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+template <typename Kern>
+static int allow_smem(Kern kern, size_t bytes) {
+    if (bytes <= 48 * 1024) return CMR_OK;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    return e == cudaSuccess ? CMR_OK : (int)e;
+}
+
+static int sm_count() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+            n = 148;
+    }
+    return n;
+}
+}  // namespace cmr
+
+using namespace cmr;
+
+#define CMR_REQUIRE(cond, code) \
+    do {                        \
+        if (!(cond)) return (code); \
+    } while (0)
+
+template <typename PixT, int CQ>
+static int launch_tile_scatter(const WsLayout &L, const char *ws, const float *img_feat, int B, int N, int C, int P,
+                               float *obs2d, cudaStream_t st) {
+    const PixT *pix = reinterpret_cast<const PixT *>(ws + L.off_pix);
+    const int *M = reinterpret_cast<const int *>(ws + L.off_m);
+    const float *featT = reinterpret_cast<const float *>(ws + L.off_feat);
+    size_t smem = sizeof(float) * kTilePix * (C + 1) + sizeof(int) * kTilePix + sizeof(unsigned) * kListCap;
+    int rc = allow_smem(k_tile_scatter<PixT, CQ>, smem);
+    if (rc) return rc;
+    const bool vec = (P % 4 == 0) && aligned(img_feat, 16) && aligned(obs2d, 16);
+    k_tile_scatter<PixT, CQ><<<dim3(ceil_div(P, kTilePix), B), 256, smem, st>>>(pix, M, featT, img_feat, N, L.ncap, C, P,
+                                                                               vec, obs2d);
+    return after_launch();
+}
+
+template <typename PixT>
+static int launch_project(const WsLayout &L, char *ws, const float *pc, const uint8_t *overlap, const float *K,
+                          const float *pose, const float *mean, int B, int N, int H, int W, float *obs3d,
+                          int32_t *pix_out, int32_t *mvis_out, cudaStream_t st) {
+    PixT *pix = reinterpret_cast<PixT *>(ws + L.off_pix);
+    const int *seg = reinterpret_cast<const int *>(ws + L.off_seg);
+    const int *Mws = reinterpret_cast<const int *>(ws + L.off_m);
+    const bool vec = (N % 4 == 0) && aligned(pc, 16) && aligned(obs3d, 16) && aligned(overlap, 4) &&
+                     (!pix_out || aligned(pix_out, 16));
+    if (mvis_out) {
+        cudaError_t e = cudaMemsetAsync(mvis_out, 0, sizeof(int32_t) * B, st);
+        if (e != cudaSuccess) return (int)e;
+    }
+    k_project<PixT><<<dim3(ceil_div(L.groups, 8), B), 256, 0, st>>>(pc, overlap, K, pose, mean, seg, Mws, N, L.ncap,
+                                                                   L.groups, H, W, vec, pix, obs3d, pix_out, mvis_out);
+    return after_launch();
+}
+
+template <typename PixT>
+static int launch_scatter(const WsLayout &L, const char *ws, const float *img_feat, int B, int N, int C, int P,
+                          float *obs2d, cudaStream_t st) {
+    if (C <= 32) return launch_tile_scatter<PixT, 1>(L, ws, img_feat, B, N, C, P, obs2d, st);
+    if (C <= 64) return launch_tile_scatter<PixT, 2>(L, ws, img_feat, B, N, C, P, obs2d, st);
+    if (C <= 128) return launch_tile_scatter<PixT, 4>(L, ws, img_feat, B, N, C, P, obs2d, st);
+    return launch_tile_scatter<PixT, 8>(L, ws, img_feat, B, N, C, P, obs2d, st);
+}
+
+template <typename VecT>
+static int launch_index_points(const void *points, const int64_t *idx, int B, int N, int S, int row_bytes, void *out,
+                               cudaStream_t st) {
+    int row_vecs = row_bytes / (int)sizeof(VecT);
+    long long total = (long long)B * S * row_vecs;
+    int grid = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 32);
+    k_index_points<VecT><<<grid, 256, 0, st>>>(static_cast<const VecT *>(points), idx, N, S, row_vecs,
+                                               static_cast<VecT *>(out), total);
+    return after_launch();
+}
+
+template <int PPT>
+static int launch_fps(const float *xyz, const int64_t *start, int B, int N, int npoint, int64_t *out, int cs,
+                      cudaStream_t st) {
+    constexpr int THREADS = 512;
+    size_t smem = sizeof(float) * 3 * THREADS * PPT;
+    int rc = allow_smem(k_fps<PPT, THREADS>, smem);
+    if (rc) return rc;
+    if (cs > 8) {
+        cudaError_t e = cudaFuncSetAttribute(k_fps<PPT, THREADS>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (e != cudaSuccess) return (int)e;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(B * cs);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k_fps<PPT, THREADS>, xyz, start, N, npoint, out);
+    ++g_launches;
+    if (e != cudaSuccess) return (int)e;
+    e = cudaGetLastError();
+    return e == cudaSuccess ? CMR_OK : (int)e;
+}
+
+extern "C" {
+
+int cmr_abi_version(void) { return CMR_ABI_VERSION; }
+
+const char *cmr_error_string(int code) {
+    switch (code) {
+        case CMR_OK: return "ok";
+        case CMR_EINVAL: return "invalid argument (null pointer or non-positive size)";
+        case CMR_EALIGN: return "pointer not aligned as documented";
+        case CMR_ERANGE: return "size outside the supported range";
+        case CMR_EUNSUPPORTED: return "unsupported configuration";
+        default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown error";
+    }
+}
+
+unsigned long long cmr_launch_count(void) { return g_launches; }
+
+int cmr_take_fault(void *stream) {
+    int v = 0;
+    cudaError_t e = cudaMemcpyFromSymbolAsync(&v, g_fault, sizeof(int), 0, cudaMemcpyDeviceToHost, S_(stream));
+    if (e == cudaSuccess) e = cudaStreamSynchronize(S_(stream));
+    if (e != cudaSuccess) return (int)e;
+    if (v) {
+        int z = 0;
+        cudaMemcpyToSymbolAsync(g_fault, &z, sizeof(int), 0, cudaMemcpyHostToDevice, S_(stream));
+        cudaStreamSynchronize(S_(stream));
+    }
+    return v;
+}
+
+// ------------------------------------------------------------------------------ environment ----
+
+size_t cmr_workspace_bytes(int B, int N, int C, int P) {
+    if (B <= 0 || N <= 0 || C <= 0 || P <= 0) return 0;
+    return ws_layout(B, N, C, P).total;
+}
+
+int cmr_cloud_mean(const float *pc, int B, int N, float *mean, void *stream) {
+    CMR_REQUIRE(pc && mean && B > 0 && N > 0, CMR_EINVAL);
+    k_cloud_mean<<<dim3(3, B), 512, 0, S_(stream)>>>(pc, N, mean);
+    return after_launch();
+}
+
+int cmr_episode_prepare(const uint8_t *overlap, const float *feat, int B, int N, int C, void *workspace,
+                        void *stream) {
+    CMR_REQUIRE(overlap && feat && workspace && B > 0 && N > 0 && C > 0, CMR_EINVAL);
+    CMR_REQUIRE(C <= kMaxC && (C % 4) == 0 && N < (1 << 24) && B <= 65535, CMR_ERANGE);
+    CMR_REQUIRE(aligned(workspace, 256), CMR_EALIGN);
+    WsLayout L = ws_layout(B, N, C, 1);
+    char *ws = static_cast<char *>(workspace);
+    int *M = reinterpret_cast<int *>(ws + L.off_m);
+    int *seg = reinterpret_cast<int *>(ws + L.off_seg);
+    float *featT = reinterpret_cast<float *>(ws + L.off_feat);
+    const bool vec = (N % 4 == 0) && aligned(overlap, 4);
+    k_overlap_scan<<<B, 1024, 0, S_(stream)>>>(overlap, N, L.groups, vec, seg, M);
+    int rc = after_launch();
+    if (rc) return rc;
+    size_t smem = sizeof(float) * kGroup * (C + 1);
+    rc = allow_smem(k_feat_compact<256>, smem);
+    if (rc) return rc;
+    k_feat_compact<256><<<dim3(L.groups, B), 256, smem, S_(stream)>>>(overlap, feat, N, C, L.groups, seg, featT);
+    return after_launch();
+}
+
+static int check_observe_dims(int B, int N, int C, int H, int W) {
+    CMR_REQUIRE(B > 0 && N > 0 && C > 0 && H > 0 && W > 0, CMR_EINVAL);
+    CMR_REQUIRE(C <= kMaxC && (C % 4) == 0 && N < (1 << 24) && B <= 65535 && (long long)H * W < (1ll << 30), CMR_ERANGE);
+    return CMR_OK;
+}
+
+int cmr_project(const float *pc, const uint8_t *overlap, const float *K, const float *pose, const float *mean,
+                void *workspace, int B, int N, int C, int H, int W, float *obs3d, int32_t *pix_out, int32_t *mvis_out,
+                void *stream) {
+    CMR_REQUIRE(pc && overlap && K && pose && mean && workspace && obs3d, CMR_EINVAL);
+    int rc = check_observe_dims(B, N, C, H, W);
+    if (rc) return rc;
+    CMR_REQUIRE(aligned(workspace, 256), CMR_EALIGN);
+    WsLayout L = ws_layout(B, N, C, H * W);
+    char *ws = static_cast<char *>(workspace);
+    if (L.pix16)
+        return launch_project<uint16_t>(L, ws, pc, overlap, K, pose, mean, B, N, H, W, obs3d, pix_out, mvis_out, S_(stream));
+    return launch_project<int32_t>(L, ws, pc, overlap, K, pose, mean, B, N, H, W, obs3d, pix_out, mvis_out, S_(stream));
+}
+
+int cmr_tile_scatter(const float *img_feat, const void *workspace, int B, int N, int C, int H, int W, float *obs2d,
+                     void *stream) {
+    CMR_REQUIRE(img_feat && workspace && obs2d, CMR_EINVAL);
+    int rc = check_observe_dims(B, N, C, H, W);
+    if (rc) return rc;
+    CMR_REQUIRE(aligned(workspace, 256), CMR_EALIGN);
+    WsLayout L = ws_layout(B, N, C, H * W);
+    const char *ws = static_cast<const char *>(workspace);
+    if (L.pix16) return launch_scatter<uint16_t>(L, ws, img_feat, B, N, C, H * W, obs2d, S_(stream));
+    return launch_scatter<int32_t>(L, ws, img_feat, B, N, C, H * W, obs2d, S_(stream));
+}
+
+int cmr_observe(const float *pc, const uint8_t *overlap, const float *img_feat, const float *K, const float *pose,
+                const float *mean, void *workspace, int B, int N, int C, int H, int W, float *obs2d, float *obs3d,
+                int32_t *pix_out, int32_t *mvis_out, void *stream) {
+    int rc = cmr_project(pc, overlap, K, pose, mean, workspace, B, N, C, H, W, obs3d, pix_out, mvis_out, stream);
+    if (rc) return rc;
+    return cmr_tile_scatter(img_feat, workspace, B, N, C, H, W, obs2d, stream);
+}
+
+int cmr_to_disentangled(float *poses, const float *mean, int B, void *stream) {
+    CMR_REQUIRE(poses && mean && B > 0, CMR_EINVAL);
+    k_to_disentangled<<<ceil_div(B, 128), 128, 0, S_(stream)>>>(poses, mean, B);
+    return after_launch();
+}
+
+int cmr_step(float *pose, const int64_t *action_r, const int64_t *action_t, const float *rot_tab, const float *t_tab,
+             int nbins, int dof6, int B, void *stream) {
+    CMR_REQUIRE(pose && action_r && action_t && rot_tab && t_tab && nbins > 0 && B > 0, CMR_EINVAL);
+    k_step<<<ceil_div(B, 128), 128, 0, S_(stream)>>>(pose, action_r, action_t, rot_tab, t_tab, nbins, dof6 ? 1 : 0, B);
+    return after_launch();
+}
+
+size_t cmr_reward_scratch_bytes(int B) { return B > 0 ? (size_t)B * kRewardSlotBytes : 0; }
+
+int cmr_reward(const float *target, const float *pc, const uint8_t *mask, const float *mean, const float *pose,
+               const float *prev, int mode, int B, int N, void *scratch, float *reward, float *dist, void *stream) {
+    CMR_REQUIRE(target && pc && mask && mean && scratch && reward && dist && B > 0 && N > 0, CMR_EINVAL);
+    CMR_REQUIRE(mode == CMR_REWARD_SHIPPED || (mode == CMR_REWARD_INTENDED && pose), CMR_EINVAL);
+    CMR_REQUIRE(aligned(scratch, 16), CMR_EALIGN);
+    CMR_REQUIRE(B <= 65535, CMR_ERANGE);
+    int nchunks = std::min(kRewardChunks, ceil_div(N, 4096));
+    int per_chunk = (int)round_up((size_t)ceil_div(N, nchunks), 1024);
+    nchunks = ceil_div(N, per_chunk);
+    const bool vec = (N % 4 == 0) && aligned(mask, 4);
+    k_reward<<<dim3(nchunks, B), 256, 0, S_(stream)>>>(target, pc, mask, mean, pose, prev, mode, N, per_chunk, vec,
+                                                       static_cast<unsigned char *>(scratch), reward, dist);
+    return after_launch();
+}
+
+// ---------------------------------------------------------------------------- pointnet_util ----
+
+int cmr_square_distance(const float *src, const int64_t src_stride[3], const float *dst, const int64_t dst_stride[3],
+                        int B, int S, int N, float *out, void *stream) {
+    CMR_REQUIRE(src && dst && out && src_stride && dst_stride && B > 0 && S > 0 && N > 0, CMR_EINVAL);
+    CMR_REQUIRE(S <= 65535 && B <= 65535, CMR_ERANGE);
+    int gx = std::min(ceil_div(N, 256), 64);
+    k_square_distance<<<dim3(gx, S, B), 256, 0, S_(stream)>>>(src, src_stride[0], src_stride[1], src_stride[2], dst,
+                                                             dst_stride[0], dst_stride[1], dst_stride[2], S, N, out);
+    return after_launch();
+}
+
+int cmr_index_points(const void *points, const int64_t *idx, int B, int N, int S, int row_bytes, void *out,
+                     void *stream) {
+    CMR_REQUIRE(points && idx && out && B > 0 && N > 0 && S > 0 && row_bytes > 0, CMR_EINVAL);
+    if (row_bytes % 16 == 0 && aligned(points, 16) && aligned(out, 16))
+        return launch_index_points<uint4>(points, idx, B, N, S, row_bytes, out, S_(stream));
+    if (row_bytes % 4 == 0 && aligned(points, 4) && aligned(out, 4))
+        return launch_index_points<unsigned>(points, idx, B, N, S, row_bytes, out, S_(stream));
+    return launch_index_points<unsigned char>(points, idx, B, N, S, row_bytes, out, S_(stream));
+}
+
+int cmr_index_points_backward(const float *grad_out, const int64_t *idx, int B, int N, int S, int C,
+                              float *grad_points, void *stream) {
+    CMR_REQUIRE(grad_out && idx && grad_points && B > 0 && N > 0 && S > 0 && C > 0, CMR_EINVAL);
+    long long total = (long long)B * S * C;
+    int grid = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 32);
+    k_index_points_bwd<<<grid, 256, 0, S_(stream)>>>(grad_out, idx, N, S, C, grad_points, total);
+    return after_launch();
+}
+
+int cmr_group_points(const float *xyz, const float *points, const float *new_xyz, const int64_t *idx, int B, int N,
+                     int S, int K, int D, float *out, void *stream) {
+    CMR_REQUIRE(xyz && new_xyz && idx && out && B > 0 && N > 0 && S > 0 && K > 0 && D >= 0, CMR_EINVAL);
+    CMR_REQUIRE(D == 0 || points, CMR_EINVAL);
+    long long total = (long long)B * S * K * (3 + D);
+    int grid = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 32);
+    k_group_points<<<grid, 256, 0, S_(stream)>>>(xyz, points, new_xyz, idx, N, S, K, D, out, total);
+    return after_launch();
+}
+
+int cmr_farthest_point_sample(const float *xyz, const int64_t *start, int B, int N, int npoint, int64_t *out,
+                              void *stream) {
+    CMR_REQUIRE(xyz && start && out && B > 0 && N > 0 && npoint > 0, CMR_EINVAL);
+    constexpr int THREADS = 512, kMaxPpt = 24;
+    // smallest cluster that holds the cloud in registers, widened while the whole batch still fits
+    // on the chip in one wave (fewer points per thread = shorter rounds; FPS is latency-bound)
+    int cs = 1;
+    while (cs < 16 && (long long)cs * THREADS * kMaxPpt < N) cs *= 2;
+    CMR_REQUIRE((long long)cs * THREADS * kMaxPpt >= N, CMR_ERANGE);
+    const int sms = sm_count();
+    while (cs < 8 && (long long)B * cs * 2 <= sms && (long long)cs * THREADS * 4 < N) cs *= 2;
+    int ppt = ceil_div(N, cs * THREADS);
+    cudaStream_t st = S_(stream);
+    if (ppt <= 4) return launch_fps<4>(xyz, start, B, N, npoint, out, cs, st);
+    if (ppt <= 8) return launch_fps<8>(xyz, start, B, N, npoint, out, cs, st);
+    if (ppt <= 12) return launch_fps<12>(xyz, start, B, N, npoint, out, cs, st);
+    if (ppt <= 16) return launch_fps<16>(xyz, start, B, N, npoint, out, cs, st);
+    if (ppt <= 20) return launch_fps<20>(xyz, start, B, N, npoint, out, cs, st);
+    return launch_fps<24>(xyz, start, B, N, npoint, out, cs, st);
+}
+
+int cmr_knn(const float *query, const float *ref, int B, int S, int N, int k, int64_t *out, void *stream) {
+    CMR_REQUIRE(query && ref && out && B > 0 && S > 0 && N > 0 && k > 0, CMR_EINVAL);
+    CMR_REQUIRE(k <= 128 && k <= N && B <= 65535, CMR_ERANGE);
+    cudaStream_t st = S_(stream);
+    if (k <= 32) {
+        k_knn<32, 4><<<dim3(ceil_div(S, 32), B), 256, 0, st>>>(query, ref, S, N, k, out);
+    } else if (k <= 64) {
+        k_knn<64, 4><<<dim3(ceil_div(S, 32), B), 256, 0, st>>>(query, ref, S, N, k, out);
+    } else {
+        k_knn<128, 2><<<dim3(ceil_div(S, 16), B), 256, 0, st>>>(query, ref, S, N, k, out);
+    }
+    return after_launch();
+}
+
+int cmr_query_ball_point(const float *query, const float *ref, float radius2, int nsample, int B, int S, int N,
+                         int64_t *out, void *stream) {
+    CMR_REQUIRE(query && ref && out && nsample > 0 && B > 0 && S > 0 && N > 0, CMR_EINVAL);
+    CMR_REQUIRE(B <= 65535, CMR_ERANGE);
+    k_ball_query<<<dim3(ceil_div(S, 8), B), 256, 0, S_(stream)>>>(query, ref, radius2, nsample, S, N, out);
+    return after_launch();
+}
+
+}  // extern "C"

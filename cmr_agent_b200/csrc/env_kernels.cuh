@@ -1,0 +1,671 @@
+// env_kernels.cuh - sm_100a kernels for the environment half of the hot path
+// (reference: environment/environment.py; every kernel cites the lines it replaces).
+//
+// Data layout in HBM (per episode batch):
+//   pc        [B,3,N]  f32  channel-major (SoA) exactly as the reference holds it
+//   overlap   [B,N]    u8   torch.bool
+//   feat      [B,C,N]  f32  channel-major; read ONCE per episode by k_feat_compact
+//   workspace: M[B] i32 | seg[B,G] i32 (exclusive prefix of overlap counts per 128 points) |
+//              pix[B,ncap] u16/i32 (pixel id of the m-th predicted-overlap point, rewritten
+//              every observe) | featT[B,N,C] f32 (rows of the predicted-overlap points, point-major)
+//   obs3d     [B,5,N]  f32 ; obs2d [B,2C,H,W] f32
+#pragma once
+#include "common.cuh"
+
+namespace cmr {
+
+constexpr int kGroup = 128;     // points per compaction group = 32 lanes x 4 points
+constexpr int kTilePix = 128;   // pixels per k_tile_scatter CTA
+constexpr int kListCap = 4096;  // candidate entries staged in shared memory per flush
+constexpr int kMaxC = 256;
+
+struct WsLayout {
+    size_t off_m, off_seg, off_pix, off_feat, total;
+    int groups, ncap;
+    bool pix16;
+};
+
+inline WsLayout ws_layout(int B, int N, int C, int P) {
+    WsLayout L;
+    L.groups = ceil_div(N, kGroup);
+    L.ncap = (int)round_up((size_t)N, 8);
+    L.pix16 = P < 65535;
+    size_t o = 0;
+    L.off_m = o;
+    o = round_up(o + sizeof(int) * (size_t)B, 256);
+    L.off_seg = o;
+    o = round_up(o + sizeof(int) * (size_t)B * L.groups, 256);
+    L.off_pix = o;
+    o = round_up(o + sizeof(int) * (size_t)B * L.ncap, 256);
+    L.off_feat = o;
+    o = round_up(o + sizeof(float) * (size_t)B * N * C, 256);
+    L.total = o;
+    return L;
+}
+
+// -------------------------------------------------------------------------------------------------
+// pc.mean(dim=2)  (environment.py:46,91,274).  One CTA per (coordinate row, episode); fp64 sum in a
+// fixed order => deterministic.
+__global__ void __launch_bounds__(512) k_cloud_mean(const float *__restrict__ pc, int N, float *__restrict__ mean) {
+    const float *row = pc + ((size_t)blockIdx.y * 3 + blockIdx.x) * N;
+    double acc = 0.0;
+    for (int j = threadIdx.x; j < N; j += blockDim.x) acc += (double)row[j];
+    __shared__ double part[16];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += part[w];
+        mean[blockIdx.y * 3 + blockIdx.x] = (float)(s / (double)N);
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// four consecutive overlap flags starting at j0 as a 4-bit mask (bit i = point j0+i)
+__device__ __forceinline__ unsigned load_flags4(const uint8_t *__restrict__ ov, int j0, int N, bool vec) {
+    unsigned m = 0;
+    if (vec && j0 + 3 < N) {
+        uchar4 f = *reinterpret_cast<const uchar4 *>(ov + j0);
+        m = (f.x ? 1u : 0u) | (f.y ? 2u : 0u) | (f.z ? 4u : 0u) | (f.w ? 8u : 0u);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (j0 + i < N && ov[j0 + i]) m |= 1u << i;
+    }
+    return m;
+}
+
+// Once per episode: number of predicted-overlap points in every 128-point group and its exclusive
+// prefix (replaces the nonzero() of the boolean index at environment.py:48-49).  One CTA per episode.
+__global__ void __launch_bounds__(1024) k_overlap_scan(const uint8_t *__restrict__ overlap, int N, int groups,
+                                                        bool vec, int *__restrict__ seg, int *__restrict__ M) {
+    const int b = blockIdx.x;
+    const uint8_t *ov = overlap + (size_t)b * N;
+    int *sg = seg + (size_t)b * groups;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    __shared__ int wtot[32];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    // pass 1: per-group counts straight into seg[]
+    for (int g = warp; g < groups; g += nwarp) {
+        unsigned f = load_flags4(ov, g * kGroup + lane * 4, N, vec);
+        int c = warp_sum(__popc(f));
+        if (lane == 0) sg[g] = c;
+    }
+    __syncthreads();
+    // pass 2: exclusive scan over groups, blockDim entries at a time
+    for (int base = 0; base < groups; base += blockDim.x) {
+        int g = base + threadIdx.x;
+        int v = g < groups ? sg[g] : 0;
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(kFull, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) wtot[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            int w = lane < nwarp ? wtot[lane] : 0;
+            int winc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(kFull, winc, o);
+                if (lane >= o) winc += t;
+            }
+            wtot[lane] = winc - w;  // exclusive prefix of warp totals
+        }
+        __syncthreads();
+        int excl = carry + wtot[warp] + inc - v;
+        if (g < groups) sg[g] = excl;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) M[b] = carry;
+}
+
+// Once per episode: features of the predicted-overlap points, transposed from the reference's
+// channel-major [C,N] to point-major rows [M,C] so that one point is one contiguous 4C-byte row
+// (replaces pc_geo_feat[i:i+1, :, overlap_pred_i], environment.py:49).  One CTA per 128-point group.
+template <int kThreads>
+__global__ void __launch_bounds__(kThreads) k_feat_compact(const uint8_t *__restrict__ overlap,
+                                                            const float *__restrict__ feat, int N, int C, int groups,
+                                                            const int *__restrict__ seg, float *__restrict__ featT) {
+    extern __shared__ float tile[];  // [kGroup][C+1]
+    __shared__ int rank[kGroup];
+    __shared__ int wbase[5];
+    const int g = blockIdx.x, b = blockIdx.y;
+    const int j0 = g * kGroup;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint8_t *ov = overlap + (size_t)b * N;
+    const int stride = C + 1;
+    // ranks of the overlap points inside the group (warps 0..3 cover 32 points each)
+    if (warp < 4) {
+        int j = j0 + warp * 32 + lane;
+        bool f = j < N && ov[j];
+        unsigned m = __ballot_sync(kFull, f);
+        rank[warp * 32 + lane] = f ? __popc(m & ((1u << lane) - 1)) : -1;
+        if (lane == 0) wbase[warp + 1] = __popc(m);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        wbase[0] = 0;
+        for (int w = 1; w <= 4; ++w) wbase[w] += wbase[w - 1];
+    }
+    __syncthreads();
+    const int total = wbase[4];
+    if (total == 0) return;
+    // coalesced read along the point axis, transposed into shared memory
+    const float *src = feat + (size_t)b * C * N;
+    for (int r = warp; r < C * 4; r += kThreads / 32) {
+        int c = r >> 2, p = (r & 3) * 32 + lane;
+        int j = j0 + p;
+        tile[p * stride + c] = j < N ? __ldg(src + (size_t)c * N + j) : 0.f;
+    }
+    __syncthreads();
+    // write the rows of the overlap points: one warp per row
+    float *dst = featT + ((size_t)b * N + seg[(size_t)b * groups + g]) * C;
+    for (int p = warp; p < kGroup; p += kThreads / 32) {
+        int rk = rank[p];
+        if (rk < 0) continue;
+        int pos = wbase[p >> 5] + rk;
+        for (int c = lane; c < C; c += 32) dst[(size_t)pos * C + c] = tile[p * stride + c];
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Per-episode constants of one observe call, staged once per CTA.
+struct PoseK {
+    float R[9], t[3], K[9], m[3];
+};
+
+__device__ __forceinline__ void load_posek(PoseK &s, const float *__restrict__ pose, const float *__restrict__ K,
+                                           const float *__restrict__ mean, int b) {
+    const float *P = pose + (size_t)b * 16;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) s.R[3 * r + c] = __ldg(P + 4 * r + c);
+        s.t[r] = __ldg(P + 4 * r + 3);
+        s.m[r] = __ldg(mean + (size_t)b * 3 + r);
+    }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) s.K[i] = __ldg(K + (size_t)b * 9 + i);
+}
+
+// environment.py:54-72 for one point.  Returns the pixel id (H*W when outside the frustum).
+// kChain selects the bmm regime of the product this column belongs to (common.cuh).
+template <bool kChain>
+__device__ __forceinline__ int project_point(const PoseK &s, float x, float y, float z, float wmax, float hmax, int W,
+                                             int P, bool &in_cam) {
+    float cx = __fsub_rn(x, s.m[0]), cy = __fsub_rn(y, s.m[1]), cz = __fsub_rn(z, s.m[2]);   // :54 / :92
+    float X0 = __fadd_rn(__fadd_rn(dot3<kChain>(s.R[0], s.R[1], s.R[2], cx, cy, cz), s.m[0]), s.t[0]);  // :55-56
+    float X1 = __fadd_rn(__fadd_rn(dot3<kChain>(s.R[3], s.R[4], s.R[5], cx, cy, cz), s.m[1]), s.t[1]);
+    float X2 = __fadd_rn(__fadd_rn(dot3<kChain>(s.R[6], s.R[7], s.R[8], cx, cy, cz), s.m[2]), s.t[2]);
+    float U0 = dot3<kChain>(s.K[0], s.K[1], s.K[2], X0, X1, X2);                               // :58
+    float U1 = dot3<kChain>(s.K[3], s.K[4], s.K[5], X0, X1, X2);
+    float U2 = dot3<kChain>(s.K[6], s.K[7], s.K[8], X0, X1, X2);
+    float u = __fdiv_rn(U0, U2), v = __fdiv_rn(U1, U2);                                        // :59
+    in_cam = (u >= 0.f) && (u <= wmax) && (v >= 0.f) && (v <= hmax) && (U2 > 0.f);             // :61-65
+    int ui = __float2int_rn(u), vi = __float2int_rn(v);                                        // :67 half-to-even
+    return in_cam ? vi * W + ui : P;                                                           // :69-72
+}
+
+// Fused: disentangled transform -> pinhole -> frustum mask -> pixel id for ALL points of every
+// episode; writes obs3d (environment.py:88-124) and the pixel id of each predicted-overlap point at
+// its compacted position (input of k_tile_scatter).  One warp = one 128-point group, 4 points/lane.
+template <typename PixT>
+__global__ void __launch_bounds__(256) k_project(const float *__restrict__ pc, const uint8_t *__restrict__ overlap,
+                                                  const float *__restrict__ K, const float *__restrict__ pose,
+                                                  const float *__restrict__ mean, const int *__restrict__ seg,
+                                                  const int *__restrict__ M, int N, int ncap, int groups, int H, int W,
+                                                  bool vec,
+                                                  PixT *__restrict__ pix, float *__restrict__ obs3d,
+                                                  int32_t *__restrict__ pix_out, int32_t *__restrict__ mvis) {
+    const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int g = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (g >= groups) return;
+    const int j0 = g * kGroup + lane * 4;
+    PoseK s;
+    load_posek(s, pose, K, mean, b);
+    const int P = H * W;
+    const float wmax = (float)(W - 1), hmax = (float)(H - 1);
+    const float *px = pc + (size_t)b * 3 * N, *py = px + N, *pz = py + N;
+    float x[4], y[4], z[4];
+    if (vec && j0 + 3 < N) {
+        float4 a = ldg_stream4(px + j0), c = ldg_stream4(py + j0), d = ldg_stream4(pz + j0);
+        x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w;
+        y[0] = c.x; y[1] = c.y; y[2] = c.z; y[3] = c.w;
+        z[0] = d.x; z[1] = d.y; z[2] = d.z; z[3] = d.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            bool ok = j0 + i < N;
+            x[i] = ok ? px[j0 + i] : 0.f;
+            y[i] = ok ? py[j0 + i] : 0.f;
+            z[i] = ok ? pz[j0 + i] : 0.f;
+        }
+    }
+    const unsigned flags = load_flags4(overlap + (size_t)b * N, j0, N, vec);
+    // The 3-D branch multiplies all N columns at once (:93,95), the 2-D branch only the M predicted-
+    // overlap columns (:55,58): each follows the bmm regime of its own column count.
+    const bool chain3d = N >= kBmmChainMinCols;
+    const bool chain2d = __ldg(M + b) >= kBmmChainMinCols;
+    int id[4], id2[4];
+    unsigned cam = 0, cam2 = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        bool in_cam;
+        id[i] = chain3d ? project_point<true>(s, x[i], y[i], z[i], wmax, hmax, W, P, in_cam)
+                        : project_point<false>(s, x[i], y[i], z[i], wmax, hmax, W, P, in_cam);
+        if (in_cam) cam |= 1u << i;
+        id2[i] = id[i];
+    }
+    cam2 = cam;
+    if (chain2d != chain3d) {   // only for clouds with fewer than 45 (predicted-overlap) points
+        cam2 = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            bool in_cam;
+            id2[i] = chain2d ? project_point<true>(s, x[i], y[i], z[i], wmax, hmax, W, P, in_cam)
+                             : project_point<false>(s, x[i], y[i], z[i], wmax, hmax, W, P, in_cam);
+            if (in_cam) cam2 |= 1u << i;
+        }
+    }
+    // ---- obs3d = cat(pc, overlap.float(), in_cam.float())  (:121-124)
+    float *o = obs3d + (size_t)b * 5 * N;
+    if (vec && j0 + 3 < N) {
+        stg_stream4(o + j0, make_float4(x[0], x[1], x[2], x[3]));
+        stg_stream4(o + (size_t)N + j0, make_float4(y[0], y[1], y[2], y[3]));
+        stg_stream4(o + 2 * (size_t)N + j0, make_float4(z[0], z[1], z[2], z[3]));
+        stg_stream4(o + 3 * (size_t)N + j0, make_float4((flags & 1) ? 1.f : 0.f, (flags & 2) ? 1.f : 0.f,
+                                                        (flags & 4) ? 1.f : 0.f, (flags & 8) ? 1.f : 0.f));
+        stg_stream4(o + 4 * (size_t)N + j0, make_float4((cam & 1) ? 1.f : 0.f, (cam & 2) ? 1.f : 0.f,
+                                                        (cam & 4) ? 1.f : 0.f, (cam & 8) ? 1.f : 0.f));
+        if (pix_out) *reinterpret_cast<int4 *>(pix_out + (size_t)b * N + j0) = make_int4(id[0], id[1], id[2], id[3]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (j0 + i >= N) break;
+            o[j0 + i] = x[i];
+            o[(size_t)N + j0 + i] = y[i];
+            o[2 * (size_t)N + j0 + i] = z[i];
+            o[3 * (size_t)N + j0 + i] = (flags >> i & 1) ? 1.f : 0.f;
+            o[4 * (size_t)N + j0 + i] = (cam >> i & 1) ? 1.f : 0.f;
+            if (pix_out) pix_out[(size_t)b * N + j0 + i] = id[i];
+        }
+    }
+    // ---- pixel ids of the predicted-overlap points, in compacted (index) order
+    const int mine = __popc(flags);
+    int incl = mine;
+#pragma unroll
+    for (int o2 = 1; o2 < 32; o2 <<= 1) {
+        int t = __shfl_up_sync(kFull, incl, o2);
+        if (lane >= o2) incl += t;
+    }
+    int pos = __ldg(seg + (size_t)b * groups + g) + incl - mine;
+    PixT *pw = pix + (size_t)b * ncap;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        if (flags >> i & 1) pw[pos++] = (PixT)id2[i];
+    if (mvis) {
+        int v = warp_sum(__popc(flags & cam2));
+        if (lane == 0 && v) atomicAdd(mvis + b, v);
+    }
+}
+
+// Scatter-mean of the predicted-overlap points' features onto the pixel grid + concat with the image
+// features (environment.py:74-86).  One CTA owns kTilePix consecutive pixels of one episode:
+//   (0) copies the image-feature half of obs2d for its pixels (does not depend on the pose),
+//   (1) scans the episode's compacted pixel-id list for points that land in its tile (ordered),
+//   (2) warp w accumulates, in point order, the feature rows of the points of pixels p%8==w into a
+//       shared-memory tile [pixel][C+1]  (deterministic, no atomics),
+//   (3) divides by max(count,1) and writes the projected half of obs2d channel-major.
+template <typename PixT, int CQ>
+__global__ void __launch_bounds__(256) k_tile_scatter(const PixT *__restrict__ pix, const int *__restrict__ M,
+                                                       const float *__restrict__ featT,
+                                                       const float *__restrict__ img_feat, int N, int ncap, int C,
+                                                       int P, bool vec, float *__restrict__ obs2d) {
+    extern __shared__ float smem[];
+    const int stride = C + 1;
+    float *acc = smem;                                              // [kTilePix][C+1]
+    int *cnt = reinterpret_cast<int *>(acc + kTilePix * stride);   // [kTilePix]
+    unsigned *list = reinterpret_cast<unsigned *>(cnt + kTilePix); // [kListCap]
+    __shared__ int wsum[8];
+    __shared__ int lcount_s;
+
+    const int b = blockIdx.y;
+    const int p0 = blockIdx.x * kTilePix;
+    const int np = min(kTilePix, P - p0);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float *out = obs2d + (size_t)b * 2 * C * P;
+
+    // (0) image half: obs2d[b, c, p0:p0+np] = img_feat[b, c, p0:p0+np]
+    {
+        const float *img = img_feat + (size_t)b * C * P;
+        if (vec && np == kTilePix) {
+            for (int c0 = 0; c0 < C; c0 += 32) {   // 8 warps x 4 channels per sweep, 4 loads in flight
+                float4 v[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    int c = c0 + warp * 4 + k;
+                    if (c < C) v[k] = ldg_stream4(img + (size_t)c * P + p0 + lane * 4);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    int c = c0 + warp * 4 + k;
+                    if (c < C) stg_stream4(out + (size_t)c * P + p0 + lane * 4, v[k]);
+                }
+            }
+        } else {
+            for (int i = tid; i < C * np; i += 256) {
+                int c = i / np, p = i - c * np;
+                out[(size_t)c * P + p0 + p] = img[(size_t)c * P + p0 + p];
+            }
+        }
+    }
+    for (int i = tid; i < kTilePix * stride; i += 256) acc[i] = 0.f;
+    if (tid < kTilePix) cnt[tid] = 0;
+    if (tid == 0) lcount_s = 0;
+    __syncthreads();
+
+    const int m_total = min(__ldg(M + b), N);
+    const PixT *pw = pix + (size_t)b * ncap;
+    const float *rows = featT + (size_t)b * N * C;
+    constexpr int kPer = 16 / sizeof(PixT);  // ids per 16-byte load
+    const unsigned lo = (unsigned)p0, hi = (unsigned)(p0 + np);
+
+    auto accumulate = [&](int lcount) {
+        // (2) warp w owns the pixels with (local id & 7) == w; entries are in point order
+        for (int i0 = 0; i0 < lcount; i0 += 32) {
+            unsigned e = (i0 + lane < lcount) ? list[i0 + lane] : 0xffffffffu;
+            unsigned mine = __ballot_sync(kFull, e != 0xffffffffu && (e & 7u) == (unsigned)warp);
+            while (mine) {
+                // up to 4 rows in flight per warp
+                unsigned ent[4];
+                int n = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (mine) {
+                        int src = __ffs(mine) - 1;
+                        mine &= mine - 1;
+                        ent[k] = __shfl_sync(kFull, e, src);
+                        n = k + 1;
+                    } else {
+                        ent[k] = 0xffffffffu;
+                    }
+                }
+                float v[4][CQ];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (k < n) {
+                        const float *row = rows + (size_t)(ent[k] >> 7) * C;
+#pragma unroll
+                        for (int q = 0; q < CQ; ++q)
+                            if (q * 32 + lane < C) v[k][q] = __ldg(row + q * 32 + lane);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (k < n) {
+                        int pl = ent[k] & 127u;
+                        float *a = acc + pl * stride;
+#pragma unroll
+                        for (int q = 0; q < CQ; ++q)
+                            if (q * 32 + lane < C) a[q * 32 + lane] = __fadd_rn(a[q * 32 + lane], v[k][q]);
+                        if (lane == 0) cnt[pl] += 1;
+                    }
+                }
+            }
+        }
+    };
+
+    // (1) ordered scan of the compacted pixel ids
+    int lcount = 0;
+    for (int base = 0; base < m_total; base += 256 * kPer) {
+        const int m0 = base + tid * kPer;
+        unsigned hit = 0;
+        alignas(16) PixT ids[kPer];
+        if (m0 < m_total) {
+            uint4 raw = *reinterpret_cast<const uint4 *>(pw + m0);
+            *reinterpret_cast<uint4 *>(ids) = raw;
+#pragma unroll
+            for (int k = 0; k < kPer; ++k) {
+                unsigned id = (unsigned)ids[k];
+                if (m0 + k < m_total && id >= lo && id < hi) hit |= 1u << k;
+            }
+        }
+        int mine = __popc(hit), incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(kFull, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        int before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            int s = wsum[w];
+            if (w < warp) before += s;
+            total += s;
+        }
+        if (lcount + total > kListCap) {  // uniform across the CTA
+            accumulate(lcount);
+            lcount = 0;
+            __syncthreads();
+        }
+        int pos = lcount + before + incl - mine;
+#pragma unroll
+        for (int k = 0; k < kPer; ++k)
+            if (hit >> k & 1) list[pos++] = ((unsigned)(m0 + k) << 7) | ((unsigned)ids[k] - lo);
+        lcount += total;
+        __syncthreads();
+    }
+    accumulate(lcount);
+    __syncthreads();
+
+    // (3) mean + channel-major store of the projected half: obs2d[b, C + c, p0 + p]
+    float *proj = out + (size_t)C * P;
+    for (int c = warp; c < C; c += 8) {
+#pragma unroll
+        for (int p = lane; p < kTilePix; p += 32) {
+            if (p < np) {
+                int n = cnt[p];
+                float v = __fdiv_rn(acc[p * stride + c], (float)(n < 1 ? 1 : n));
+                stg_stream1(proj + (size_t)c * P + p0 + p, v);
+            }
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// to_disentangled (environment.py:15-21): t <- (t - m) + R m, one thread per pose.
+__global__ void k_to_disentangled(float *__restrict__ poses, const float *__restrict__ mean, int B) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    float *P = poses + (size_t)b * 16;
+    float m0 = mean[b * 3], m1 = mean[b * 3 + 1], m2 = mean[b * 3 + 2];
+    float t[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        float rm = dot3_plain(P[4 * r], P[4 * r + 1], P[4 * r + 2], m0, m1, m2);   // 3x3 @ 3x1: plain regime
+        float mr = r == 0 ? m0 : (r == 1 ? m1 : m2);
+        t[r] = __fadd_rn(__fsub_rn(P[4 * r + 3], mr), rm);
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) P[4 * r + 3] = t[r];
+}
+
+// 3x3 @ 3x3 as torch's CPU bmm evaluates it (plain regime, common.cuh)
+__device__ __forceinline__ void mat3_plain(const float *A, const float *Bm, float *Cm) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) Cm[3 * r + c] = dot3_plain(A[3 * r], A[3 * r + 1], A[3 * r + 2], Bm[c], Bm[3 + c], Bm[6 + c]);
+}
+
+// step (environment.py:179-207): R <- ((Rx @ Ry) @ Rz) @ R ; t <- t + move_t (3x3 products: plain regime).  rot_tab holds the
+// per-axis matrices for every bin plus, at index nbins, the matrix of angle 0.0 (3-DoF x/z axes).
+__global__ void k_step(float *__restrict__ pose, const int64_t *__restrict__ ar, const int64_t *__restrict__ at,
+                       const float *__restrict__ rot_tab, const float *__restrict__ t_tab, int nbins, int dof6, int B) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    // torch indexing wraps negative indices once (r_steps[-1] is the last bin)
+    auto wrap = [nbins](int64_t i) { return i < 0 ? i + nbins : i; };
+    int64_t ir[3], it[3];
+    bool bad = false;
+    if (dof6) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            ir[i] = wrap(ar[b * 3 + i]);
+            it[i] = wrap(at[b * 3 + i]);
+            bad |= ir[i] < 0 || ir[i] >= nbins || it[i] < 0 || it[i] >= nbins;
+        }
+    } else {  // :195-201: rotation about y only, translation along x and z
+        ir[0] = nbins; ir[1] = wrap(ar[b]); ir[2] = nbins;
+        it[0] = wrap(at[b * 2]); it[1] = -1; it[2] = wrap(at[b * 2 + 1]);
+        bad = ir[1] < 0 || ir[1] >= nbins || it[0] < 0 || it[0] >= nbins || it[2] < 0 || it[2] >= nbins;
+    }
+    if (bad) {
+        atomicExch(&g_fault, 2);
+        return;
+    }
+    const int per = (nbins + 1) * 9;
+    float Rx[9], Ry[9], Rz[9], A[9], Rn[9], R[9], Ro[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        Rx[i] = rot_tab[ir[0] * 9 + i];
+        Ry[i] = rot_tab[per + ir[1] * 9 + i];
+        Rz[i] = rot_tab[2 * per + ir[2] * 9 + i];
+    }
+    mat3_plain(Rx, Ry, A);   // functools.reduce(torch.matmul, ...) is a left fold (:231-232)
+    mat3_plain(A, Rz, Rn);
+    float *Pp = pose + (size_t)b * 16;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) R[3 * r + c] = Pp[4 * r + c];
+    mat3_plain(Rn, R, Ro);   // :204
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) Pp[4 * r + c] = Ro[3 * r + c];
+        float mv = it[r] < 0 ? 0.f : t_tab[it[r]];
+        Pp[4 * r + 3] = __fadd_rn(Pp[4 * r + 3], mv);   // :205
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// reward (environment.py:263-302).  grid (chunks, B): every CTA reduces a slab of points to one fp64
+// partial; the last CTA of an episode to finish adds the partials in slab order (deterministic) and
+// writes distance and reward.  scratch per episode: [counter u32, pad][kRewardChunks x {sum f64, n i64}].
+constexpr int kRewardChunks = 32;
+constexpr int kRewardSlotBytes = 16 + kRewardChunks * 16;
+
+__global__ void __launch_bounds__(256) k_reward(const float *__restrict__ target, const float *__restrict__ pc,
+                                                 const uint8_t *__restrict__ mask, const float *__restrict__ mean,
+                                                 const float *__restrict__ pose, const float *__restrict__ prev,
+                                                 int mode, int N, int per_chunk, bool vec, unsigned char *scratch,
+                                                 float *__restrict__ reward, float *__restrict__ dist) {
+    const int b = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    PoseK s;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        s.m[r] = __ldg(mean + (size_t)b * 3 + r);
+        s.t[r] = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) s.R[3 * r + c] = 0.f;
+    }
+    if (mode == CMR_REWARD_INTENDED) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            s.t[r] = __ldg(pose + (size_t)b * 16 + 4 * r + 3);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) s.R[3 * r + c] = __ldg(pose + (size_t)b * 16 + 4 * r + c);
+        }
+    }
+    const float *px = pc + (size_t)b * 3 * N, *tx = target + (size_t)b * 3 * N;
+    const uint8_t *mk = mask + (size_t)b * N;
+    const int beg = chunk * per_chunk, end = min(N, beg + per_chunk);
+    double acc = 0.0;
+    int n = 0;
+    for (int j0 = beg + threadIdx.x * 4; j0 < end; j0 += 256 * 4) {
+        unsigned f = load_flags4(mk, j0, end, vec);
+        if (!f) continue;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (!(f >> i & 1)) continue;
+            int j = j0 + i;
+            float cx = __fsub_rn(px[j], s.m[0]), cy = __fsub_rn(px[(size_t)N + j], s.m[1]),
+                  cz = __fsub_rn(px[2 * (size_t)N + j], s.m[2]);                                       // :275
+            float bx = cx, by = cy, bz = cz;
+            if (mode == CMR_REWARD_INTENDED) {  // the transform of the commented line :273, disentangled
+                if (N >= kBmmChainMinCols) {
+                    bx = __fadd_rn(__fadd_rn(dot3_chain(s.R[0], s.R[1], s.R[2], cx, cy, cz), s.m[0]), s.t[0]);
+                    by = __fadd_rn(__fadd_rn(dot3_chain(s.R[3], s.R[4], s.R[5], cx, cy, cz), s.m[1]), s.t[1]);
+                    bz = __fadd_rn(__fadd_rn(dot3_chain(s.R[6], s.R[7], s.R[8], cx, cy, cz), s.m[2]), s.t[2]);
+                } else {
+                    bx = __fadd_rn(__fadd_rn(dot3_plain(s.R[0], s.R[1], s.R[2], cx, cy, cz), s.m[0]), s.t[0]);
+                    by = __fadd_rn(__fadd_rn(dot3_plain(s.R[3], s.R[4], s.R[5], cx, cy, cz), s.m[1]), s.t[1]);
+                    bz = __fadd_rn(__fadd_rn(dot3_plain(s.R[6], s.R[7], s.R[8], cx, cy, cz), s.m[2]), s.t[2]);
+                }
+            }
+            acc += (double)sqdist3(tx[j], tx[(size_t)N + j], tx[2 * (size_t)N + j], bx, by, bz);     // :287-288
+            ++n;
+        }
+    }
+    __shared__ double psum[8];
+    __shared__ int pcnt[8];
+    __shared__ bool last;
+    acc = warp_sum(acc);
+    n = warp_sum(n);
+    if (lane == 0) {
+        psum[warp] = acc;
+        pcnt[warp] = n;
+    }
+    __syncthreads();
+    unsigned char *slot = scratch + (size_t)b * kRewardSlotBytes;
+    unsigned *counter = reinterpret_cast<unsigned *>(slot);
+    double *sums = reinterpret_cast<double *>(slot + 16);
+    long long *cnts = reinterpret_cast<long long *>(slot + 16 + kRewardChunks * 8);
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        long long c = 0;
+        for (int w = 0; w < 8; ++w) {
+            t += psum[w];
+            c += pcnt[w];
+        }
+        sums[chunk] = t;
+        cnts[chunk] = c;
+        __threadfence();
+        unsigned done = atomicAdd(counter, 1u);
+        last = (done == (unsigned)nchunks - 1);
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        __threadfence();
+        double t = 0.0;
+        long long c = 0;
+        for (int k = 0; k < nchunks; ++k) {
+            t += *((volatile double *)&sums[k]);
+            c += *((volatile long long *)&cnts[k]);
+        }
+        float d = (float)(t / (double)c);   // empty mask: 0/0 = NaN like torch's mean of an empty tensor (:289)
+        dist[b] = d;
+        float r = 0.f;
+        if (prev) {                                                                                  // :294-299
+            float pd = prev[b];
+            r = (d < pd ? 0.5f : 0.f) - (d > pd ? 0.5f : 0.f);
+        }
+        reward[b] = r;
+        *counter = 0;   // self-resetting for the next call
+    }
+}
+
+}  // namespace cmr

@@ -1,0 +1,158 @@
+/*
+ * cmr_b200.h - C ABI of libcmr_b200.so, the sm_100a implementation of CMR-Agent's
+ * per-iteration geometric hot path (environment step + PointNet++ front-end).
+ *
+ * The reference (y2w-oc/CMR-Agent) is pure Python; its "FFI" for this path is the set of
+ * module-level functions in environment/environment.py and models/pointnet_util.py.  Each entry
+ * point below names the reference lines it replaces (paths relative to the reference root).
+ * The Python drop-ins in cmr_agent_b200/{environment,pointnet_util}.py bind these through ctypes
+ * and keep the reference's signatures; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless marked "host"; tensors are dense, row-major,
+ *     in exactly the layout the reference's tensors have (shapes in brackets);
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous and never
+ *     synchronises the host;
+ *   - return value: 0 = ok; CMR_E* (< 0) = bad argument, nothing was launched;
+ *     > 0 = the cudaError_t of a failed launch.  cmr_error_string() explains any of them;
+ *   - there is no CPU fallback: without a CUDA device every call returns a cudaError_t.
+ */
+#ifndef CMR_B200_H_
+#define CMR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define CMR_API __attribute__((visibility("default")))
+#else
+#define CMR_API
+#endif
+
+#define CMR_ABI_VERSION 1
+
+#define CMR_OK 0
+#define CMR_EINVAL (-1)      /* null pointer, non-positive size */
+#define CMR_EALIGN (-2)      /* pointer not aligned as documented */
+#define CMR_ERANGE (-3)      /* size outside what the kernels support */
+#define CMR_EUNSUPPORTED (-4)
+
+#define CMR_REWARD_SHIPPED 0  /* environment.py:272-290 as shipped: pose is ignored */
+#define CMR_REWARD_INTENDED 1 /* applies the disentangled transform of the commented line :273 */
+
+CMR_API int cmr_abi_version(void);
+CMR_API const char *cmr_error_string(int code);
+/* number of kernel launches issued through this library since load (bench.py's gpu_launches) */
+CMR_API unsigned long long cmr_launch_count(void);
+
+/* ------------------------------------------------------------------ environment ---- */
+
+/* Bytes of scratch cmr_episode_prepare/cmr_observe need for (B, N, C, H*W). */
+CMR_API size_t cmr_workspace_bytes(int B, int N, int C, int P);
+
+/* pc.mean(dim=2) - environment.py:46,91,274.  pc [B,3,N] f32 -> mean [B,3] f32.
+ * Deterministic, accumulated in fp64 (correctly rounded in practice).  NOTE torch's own fp32 mean
+ * is not correctly rounded; a host that needs the reference's bits on a given device passes
+ * torch's mean to the calls below instead (the Python drop-in does). */
+CMR_API int cmr_cloud_mean(const float *pc, int B, int N, float *mean, void *stream);
+
+/* Once per episode batch: the boolean-mask compaction of environment.py:48-49, hoisted out of the
+ * iteration loop.  overlap [B,N] u8 (torch.bool), feat [B,C,N] f32 channel-major.
+ * Writes into `workspace` (cmr_workspace_bytes): per-128-point prefix counts, the number M[b] of
+ * predicted-overlap points and their features transposed to point-major rows [B, M, C].
+ * C must be a multiple of 4 and <= 256. */
+CMR_API int cmr_episode_prepare(const uint8_t *overlap, const float *feat, int B, int N, int C, void *workspace,
+                        void *stream);
+
+/* observation_from_a_pose - environment.py:25-126.
+ *   pc [B,3,N] f32, overlap [B,N] u8, img_feat [B,C,H,W] f32, K [B,3,3] f32, pose [B,4,4] f32,
+ *   mean [B,3] f32 (the cloud mean, see cmr_cloud_mean), workspace from cmr_episode_prepare.
+ *   obs2d [B,2C,H,W] f32 = cat(img_feat, scatter-mean of the predicted-overlap points' features at
+ *   their round-half-even pixel) ; obs3d [B,5,N] f32 = cat(pc, overlap, in_frustum).
+ *   pix_out (optional, may be NULL) [B,N] i32: v*W+u of every point, H*W when out of frustum -
+ *   the integer by-product of :67-72, exported for parity checks.
+ *   mvis_out (optional) [B] i32: predicted-overlap points that landed inside the frustum.
+ * Sums run in point order per pixel (deterministic, no atomics).  The workspace's pixel-id scratch is
+ * rewritten by every call: do not run two observes on one workspace concurrently. */
+CMR_API int cmr_observe(const float *pc, const uint8_t *overlap, const float *img_feat, const float *K,
+                const float *pose, const float *mean, void *workspace, int B, int N, int C, int H,
+                int W, float *obs2d, float *obs3d, int32_t *pix_out, int32_t *mvis_out, void *stream);
+
+/* The two halves of cmr_observe, for callers that need only one observation or time them apart:
+ *   cmr_project      environment.py:88-124 (obs3d) + :54-72 for the predicted-overlap points
+ *                    (pixel ids into the workspace);
+ *   cmr_tile_scatter environment.py:74-86 (obs2d) from the pixel ids the last cmr_project left. */
+CMR_API int cmr_project(const float *pc, const uint8_t *overlap, const float *K, const float *pose, const float *mean,
+                        void *workspace, int B, int N, int C, int H, int W, float *obs3d, int32_t *pix_out,
+                        int32_t *mvis_out, void *stream);
+CMR_API int cmr_tile_scatter(const float *img_feat, const void *workspace, int B, int N, int C, int H, int W,
+                             float *obs2d, void *stream);
+
+/* to_disentangled - environment.py:15-21.  poses [B,4,4] in place: t <- (t - m) + R m. */
+CMR_API int cmr_to_disentangled(float *poses, const float *mean, int B, void *stream);
+
+/* step - environment.py:179-207, in place on pose [B,4,4].
+ *   action_r [B,1] (3-DoF) or [B,3] (6-DoF) i64, action_t [B,2] or [B,3] i64;
+ *   rot_tab [3,nbins,3,3] f32: per-axis rotation matrices Rx,Ry,Rz(r_steps[i]) exactly as
+ *   environment.py:235-260 builds them; t_tab [nbins] f32 = float32(t_steps).
+ *   R <- ((Rx @ Ry) @ Rz) @ R with every 3x3 product an FMA chain; t <- t + move_t.
+ * Out-of-range actions leave that pose untouched and raise the sticky flag of cmr_take_fault. */
+CMR_API int cmr_step(float *pose, const int64_t *action_r, const int64_t *action_t, const float *rot_tab,
+             const float *t_tab, int nbins, int dof6, int B, void *stream);
+
+/* reward - environment.py:263-302.
+ *   target = pc_in_cam_space [B,3,N] f32, mask = pc_mask [B,N] u8, prev (may be NULL) [B] f32.
+ *   dist [B] f32 = mean over masked points of |target - moved|^2 (NaN when the mask is empty);
+ *   reward [B] f32 = +0.5 / -0.5 / 0 against prev (zeros when prev is NULL).
+ *   scratch: >= cmr_reward_scratch_bytes(B) bytes. */
+CMR_API size_t cmr_reward_scratch_bytes(int B);
+CMR_API int cmr_reward(const float *target, const float *pc, const uint8_t *mask, const float *mean, const float *pose,
+               const float *prev, int mode, int B, int N, void *scratch, float *reward, float *dist,
+               void *stream);
+
+/* ------------------------------------------------------------------ pointnet_util ---- */
+
+/* square_distance - pointnet_util.py:19-33. src [B,S,3], dst [B,N,3] (any strides, in floats) ->
+ * out [B,S,N] f32, (dx*dx + dy*dy) + dz*dz unfused. */
+CMR_API int cmr_square_distance(const float *src, const int64_t src_stride[3], const float *dst,
+                        const int64_t dst_stride[3], int B, int S, int N, float *out, void *stream);
+
+/* index_points - pointnet_util.py:36-47.  points [B,N,C] rows of `row_bytes` bytes, idx [B,S] i64
+ * (flatten [B,S,K] to [B,S*K]) -> out [B,S,row_bytes].  Out-of-range indices write zeros and raise
+ * the sticky flag of cmr_take_fault. */
+CMR_API int cmr_index_points(const void *points, const int64_t *idx, int B, int N, int S, int row_bytes, void *out,
+                     void *stream);
+/* backward of index_points for f32: grad_points [B,N,C] += grad_out rows (grad_points pre-zeroed). */
+CMR_API int cmr_index_points_backward(const float *grad_out, const int64_t *idx, int B, int N, int S, int C,
+                              float *grad_points, void *stream);
+
+/* farthest_point_sample - pointnet_util.py:50-70.  xyz [B,N,3] f32, start [B] i64 (the draw of
+ * :62, made by the host on the CPU generator) -> out [B,npoint] i64.  Lowest index wins ties. */
+CMR_API int cmr_farthest_point_sample(const float *xyz, const int64_t *start, int B, int N, int npoint, int64_t *out,
+                              void *stream);
+
+/* kNN = square_distance(...).argsort()[:, :, :k] - pointnet_util.py:115-116,233-234,
+ * models/PointNN.py:215-216, with the stable order (distance, index).  out [B,S,k] i64. k <= 128. */
+CMR_API int cmr_knn(const float *query, const float *ref, int B, int S, int N, int k, int64_t *out, void *stream);
+
+/* query_ball_point - pointnet_util.py:73-93.  radius2 = float32(radius**2). out [B,S,nsample] i64. */
+CMR_API int cmr_query_ball_point(const float *query, const float *ref, float radius2, int nsample, int B, int S, int N,
+                         int64_t *out, void *stream);
+
+/* grouping tail of sample_and_group - pointnet_util.py:120-129 fused: out [B,S,K,3+D] f32 =
+ * cat(xyz[idx] - new_xyz, points[idx]); points may be NULL (D = 0). */
+CMR_API int cmr_group_points(const float *xyz, const float *points, const float *new_xyz, const int64_t *idx, int B,
+                     int N, int S, int K, int D, float *out, void *stream);
+
+/* Sticky device-side fault flag (out-of-range index / action).  Reads and clears it; this call
+ * synchronises `stream`.  0 = none. */
+CMR_API int cmr_take_fault(void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CMR_B200_H_ */

@@ -1,0 +1,162 @@
+"""Generate the golden fixtures in this directory FROM THE REAL REFERENCE.
+
+Run in the build container only (needs /root/reference):
+    python tests/golden/make_golden.py
+It imports /root/reference/environment/environment.py and models/pointnet_util.py by file path
+(with the torch_scatter/open3d shims of oracle/shims.py), feeds them seeded synthetic inputs from
+cmr_agent_b200.synth, and stores the OUTPUTS (plus the tiny inputs that cannot be regenerated:
+poses, cloud means, FPS start indices).  Bulk inputs are regenerated from the seed at test time and
+verified against the sha256 stored here.  The fixtures travel to the GPU box; the reference does not.
+"""
+import hashlib
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from cmr_agent_b200 import synth  # noqa: E402
+from oracle import reference_loader  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+ENV_CASES = {
+    # name: (batch, shape kwargs, iterations, store_full_obs2d)
+    "env_small": (2, dict(num_pt=4096, img_h=64, img_w=256), 4, True),
+    "env_ragged": (2, dict(num_pt=1531, img_h=36, img_w=100), 3, True),     # N % 4 != 0, P % 128 != 0
+    "env_kitti": (2, dict(num_pt=40960, img_h=160, img_w=512), 4, False),
+    "env_nuscenes": (1, dict(num_pt=40960, img_h=160, img_w=320, unique=(26000, 34000)), 3, False),
+}
+SEED = 2023
+
+
+def sha(*tensors):
+    h = hashlib.sha256()
+    for t in tensors:
+        h.update(np.ascontiguousarray(t.numpy()).tobytes())
+    return h.hexdigest()
+
+
+def env_case(name, batch, shape, iters, full):
+    env = reference_loader.environment()
+    data = synth.make_batch(batch, seed=SEED, **shape)
+    cfg = synth.StepConfig()
+    a_r, a_t = synth.make_actions(batch, iters, seed=SEED)
+    H, W = shape["img_h"] // 4, shape["img_w"] // 4
+    pose, target = env.init(data)
+    target = env.to_disentangled(target.clone(), data["pc"])
+    out = {
+        "inputs_sha": sha(data["pc"], data["pc_geo_feat"], data["img_geo_feat"], data["pc_overlap_pred"],
+                          data["pc_mask"], data["pc_in_cam_space"], data["K"]),
+        "mean": data["pc"].mean(dim=2).numpy(),
+        "pose_target_disentangled": target.numpy(),
+        "a_r": a_r.numpy(), "a_t": a_t.numpy(),
+    }
+    # start from a non-trivial pose so that points are visible: apply two expert-free random steps first
+    prev = None
+    for it in range(iters):
+        o2, o3 = env.observation_from_a_pose(data, pose)
+        out[f"pose_{it}"] = pose.clone().numpy()
+        # integer by-products recomputed with the reference's own lines (54-72) for ALL points
+        mean = data["pc"].mean(dim=2, keepdim=True)
+        X = pose[:, :3, :3] @ (data["pc"] - mean) + mean + pose[:, :3, 3:4]
+        U = data["K"] @ X
+        U[:, 0:2] = U[:, 0:2] / U[:, 2:3]
+        inc = (U[:, 0] >= 0) & (U[:, 0] <= W - 1) & (U[:, 1] >= 0) & (U[:, 1] <= H - 1) & (U[:, 2] > 0)
+        uv = U[:, 0:2].round().int()
+        idx = uv[:, 1] * W + uv[:, 0]
+        idx[~inc] = H * W
+        assert torch.equal(inc.float(), o3[:, 4]), "in-frustum by-product disagrees with observation_3d"
+        out[f"idx_{it}"] = idx.numpy().astype(np.int32)
+        out[f"incam_{it}"] = np.packbits(inc.numpy(), axis=1)
+        if full:
+            out[f"obs2d_proj_{it}"] = o2[:, 64:].numpy()
+        else:
+            out[f"obs2d_proj_chansum_{it}"] = o2[:, 64:].double().sum(dim=1).numpy()
+            out[f"obs2d_proj_absmax_{it}"] = o2[:, 64:].abs().amax(dim=1).numpy()
+        assert torch.equal(o2[:, :64], data["img_geo_feat"])
+        assert torch.equal(o3[:, :3], data["pc"]) and torch.equal(o3[:, 3], data["pc_overlap_pred"].float())
+        env.step(a_r[it], a_t[it], pose, cfg)
+        rew, dist = env.reward(pose, data, prev)
+        out[f"reward_{it}"] = rew.numpy()
+        out[f"dist_{it}"] = dist.numpy()
+        prev = dist
+    out["pose_final"] = pose.numpy()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, {k: getattr(v, "shape", v) for k, v in out.items() if k.startswith(("idx_0", "obs2d", "mean"))})
+
+
+def step_case():
+    """Every (bin) of the 3-DoF tables and a batch of random 6-DoF actions through the reference's step()."""
+    env = reference_loader.environment()
+    out = {}
+    for dof6 in (False, True):
+        cfg = synth.StepConfig(is_6_DoF=dof6)
+        B = 121 if not dof6 else 256
+        g = torch.Generator().manual_seed(SEED + 5)
+        pose = torch.eye(4).repeat(B, 1, 1)
+        # random but valid starting rotations/translations
+        ang = torch.rand(B, 3, generator=g) * 6.0 - 3.0
+        pose[:, :3, :3] = env.euler_angles_to_matrix(ang, "XYZ")
+        pose[:, :3, 3] = torch.randn(B, 3, generator=g) * 5
+        if dof6:
+            a_r = torch.randint(0, 11, (B, 3), generator=g)
+            a_t = torch.randint(0, 11, (B, 3), generator=g)
+        else:
+            grid = torch.arange(121)
+            a_r = (grid % 11).view(B, 1)
+            a_t = torch.stack([grid // 11, (grid * 7) % 11], 1)
+        tag = "6" if dof6 else "3"
+        out[f"pose_in_{tag}"] = pose.clone().numpy()
+        out[f"a_r_{tag}"] = a_r.numpy()
+        out[f"a_t_{tag}"] = a_t.numpy()
+        out[f"pose_out_{tag}"] = env.step(a_r, a_t, pose, cfg).numpy()
+    np.savez_compressed(os.path.join(HERE, "step.npz"), **out)
+    print("step", {k: v.shape for k, v in out.items()})
+
+
+def pointnet_case():
+    pn = reference_loader.pointnet_util()
+    out = {}
+    # duplicate-padded cloud (exact distance ties) and a plain one
+    for tag, unique in (("dup", (2600, 2600)), ("plain", None)):
+        xyz = synth.make_cloud_batch(2, num_pt=4096, seed=SEED, unique=unique)
+        out[f"xyz_sha_{tag}"] = sha(xyz)
+        torch.manual_seed(SEED)
+        fps = pn.farthest_point_sample(xyz, 128)
+        out[f"fps_{tag}"] = fps.numpy()
+        new_xyz = pn.index_points(xyz, fps)
+        out[f"new_xyz_{tag}"] = new_xyz.numpy()
+        d = pn.square_distance(new_xyz, xyz)
+        out[f"sqdist_rowsum_{tag}"] = d.double().sum(-1).numpy()
+        out[f"knn16_raw_{tag}"] = d.argsort()[:, :, :16].numpy()                 # unstable order (A.7)
+        out[f"knn16_stable_{tag}"] = d.argsort(stable=True)[:, :, :16].numpy()
+        for r in (0.5, 2.0):
+            out[f"ball_{r}_{tag}"] = pn.query_ball_point(r, 32, xyz, new_xyz).numpy()
+        torch.manual_seed(SEED + 1)
+        nx, npts, gxyz, fidx = pn.sample_and_group(64, 1.5, 16, xyz, xyz * 0.5 + 1.0, returnfps=True)
+        out[f"sag_new_xyz_{tag}"] = nx.numpy()
+        out[f"sag_new_points_{tag}"] = npts.numpy()
+        out[f"sag_fps_{tag}"] = fidx.numpy()
+    # full-size FPS (config 4 shape, one cloud): 40960 -> 1280
+    xyz = synth.make_cloud_batch(1, num_pt=40960, seed=SEED + 100)
+    out["xyz_sha_full"] = sha(xyz)
+    torch.manual_seed(SEED + 2)
+    out["fps_full"] = pn.farthest_point_sample(xyz, 1280).numpy()
+    np.savez_compressed(os.path.join(HERE, "pointnet.npz"), **out)
+    print("pointnet", {k: getattr(v, "shape", v) for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    assert reference_loader.available(), "needs /root/reference"
+    torch.set_num_threads(1)
+    for name, (b, shape, iters, full) in ENV_CASES.items():
+        env_case(name, b, shape, iters, full)
+    step_case()
+    pointnet_case()
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

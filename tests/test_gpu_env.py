@@ -1,0 +1,331 @@
+"""GPU parity of the environment half: libcmr_b200.so (through its C ABI, bound by the drop-in
+module) against the golden fixtures produced by the real reference and against the oracle.
+
+Bars (BASELINE.json north_star / SURVEY.md A.7): pixel ids, frustum masks, obs3d, poses after
+step: BIT-EXACT.  obs2d, reward distance: <= 1e-5 relative (we additionally observe bit-equality
+for obs2d because the kernel sums in the oracle's point order)."""
+import numpy as np
+import pytest
+import torch
+
+from cmr_agent_b200 import synth
+from oracle import cref, env_oracle as eo
+from tests import helpers as hp
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def _env():
+    from cmr_agent_b200 import environment
+    return environment
+
+
+def _observe(env, data, pose, dev):
+    o2, o3, pix, mvis = env.observation_from_a_pose(data, pose.to(dev), return_pixels=True)
+    torch.cuda.synchronize()
+    return o2.cpu(), o3.cpu(), pix.cpu(), mvis.cpu()
+
+
+@pytest.mark.parametrize("name", list(hp.ENV_CASES))
+def test_observe_step_reward_match_reference_golden(cuda, name):
+    env = _env()
+    data_cpu, g, iters, full, shape = hp.env_inputs(name)
+    H, W = shape["img_h"] // 4, shape["img_w"] // 4
+    data = hp.to_device(data_cpu, cuda)
+    # the reference's own cloud mean (torch CPU fp32) travels with the fixture: everything
+    # downstream of it must then agree bit for bit
+    data["_cmr_b200_mean_override"] = torch.from_numpy(g["mean"])
+    cfg = synth.StepConfig(device=cuda)
+    B = data_cpu["pc"].shape[0]
+    pose = torch.eye(4, device=cuda).repeat(B, 1, 1)
+    prev = None
+    for it in range(iters):
+        want_pose = torch.from_numpy(g[f"pose_{it}"])
+        assert torch.equal(pose.cpu(), want_pose), f"pose before iteration {it}"
+        o2, o3, pix, mvis = _observe(env, data, pose, cuda)
+        idx = torch.from_numpy(g[f"idx_{it}"])
+        assert torch.equal(pix, idx), f"{name} it{it}: {(pix != idx).sum().item()} pixel ids differ"
+        inc = torch.from_numpy(np.unpackbits(g[f"incam_{it}"], axis=1)[:, : idx.shape[1]]).float()
+        assert torch.equal(o3[:, 4], inc)
+        assert torch.equal(o3[:, :3], data_cpu["pc"])
+        assert torch.equal(o3[:, 3], data_cpu["pc_overlap_pred"].float())
+        assert torch.equal(o2[:, :64], data_cpu["img_geo_feat"])
+        vis = (data_cpu["pc_overlap_pred"] & (idx < H * W)).sum(dim=1).int()
+        assert torch.equal(mvis, vis)
+        if full:
+            want = torch.from_numpy(g[f"obs2d_proj_{it}"])
+            assert hp.rel_err(o2[:, 64:], want) <= TOL
+            assert torch.equal(o2[:, 64:], want), "point-order sums should reproduce the CPU reference exactly"
+        else:
+            assert hp.rel_err(o2[:, 64:].double().sum(dim=1), torch.from_numpy(g[f"obs2d_proj_chansum_{it}"]),
+                              floor=1e-6) <= TOL
+            assert torch.equal(o2[:, 64:].abs().amax(dim=1), torch.from_numpy(g[f"obs2d_proj_absmax_{it}"]))
+        a_r = torch.from_numpy(g["a_r"][it]).to(cuda)
+        a_t = torch.from_numpy(g["a_t"][it]).to(cuda)
+        ret = env.step(a_r, a_t, pose, cfg)
+        assert ret is pose                                            # in place, same tensor (environment.py:207)
+        rew, dist = env.reward(pose, data, prev)
+        assert rew.shape == (B, 1, 1) and dist.shape == (B, 1, 1)
+        assert hp.rel_err(dist.cpu(), torch.from_numpy(g[f"dist_{it}"])) <= TOL
+        # the shipped reward is pose independent -> distances repeat exactly -> reward is exactly 0 after call 1
+        assert torch.equal(rew.cpu(), torch.from_numpy(g[f"reward_{it}"]))
+        prev = dist
+    assert torch.equal(pose.cpu(), torch.from_numpy(g["pose_final"]))
+
+
+def test_to_disentangled_and_init_match_golden(cuda):
+    env = _env()
+    data_cpu, g, *_ = hp.env_inputs("env_small")
+    data = hp.to_device(data_cpu, cuda)
+    ps, pt = env.init(data)
+    assert torch.equal(ps.cpu(), torch.eye(4).repeat(2, 1, 1)) and torch.equal(pt.cpu(), data_cpu["P"])
+    from cmr_agent_b200 import _lib
+    mean = torch.from_numpy(g["mean"]).to(cuda)
+    poses = pt.clone()
+    _lib.call("cmr_to_disentangled", _lib.ptr(poses), _lib.ptr(mean), 2, _lib.stream())
+    assert torch.equal(poses.cpu(), torch.from_numpy(g["pose_target_disentangled"]))
+    # through the drop-in (device mean): identical up to the mean's last bit
+    out = env.to_disentangled(pt, data["pc"])
+    assert out is pt
+    assert hp.rel_err(pt.cpu(), torch.from_numpy(g["pose_target_disentangled"])) <= 1e-5
+
+
+@pytest.mark.parametrize("tag", ["3", "6"])
+def test_step_matches_reference_golden(cuda, tag):
+    env = _env()
+    g = hp.golden("step")
+    cfg = synth.StepConfig(device=cuda, is_6_DoF=(tag == "6"))
+    pose = torch.from_numpy(g[f"pose_in_{tag}"]).to(cuda)
+    env.step(torch.from_numpy(g[f"a_r_{tag}"]).to(cuda), torch.from_numpy(g[f"a_t_{tag}"]).to(cuda), pose, cfg)
+    assert torch.equal(pose.cpu(), torch.from_numpy(g[f"pose_out_{tag}"]))
+
+
+def test_step_rejects_out_of_range_action(cuda):
+    env = _env()
+    from cmr_agent_b200 import _lib
+    cfg = synth.StepConfig(device=cuda)
+    pose = torch.eye(4, device=cuda).repeat(2, 1, 1)
+    env.step(torch.tensor([[3], [11]], device=cuda), torch.tensor([[0, 0], [0, 0]], device=cuda), pose, cfg)
+    assert _lib.take_fault() == 2
+    assert _lib.take_fault() == 0
+    assert torch.equal(pose[1].cpu(), torch.eye(4))          # the bad row is left untouched
+
+
+def _oracle_obs(data_cpu, pose_cpu, mean_cpu, H, W):
+    """C-oracle observation for every episode given an explicit mean: (pix, in_cam, obs2d projected half)."""
+    B, _, N = data_cpu["pc"].shape
+    pix = np.empty((B, N), np.int32)
+    inc = np.empty((B, N), np.uint8)
+    proj = []
+    for b in range(B):
+        ov = data_cpu["pc_overlap_pred"][b].numpy()
+        pix[b], inc[b] = cref.project(data_cpu["pc"][b].numpy(), mean_cpu[b].numpy(), pose_cpu[b].numpy(),
+                                      data_cpu["K"][b].numpy(), H, W)
+        m = int(ov.sum())
+        if (m >= 45) != (N >= 45):           # 2-D branch in the other bmm regime (tiny overlap sets)
+            p2, _ = cref.project(data_cpu["pc"][b].numpy(), mean_cpu[b].numpy(), pose_cpu[b].numpy(),
+                                 data_cpu["K"][b].numpy(), H, W, fused=(m >= 45))
+        else:
+            p2 = pix[b]
+        C = data_cpu["pc_geo_feat"].shape[1]
+        proj.append(cref.scatter_mean(data_cpu["pc_geo_feat"][b].numpy(), ov, p2, H * W).reshape(C, H, W))
+    return torch.from_numpy(pix), torch.from_numpy(inc), torch.from_numpy(np.stack(proj))
+
+
+def _random_poses(B, seed, scale_t=6.0):
+    g = torch.Generator().manual_seed(seed)
+    ang = torch.zeros(B, 3)
+    ang[:, 1] = torch.rand(B, generator=g) * 6.28 - 3.14
+    pose = torch.eye(4).repeat(B, 1, 1)
+    pose[:, :3, :3] = eo.euler_angles_to_matrix(ang, "XYZ")
+    pose[:, :3, 3] = (torch.rand(B, 3, generator=g) - 0.5) * scale_t
+    return pose
+
+
+@pytest.mark.parametrize("shape,B", [
+    (dict(num_pt=40960, img_h=160, img_w=512), 4),                                   # KITTI (config 2 shapes)
+    (dict(num_pt=40960, img_h=160, img_w=320, unique=(26000, 34000)), 3),            # NuScenes-shaped, duplicates
+    (dict(num_pt=16384, img_h=160, img_w=512), 2),
+    (dict(num_pt=131072, img_h=160, img_w=512), 1),                                  # sweep upper end
+    (dict(num_pt=1001, img_h=44, img_w=68), 3),                                      # ragged: N%4, P%128
+    (dict(num_pt=44, img_h=160, img_w=512), 2),                                      # plain-bmm regime
+    (dict(num_pt=45, img_h=160, img_w=512), 2),
+    (dict(num_pt=5, img_h=160, img_w=512), 1),
+])
+def test_observe_matches_oracle_with_device_mean(cuda, shape, B):
+    """The drop-in with its default mean (torch on the device, the reference's own expression): the
+    oracle is given that mean, so every integer output must match bit for bit at full size."""
+    env = _env()
+    data_cpu = synth.make_batch(B, seed=77, **shape)
+    H, W = shape["img_h"] // 4, shape["img_w"] // 4
+    data = hp.to_device(data_cpu, cuda)
+    for trial in range(3):
+        pose = _random_poses(B, 100 + trial, scale_t=2.0 if trial else 0.0)
+        o2, o3, pix, mvis = _observe(env, data, pose, cuda)
+        mean = data["_cmr_b200_episode"][1].mean.cpu()
+        wpix, winc, wproj = _oracle_obs(data_cpu, pose, mean, H, W)
+        assert torch.equal(pix, wpix), f"{(pix != wpix).sum().item()} of {pix.numel()} pixel ids differ"
+        assert torch.equal(o3[:, 4], winc.float())
+        assert torch.equal(o3[:, :3], data_cpu["pc"]) and torch.equal(o3[:, 3], data_cpu["pc_overlap_pred"].float())
+        assert torch.equal(o2[:, :64], data_cpu["img_geo_feat"])
+        assert hp.rel_err(o2[:, 64:], wproj) <= TOL
+        assert torch.equal(o2[:, 64:], wproj)
+    # device mean vs the CPU reference's mean: same value to fp32 rounding (not necessarily the same bits)
+    assert hp.rel_err(mean, data_cpu["pc"].mean(dim=2), floor=1e-6) <= 1e-5
+
+
+def test_cloud_mean_kernel_is_correctly_rounded(cuda):
+    from cmr_agent_b200 import _lib
+    pc = synth.make_batch(3, seed=5, num_pt=40960, img_h=32, img_w=32)["pc"]
+    out = torch.empty(3, 3, device=cuda)
+    d = pc.to(cuda)
+    _lib.call("cmr_cloud_mean", _lib.ptr(d), 3, 40960, _lib.ptr(out), _lib.stream())
+    want = (pc.double().sum(dim=2) / 40960).float()
+    assert torch.equal(out.cpu(), want)
+
+
+@pytest.mark.parametrize("case", ["no_overlap", "all_overlap", "behind_camera", "one_pixel", "exact_edges"])
+def test_observe_edge_cases(cuda, case):
+    env = _env()
+    shape = dict(num_pt=4096, img_h=64, img_w=256)
+    H, W = 16, 64
+    data_cpu = synth.make_batch(2, seed=31, **shape)
+    pose = _random_poses(2, 7, scale_t=1.0)
+    if case == "no_overlap":
+        data_cpu["pc_overlap_pred"][:] = False
+    elif case == "all_overlap":
+        data_cpu["pc_overlap_pred"][:] = True
+    elif case == "behind_camera":
+        data_cpu["pc"][:, 2] = -data_cpu["pc"][:, 2].abs() - 100.0
+        pose = torch.eye(4).repeat(2, 1, 1)
+    elif case == "one_pixel":
+        # every point on the optical axis: all visible points fall into a single pixel (worst-case bin)
+        data_cpu["pc"][:, 0] = 0.0
+        data_cpu["pc"][:, 1] = 0.0
+        data_cpu["pc"][:, 2] = data_cpu["pc"][:, 2].abs() + 1.0
+        data_cpu["pc_overlap_pred"][:] = True
+        pose = torch.eye(4).repeat(2, 1, 1)
+    elif case == "exact_edges":
+        # identity pose, unit intrinsics, z = 1: u = x, v = y exactly -> borders and .5 roundings
+        data_cpu["K"][:] = torch.eye(3)
+        xs = torch.tensor([0.0, -0.0, 0.5, 1.5, 2.5, 62.5, 63.0, 63.00001, -1e-7, 62.99999])
+        ys = torch.tensor([0.0, 15.0, 0.5, 1.5, 14.5, 15.00001, 7.5, 8.5, 3.0, 15.0])
+        n = data_cpu["pc"].shape[2]
+        data_cpu["pc"][:, 0] = xs.repeat(n // 10 + 1)[:n]
+        data_cpu["pc"][:, 1] = ys.repeat(n // 10 + 1)[:n]
+        data_cpu["pc"][:, 2] = 1.0
+        data_cpu["pc_overlap_pred"][:] = True
+        pose = torch.eye(4).repeat(2, 1, 1)
+    data = hp.to_device(data_cpu, cuda)
+    if case == "exact_edges":
+        data["_cmr_b200_mean_override"] = torch.zeros(2, 3)     # keep u = x exact
+    o2, o3, pix, mvis = _observe(env, data, pose, cuda)
+    mean = data["_cmr_b200_episode"][1].mean.cpu()
+    wpix, winc, wproj = _oracle_obs(data_cpu, pose, mean, H, W)
+    assert torch.equal(pix, wpix) and torch.equal(o3[:, 4], winc.float())
+    assert torch.equal(o2[:, 64:], wproj)
+    if case in ("no_overlap", "behind_camera"):
+        assert float(o2[:, 64:].abs().max()) == 0.0 and int(mvis.sum()) == 0
+    if case == "one_pixel":
+        assert int((o2[:, 64:].abs().amax(dim=1) > 0).sum()) <= 2   # one pixel per episode
+    if case == "exact_edges":
+        # the oracle itself is pinned; also spell the expected roundings out (half-to-even, inclusive borders)
+        assert pix[0, 2].item() == 0 * W + 0 and pix[0, 3].item() == 2 * W + 2 and pix[0, 4].item() == 14 * W + 2
+        assert pix[0, 5].item() == H * W and pix[0, 7].item() == H * W and pix[0, 8].item() == H * W
+
+
+@pytest.mark.parametrize("C,img_h,img_w", [(32, 64, 256), (128, 64, 128), (64, 1024, 1024)])
+def test_observe_other_channel_counts_and_32bit_pixels(cuda, C, img_h, img_w):
+    """The reference hard-codes 64 channels (environment.py:79); the kernel is generic in C and switches
+    to 32-bit pixel ids when H*W >= 65535 (here 256x256)."""
+    env = _env()
+    data_cpu = synth.make_batch(1, seed=9, num_pt=8192, img_h=img_h, img_w=img_w, channels=C)
+    H, W = img_h // 4, img_w // 4
+    data = hp.to_device(data_cpu, cuda)
+    pose = _random_poses(1, 3, scale_t=1.0)
+    o2, o3, pix, mvis = _observe(env, data, pose, cuda)
+    mean = data["_cmr_b200_episode"][1].mean.cpu()
+    wpix, winc, wproj = _oracle_obs(data_cpu, pose, mean, H, W)
+    assert torch.equal(pix, wpix) and torch.equal(o3[:, 4], winc.float())
+    assert torch.equal(o2[:, :C], data_cpu["img_geo_feat"])
+    assert torch.equal(o2[:, C:], wproj)
+
+
+def test_reward_modes_against_c_oracle(cuda):
+    env = _env()
+    data_cpu = synth.make_batch(3, seed=13, num_pt=40960, img_h=160, img_w=512)
+    data_cpu["pc_mask"][2] = 0                                    # empty mask -> NaN like torch's empty mean
+    data = hp.to_device(data_cpu, cuda)
+    pose = _random_poses(3, 17).to(cuda)
+    try:
+        for mode, flag in (("shipped", 0), ("intended", 1)):
+            env.set_reward_mode(mode)
+            rew, dist = env.reward(pose, data, None)
+            mean = data["_cmr_b200_reward"][1].mean.cpu()
+            assert float(rew.abs().sum()) == 0.0
+            for b in range(2):
+                want = cref.p2p(data_cpu["pc_in_cam_space"][b].numpy(), data_cpu["pc"][b].numpy(),
+                                data_cpu["pc_mask"][b].numpy(), mean[b].numpy(), pose[b].cpu().numpy(), flag)
+                assert abs(float(dist[b]) - want) <= TOL * abs(want)
+            assert torch.isnan(dist[2]).all()
+            better = dist * 2.0
+            worse = dist * 0.5
+            r_b, _ = env.reward(pose, data, better)
+            r_w, _ = env.reward(pose, data, worse)
+            r_s, _ = env.reward(pose, data, dist)
+            assert torch.equal(r_b[:2].cpu().flatten(), torch.tensor([0.5, 0.5]))
+            assert torch.equal(r_w[:2].cpu().flatten(), torch.tensor([-0.5, -0.5]))
+            assert float(r_s[:2].abs().sum()) == 0.0 and float(r_b[2]) == 0.0      # NaN compares false
+    finally:
+        env.set_reward_mode("shipped")
+
+
+def test_fresh_outputs_cache_invalidation_and_cpu_rejection(cuda):
+    env = _env()
+    from cmr_agent_b200 import _lib
+    data_cpu = synth.make_batch(2, seed=3, num_pt=2048, img_h=32, img_w=64)
+    data = hp.to_device(data_cpu, cuda)
+    pose = torch.eye(4, device=cuda).repeat(2, 1, 1)
+    a2, a3 = env.observation_from_a_pose(data, pose)
+    b2, b3 = env.observation_from_a_pose(data, pose)
+    # buffer.py:105-106 keeps references to the observations: every call must return fresh storage
+    assert a2.data_ptr() != b2.data_ptr() and a3.data_ptr() != b3.data_ptr()
+    assert torch.equal(a2, b2) and torch.equal(a3, b3)
+    ep = data["_cmr_b200_episode"][1]
+    assert env.observation_from_a_pose(data, pose) is not None and data["_cmr_b200_episode"][1] is ep
+    data["pc_overlap_pred"].logical_not_()                      # in-place edit bumps the version counter
+    c2, c3 = env.observation_from_a_pose(data, pose)
+    assert data["_cmr_b200_episode"][1] is not ep
+    assert torch.equal(c3[:, 3], data["pc_overlap_pred"].float())
+    with pytest.raises(_lib.CmrError):
+        env.observation_from_a_pose(data_cpu, torch.eye(4).repeat(2, 1, 1))
+    with pytest.raises(_lib.CmrError):
+        env.step(torch.zeros(2, 1, dtype=torch.long), torch.zeros(2, 2, dtype=torch.long), torch.eye(4).repeat(2, 1, 1),
+                 synth.StepConfig())
+
+
+def test_ten_iteration_rollout_matches_oracle_port(cuda):
+    """Test_Agent.py:154-170 with a scripted policy: the drop-in and the torch-CPU port walk the same
+    10 iterations (config.action_num); poses, masks and pixel ids stay identical throughout."""
+    env = _env()
+    B = 4
+    data_cpu = synth.make_batch(B, seed=2023, num_pt=40960, img_h=160, img_w=512)
+    data = hp.to_device(data_cpu, cuda)
+    cfg_d, cfg_h = synth.StepConfig(device=cuda), synth.StepConfig()
+    a_r, a_t = synth.make_actions(B, 10, seed=4)
+    pose_d, target_d = env.init(data)
+    pose_h, target_h = eo.init(data_cpu)
+    mean = None
+    for it in range(10):
+        o2, o3, pix, _ = env.observation_from_a_pose(data, pose_d, return_pixels=True)
+        if mean is None:
+            mean = data["_cmr_b200_episode"][1].mean.cpu()
+        p2, p3 = eo.observation_from_a_pose(data_cpu, pose_h, mean=mean.unsqueeze(-1))
+        wpix, _ = eo.projected_pixels(data_cpu, pose_h, mean=mean.unsqueeze(-1))
+        assert torch.equal(pix.cpu(), wpix)
+        assert torch.equal(o3.cpu(), p3)
+        assert torch.equal(o2.cpu(), p2)
+        env.step(a_r[it].to(cuda), a_t[it].to(cuda), pose_d, cfg_d)
+        eo.step(a_r[it], a_t[it], pose_h, cfg_h)
+        assert torch.equal(pose_d.cpu(), pose_h)

@@ -1,0 +1,137 @@
+"""Host-side logic of the product that needs no GPU: step tables, sys.modules aliasing, episode
+sharding, the scalar all-reduce payload (world_size-2 gloo)."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import pytest
+import torch
+
+from cmr_agent_b200 import dist as cdist
+from cmr_agent_b200 import environment as drop_in
+from cmr_agent_b200 import synth
+from oracle import env_oracle as eo
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_step_tables_equal_the_reference_expression():
+    cfg = synth.StepConfig()
+    rot, tt = drop_in.build_step_tables(cfg.r_steps, cfg.t_steps)
+    assert rot.dtype == torch.float32 and tt.dtype == torch.float32
+    for i in range(11):
+        move = torch.zeros(1, 3)
+        move[0, 1] = cfg.r_steps[i]          # f64 -> f32 on assignment, like environment.py:197
+        want = eo.euler_angles_to_matrix(move, "XYZ")[0]
+        # (Rx(0) @ Ry) @ Rz(0) equals Ry up to the sign of zeros
+        assert torch.equal(rot[1, i] + 0.0, want + 0.0)
+        assert float(tt[i]) == float(cfg.t_steps[i].float())
+    with pytest.raises(ValueError):
+        drop_in.euler_angles_to_matrix(torch.zeros(2, 3), "XX")
+    with pytest.raises(ValueError):
+        drop_in.euler_angles_to_matrix(torch.zeros(2, 2), "XYZ")
+    ang = torch.rand(5, 3)
+    assert torch.equal(drop_in.euler_angles_to_matrix(ang, "XYZ"), eo.euler_angles_to_matrix(ang, "XYZ"))
+
+
+def test_install_aliases_the_reference_import_names():
+    code = textwrap.dedent("""
+        import sys
+        sys.path.insert(0, %r)
+        import cmr_agent_b200
+        cmr_agent_b200.install()
+        from environment import environment as env
+        import importlib
+        pn = importlib.import_module("models.pointnet_util")
+        assert env.__name__ == "cmr_agent_b200.environment", env.__name__
+        assert pn.__name__ == "cmr_agent_b200.pointnet_util"
+        for f in ("init", "to_disentangled", "observation_from_a_pose", "expert", "step", "reward",
+                  "euler_angles_to_matrix", "_axis_angle_rotation", "DEVICE"):
+            assert hasattr(env, f), f
+        for f in ("square_distance", "index_points", "farthest_point_sample", "query_ball_point",
+                  "sample_and_group", "sample_and_group_all"):
+            assert hasattr(pn, f), f
+        cmr_agent_b200.uninstall()
+        assert "environment.environment" not in sys.modules
+        print("ok")
+    """ % ROOT)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
+def test_signatures_match_the_reference_functions():
+    import inspect
+    from cmr_agent_b200 import pointnet_util as pn
+    from oracle import reference_loader as rl
+    if not rl.available():
+        pytest.skip("/root/reference not present")
+    ref_env, ref_pn = rl.environment(), rl.pointnet_util()
+
+    def names(f):
+        return list(inspect.signature(f).parameters)
+
+    for f in ("init", "to_disentangled", "expert", "step", "reward", "euler_angles_to_matrix"):
+        assert names(getattr(drop_in, f))[: len(names(getattr(ref_env, f)))] == names(getattr(ref_env, f)), f
+    assert names(drop_in.observation_from_a_pose)[:2] == names(ref_env.observation_from_a_pose)
+    for f in ("square_distance", "index_points", "farthest_point_sample", "query_ball_point", "sample_and_group",
+              "sample_and_group_all"):
+        assert names(getattr(pn, f)) == names(getattr(ref_pn, f)), f
+
+
+@pytest.mark.parametrize("total,world", [(32, 1), (32, 8), (64, 8), (10, 4), (3, 8), (0, 2)])
+def test_shard_range_partitions_episodes(total, world):
+    seen = []
+    for r in range(world):
+        lo, hi = cdist.shard_range(total, r, world)
+        assert 0 <= lo <= hi <= total
+        seen += list(range(lo, hi))
+        for e in range(lo, hi):
+            assert cdist.owner_of(e, total, world) == r
+    assert seen == list(range(total))
+    sizes = [cdist.shard_range(total, r, world)[1] - cdist.shard_range(total, r, world)[0] for r in range(world)]
+    assert max(sizes) - min(sizes) <= 1
+
+
+def test_metric_sums_single_process():
+    m = cdist.MetricSums()
+    m.add([1.0, 20.0, 3.0], [1.0, 1.0, 6.0], reward=[0.5, -0.5, 0.0])
+    s = m.all_reduce().summary()
+    assert s["episodes"] == 3 and abs(s["recall"] - 1 / 3) < 1e-12 and abs(s["rre_mean"] - 8.0) < 1e-12
+
+
+_WORKER = """
+import os, sys, json
+sys.path.insert(0, %r)
+import torch
+from cmr_agent_b200 import dist as cdist, synth
+rank, world, _ = cdist.init_from_env(backend="gloo")
+total = 11
+lo, hi = cdist.shard_range(total, rank, world)
+# every rank scores only its own episodes; errors are a deterministic function of the episode id
+eps = torch.arange(lo, hi, dtype=torch.float64)
+m = cdist.MetricSums().add(eps * 2.0, eps * 0.5, reward=eps * 0.1).all_reduce()
+slow = cdist.max_over_ranks(float(rank + 1), "cpu")
+cdist.barrier()
+if rank == 0:
+    print(json.dumps({"summary": m.summary(), "slow": slow, "world": world}))
+"""
+
+
+def test_world_size_2_gloo_sharding_and_allreduce(tmp_path):
+    import json
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER % ROOT)
+    port = 29500 + (os.getpid() % 2000)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+           "127.0.0.1", "--master-port", str(port), str(script)]
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0, out.stderr[-3000:]
+    line = [ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1]
+    res = json.loads(line)
+    eps = torch.arange(11, dtype=torch.float64)
+    ref = cdist.MetricSums().add(eps * 2.0, eps * 0.5, reward=eps * 0.1).summary()
+    assert res["world"] == 2 and res["slow"] == 2.0
+    for k, v in ref.items():
+        assert abs(res["summary"][k] - v) < 1e-9, k
