@@ -46,12 +46,12 @@ SEED = 2023
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="episodes per GPU")
     ap.add_argument("--iters", type=int, default=10, help="agent iterations per episode (config.action_num)")
-    ap.add_argument("--cpu-episodes", type=int, default=8, help="episodes in the bounded CPU sample")
+    ap.add_argument("--cpu-episodes", type=int, default=32, help="episodes in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -76,23 +76,32 @@ class ClockSampler:
                  "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
+            t0 = time.time()
+            while not self.lines and time.time() - t0 < 10.0:      # nvidia-smi takes a moment to come up
+                time.sleep(0.05)
         except Exception:
             self.proc = None
 
     def _pump(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln)
+            self.lines.append((time.time(), ln))
 
-    def stop(self):
+    def mark(self):
+        return time.time()
+
+    def stop(self, t_begin, t_end):
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        time.sleep(0.15)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
         sm, smax, reasons = [], None, set()
-        for ln in self.lines:
+        for ts, ln in self.lines:
+            if ts < t_begin or ts > t_end + 0.12:
+                continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -327,7 +336,7 @@ def run_b200_arm(args, rank, world, local):
         roll.run()
     torch.cuda.synchronize(dev)
 
-    sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local)
+    sampler = ClockSampler(local)
     events = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
               for _ in range(args.steps)]
     step_no = [0]
@@ -336,11 +345,23 @@ def run_b200_arm(args, rank, world, local):
         roll.run(events[step_no[0]])
         step_no[0] += 1
 
-    launches0 = _lib.launch_count()
     sampler.start()
+    launches0 = _lib.launch_count()
+    t_begin = sampler.mark()
     dt = timed(one, args.steps, dev)
-    clocks = sampler.stop()
+    t_end = sampler.mark()
     launches = _lib.launch_count() - launches0
+    note = "sampled during the timed region"
+    if t_end - t_begin < 0.5:
+        # the timed region is shorter than a few nvidia-smi periods: keep the identical load running
+        # (untimed) until ~0.6 s of samples exist, so the clocks are still read UNDER THIS LOAD
+        while time.time() - t_begin < 0.6:
+            roll.run()
+            torch.cuda.synchronize(dev)
+        t_end = sampler.mark()
+        note = "timed region < 0.5 s: sampled over the timed region plus an identical untimed load that follows it"
+    clocks = sampler.stop(t_begin, t_end)
+    clocks["note"] = note
     dt = cdist.max_over_ranks(dt, dev)
     steps_done = B * iters * args.steps * world
     value = steps_done / dt
@@ -376,9 +397,9 @@ def run_b200_arm(args, rank, world, local):
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         ncores = os.cpu_count() or 1
-        rate, nt, sec = time_cpu_port(args.cpu_episodes, iters, repeats=3, threads_options=sorted({ncores, 1}))
+        rate, nt, sec = time_cpu_port(args.cpu_episodes, iters, repeats=8, threads_options=sorted({ncores, 1}))
         cpu_base = {"value": rate, "unit": UNIT, "cores": nt, "kind": "port", "host_cores": ncores,
-                    "sample": f"{args.cpu_episodes} episodes x {iters} iterations, median of 3 "
+                    "sample": f"{args.cpu_episodes} episodes x {iters} iterations, median of 8 "
                               f"({sec:.2f} s each), better of 1 and {ncores} threads"}
 
     if rank == 0:

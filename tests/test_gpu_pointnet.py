@@ -145,6 +145,9 @@ def test_index_points_shapes_dtypes_and_faults(cuda):
         for shape in ((3, 40), (3, 10, 16), (3, 0)):
             idx = torch.randint(0, 500, shape, generator=g)
             got = pn.index_points(pts.to(cuda), idx.to(cuda))
+            if idx.numel() == 0:          # the reference's reshape(-1) cannot infer C for an empty gather
+                assert got.shape == (*shape, C) and got.dtype == dtype
+                continue
             assert got.dtype == dtype and torch.equal(got.cpu(), po.index_points(pts, idx))
     assert _lib.take_fault() == 0
     bad = torch.tensor([[0, 500, 2]] * 3)
