@@ -258,7 +258,7 @@ class DeviceRollout:
                    B, N, C, H, W, p(self.obs3d), None, p(self.mvis[it]), st)
             if scatter_events is not None:
                 scatter_events[it][0].record()
-            L.call("cmr_tile_scatter", p(self.img_feat), p(self.ws), B, N, C, H, W, p(self.obs2d), st)
+            L.call("cmr_tile_scatter", p(self.img_feat), p(self.K), p(self.ws), B, N, C, H, W, p(self.obs2d), st)
             if scatter_events is not None:
                 scatter_events[it][1].record()
             L.call("cmr_step", p(self.pose), p(self.a_r[it]), p(self.a_t[it]), p(self.rot), p(self.tt), self.nbins,

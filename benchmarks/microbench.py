@@ -1,0 +1,168 @@
+#!/usr/bin/env python
+"""Micro-benchmarks for BASELINE.json configs 4 and 5 (not the driver's bench contract - that is
+bench.py).  Prints one JSON line per case; all timings are CUDA events on the launch stream after
+warm-up, inputs resident in HBM.
+
+  python benchmarks/microbench.py frontend [--batch 128]   FPS 40960->1280 + kNN k=64 + grouping
+  python benchmarks/microbench.py sweep                    observe (project + tile scatter), 16K-128K points
+  python benchmarks/microbench.py env [--batch 32]         per-kernel times of one rollout iteration
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from cmr_agent_b200 import _lib, synth  # noqa: E402
+from cmr_agent_b200 import environment as env  # noqa: E402
+from cmr_agent_b200 import pointnet_util as pn  # noqa: E402
+
+PEAK = 6553.0
+try:
+    PEAK = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    pass
+
+
+def time_cuda(fn, warm=3, reps=10):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for a, b in ev:
+        a.record()
+        fn()
+        b.record()
+    torch.cuda.synchronize()
+    t = sorted(a.elapsed_time(b) for a, b in ev)
+    return t[len(t) // 2] / 1e3
+
+
+def frontend(args):
+    dev = torch.device("cuda:0")
+    B, N, S, K = args.batch, 40960, 1280, 64
+    g = torch.Generator().manual_seed(1)
+    # clouds with the KITTI-shaped distribution; generated once on the host
+    xyz = synth.make_cloud_batch(min(B, 8), num_pt=N, seed=2023)
+    xyz = xyz.repeat((B + xyz.shape[0] - 1) // xyz.shape[0], 1, 1)[:B].contiguous()
+    xyz += torch.randn(B, 1, 3, generator=g) * 0.01          # distinct clouds
+    xyz = xyz.to(dev)
+    start = torch.randint(0, N, (B,), generator=g).to(dev)
+    feats = torch.randn(B, N, 3, generator=g).to(dev)
+    t_fps = time_cuda(lambda: pn.farthest_point_sample_from(xyz, S, start), reps=5)
+    fps = pn.farthest_point_sample_from(xyz, S, start)
+    new_xyz = pn.index_points(xyz, fps)
+    t_knn = time_cuda(lambda: pn.knn_point(K, xyz, new_xyz), reps=5)
+    idx = pn.knn_point(K, xyz, new_xyz)
+    t_ball = time_cuda(lambda: pn.query_ball_point(1.0, K, xyz, new_xyz), reps=5)
+    t_grp = time_cuda(lambda: pn.group_points(xyz, feats, new_xyz, idx), reps=5)
+    t_idx = time_cuda(lambda: pn.index_points(xyz, idx), reps=5)
+    out = {
+        "bench": "frontend", "batch": B, "N": N, "npoint": S, "k": K,
+        "fps_ms": t_fps * 1e3, "fps_rounds_per_s": B * S / t_fps, "fps_clouds_per_s": B / t_fps,
+        "fps_byte_floor_frac": (12.0 * N + 8 * S) * B / t_fps / 1e9 / PEAK,
+        "knn_ms": t_knn * 1e3, "knn_queries_per_s": B * S / t_knn, "knn_pair_evals_per_s": B * S * N / t_knn,
+        "knn_byte_floor_frac": (12.0 * (N + S) + 8 * S * K) * B / t_knn / 1e9 / PEAK,
+        "ball_ms": t_ball * 1e3, "group_ms": t_grp * 1e3, "index_points_ms": t_idx * 1e3,
+        "group_gbs": (8.0 * S * K + 4.0 * S * K * 6 * 2) * B / t_grp / 1e9,
+        "total_ms": (t_fps + t_knn + t_grp) * 1e3,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def sweep(args):
+    dev = torch.device("cuda:0")
+    for N in (16384, 32768, 65536, 131072):
+        for frac in (0.25, 1.0):
+            B = max(1, min(256, int(1.2e9 // (33 * N + 12 * 64 * 5120 + 256 * N * frac * 0.3))))
+            cpu = synth.make_batch(min(B, 4), seed=7, num_pt=N, img_h=160, img_w=512)
+            rep = (B + 3) // 4
+            data = {}
+            for k in ("pc", "pc_overlap_pred", "pc_geo_feat", "img_geo_feat"):
+                data[k] = cpu[k].repeat(rep, *([1] * (cpu[k].dim() - 1)))[:B].contiguous().to(dev)
+            data["K"] = cpu["K"].repeat(rep, 1, 1)[:B].contiguous()
+            data["img"] = torch.zeros(1, 1, 1, 1).expand(B, 3, 160, 512)
+            if frac == 1.0:
+                data["pc_overlap_pred"][:] = True
+            pose = torch.eye(4, device=dev).repeat(B, 1, 1)
+            pose[:, 2, 3] = 3.0
+            o = env.observation_from_a_pose(data, pose, return_pixels=True)
+            mvis = int(o[3].sum())
+            ep = data["_cmr_b200_episode"][1]
+            st = _lib.stream
+            obs2d = torch.empty(B, 128, 40, 128, device=dev)
+            obs3d = torch.empty(B, 5, N, device=dev)
+            p = _lib.ptr
+
+            def proj():
+                _lib.call("cmr_project", p(ep.pc), p(ep.overlap), p(ep.K), p(pose), p(ep.mean), p(ep.ws), B, N, 64, 40,
+                          128, p(obs3d), None, None, st())
+
+            def scat():
+                _lib.call("cmr_tile_scatter", p(ep.img_feat), p(ep.K), p(ep.ws), B, N, 64, 40, 128, p(obs2d), st())
+
+            t_p, t_s = time_cuda(proj), time_cuda(scat)
+            bytes_p = 33.0 * N * B
+            bytes_s = 4.0 * 64 * mvis + 12.0 * 64 * 5120 * B
+            print(json.dumps({
+                "bench": "sweep", "N": N, "overlap_frac": frac, "batch": B, "m_vis_per_episode": mvis / B,
+                "project_us": t_p * 1e6, "project_gbs": bytes_p / t_p / 1e9, "project_frac": bytes_p / t_p / 1e9 / PEAK,
+                "scatter_us": t_s * 1e6, "scatter_gbs": bytes_s / t_s / 1e9, "scatter_frac": bytes_s / t_s / 1e9 / PEAK,
+                "observe_steps_per_s": B / (t_p + t_s),
+                "observe_frac": (bytes_p + bytes_s) / (t_p + t_s) / 1e9 / PEAK}), flush=True)
+            del data, obs2d, obs3d, ep
+            torch.cuda.empty_cache()
+
+
+def env_kernels(args):
+    dev = torch.device("cuda:0")
+    B, N = args.batch, 40960
+    cpu = synth.make_batch(B, seed=2023, num_pt=N, img_h=160, img_w=512)
+    data = dict(cpu)
+    for k in ("pc", "pc_overlap_pred", "pc_geo_feat", "img_geo_feat"):
+        data[k] = cpu[k].to(dev)
+    cfg = synth.StepConfig(device=dev)
+    a_r, a_t = synth.make_actions(B, 1)
+    a_r, a_t = a_r[0].to(dev), a_t[0].to(dev)
+    pose, _ = env.init(data)
+    o = env.observation_from_a_pose(data, pose, return_pixels=True)
+    mvis = int(o[3].sum())
+    ep = data["_cmr_b200_episode"][1]
+    p, st = _lib.ptr, _lib.stream
+    obs2d = torch.empty(B, 128, 40, 128, device=dev)
+    obs3d = torch.empty(B, 5, N, device=dev)
+    feat = data["pc_geo_feat"]
+    res = {"bench": "env", "batch": B, "m_vis_per_episode": mvis / B, "m_per_episode": float(cpu["pc_overlap_pred"].sum()) / B}
+
+    def rec(name, fn, nbytes):
+        t = time_cuda(fn, reps=20)
+        res[name + "_us"] = t * 1e6
+        res[name + "_gbs"] = nbytes / t / 1e9
+        res[name + "_frac"] = nbytes / t / 1e9 / PEAK
+
+    M = float(cpu["pc_overlap_pred"].sum())
+    rec("prepare", lambda: _lib.call("cmr_episode_prepare", p(ep.overlap), p(feat), B, N, 64, p(ep.ws), st()),
+        B * N * (1 + 256.0) + M * 256.0)
+    rec("project", lambda: _lib.call("cmr_project", p(ep.pc), p(ep.overlap), p(ep.K), p(pose), p(ep.mean), p(ep.ws), B,
+                                     N, 64, 40, 128, p(obs3d), None, None, st()), 33.0 * N * B)
+    rec("scatter", lambda: _lib.call("cmr_tile_scatter", p(ep.img_feat), p(ep.K), p(ep.ws), B, N, 64, 40, 128, p(obs2d), st()),
+        256.0 * mvis + 12.0 * 64 * 5120 * B)
+    rec("step", lambda: env.step(a_r, a_t, pose, cfg), 64.0 * B)
+    env.reward(pose, data, None)
+    rec("reward", lambda: env.reward(pose, data, None), 25.0 * N * B)
+    rec("observe_api", lambda: env.observation_from_a_pose(data, pose), 33.0 * N * B + 256.0 * mvis + 12.0 * 64 * 5120 * B)
+    print(json.dumps(res), flush=True)
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("which", choices=["frontend", "sweep", "env"])
+    ap.add_argument("--batch", type=int, default=None)
+    a = ap.parse_args()
+    if a.batch is None:
+        a.batch = 128 if a.which == "frontend" else 32
+    {"frontend": frontend, "sweep": sweep, "env": env_kernels}[a.which](a)

@@ -28,7 +28,7 @@ SIGNATURES = {
     "cmr_episode_prepare": (_c_int, [_c_vp, _c_vp, _c_int, _c_int, _c_int, _c_vp, _c_vp]),
     "cmr_observe": (_c_int, [_c_vp] * 7 + [_c_int] * 5 + [_c_vp] * 5),
     "cmr_project": (_c_int, [_c_vp] * 6 + [_c_int] * 5 + [_c_vp] * 4),
-    "cmr_tile_scatter": (_c_int, [_c_vp] * 2 + [_c_int] * 5 + [_c_vp] * 2),
+    "cmr_tile_scatter": (_c_int, [_c_vp] * 3 + [_c_int] * 5 + [_c_vp] * 2),
     "cmr_to_disentangled": (_c_int, [_c_vp, _c_vp, _c_int, _c_vp]),
     "cmr_step": (_c_int, [_c_vp] * 5 + [_c_int] * 3 + [_c_vp]),
     "cmr_reward_scratch_bytes": (_c_sz, [_c_int]),

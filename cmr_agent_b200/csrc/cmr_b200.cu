@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstring>
 
 #include "env_kernels.cuh"
 #include "pointnet_kernels.cuh"
@@ -18,6 +19,36 @@ static int allow_smem(Kern kern, size_t bytes) {
     if (bytes <= 32 * 1024) return CMR_OK;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     return e == cudaSuccess ? CMR_OK : (int)e;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+// fp32 tensor [d2][d1][d0] (d0 contiguous), boxes of [1][b1][b0]
+static bool make_map3d(CUtensorMap *m, const float *base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1) {
+    EncodeTiledFn fn = encode_tiled();
+    if (!fn) return false;
+    cuuint64_t dims[3] = {d0, d1, d2};
+    cuuint64_t strides[2] = {d0 * sizeof(float), d0 * d1 * sizeof(float)};
+    cuuint32_t box[3] = {b0, b1, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(base), dims, strides, box, es,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 static int sm_count() {
@@ -39,18 +70,41 @@ using namespace cmr;
     } while (0)
 
 template <typename PixT, int CQ>
-static int launch_tile_scatter(const WsLayout &L, const char *ws, const float *img_feat, int B, int N, int C, int P,
-                               float *obs2d, cudaStream_t st) {
+static int launch_tile_scatter(const WsLayout &L, const char *ws, const float *img_feat, const float *K, int W, int B,
+                               int N, int C, int P, float *obs2d, cudaStream_t st) {
     const PixT *pix = reinterpret_cast<const PixT *>(ws + L.off_pix);
     const int *M = reinterpret_cast<const int *>(ws + L.off_m);
     const float *featT = reinterpret_cast<const float *>(ws + L.off_feat);
-    size_t smem = sizeof(float) * kTilePix * (C + 1) + sizeof(int) * kTilePix + sizeof(unsigned) * kListCap;
+    size_t smem = sizeof(float) * kTilePix * C + sizeof(float) * kTilePix * (C + 1) + sizeof(int) * kTilePix +
+                  sizeof(unsigned) * 8 * kWarpList;
     int rc = allow_smem(k_tile_scatter<PixT, CQ>, smem);
     if (rc) return rc;
-    const bool vec = (P % 4 == 0) && aligned(img_feat, 16) && aligned(obs2d, 16);
-    k_tile_scatter<PixT, CQ><<<dim3(ceil_div(P, kTilePix), B), 256, smem, st>>>(pix, M, featT, img_feat, N, L.ncap, C, P,
-                                                                               vec, obs2d);
-    return after_launch();
+    // tiled TMA moves the [C][128-pixel] boxes of both halves of obs2d; it needs 16-byte aligned bases and
+    // row pitches.  Otherwise the kernel falls back to plain loads/stores for those copies.
+    alignas(64) CUtensorMap map_img, map_out;
+    memset(&map_img, 0, sizeof(map_img));
+    memset(&map_out, 0, sizeof(map_out));
+    bool tma = (P % 4 == 0) && P >= kTilePix && aligned(img_feat, 16) && aligned(obs2d, 16) &&
+               make_map3d(&map_img, img_feat, P, C, B, kTilePix, C) &&
+               make_map3d(&map_out, obs2d, P, 2 * (uint64_t)C, B, kTilePix, C);
+    // programmatic dependent launch: the preamble (image-tile TMA load, accumulator clear) overlaps the
+    // tail of the preceding k_project; the kernel waits (griddepcontrol.wait) before reading pixel ids
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(B, ceil_div(P, kTilePix));   // x = episode, y = tile rank (heavy tiles first)
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k_tile_scatter<PixT, CQ>, pix, M, featT, img_feat, K, W, N, L.ncap, C, P, tma, map_img,
+                                       map_out, obs2d);
+    ++g_launches;
+    if (e != cudaSuccess) return (int)e;
+    e = cudaGetLastError();
+    return e == cudaSuccess ? CMR_OK : (int)e;
 }
 
 template <typename PixT>
@@ -72,12 +126,12 @@ static int launch_project(const WsLayout &L, char *ws, const float *pc, const ui
 }
 
 template <typename PixT>
-static int launch_scatter(const WsLayout &L, const char *ws, const float *img_feat, int B, int N, int C, int P,
-                          float *obs2d, cudaStream_t st) {
-    if (C <= 32) return launch_tile_scatter<PixT, 1>(L, ws, img_feat, B, N, C, P, obs2d, st);
-    if (C <= 64) return launch_tile_scatter<PixT, 2>(L, ws, img_feat, B, N, C, P, obs2d, st);
-    if (C <= 128) return launch_tile_scatter<PixT, 4>(L, ws, img_feat, B, N, C, P, obs2d, st);
-    return launch_tile_scatter<PixT, 8>(L, ws, img_feat, B, N, C, P, obs2d, st);
+static int launch_scatter(const WsLayout &L, const char *ws, const float *img_feat, const float *K, int W, int B, int N,
+                          int C, int P, float *obs2d, cudaStream_t st) {
+    if (C <= 32) return launch_tile_scatter<PixT, 1>(L, ws, img_feat, K, W, B, N, C, P, obs2d, st);
+    if (C <= 64) return launch_tile_scatter<PixT, 2>(L, ws, img_feat, K, W, B, N, C, P, obs2d, st);
+    if (C <= 128) return launch_tile_scatter<PixT, 4>(L, ws, img_feat, K, W, B, N, C, P, obs2d, st);
+    return launch_tile_scatter<PixT, 8>(L, ws, img_feat, K, W, B, N, C, P, obs2d, st);
 }
 
 template <typename VecT>
@@ -181,7 +235,8 @@ int cmr_episode_prepare(const uint8_t *overlap, const float *feat, int B, int N,
     size_t smem = sizeof(float) * kGroup * (C + 1);
     rc = allow_smem(k_feat_compact<256>, smem);
     if (rc) return rc;
-    k_feat_compact<256><<<dim3(L.groups, B), 256, smem, S_(stream)>>>(overlap, feat, N, C, L.groups, seg, featT);
+    k_feat_compact<256><<<dim3(L.groups, B), 256, smem, S_(stream)>>>(overlap, feat, N, C, L.groups,
+                                                                      (N % 4 == 0) && aligned(feat, 16), seg, featT);
     return after_launch();
 }
 
@@ -205,16 +260,17 @@ int cmr_project(const float *pc, const uint8_t *overlap, const float *K, const f
     return launch_project<int32_t>(L, ws, pc, overlap, K, pose, mean, B, N, H, W, obs3d, pix_out, mvis_out, S_(stream));
 }
 
-int cmr_tile_scatter(const float *img_feat, const void *workspace, int B, int N, int C, int H, int W, float *obs2d,
-                     void *stream) {
-    CMR_REQUIRE(img_feat && workspace && obs2d, CMR_EINVAL);
+int cmr_tile_scatter(const float *img_feat, const float *K, const void *workspace, int B, int N, int C, int H, int W,
+                     float *obs2d, void *stream) {
+    CMR_REQUIRE(img_feat && K && workspace && obs2d, CMR_EINVAL);
+    CMR_REQUIRE((long long)ceil_div(H * W, kTilePix) <= 65535, CMR_ERANGE);
     int rc = check_observe_dims(B, N, C, H, W);
     if (rc) return rc;
     CMR_REQUIRE(aligned(workspace, 256), CMR_EALIGN);
     WsLayout L = ws_layout(B, N, C, H * W);
     const char *ws = static_cast<const char *>(workspace);
-    if (L.pix16) return launch_scatter<uint16_t>(L, ws, img_feat, B, N, C, H * W, obs2d, S_(stream));
-    return launch_scatter<int32_t>(L, ws, img_feat, B, N, C, H * W, obs2d, S_(stream));
+    if (L.pix16) return launch_scatter<uint16_t>(L, ws, img_feat, K, W, B, N, C, H * W, obs2d, S_(stream));
+    return launch_scatter<int32_t>(L, ws, img_feat, K, W, B, N, C, H * W, obs2d, S_(stream));
 }
 
 int cmr_observe(const float *pc, const uint8_t *overlap, const float *img_feat, const float *K, const float *pose,
@@ -222,7 +278,7 @@ int cmr_observe(const float *pc, const uint8_t *overlap, const float *img_feat, 
                 int32_t *pix_out, int32_t *mvis_out, void *stream) {
     int rc = cmr_project(pc, overlap, K, pose, mean, workspace, B, N, C, H, W, obs3d, pix_out, mvis_out, stream);
     if (rc) return rc;
-    return cmr_tile_scatter(img_feat, workspace, B, N, C, H, W, obs2d, stream);
+    return cmr_tile_scatter(img_feat, K, workspace, B, N, C, H, W, obs2d, stream);
 }
 
 int cmr_to_disentangled(float *poses, const float *mean, int B, void *stream) {
@@ -246,7 +302,7 @@ int cmr_reward(const float *target, const float *pc, const uint8_t *mask, const 
     CMR_REQUIRE(mode == CMR_REWARD_SHIPPED || (mode == CMR_REWARD_INTENDED && pose), CMR_EINVAL);
     CMR_REQUIRE(aligned(scratch, 16), CMR_EALIGN);
     CMR_REQUIRE(B <= 65535, CMR_ERANGE);
-    int nchunks = std::min(kRewardChunks, ceil_div(N, 4096));
+    int nchunks = std::min(kRewardChunks, ceil_div(N, 2048));
     int per_chunk = (int)round_up((size_t)ceil_div(N, nchunks), 1024);
     nchunks = ceil_div(N, per_chunk);
     const bool vec = (N % 4 == 0) && aligned(mask, 4);

@@ -16,7 +16,6 @@ namespace cmr {
 
 constexpr int kGroup = 128;     // points per compaction group = 32 lanes x 4 points
 constexpr int kTilePix = 128;   // pixels per k_tile_scatter CTA
-constexpr int kListCap = 4096;  // candidate entries staged in shared memory per flush
 constexpr int kMaxC = 256;
 
 struct WsLayout {
@@ -133,7 +132,8 @@ __global__ void __launch_bounds__(1024) k_overlap_scan(const uint8_t *__restrict
 template <int kThreads>
 __global__ void __launch_bounds__(kThreads) k_feat_compact(const uint8_t *__restrict__ overlap,
                                                             const float *__restrict__ feat, int N, int C, int groups,
-                                                            const int *__restrict__ seg, float *__restrict__ featT) {
+                                                            bool vec, const int *__restrict__ seg,
+                                                            float *__restrict__ featT) {
     extern __shared__ float tile[];  // [kGroup][C+1]
     __shared__ int rank[kGroup];
     __shared__ int wbase[5];
@@ -160,10 +160,27 @@ __global__ void __launch_bounds__(kThreads) k_feat_compact(const uint8_t *__rest
     if (total == 0) return;
     // coalesced read along the point axis, transposed into shared memory
     const float *src = feat + (size_t)b * C * N;
-    for (int r = warp; r < C * 4; r += kThreads / 32) {
-        int c = r >> 2, p = (r & 3) * 32 + lane;
-        int j = j0 + p;
-        tile[p * stride + c] = j < N ? __ldg(src + (size_t)c * N + j) : 0.f;
+    if (vec && j0 + kGroup <= N) {
+        // one warp reads the 128 points of a channel as 32 x 16 bytes; 4 channels in flight per warp
+        for (int c0 = warp * 4; c0 < C; c0 += (kThreads / 32) * 4) {
+            float4 v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (c0 + k < C) v[k] = ldg_stream4(src + (size_t)(c0 + k) * N + j0 + lane * 4);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (c0 + k < C) {
+                    float *t = tile + (lane * 4) * stride + c0 + k;
+                    t[0] = v[k].x; t[stride] = v[k].y; t[2 * stride] = v[k].z; t[3 * stride] = v[k].w;
+                }
+            }
+        }
+    } else {
+        for (int r = warp; r < C * 4; r += kThreads / 32) {
+            int c = r >> 2, p = (r & 3) * 32 + lane;
+            int j = j0 + p;
+            tile[p * stride + c] = j < N ? __ldg(src + (size_t)c * N + j) : 0.f;
+        }
     }
     __syncthreads();
     // write the rows of the overlap points: one warp per row
@@ -225,6 +242,7 @@ __global__ void __launch_bounds__(256) k_project(const float *__restrict__ pc, c
                                                   bool vec,
                                                   PixT *__restrict__ pix, float *__restrict__ obs3d,
                                                   int32_t *__restrict__ pix_out, int32_t *__restrict__ mvis) {
+    pdl_launch_dependents();   // k_tile_scatter may start its pose-independent preamble now
     const int b = blockIdx.y;
     const int lane = threadIdx.x & 31;
     const int g = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -312,6 +330,12 @@ __global__ void __launch_bounds__(256) k_project(const float *__restrict__ pc, c
 #pragma unroll
     for (int i = 0; i < 4; ++i)
         if (flags >> i & 1) pw[pos++] = (PixT)id2[i];
+    // k_tile_scatter reads the list in 16-byte words: the warp of the last group pads the ids between
+    // M and the next word boundary with all-ones (never inside a tile)
+    if (g == groups - 1 && lane == 31) {
+        constexpr int kPer = 16 / sizeof(PixT);
+        for (int m = pos; m < (pos + kPer - 1) / kPer * kPer; ++m) pw[m] = (PixT)~(PixT)0;
+    }
     if (mvis) {
         int v = warp_sum(__popc(flags & cam2));
         if (lane == 0 && v) atomicAdd(mvis + b, v);
@@ -321,163 +345,294 @@ __global__ void __launch_bounds__(256) k_project(const float *__restrict__ pc, c
 // Scatter-mean of the predicted-overlap points' features onto the pixel grid + concat with the image
 // features (environment.py:74-86).  One CTA owns kTilePix consecutive pixels of one episode:
 //   (0) copies the image-feature half of obs2d for its pixels (does not depend on the pose),
-//   (1) scans the episode's compacted pixel-id list for points that land in its tile (ordered),
-//   (2) warp w accumulates, in point order, the feature rows of the points of pixels p%8==w into a
+//   (1) every warp scans one contiguous eighth of the episode's compacted pixel-id list (SIMD
+//       compares, 16-byte loads) and appends the points that land in the tile to ITS list in shared
+//       memory - the eight lists read in warp order are the tile's points in point order,
+//   (2) warp w accumulates, in that order, the feature rows of the points of pixels p%8==w into a
 //       shared-memory tile [pixel][C+1]  (deterministic, no atomics),
 //   (3) divides by max(count,1) and writes the projected half of obs2d channel-major.
+// A tile whose lists would overflow (thousands of points in 128 pixels) takes a slower path in
+// which every warp walks the whole id list itself.
+constexpr int kWarpList = 256;   // entries per warp list
+
+// bit k of the result: id k of the 16-byte word group lies in [lo, lo+np)
+__device__ __forceinline__ unsigned tile_hits(const uint4 &raw, unsigned lo, unsigned np, uint16_t) {
+    const unsigned lo2 = lo | (lo << 16), np2 = np | (np << 16);
+    unsigned m0 = __vcmpltu2(__vsub2(raw.x, lo2), np2), m1 = __vcmpltu2(__vsub2(raw.y, lo2), np2);
+    unsigned m2 = __vcmpltu2(__vsub2(raw.z, lo2), np2), m3 = __vcmpltu2(__vsub2(raw.w, lo2), np2);
+    if ((m0 | m1 | m2 | m3) == 0) return 0;
+    return ((m0 & 1u) | ((m0 >> 15) & 2u)) | (((m1 & 1u) | ((m1 >> 15) & 2u)) << 2) |
+           (((m2 & 1u) | ((m2 >> 15) & 2u)) << 4) | (((m3 & 1u) | ((m3 >> 15) & 2u)) << 6);
+}
+__device__ __forceinline__ unsigned tile_hits(const uint4 &raw, unsigned lo, unsigned np, int32_t) {
+    return ((raw.x - lo < np) ? 1u : 0u) | ((raw.y - lo < np) ? 2u : 0u) | ((raw.z - lo < np) ? 4u : 0u) |
+           ((raw.w - lo < np) ? 8u : 0u);
+}
+__device__ __forceinline__ unsigned tile_id(const uint4 &raw, int k, uint16_t) {
+    unsigned w = (k >> 1) == 0 ? raw.x : ((k >> 1) == 1 ? raw.y : ((k >> 1) == 2 ? raw.z : raw.w));
+    return (k & 1) ? (w >> 16) : (w & 0xffffu);
+}
+__device__ __forceinline__ unsigned tile_id(const uint4 &raw, int k, int32_t) {
+    return k == 0 ? raw.x : (k == 1 ? raw.y : (k == 2 ? raw.z : raw.w));
+}
+
 template <typename PixT, int CQ>
 __global__ void __launch_bounds__(256) k_tile_scatter(const PixT *__restrict__ pix, const int *__restrict__ M,
                                                        const float *__restrict__ featT,
-                                                       const float *__restrict__ img_feat, int N, int ncap, int C,
-                                                       int P, bool vec, float *__restrict__ obs2d) {
-    extern __shared__ float smem[];
+                                                       const float *__restrict__ img_feat,
+                                                       const float *__restrict__ K, int W, int N, int ncap, int C,
+                                                       int P, bool tma, const __grid_constant__ CUtensorMap map_img,
+                                                       const __grid_constant__ CUtensorMap map_out,
+                                                       float *__restrict__ obs2d) {
+    extern __shared__ __align__(1024) float smem[];
     const int stride = C + 1;
-    float *acc = smem;                                              // [kTilePix][C+1]
-    int *cnt = reinterpret_cast<int *>(acc + kTilePix * stride);   // [kTilePix]
-    unsigned *list = reinterpret_cast<unsigned *>(cnt + kTilePix); // [kListCap]
-    __shared__ int wsum[8];
-    __shared__ int lcount_s;
+    float *stage = smem;                                             // [C][kTilePix] TMA staging tile
+    float *acc = stage + C * kTilePix;                               // [kTilePix][C+1]
+    int *cnt = reinterpret_cast<int *>(acc + kTilePix * stride);    // [kTilePix]
+    unsigned *wlist = reinterpret_cast<unsigned *>(cnt + kTilePix); // [8][kWarpList]
+    __shared__ int wcount[8];
+    __shared__ int overflow;
+    __shared__ __align__(8) uint64_t img_bar;
 
-    const int b = blockIdx.y;
-    const int p0 = blockIdx.x * kTilePix;
+    // Scheduling: far points pile up on the horizon row v = cy, so the tiles around it carry most of the
+    // gather work.  CTAs are handed out in launch order (x fastest): spread the episodes over x and walk
+    // the tiles outwards from the horizon tile over y, so that the heavy tiles of ALL episodes start first.
+    const int b = blockIdx.x;
+    const int tiles = gridDim.y;
+    int tile;
+    {
+        const float cy = __ldg(K + (size_t)b * 9 + 5);
+        int row = (int)cy;
+        row = row < 0 ? 0 : row;
+        long long pc = (long long)row * W;
+        int c = (int)(pc / kTilePix);
+        c = c > tiles - 1 ? tiles - 1 : c;
+        const int k = blockIdx.y, m = min(c, tiles - 1 - c);
+        if (k <= 2 * m)
+            tile = (k & 1) ? c + (k + 1) / 2 : c - k / 2;
+        else
+            tile = (c < tiles - 1 - c) ? k : tiles - 1 - k;
+    }
+    const int p0 = tile * kTilePix;
     const int np = min(kTilePix, P - p0);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float *out = obs2d + (size_t)b * 2 * C * P;
+    const float *img = img_feat + (size_t)b * C * P;
 
-    // (0) image half: obs2d[b, c, p0:p0+np] = img_feat[b, c, p0:p0+np]
-    {
-        const float *img = img_feat + (size_t)b * C * P;
-        if (vec && np == kTilePix) {
-            for (int c0 = 0; c0 < C; c0 += 32) {   // 8 warps x 4 channels per sweep, 4 loads in flight
-                float4 v[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    int c = c0 + warp * 4 + k;
-                    if (c < C) v[k] = ldg_stream4(img + (size_t)c * P + p0 + lane * 4);
-                }
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    int c = c0 + warp * 4 + k;
-                    if (c < C) stg_stream4(out + (size_t)c * P + p0 + lane * 4, v[k]);
-                }
-            }
-        } else {
-            for (int i = tid; i < C * np; i += 256) {
-                int c = i / np, p = i - c * np;
-                out[(size_t)c * P + p0 + p] = img[(size_t)c * P + p0 + p];
-            }
-        }
+    if (tid == 0) {
+        mbar_init(&img_bar, 1);
+        overflow = 0;
     }
-    for (int i = tid; i < kTilePix * stride; i += 256) acc[i] = 0.f;
-    if (tid < kTilePix) cnt[tid] = 0;
-    if (tid == 0) lcount_s = 0;
     __syncthreads();
+    // (0) image half of obs2d, obs2d[b, 0:C, p0:p0+np] = img_feat[b, :, p0:p0+np]: ONE tiled TMA load of
+    //     the [C][128] box into shared memory now, one TMA store after the scan; no registers, no LSU
+    if (tid == 0 && tma) {
+        mbar_arrive_expect_tx(&img_bar, (unsigned)(C * kTilePix * sizeof(float)));
+        tma_load_3d(stage, &map_img, p0, 0, b, &img_bar);
+    }
+    {
+        float4 *a4 = reinterpret_cast<float4 *>(acc);   // acc starts 16-byte aligned; cnt follows contiguously
+        const int n4 = (kTilePix * stride + kTilePix) / 4;
+        for (int i = tid; i < n4; i += 256) a4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
 
+    pdl_wait();   // everything below reads what k_project wrote (pixel ids) or writes obs2d
+
+    constexpr int kPer = 16 / sizeof(PixT);   // ids per 16-byte load
     const int m_total = min(__ldg(M + b), N);
+    const int m_pad = (m_total + kPer - 1) / kPer * kPer;   // ids in [m_total, m_pad) are all-ones (k_project)
     const PixT *pw = pix + (size_t)b * ncap;
     const float *rows = featT + (size_t)b * N * C;
-    constexpr int kPer = 16 / sizeof(PixT);  // ids per 16-byte load
-    const unsigned lo = (unsigned)p0, hi = (unsigned)(p0 + np);
+    const unsigned lo = (unsigned)p0;
+    unsigned *mylist = wlist + warp * kWarpList;
 
-    auto accumulate = [&](int lcount) {
-        // (2) warp w owns the pixels with (local id & 7) == w; entries are in point order
-        for (int i0 = 0; i0 < lcount; i0 += 32) {
-            unsigned e = (i0 + lane < lcount) ? list[i0 + lane] : 0xffffffffu;
-            unsigned mine = __ballot_sync(kFull, e != 0xffffffffu && (e & 7u) == (unsigned)warp);
-            while (mine) {
-                // up to 4 rows in flight per warp
-                unsigned ent[4];
-                int n = 0;
+    // feature rows (point-major, 4C contiguous bytes each) added, in order, to their pixels' accumulator
+    // rows; all kBatch rows are requested before the first one is consumed
+    constexpr int kBatch = 8;
+    auto add_rows = [&](const unsigned (&ent)[kBatch], int n) {
+        float v[kBatch][CQ];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (mine) {
-                        int src = __ffs(mine) - 1;
-                        mine &= mine - 1;
-                        ent[k] = __shfl_sync(kFull, e, src);
-                        n = k + 1;
-                    } else {
-                        ent[k] = 0xffffffffu;
-                    }
+        for (int k = 0; k < kBatch; ++k) {
+            if (k < n) {
+                const float *row = rows + (size_t)(ent[k] >> 7) * C;
+#pragma unroll
+                for (int q = 0; q < CQ; ++q)
+                    if (q * 32 + lane < C) v[k][q] = __ldg(row + q * 32 + lane);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kBatch; ++k) {
+            if (k < n) {
+                int pl = ent[k] & 127u;
+                float *a = acc + pl * stride;
+#pragma unroll
+                for (int q = 0; q < CQ; ++q)
+                    if (q * 32 + lane < C) a[q * 32 + lane] = __fadd_rn(a[q * 32 + lane], v[k][q]);
+                if (lane == 0) cnt[pl] += 1;
+            }
+        }
+    };
+    // consume, in order, the entries of `e` (one per lane) selected by `mine`
+    auto drain = [&](unsigned e, unsigned mine) {
+        while (mine) {
+            unsigned ent[kBatch];
+            int n = 0;
+#pragma unroll
+            for (int k = 0; k < kBatch; ++k) {
+                if (mine) {
+                    int src = __ffs(mine) - 1;
+                    mine &= mine - 1;
+                    ent[k] = __shfl_sync(kFull, e, src);
+                    n = k + 1;
+                } else {
+                    ent[k] = 0;
                 }
-                float v[4][CQ];
+            }
+            add_rows(ent, n);
+        }
+    };
+    // ordered scan of ids [beg, end) by one warp: hits appended to the warp's list; returns their number
+    auto scan_slice = [&](int beg, int end) {
+        int lc = 0;
+        for (int base = beg; base < end; base += 4 * 32 * kPer) {
+            uint4 raw[4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (k < n) {
-                        const float *row = rows + (size_t)(ent[k] >> 7) * C;
+            for (int u = 0; u < 4; ++u) {   // four independent 16-byte loads in flight per lane
+                const int m0 = base + (u * 32 + lane) * kPer;
+                raw[u] = m0 < end ? __ldg(reinterpret_cast<const uint4 *>(pw + m0)) : make_uint4(~0u, ~0u, ~0u, ~0u);
+            }
 #pragma unroll
-                        for (int q = 0; q < CQ; ++q)
-                            if (q * 32 + lane < C) v[k][q] = __ldg(row + q * 32 + lane);
-                    }
+            for (int u = 0; u < 4; ++u) {
+                const int m0 = base + (u * 32 + lane) * kPer;
+                const unsigned hit = tile_hits(raw[u], lo, (unsigned)np, PixT());
+                if (__ballot_sync(kFull, hit != 0) == 0) continue;
+                const int mine = __popc(hit);
+                int incl = mine;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    int t = __shfl_up_sync(kFull, incl, o);
+                    if (lane >= o) incl += t;
                 }
+                const int total = __shfl_sync(kFull, incl, 31);
+                if (lc + total <= kWarpList) {
+                    int pos = lc + incl - mine;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (k < n) {
-                        int pl = ent[k] & 127u;
-                        float *a = acc + pl * stride;
+                    for (int k = 0; k < kPer; ++k) {
+                        if (hit >> k & 1) {
+                            mylist[pos++] = ((unsigned)(m0 + k) << 7) | (tile_id(raw[u], k, PixT()) - lo);
+                            // start the row on its way to L2 now; the ordered gather comes later
+                            const float *row = rows + (size_t)(m0 + k) * C;
 #pragma unroll
-                        for (int q = 0; q < CQ; ++q)
-                            if (q * 32 + lane < C) a[q * 32 + lane] = __fadd_rn(a[q * 32 + lane], v[k][q]);
-                        if (lane == 0) cnt[pl] += 1;
+                            for (int q = 0; q < CQ; ++q) prefetch_l2(row + q * 32);
+                        }
                     }
+                } else if (lane == 0) {
+                    overflow = 1;
                 }
+                lc += total;
+            }
+        }
+        return lc;
+    };
+    // the eight lists in warp order = the tile's points in point order; warp w owns pixels with p%8==w
+    auto accumulate_lists = [&]() {
+        for (int wl = 0; wl < 8; ++wl) {
+            const int n = wcount[wl];
+            const unsigned *L = wlist + wl * kWarpList;
+            for (int i0 = 0; i0 < n; i0 += 32) {
+                unsigned e = (i0 + lane < n) ? L[i0 + lane] : 0xffffffffu;
+                drain(e, __ballot_sync(kFull, e != 0xffffffffu && (e & 7u) == (unsigned)warp));
             }
         }
     };
 
-    // (1) ordered scan of the compacted pixel ids
-    int lcount = 0;
-    for (int base = 0; base < m_total; base += 256 * kPer) {
-        const int m0 = base + tid * kPer;
-        unsigned hit = 0;
-        alignas(16) PixT ids[kPer];
-        if (m0 < m_total) {
-            uint4 raw = *reinterpret_cast<const uint4 *>(pw + m0);
-            *reinterpret_cast<uint4 *>(ids) = raw;
-#pragma unroll
-            for (int k = 0; k < kPer; ++k) {
-                unsigned id = (unsigned)ids[k];
-                if (m0 + k < m_total && id >= lo && id < hi) hit |= 1u << k;
-            }
-        }
-        int mine = __popc(hit), incl = mine;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            int t = __shfl_up_sync(kFull, incl, o);
-            if (lane >= o) incl += t;
-        }
-        if (lane == 31) wsum[warp] = incl;
-        __syncthreads();
-        int before = 0, total = 0;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) {
-            int s = wsum[w];
-            if (w < warp) before += s;
-            total += s;
-        }
-        if (lcount + total > kListCap) {  // uniform across the CTA
-            accumulate(lcount);
-            lcount = 0;
-            __syncthreads();
-        }
-        int pos = lcount + before + incl - mine;
-#pragma unroll
-        for (int k = 0; k < kPer; ++k)
-            if (hit >> k & 1) list[pos++] = ((unsigned)(m0 + k) << 7) | ((unsigned)ids[k] - lo);
-        lcount += total;
-        __syncthreads();
+    // (1) one pass: every warp scans a contiguous eighth of the list
+    {
+        const int per_warp = ((m_pad + 7) / 8 + 32 * kPer - 1) / (32 * kPer) * (32 * kPer);
+        const int beg = warp * per_warp;
+        const int lc = scan_slice(beg, min(beg + per_warp, m_pad));
+        if (lane == 0) wcount[warp] = lc;
     }
-    accumulate(lcount);
+    // the image tile has landed by now: push it out (asynchronously) before the gather
+    if (tid == 0 && tma) {
+        mbar_wait(&img_bar, 0);
+        tma_store_3d(&map_out, p0, 0, b, stage);
+        bulk_commit();
+    }
+    if (!tma) {
+        for (int i = tid; i < C * np; i += 256) {
+            int c = i / np, p = i - c * np;
+            out[(size_t)c * P + p0 + p] = img[(size_t)c * P + p0 + p];
+        }
+    }
     __syncthreads();
 
-    // (3) mean + channel-major store of the projected half: obs2d[b, C + c, p0 + p]
+    // (2) accumulate
+    if (!overflow) {
+        accumulate_lists();
+    } else {
+        // dense tile (more than kWarpList hits in one warp's slice): rounds of 8 x kWarpList ids, in which
+        // no list can overflow
+        for (int r0 = 0; r0 < m_pad; r0 += 8 * kWarpList) {
+            __syncthreads();
+            const int beg = r0 + warp * kWarpList;
+            const int lc = scan_slice(beg, min(beg + kWarpList, m_pad));
+            if (lane == 0) wcount[warp] = lc;
+            __syncthreads();
+            accumulate_lists();
+        }
+    }
+    __syncthreads();
+
+    // (3) mean + channel-major store of the projected half: obs2d[b, C + c, p0 + p].
+    // lane <-> pixel (conflict-free transposed reads); the divisor is per pixel, so classify it once:
+    // n <= 1 and powers of two scale exactly by a multiplication, anything else needs the IEEE division.
     float *proj = out + (size_t)C * P;
-    for (int c = warp; c < C; c += 8) {
+    float scale[kTilePix / 32], nf[kTilePix / 32];
+    bool hard = false;
 #pragma unroll
-        for (int p = lane; p < kTilePix; p += 32) {
-            if (p < np) {
-                int n = cnt[p];
-                float v = __fdiv_rn(acc[p * stride + c], (float)(n < 1 ? 1 : n));
-                stg_stream1(proj + (size_t)c * P + p0 + p, v);
+    for (int k = 0; k < kTilePix / 32; ++k) {
+        int n = cnt[lane + 32 * k];
+        n = n < 1 ? 1 : n;
+        nf[k] = (float)n;
+        scale[k] = 0.f;
+        if ((n & (n - 1)) == 0)
+            scale[k] = __fdiv_rn(1.f, nf[k]);   // exact
+        else
+            hard = true;
+    }
+    const bool any_hard = __any_sync(kFull, hard);
+    if (tma) {
+        // results go back through the staging tile ([c][128], lanes on consecutive pixels: conflict-free)
+        // and leave as ONE tiled TMA store; first make sure the image store has finished reading the tile
+        if (tid == 0) bulk_wait_read_all();
+        __syncthreads();
+        for (int c = warp; c < C; c += 8) {
+#pragma unroll
+            for (int k = 0; k < kTilePix / 32; ++k) {
+                const int p = lane + 32 * k;
+                float a = acc[p * stride + c];
+                float v = __fmul_rn(a, scale[k]);
+                if (any_hard && scale[k] == 0.f) v = __fdiv_rn(a, nf[k]);
+                stage[c * kTilePix + p] = v;
+            }
+        }
+        fence_async_proxy();   // generic-proxy writes -> visible to the TMA (async proxy)
+        __syncthreads();
+        if (tid == 0) {
+            tma_store_3d(&map_out, p0, C, b, stage);
+            bulk_commit();
+            bulk_wait_read_all();   // the staging tile must outlive the store's reads
+        }
+    } else {
+        for (int c = warp; c < C; c += 8) {
+#pragma unroll
+            for (int k = 0; k < kTilePix / 32; ++k) {
+                const int p = lane + 32 * k;
+                float a = acc[p * stride + c];
+                float v = __fmul_rn(a, scale[k]);
+                if (any_hard && scale[k] == 0.f) v = __fdiv_rn(a, nf[k]);
+                if (p < np) stg_stream1(proj + (size_t)c * P + p0 + p, v);
             }
         }
     }
@@ -593,20 +748,38 @@ __global__ void __launch_bounds__(256) k_reward(const float *__restrict__ target
     const float *px = pc + (size_t)b * 3 * N, *tx = target + (size_t)b * 3 * N;
     const uint8_t *mk = mask + (size_t)b * N;
     const int beg = chunk * per_chunk, end = min(N, beg + per_chunk);
+    const bool chain = N >= kBmmChainMinCols;
     double acc = 0.0;
     int n = 0;
     for (int j0 = beg + threadIdx.x * 4; j0 < end; j0 += 256 * 4) {
-        unsigned f = load_flags4(mk, j0, end, vec);
-        if (!f) continue;
+        const unsigned f = load_flags4(mk, j0, end, vec);
+        float p[3][4], t[3][4];
+        if (vec && j0 + 3 < end) {
+            // ~20 % of the points are masked in at random: nearly every 32-byte sector is needed, so
+            // load whole rows coalesced and unconditionally (six 16-byte loads in flight per thread)
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                float4 a = ldg_stream4(px + (size_t)r * N + j0), c = ldg_stream4(tx + (size_t)r * N + j0);
+                p[r][0] = a.x; p[r][1] = a.y; p[r][2] = a.z; p[r][3] = a.w;
+                t[r][0] = c.x; t[r][1] = c.y; t[r][2] = c.z; t[r][3] = c.w;
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    bool ok = (f >> i & 1) && j0 + i < end;
+                    p[r][i] = ok ? px[(size_t)r * N + j0 + i] : 0.f;
+                    t[r][i] = ok ? tx[(size_t)r * N + j0 + i] : 0.f;
+                }
+        }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             if (!(f >> i & 1)) continue;
-            int j = j0 + i;
-            float cx = __fsub_rn(px[j], s.m[0]), cy = __fsub_rn(px[(size_t)N + j], s.m[1]),
-                  cz = __fsub_rn(px[2 * (size_t)N + j], s.m[2]);                                       // :275
+            float cx = __fsub_rn(p[0][i], s.m[0]), cy = __fsub_rn(p[1][i], s.m[1]), cz = __fsub_rn(p[2][i], s.m[2]);  // :275
             float bx = cx, by = cy, bz = cz;
             if (mode == CMR_REWARD_INTENDED) {  // the transform of the commented line :273, disentangled
-                if (N >= kBmmChainMinCols) {
+                if (chain) {
                     bx = __fadd_rn(__fadd_rn(dot3_chain(s.R[0], s.R[1], s.R[2], cx, cy, cz), s.m[0]), s.t[0]);
                     by = __fadd_rn(__fadd_rn(dot3_chain(s.R[3], s.R[4], s.R[5], cx, cy, cz), s.m[1]), s.t[1]);
                     bz = __fadd_rn(__fadd_rn(dot3_chain(s.R[6], s.R[7], s.R[8], cx, cy, cz), s.m[2]), s.t[2]);
@@ -616,7 +789,7 @@ __global__ void __launch_bounds__(256) k_reward(const float *__restrict__ target
                     bz = __fadd_rn(__fadd_rn(dot3_plain(s.R[6], s.R[7], s.R[8], cx, cy, cz), s.m[2]), s.t[2]);
                 }
             }
-            acc += (double)sqdist3(tx[j], tx[(size_t)N + j], tx[2 * (size_t)N + j], bx, by, bz);     // :287-288
+            acc += (double)sqdist3(t[0][i], t[1][i], t[2][i], bx, by, bz);                                       // :287-288
             ++n;
         }
     }
