@@ -100,14 +100,14 @@ def sweep(args):
 
             def proj():
                 _lib.call("cmr_project", p(ep.pc), p(ep.overlap), p(ep.K), p(pose), p(ep.mean), p(ep.ws), B, N, 64, 40,
-                          128, p(obs3d), None, None, st())
+                          128, p(obs3d), None, None, p(ep.img_feat), p(obs2d), None, st())
 
             def scat():
-                _lib.call("cmr_tile_scatter", p(ep.img_feat), p(ep.K), p(ep.ws), B, N, 64, 40, 128, p(obs2d), st())
+                _lib.call("cmr_tile_scatter", p(ep.img_feat), p(ep.K), p(ep.ws), B, N, 64, 40, 128, 0, p(obs2d), st())
 
             t_p, t_s = time_cuda(proj), time_cuda(scat)
-            bytes_p = 33.0 * N * B
-            bytes_s = 4.0 * 64 * mvis + 12.0 * 64 * 5120 * B
+            bytes_p = 33.0 * N * B + 8.0 * 64 * 5120 * B     # obs3d stream + image half of obs2d (TMA)
+            bytes_s = 4.0 * 64 * mvis + 4.0 * 64 * 5120 * B  # feature rows + projected half of obs2d
             print(json.dumps({
                 "bench": "sweep", "N": N, "overlap_frac": frac, "batch": B, "m_vis_per_episode": mvis / B,
                 "project_us": t_p * 1e6, "project_gbs": bytes_p / t_p / 1e9, "project_frac": bytes_p / t_p / 1e9 / PEAK,
@@ -148,9 +148,10 @@ def env_kernels(args):
     rec("prepare", lambda: _lib.call("cmr_episode_prepare", p(ep.overlap), p(feat), B, N, 64, p(ep.ws), st()),
         B * N * (1 + 256.0) + M * 256.0)
     rec("project", lambda: _lib.call("cmr_project", p(ep.pc), p(ep.overlap), p(ep.K), p(pose), p(ep.mean), p(ep.ws), B,
-                                     N, 64, 40, 128, p(obs3d), None, None, st()), 33.0 * N * B)
-    rec("scatter", lambda: _lib.call("cmr_tile_scatter", p(ep.img_feat), p(ep.K), p(ep.ws), B, N, 64, 40, 128, p(obs2d), st()),
-        256.0 * mvis + 12.0 * 64 * 5120 * B)
+                                     N, 64, 40, 128, p(obs3d), None, None, p(ep.img_feat), p(obs2d), None, st()),
+        33.0 * N * B + 8.0 * 64 * 5120 * B)
+    rec("scatter", lambda: _lib.call("cmr_tile_scatter", p(ep.img_feat), p(ep.K), p(ep.ws), B, N, 64, 40, 128, 0, p(obs2d), st()),
+        256.0 * mvis + 4.0 * 64 * 5120 * B)
     rec("step", lambda: env.step(a_r, a_t, pose, cfg), 64.0 * B)
     env.reward(pose, data, None)
     rec("reward", lambda: env.reward(pose, data, None), 25.0 * N * B)

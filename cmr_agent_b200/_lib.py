@@ -10,7 +10,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcmr_b200.so")
+LIB_PATH = os.environ.get("CMR_B200_LIB", os.path.join(_HERE, "libcmr_b200.so"))
 
 _c_int = ctypes.c_int
 _c_vp = ctypes.c_void_p
@@ -27,8 +27,8 @@ SIGNATURES = {
     "cmr_cloud_mean": (_c_int, [_c_vp, _c_int, _c_int, _c_vp, _c_vp]),
     "cmr_episode_prepare": (_c_int, [_c_vp, _c_vp, _c_int, _c_int, _c_int, _c_vp, _c_vp]),
     "cmr_observe": (_c_int, [_c_vp] * 7 + [_c_int] * 5 + [_c_vp] * 5),
-    "cmr_project": (_c_int, [_c_vp] * 6 + [_c_int] * 5 + [_c_vp] * 4),
-    "cmr_tile_scatter": (_c_int, [_c_vp] * 3 + [_c_int] * 5 + [_c_vp] * 2),
+    "cmr_project": (_c_int, [_c_vp] * 6 + [_c_int] * 5 + [_c_vp] * 7),
+    "cmr_tile_scatter": (_c_int, [_c_vp] * 3 + [_c_int] * 6 + [_c_vp] * 2),
     "cmr_to_disentangled": (_c_int, [_c_vp, _c_vp, _c_int, _c_vp]),
     "cmr_step": (_c_int, [_c_vp] * 5 + [_c_int] * 3 + [_c_vp]),
     "cmr_reward_scratch_bytes": (_c_sz, [_c_int]),

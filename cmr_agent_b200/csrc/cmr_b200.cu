@@ -71,24 +71,16 @@ using namespace cmr;
 
 template <typename PixT, int CQ>
 static int launch_tile_scatter(const WsLayout &L, const char *ws, const float *img_feat, const float *K, int W, int B,
-                               int N, int C, int P, float *obs2d, cudaStream_t st) {
+                               int N, int C, int P, bool copy_image, float *obs2d, cudaStream_t st) {
     const PixT *pix = reinterpret_cast<const PixT *>(ws + L.off_pix);
     const int *M = reinterpret_cast<const int *>(ws + L.off_m);
     const float *featT = reinterpret_cast<const float *>(ws + L.off_feat);
-    size_t smem = sizeof(float) * kTilePix * C + sizeof(float) * kTilePix * (C + 1) + sizeof(int) * kTilePix +
-                  sizeof(unsigned) * 8 * kWarpList;
+    size_t smem = sizeof(float) * kTilePix * (C + 1) + sizeof(int) * kTilePix + sizeof(unsigned) * 16 * kWarpList;
     int rc = allow_smem(k_tile_scatter<PixT, CQ>, smem);
     if (rc) return rc;
-    // tiled TMA moves the [C][128-pixel] boxes of both halves of obs2d; it needs 16-byte aligned bases and
-    // row pitches.  Otherwise the kernel falls back to plain loads/stores for those copies.
-    alignas(64) CUtensorMap map_img, map_out;
-    memset(&map_img, 0, sizeof(map_img));
-    memset(&map_out, 0, sizeof(map_out));
-    bool tma = (P % 4 == 0) && P >= kTilePix && aligned(img_feat, 16) && aligned(obs2d, 16) &&
-               make_map3d(&map_img, img_feat, P, C, B, kTilePix, C) &&
-               make_map3d(&map_out, obs2d, P, 2 * (uint64_t)C, B, kTilePix, C);
-    // programmatic dependent launch: the preamble (image-tile TMA load, accumulator clear) overlaps the
-    // tail of the preceding k_project; the kernel waits (griddepcontrol.wait) before reading pixel ids
+    const bool vec = (P % 4 == 0) && aligned(img_feat, 16) && aligned(obs2d, 16);
+    // programmatic dependent launch: the preamble (accumulator clear) overlaps the tail of the preceding
+    // k_project; the kernel waits (griddepcontrol.wait) before reading pixel ids or writing obs2d
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(B, ceil_div(P, kTilePix));   // x = episode, y = tile rank (heavy tiles first)
     cfg.blockDim = dim3(256);
@@ -99,18 +91,29 @@ static int launch_tile_scatter(const WsLayout &L, const char *ws, const float *i
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, k_tile_scatter<PixT, CQ>, pix, M, featT, img_feat, K, W, N, L.ncap, C, P, tma, map_img,
-                                       map_out, obs2d);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k_tile_scatter<PixT, CQ>, pix, M, featT, img_feat, K, W, N, L.ncap, C, P,
+                                       copy_image, vec, obs2d);
     ++g_launches;
     if (e != cudaSuccess) return (int)e;
     e = cudaGetLastError();
     return e == cudaSuccess ? CMR_OK : (int)e;
 }
 
+// true when the image half of obs2d can travel as tiled TMA boxes inside k_project
+static bool image_copy_by_tma(const float *img_feat, const float *obs2d, int B, int C, int P, CUtensorMap *map_img,
+                              CUtensorMap *map_out) {
+    memset(map_img, 0, sizeof(*map_img));
+    memset(map_out, 0, sizeof(*map_out));
+    return img_feat && obs2d && (P % 4 == 0) && P >= kTilePix && aligned(img_feat, 16) && aligned(obs2d, 16) &&
+           make_map3d(map_img, img_feat, P, C, B, kTilePix, C) &&
+           make_map3d(map_out, obs2d, P, 2 * (uint64_t)C, B, kTilePix, C);
+}
+
 template <typename PixT>
 static int launch_project(const WsLayout &L, char *ws, const float *pc, const uint8_t *overlap, const float *K,
-                          const float *pose, const float *mean, int B, int N, int H, int W, float *obs3d,
-                          int32_t *pix_out, int32_t *mvis_out, cudaStream_t st) {
+                          const float *pose, const float *mean, int B, int N, int C, int H, int W, float *obs3d,
+                          int32_t *pix_out, int32_t *mvis_out, bool img_tma, const CUtensorMap &map_img,
+                          const CUtensorMap &map_out, cudaStream_t st) {
     PixT *pix = reinterpret_cast<PixT *>(ws + L.off_pix);
     const int *seg = reinterpret_cast<const int *>(ws + L.off_seg);
     const int *Mws = reinterpret_cast<const int *>(ws + L.off_m);
@@ -120,18 +123,23 @@ static int launch_project(const WsLayout &L, char *ws, const float *pc, const ui
         cudaError_t e = cudaMemsetAsync(mvis_out, 0, sizeof(int32_t) * B, st);
         if (e != cudaSuccess) return (int)e;
     }
-    k_project<PixT><<<dim3(ceil_div(L.groups, 8), B), 256, 0, st>>>(pc, overlap, K, pose, mean, seg, Mws, N, L.ncap,
-                                                                   L.groups, H, W, vec, pix, obs3d, pix_out, mvis_out);
+    const int img_tiles = img_tma ? ceil_div(H * W, kTilePix) : 0;
+    const size_t smem = img_tma ? sizeof(float) * kTilePix * C : 0;
+    int rc = allow_smem(k_project<PixT>, smem);
+    if (rc) return rc;
+    k_project<PixT><<<dim3(ceil_div(L.groups, 8), B), 256, smem, st>>>(pc, overlap, K, pose, mean, seg, Mws, N, L.ncap,
+                                                                      L.groups, H, W, vec, pix, obs3d, pix_out, mvis_out,
+                                                                      img_tiles, C, map_img, map_out);
     return after_launch();
 }
 
 template <typename PixT>
 static int launch_scatter(const WsLayout &L, const char *ws, const float *img_feat, const float *K, int W, int B, int N,
-                          int C, int P, float *obs2d, cudaStream_t st) {
-    if (C <= 32) return launch_tile_scatter<PixT, 1>(L, ws, img_feat, K, W, B, N, C, P, obs2d, st);
-    if (C <= 64) return launch_tile_scatter<PixT, 2>(L, ws, img_feat, K, W, B, N, C, P, obs2d, st);
-    if (C <= 128) return launch_tile_scatter<PixT, 4>(L, ws, img_feat, K, W, B, N, C, P, obs2d, st);
-    return launch_tile_scatter<PixT, 8>(L, ws, img_feat, K, W, B, N, C, P, obs2d, st);
+                          int C, int P, bool copy_image, float *obs2d, cudaStream_t st) {
+    if (C <= 32) return launch_tile_scatter<PixT, 1>(L, ws, img_feat, K, W, B, N, C, P, copy_image, obs2d, st);
+    if (C <= 64) return launch_tile_scatter<PixT, 2>(L, ws, img_feat, K, W, B, N, C, P, copy_image, obs2d, st);
+    if (C <= 128) return launch_tile_scatter<PixT, 4>(L, ws, img_feat, K, W, B, N, C, P, copy_image, obs2d, st);
+    return launch_tile_scatter<PixT, 8>(L, ws, img_feat, K, W, B, N, C, P, copy_image, obs2d, st);
 }
 
 template <typename VecT>
@@ -248,37 +256,46 @@ static int check_observe_dims(int B, int N, int C, int H, int W) {
 
 int cmr_project(const float *pc, const uint8_t *overlap, const float *K, const float *pose, const float *mean,
                 void *workspace, int B, int N, int C, int H, int W, float *obs3d, int32_t *pix_out, int32_t *mvis_out,
-                void *stream) {
+                const float *img_feat, float *obs2d, int *image_copied, void *stream) {
     CMR_REQUIRE(pc && overlap && K && pose && mean && workspace && obs3d, CMR_EINVAL);
     int rc = check_observe_dims(B, N, C, H, W);
     if (rc) return rc;
     CMR_REQUIRE(aligned(workspace, 256), CMR_EALIGN);
     WsLayout L = ws_layout(B, N, C, H * W);
     char *ws = static_cast<char *>(workspace);
+    alignas(64) CUtensorMap map_img, map_out;
+    const bool img_tma = image_copy_by_tma(img_feat, obs2d, B, C, H * W, &map_img, &map_out);
+    if (image_copied) *image_copied = img_tma ? 1 : 0;
     if (L.pix16)
-        return launch_project<uint16_t>(L, ws, pc, overlap, K, pose, mean, B, N, H, W, obs3d, pix_out, mvis_out, S_(stream));
-    return launch_project<int32_t>(L, ws, pc, overlap, K, pose, mean, B, N, H, W, obs3d, pix_out, mvis_out, S_(stream));
+        return launch_project<uint16_t>(L, ws, pc, overlap, K, pose, mean, B, N, C, H, W, obs3d, pix_out, mvis_out, img_tma,
+                                        map_img, map_out, S_(stream));
+    return launch_project<int32_t>(L, ws, pc, overlap, K, pose, mean, B, N, C, H, W, obs3d, pix_out, mvis_out, img_tma,
+                                   map_img, map_out, S_(stream));
 }
 
 int cmr_tile_scatter(const float *img_feat, const float *K, const void *workspace, int B, int N, int C, int H, int W,
-                     float *obs2d, void *stream) {
-    CMR_REQUIRE(img_feat && K && workspace && obs2d, CMR_EINVAL);
+                     int copy_image, float *obs2d, void *stream) {
+    CMR_REQUIRE(K && workspace && obs2d && (img_feat || !copy_image), CMR_EINVAL);
     CMR_REQUIRE((long long)ceil_div(H * W, kTilePix) <= 65535, CMR_ERANGE);
     int rc = check_observe_dims(B, N, C, H, W);
     if (rc) return rc;
     CMR_REQUIRE(aligned(workspace, 256), CMR_EALIGN);
     WsLayout L = ws_layout(B, N, C, H * W);
     const char *ws = static_cast<const char *>(workspace);
-    if (L.pix16) return launch_scatter<uint16_t>(L, ws, img_feat, K, W, B, N, C, H * W, obs2d, S_(stream));
-    return launch_scatter<int32_t>(L, ws, img_feat, K, W, B, N, C, H * W, obs2d, S_(stream));
+    if (L.pix16)
+        return launch_scatter<uint16_t>(L, ws, img_feat, K, W, B, N, C, H * W, copy_image != 0, obs2d, S_(stream));
+    return launch_scatter<int32_t>(L, ws, img_feat, K, W, B, N, C, H * W, copy_image != 0, obs2d, S_(stream));
 }
 
 int cmr_observe(const float *pc, const uint8_t *overlap, const float *img_feat, const float *K, const float *pose,
                 const float *mean, void *workspace, int B, int N, int C, int H, int W, float *obs2d, float *obs3d,
                 int32_t *pix_out, int32_t *mvis_out, void *stream) {
-    int rc = cmr_project(pc, overlap, K, pose, mean, workspace, B, N, C, H, W, obs3d, pix_out, mvis_out, stream);
+    CMR_REQUIRE(img_feat && obs2d, CMR_EINVAL);
+    int copied = 0;
+    int rc = cmr_project(pc, overlap, K, pose, mean, workspace, B, N, C, H, W, obs3d, pix_out, mvis_out, img_feat, obs2d,
+                         &copied, stream);
     if (rc) return rc;
-    return cmr_tile_scatter(img_feat, K, workspace, B, N, C, H, W, obs2d, stream);
+    return cmr_tile_scatter(img_feat, K, workspace, B, N, C, H, W, copied ? 0 : 1, obs2d, stream);
 }
 
 int cmr_to_disentangled(float *poses, const float *mean, int B, void *stream) {

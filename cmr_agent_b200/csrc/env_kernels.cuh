@@ -241,11 +241,29 @@ __global__ void __launch_bounds__(256) k_project(const float *__restrict__ pc, c
                                                   const int *__restrict__ M, int N, int ncap, int groups, int H, int W,
                                                   bool vec,
                                                   PixT *__restrict__ pix, float *__restrict__ obs3d,
-                                                  int32_t *__restrict__ pix_out, int32_t *__restrict__ mvis) {
+                                                  int32_t *__restrict__ pix_out, int32_t *__restrict__ mvis,
+                                                  int img_tiles, int C, const __grid_constant__ CUtensorMap map_img,
+                                                  const __grid_constant__ CUtensorMap map_out) {
     pdl_launch_dependents();   // k_tile_scatter may start its pose-independent preamble now
     const int b = blockIdx.y;
     const int lane = threadIdx.x & 31;
     const int g = blockIdx.x * 8 + (threadIdx.x >> 5);
+    // The image half of obs2d (obs2d[b, 0:C] = img_geo_feat[b], environment.py:83) is a pure copy that does
+    // not depend on the pose.  It rides along here as tiled TMA traffic: thread 0 of every CTA moves
+    // [C][128-pixel] boxes global -> shared -> global while the CTA's threads do the projection maths -
+    // no registers, no LSU instructions.  img_tiles == 0 switches it off (k_tile_scatter copies instead).
+    extern __shared__ __align__(1024) float img_stage[];
+    __shared__ __align__(8) uint64_t img_bar;
+    const bool copier = img_tiles > 0 && threadIdx.x == 0;
+    int tile = blockIdx.x;
+    if (copier) {
+        mbar_init(&img_bar, 1);
+        fence_async_proxy();
+        if (tile < img_tiles) {
+            mbar_arrive_expect_tx(&img_bar, (unsigned)(C * kTilePix * sizeof(float)));
+            tma_load_3d(img_stage, &map_img, tile * kTilePix, 0, b, &img_bar);
+        }
+    }
     if (g >= groups) return;
     const int j0 = g * kGroup + lane * 4;
     PoseK s;
@@ -340,6 +358,21 @@ __global__ void __launch_bounds__(256) k_project(const float *__restrict__ pc, c
         int v = warp_sum(__popc(flags & cam2));
         if (lane == 0 && v) atomicAdd(mvis + b, v);
     }
+    if (copier) {
+        unsigned parity = 0;
+        while (tile < img_tiles) {
+            mbar_wait(&img_bar, parity);
+            parity ^= 1;
+            tma_store_3d(&map_out, tile * kTilePix, 0, b, img_stage);
+            bulk_commit();
+            bulk_wait_read_all();   // the box has been read out of shared memory: the stage may be reused / freed
+            tile += gridDim.x;
+            if (tile < img_tiles) {
+                mbar_arrive_expect_tx(&img_bar, (unsigned)(C * kTilePix * sizeof(float)));
+                tma_load_3d(img_stage, &map_img, tile * kTilePix, 0, b, &img_bar);
+            }
+        }
+    }
 }
 
 // Scatter-mean of the predicted-overlap points' features onto the pixel grid + concat with the image
@@ -376,23 +409,65 @@ __device__ __forceinline__ unsigned tile_id(const uint4 &raw, int k, int32_t) {
     return k == 0 ? raw.x : (k == 1 ? raw.y : (k == 2 ? raw.z : raw.w));
 }
 
+// Consume, in order, the list entries `e` (one per lane, (point << 7) | local pixel) selected by `mine`:
+// feature rows (point-major, 4C contiguous bytes each) are added to their pixels' accumulator rows;
+// kBatch rows are requested before the first one is consumed.  Called by a whole warp.
+template <int CQ>
+__device__ __noinline__ void drain_rows(unsigned e, unsigned mine, const float *__restrict__ rows, float *acc, int *cnt,
+                                        int stride, int C, int lane) {
+    constexpr int kBatch = 8;
+    while (mine) {
+        unsigned ent[kBatch];
+        int n = 0;
+#pragma unroll
+        for (int k = 0; k < kBatch; ++k) {
+            if (mine) {
+                int src = __ffs(mine) - 1;
+                mine &= mine - 1;
+                ent[k] = __shfl_sync(kFull, e, src);
+                n = k + 1;
+            } else {
+                ent[k] = 0;
+            }
+        }
+        float v[kBatch][CQ];
+#pragma unroll
+        for (int k = 0; k < kBatch; ++k) {
+            if (k < n) {
+                const float *row = rows + (size_t)(ent[k] >> 7) * C;
+#pragma unroll
+                for (int q = 0; q < CQ; ++q)
+                    if (q * 32 + lane < C) v[k][q] = __ldg(row + q * 32 + lane);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kBatch; ++k) {
+            if (k < n) {
+                int pl = ent[k] & 127u;
+                float *a = acc + pl * stride;
+#pragma unroll
+                for (int q = 0; q < CQ; ++q)
+                    if (q * 32 + lane < C) a[q * 32 + lane] = __fadd_rn(a[q * 32 + lane], v[k][q]);
+                if (lane == 0) cnt[pl] += 1;
+            }
+        }
+    }
+}
+
 template <typename PixT, int CQ>
-__global__ void __launch_bounds__(256) k_tile_scatter(const PixT *__restrict__ pix, const int *__restrict__ M,
+__global__ void __launch_bounds__(256, CQ <= 2 ? 4 : 2) k_tile_scatter(const PixT *pix, const int *M,
                                                        const float *__restrict__ featT,
                                                        const float *__restrict__ img_feat,
                                                        const float *__restrict__ K, int W, int N, int ncap, int C,
-                                                       int P, bool tma, const __grid_constant__ CUtensorMap map_img,
-                                                       const __grid_constant__ CUtensorMap map_out,
-                                                       float *__restrict__ obs2d) {
-    extern __shared__ __align__(1024) float smem[];
+                                                       int P, bool copy_image, bool vec, float *__restrict__ obs2d) {
+    extern __shared__ __align__(16) float smem[];
     const int stride = C + 1;
-    float *stage = smem;                                             // [C][kTilePix] TMA staging tile
-    float *acc = stage + C * kTilePix;                               // [kTilePix][C+1]
+    float *acc = smem;                                               // [kTilePix][C+1]
     int *cnt = reinterpret_cast<int *>(acc + kTilePix * stride);    // [kTilePix]
-    unsigned *wlist = reinterpret_cast<unsigned *>(cnt + kTilePix); // [8][kWarpList]
+    unsigned *wlist = reinterpret_cast<unsigned *>(cnt + kTilePix); // [8][kWarpList] hits found by warp w, in order
+    unsigned *own = wlist + 8 * kWarpList;                           // [8][kWarpList] entries owned by warp w, in order
     __shared__ int wcount[8];
     __shared__ int overflow;
-    __shared__ __align__(8) uint64_t img_bar;
 
     // Scheduling: far points pile up on the horizon row v = cy, so the tiles around it carry most of the
     // gather work.  CTAs are handed out in launch order (x fastest): spread the episodes over x and walk
@@ -419,93 +494,52 @@ __global__ void __launch_bounds__(256) k_tile_scatter(const PixT *__restrict__ p
     float *out = obs2d + (size_t)b * 2 * C * P;
     const float *img = img_feat + (size_t)b * C * P;
 
-    if (tid == 0) {
-        mbar_init(&img_bar, 1);
-        overflow = 0;
-    }
-    __syncthreads();
-    // (0) image half of obs2d, obs2d[b, 0:C, p0:p0+np] = img_feat[b, :, p0:p0+np]: ONE tiled TMA load of
-    //     the [C][128] box into shared memory now, one TMA store after the scan; no registers, no LSU
-    if (tid == 0 && tma) {
-        mbar_arrive_expect_tx(&img_bar, (unsigned)(C * kTilePix * sizeof(float)));
-        tma_load_3d(stage, &map_img, p0, 0, b, &img_bar);
-    }
+    if (tid == 0) overflow = 0;
     {
-        float4 *a4 = reinterpret_cast<float4 *>(acc);   // acc starts 16-byte aligned; cnt follows contiguously
+        float4 *a4 = reinterpret_cast<float4 *>(acc);   // acc is 16-byte aligned; cnt follows contiguously
         const int n4 = (kTilePix * stride + kTilePix) / 4;
         for (int i = tid; i < n4; i += 256) a4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    __syncthreads();
 
     pdl_wait();   // everything below reads what k_project wrote (pixel ids) or writes obs2d
 
     constexpr int kPer = 16 / sizeof(PixT);   // ids per 16-byte load
-    const int m_total = min(__ldg(M + b), N);
+    // NOTE: this grid can be resident while k_project is still writing the id list (programmatic dependent
+    // launch), so the list is not read-only for its lifetime: no ld.global.nc / __ldg on it
+    const int m_total = min(ld_cg_s32(M + b), N);
     const int m_pad = (m_total + kPer - 1) / kPer * kPer;   // ids in [m_total, m_pad) are all-ones (k_project)
     const PixT *pw = pix + (size_t)b * ncap;
     const float *rows = featT + (size_t)b * N * C;
     const unsigned lo = (unsigned)p0;
     unsigned *mylist = wlist + warp * kWarpList;
 
-    // feature rows (point-major, 4C contiguous bytes each) added, in order, to their pixels' accumulator
-    // rows; all kBatch rows are requested before the first one is consumed
-    constexpr int kBatch = 8;
-    auto add_rows = [&](const unsigned (&ent)[kBatch], int n) {
-        float v[kBatch][CQ];
-#pragma unroll
-        for (int k = 0; k < kBatch; ++k) {
-            if (k < n) {
-                const float *row = rows + (size_t)(ent[k] >> 7) * C;
-#pragma unroll
-                for (int q = 0; q < CQ; ++q)
-                    if (q * 32 + lane < C) v[k][q] = __ldg(row + q * 32 + lane);
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < kBatch; ++k) {
-            if (k < n) {
-                int pl = ent[k] & 127u;
-                float *a = acc + pl * stride;
-#pragma unroll
-                for (int q = 0; q < CQ; ++q)
-                    if (q * 32 + lane < C) a[q * 32 + lane] = __fadd_rn(a[q * 32 + lane], v[k][q]);
-                if (lane == 0) cnt[pl] += 1;
-            }
-        }
-    };
-    // consume, in order, the entries of `e` (one per lane) selected by `mine`
-    auto drain = [&](unsigned e, unsigned mine) {
-        while (mine) {
-            unsigned ent[kBatch];
-            int n = 0;
-#pragma unroll
-            for (int k = 0; k < kBatch; ++k) {
-                if (mine) {
-                    int src = __ffs(mine) - 1;
-                    mine &= mine - 1;
-                    ent[k] = __shfl_sync(kFull, e, src);
-                    n = k + 1;
-                } else {
-                    ent[k] = 0;
-                }
-            }
-            add_rows(ent, n);
-        }
-    };
-    // ordered scan of ids [beg, end) by one warp: hits appended to the warp's list; returns their number
+    auto drain = [&](unsigned e, unsigned mine) { drain_rows<CQ>(e, mine, rows, acc, cnt, stride, C, lane); };
+    // ordered scan of ids [beg, end) by one warp: hits appended to the warp's list; returns their number.
+    // All loads of a batch are issued before the first compare; only the 8-bit hit masks stay live, the
+    // (rare) append path re-reads its word from L1.
     auto scan_slice = [&](int beg, int end) {
+        constexpr int kScanBatch = 8;
         int lc = 0;
-        for (int base = beg; base < end; base += 4 * 32 * kPer) {
-            uint4 raw[4];
+        for (int base = beg; base < end; base += kScanBatch * 32 * kPer) {
+            unsigned long long packed = 0;
+            {
+                uint4 raw[kScanBatch];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {   // four independent 16-byte loads in flight per lane
-                const int m0 = base + (u * 32 + lane) * kPer;
-                raw[u] = m0 < end ? __ldg(reinterpret_cast<const uint4 *>(pw + m0)) : make_uint4(~0u, ~0u, ~0u, ~0u);
+                for (int u = 0; u < kScanBatch; ++u) {
+                    const int m0 = base + (u * 32 + lane) * kPer;
+                    raw[u] = m0 < end ? ld_cg_u4(pw + m0) : make_uint4(~0u, ~0u, ~0u, ~0u);
+                }
+#pragma unroll
+                for (int u = 0; u < kScanBatch; ++u)
+                    packed |= (unsigned long long)tile_hits(raw[u], lo, (unsigned)np, PixT()) << (8 * u);
             }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int m0 = base + (u * 32 + lane) * kPer;
-                const unsigned hit = tile_hits(raw[u], lo, (unsigned)np, PixT());
+            if (__ballot_sync(kFull, packed != 0) == 0) continue;
+#pragma unroll 1
+            for (int u = 0; u < kScanBatch; ++u) {
+                const unsigned hit = (unsigned)(packed >> (8 * u)) & 0xffu;
                 if (__ballot_sync(kFull, hit != 0) == 0) continue;
+                const int m0 = base + (u * 32 + lane) * kPer;
                 const int mine = __popc(hit);
                 int incl = mine;
 #pragma unroll
@@ -515,15 +549,18 @@ __global__ void __launch_bounds__(256) k_tile_scatter(const PixT *__restrict__ p
                 }
                 const int total = __shfl_sync(kFull, incl, 31);
                 if (lc + total <= kWarpList) {
-                    int pos = lc + incl - mine;
+                    if (hit) {
+                        const uint4 raw = ld_cg_u4(pw + m0);
+                        int pos = lc + incl - mine;
 #pragma unroll
-                    for (int k = 0; k < kPer; ++k) {
-                        if (hit >> k & 1) {
-                            mylist[pos++] = ((unsigned)(m0 + k) << 7) | (tile_id(raw[u], k, PixT()) - lo);
-                            // start the row on its way to L2 now; the ordered gather comes later
-                            const float *row = rows + (size_t)(m0 + k) * C;
+                        for (int k = 0; k < kPer; ++k) {
+                            if (hit >> k & 1) {
+                                mylist[pos++] = ((unsigned)(m0 + k) << 7) | (tile_id(raw, k, PixT()) - lo);
+                                // start the row on its way to L2 now; the ordered gather comes later
+                                const float *row = rows + (size_t)(m0 + k) * C;
 #pragma unroll
-                            for (int q = 0; q < CQ; ++q) prefetch_l2(row + q * 32);
+                                for (int q = 0; q < CQ; ++q) prefetch_l2(row + q * 32);
+                            }
                         }
                     }
                 } else if (lane == 0) {
@@ -534,52 +571,100 @@ __global__ void __launch_bounds__(256) k_tile_scatter(const PixT *__restrict__ p
         }
         return lc;
     };
-    // the eight lists in warp order = the tile's points in point order; warp w owns pixels with p%8==w
+
+    // The eight lists read in warp order are the tile's points in point order.  Warp w owns the pixels with
+    // p%8==w: it first collects ITS entries (still in order) from all lists into a private list - shared
+    // memory traffic only - and then gathers the feature rows in full batches, so a light tile costs one
+    // memory round trip instead of one per list.
     auto accumulate_lists = [&]() {
-        for (int wl = 0; wl < 8; ++wl) {
+        unsigned *mine_list = own + warp * kWarpList;
+        // pass 1 (shared memory only): collect my entries, in order, while they fit
+        int n_own = 0;
+        bool fits = true;
+        for (int wl = 0; wl < 8 && fits; ++wl) {
             const int n = wcount[wl];
             const unsigned *L = wlist + wl * kWarpList;
             for (int i0 = 0; i0 < n; i0 += 32) {
-                unsigned e = (i0 + lane < n) ? L[i0 + lane] : 0xffffffffu;
-                drain(e, __ballot_sync(kFull, e != 0xffffffffu && (e & 7u) == (unsigned)warp));
+                const unsigned e = (i0 + lane < n) ? L[i0 + lane] : 0xffffffffu;
+                const bool is_mine = e != 0xffffffffu && (e & 7u) == (unsigned)warp;
+                const unsigned mask = __ballot_sync(kFull, is_mine);
+                const int add = __popc(mask);
+                if (n_own + add > kWarpList) {
+                    fits = false;
+                    break;
+                }
+                if (is_mine) mine_list[n_own + __popc(mask & ((1u << lane) - 1))] = e;
+                n_own += add;
+            }
+        }
+        __syncwarp();
+        if (fits) {
+            // pass 2: gather + accumulate, in order, kBatch rows in flight
+            for (int j0 = 0; j0 < n_own; j0 += 32) {
+                const unsigned q = (j0 + lane < n_own) ? mine_list[j0 + lane] : 0xffffffffu;
+                drain(q, __ballot_sync(kFull, q != 0xffffffffu));
+            }
+        } else {
+            // more than kWarpList of the tile's points belong to this warp: consume the lists directly
+            for (int wl = 0; wl < 8; ++wl) {
+                const int n = wcount[wl];
+                const unsigned *L = wlist + wl * kWarpList;
+                for (int i0 = 0; i0 < n; i0 += 32) {
+                    const unsigned e = (i0 + lane < n) ? L[i0 + lane] : 0xffffffffu;
+                    drain(e, __ballot_sync(kFull, e != 0xffffffffu && (e & 7u) == (unsigned)warp));
+                }
             }
         }
     };
 
-    // (1) one pass: every warp scans a contiguous eighth of the list
-    {
-        const int per_warp = ((m_pad + 7) / 8 + 32 * kPer - 1) / (32 * kPer) * (32 * kPer);
-        const int beg = warp * per_warp;
-        const int lc = scan_slice(beg, min(beg + per_warp, m_pad));
-        if (lane == 0) wcount[warp] = lc;
-    }
-    // the image tile has landed by now: push it out (asynchronously) before the gather
-    if (tid == 0 && tma) {
-        mbar_wait(&img_bar, 0);
-        tma_store_3d(&map_out, p0, 0, b, stage);
-        bulk_commit();
-    }
-    if (!tma) {
-        for (int i = tid; i < C * np; i += 256) {
-            int c = i / np, p = i - c * np;
-            out[(size_t)c * P + p0 + p] = img[(size_t)c * P + p0 + p];
+    // (0) image half of obs2d when k_project did not carry it (no TMA-compatible layout): plain copy
+    if (copy_image) {
+        if (vec && np == kTilePix) {
+            for (int c0 = 0; c0 < C; c0 += 32) {   // 8 warps x 4 channels per sweep, 4 loads in flight
+                float4 v[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    int c = c0 + warp * 4 + k;
+                    if (c < C) v[k] = ldg_stream4(img + (size_t)c * P + p0 + lane * 4);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    int c = c0 + warp * 4 + k;
+                    if (c < C) stg_stream4(out + (size_t)c * P + p0 + lane * 4, v[k]);
+                }
+            }
+        } else {
+            for (int i = tid; i < C * np; i += 256) {
+                int c = i / np, p = i - c * np;
+                out[(size_t)c * P + p0 + p] = img[(size_t)c * P + p0 + p];
+            }
         }
     }
-    __syncthreads();
 
-    // (2) accumulate
-    if (!overflow) {
-        accumulate_lists();
-    } else {
-        // dense tile (more than kWarpList hits in one warp's slice): rounds of 8 x kWarpList ids, in which
-        // no list can overflow
-        for (int r0 = 0; r0 < m_pad; r0 += 8 * kWarpList) {
-            __syncthreads();
-            const int beg = r0 + warp * kWarpList;
-            const int lc = scan_slice(beg, min(beg + kWarpList, m_pad));
+    // (1)+(2) rounds of {ordered scan, ordered accumulate}.  Normally ONE round: every warp scans a
+    // contiguous eighth of the whole id list.  If a warp finds more than kWarpList hits in its slice (a
+    // very dense tile) the tile restarts in rounds of 8 x kWarpList ids, in which no list can overflow.
+    {
+        int slice = ((m_pad + 7) / 8 + 32 * kPer - 1) / (32 * kPer) * (32 * kPer);
+        int r0 = 0;
+        bool dense = false;
+        while (true) {
+            const int r_end = min(r0 + 8 * slice, m_pad);
+            const int beg = r0 + warp * slice;
+            const int lc = scan_slice(beg, min(beg + slice, r_end));
             if (lane == 0) wcount[warp] = lc;
             __syncthreads();
+            if (!dense && overflow) {
+                dense = true;
+                slice = kWarpList;
+                r0 = 0;
+                __syncthreads();   // everybody has seen `overflow` before the lists are rewritten
+                continue;
+            }
             accumulate_lists();
+            r0 += 8 * slice;
+            if (r0 >= m_pad) break;
+            __syncthreads();       // lists are rewritten by the next round
         }
     }
     __syncthreads();
@@ -602,38 +687,14 @@ __global__ void __launch_bounds__(256) k_tile_scatter(const PixT *__restrict__ p
             hard = true;
     }
     const bool any_hard = __any_sync(kFull, hard);
-    if (tma) {
-        // results go back through the staging tile ([c][128], lanes on consecutive pixels: conflict-free)
-        // and leave as ONE tiled TMA store; first make sure the image store has finished reading the tile
-        if (tid == 0) bulk_wait_read_all();
-        __syncthreads();
-        for (int c = warp; c < C; c += 8) {
+    for (int c = warp; c < C; c += 8) {
 #pragma unroll
-            for (int k = 0; k < kTilePix / 32; ++k) {
-                const int p = lane + 32 * k;
-                float a = acc[p * stride + c];
-                float v = __fmul_rn(a, scale[k]);
-                if (any_hard && scale[k] == 0.f) v = __fdiv_rn(a, nf[k]);
-                stage[c * kTilePix + p] = v;
-            }
-        }
-        fence_async_proxy();   // generic-proxy writes -> visible to the TMA (async proxy)
-        __syncthreads();
-        if (tid == 0) {
-            tma_store_3d(&map_out, p0, C, b, stage);
-            bulk_commit();
-            bulk_wait_read_all();   // the staging tile must outlive the store's reads
-        }
-    } else {
-        for (int c = warp; c < C; c += 8) {
-#pragma unroll
-            for (int k = 0; k < kTilePix / 32; ++k) {
-                const int p = lane + 32 * k;
-                float a = acc[p * stride + c];
-                float v = __fmul_rn(a, scale[k]);
-                if (any_hard && scale[k] == 0.f) v = __fdiv_rn(a, nf[k]);
-                if (p < np) stg_stream1(proj + (size_t)c * P + p0 + p, v);
-            }
+        for (int k = 0; k < kTilePix / 32; ++k) {
+            const int p = lane + 32 * k;
+            float a = acc[p * stride + c];
+            float v = __fmul_rn(a, scale[k]);
+            if (any_hard && scale[k] == 0.f) v = __fdiv_rn(a, nf[k]);
+            if (p < np) stg_stream1(proj + (size_t)c * P + p0 + p, v);
         }
     }
 }

@@ -83,14 +83,18 @@ CMR_API int cmr_observe(const float *pc, const uint8_t *overlap, const float *im
                 int W, float *obs2d, float *obs3d, int32_t *pix_out, int32_t *mvis_out, void *stream);
 
 /* The two halves of cmr_observe, for callers that need only one observation or time them apart:
- *   cmr_project      environment.py:88-124 (obs3d) + :54-72 for the predicted-overlap points
- *                    (pixel ids into the workspace);
- *   cmr_tile_scatter environment.py:74-86 (obs2d) from the pixel ids the last cmr_project left. */
+ *   cmr_project      environment.py:88-124 (obs3d) + :54-72 for the predicted-overlap points (pixel ids
+ *                    into the workspace).  When img_feat and obs2d are given it also carries the image
+ *                    half of obs2d (obs2d[:, 0:C] = img_feat, :83) as tiled TMA traffic, if their layout
+ *                    allows (16-byte aligned, H*W % 4 == 0, H*W >= 128); *image_copied (host, optional)
+ *                    reports whether it did.
+ *   cmr_tile_scatter environment.py:74-86: the projected half obs2d[:, C:2C] from the pixel ids the last
+ *                    cmr_project left; with copy_image != 0 it also copies the image half itself. */
 CMR_API int cmr_project(const float *pc, const uint8_t *overlap, const float *K, const float *pose, const float *mean,
                         void *workspace, int B, int N, int C, int H, int W, float *obs3d, int32_t *pix_out,
-                        int32_t *mvis_out, void *stream);
+                        int32_t *mvis_out, const float *img_feat, float *obs2d, int *image_copied, void *stream);
 CMR_API int cmr_tile_scatter(const float *img_feat, const float *K, const void *workspace, int B, int N, int C, int H,
-                             int W, float *obs2d, void *stream);
+                             int W, int copy_image, float *obs2d, void *stream);
 
 /* to_disentangled - environment.py:15-21.  poses [B,4,4] in place: t <- (t - m) + R m. */
 CMR_API int cmr_to_disentangled(float *poses, const float *mean, int B, void *stream);
