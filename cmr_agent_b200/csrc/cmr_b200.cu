@@ -8,6 +8,7 @@
 
 #include "env_kernels.cuh"
 #include "pointnet_kernels.cuh"
+#include "scatter_kernels.cuh"
 
 namespace cmr {
 
@@ -97,6 +98,64 @@ static int launch_tile_scatter(const WsLayout &L, const char *ws, const float *i
     if (e != cudaSuccess) return (int)e;
     e = cudaGetLastError();
     return e == cudaSuccess ? CMR_OK : (int)e;
+}
+
+static_assert(kBoffStride == 392, "ws_layout reserves 392 ints per episode for the bucket offsets");
+
+template <typename Kern, typename... Args>
+static int launch_pdl(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, args...);
+    ++g_launches;
+    if (e != cudaSuccess) return (int)e;
+    e = cudaGetLastError();
+    return e == cudaSuccess ? CMR_OK : (int)e;
+}
+
+// projected half of obs2d through the CSR path: k_bin + k_tile_gather (scatter_kernels.cuh)
+template <typename PixT>
+static int launch_bin_gather(const WsLayout &L, const char *ws, const float *img_feat, const float *K, int W, int B,
+                             int N, int C, int P, bool copy_image, float *obs2d, cudaStream_t st) {
+    const PixT *pix = reinterpret_cast<const PixT *>(ws + L.off_pix);
+    const int *M = reinterpret_cast<const int *>(ws + L.off_m);
+    const float *featT = reinterpret_cast<const float *>(ws + L.off_feat);
+    unsigned *order = reinterpret_cast<unsigned *>(const_cast<char *>(ws) + L.off_order);
+    int *boff = reinterpret_cast<int *>(const_cast<char *>(ws) + L.off_boff);
+    const int T = ceil_div(P, kBucketPix);
+    size_t smem_bin = sizeof(int) * 32 * (size_t)T;
+    int rc = allow_smem(k_bin<PixT>, smem_bin);
+    if (rc) return rc;
+    rc = launch_pdl(k_bin<PixT>, dim3(B), dim3(kBinThreads), smem_bin, st, pix, M, N, L.ncap, P, order, boff);
+    if (rc) return rc;
+    const int tiles = ceil_div(P, kGatherTile);
+    size_t smem = sizeof(float) * kGatherTile * (C + 2) + sizeof(int) * kGatherTile + sizeof(unsigned) * kChunk +
+                  sizeof(unsigned) * 8 * kOwnCap;
+    dim3 grid(B, 4 * tiles);
+    if (C <= 64) {
+        rc = allow_smem(k_tile_gather<1>, smem);
+        if (rc) return rc;
+        return launch_pdl(k_tile_gather<1>, grid, dim3(256), smem, st, (const unsigned *)order, (const int *)boff, featT,
+                          img_feat, K, W, N, L.ncap, C, P, tiles, copy_image, obs2d);
+    }
+    if (C <= 128) {
+        rc = allow_smem(k_tile_gather<2>, smem);
+        if (rc) return rc;
+        return launch_pdl(k_tile_gather<2>, grid, dim3(256), smem, st, (const unsigned *)order, (const int *)boff, featT,
+                          img_feat, K, W, N, L.ncap, C, P, tiles, copy_image, obs2d);
+    }
+    rc = allow_smem(k_tile_gather<4>, smem);
+    if (rc) return rc;
+    return launch_pdl(k_tile_gather<4>, grid, dim3(256), smem, st, (const unsigned *)order, (const int *)boff, featT,
+                      img_feat, K, W, N, L.ncap, C, P, tiles, copy_image, obs2d);
 }
 
 // true when the image half of obs2d can travel as tiled TMA boxes inside k_project
@@ -273,7 +332,7 @@ int cmr_project(const float *pc, const uint8_t *overlap, const float *K, const f
                                    map_img, map_out, S_(stream));
 }
 
-int cmr_tile_scatter(const float *img_feat, const float *K, const void *workspace, int B, int N, int C, int H, int W,
+int cmr_tile_scatter(const float *img_feat, const float *K, void *workspace, int B, int N, int C, int H, int W,
                      int copy_image, float *obs2d, void *stream) {
     CMR_REQUIRE(K && workspace && obs2d && (img_feat || !copy_image), CMR_EINVAL);
     CMR_REQUIRE((long long)ceil_div(H * W, kTilePix) <= 65535, CMR_ERANGE);
@@ -282,9 +341,16 @@ int cmr_tile_scatter(const float *img_feat, const float *K, const void *workspac
     CMR_REQUIRE(aligned(workspace, 256), CMR_EALIGN);
     WsLayout L = ws_layout(B, N, C, H * W);
     const char *ws = static_cast<const char *>(workspace);
+    const int P = H * W;
+    if (ceil_div(P, kBucketPix) <= kBinMaxBuckets && 4 * ceil_div(P, kGatherTile) <= 65535) {
+        // binned path: counting sort by 32-pixel bucket + one CTA per tile that reads only its own points
+        if (L.pix16) return launch_bin_gather<uint16_t>(L, ws, img_feat, K, W, B, N, C, P, copy_image != 0, obs2d, S_(stream));
+        return launch_bin_gather<int32_t>(L, ws, img_feat, K, W, B, N, C, P, copy_image != 0, obs2d, S_(stream));
+    }
+    // large grids: every tile CTA searches the episode's id list itself
     if (L.pix16)
-        return launch_scatter<uint16_t>(L, ws, img_feat, K, W, B, N, C, H * W, copy_image != 0, obs2d, S_(stream));
-    return launch_scatter<int32_t>(L, ws, img_feat, K, W, B, N, C, H * W, copy_image != 0, obs2d, S_(stream));
+        return launch_scatter<uint16_t>(L, ws, img_feat, K, W, B, N, C, P, copy_image != 0, obs2d, S_(stream));
+    return launch_scatter<int32_t>(L, ws, img_feat, K, W, B, N, C, P, copy_image != 0, obs2d, S_(stream));
 }
 
 int cmr_observe(const float *pc, const uint8_t *overlap, const float *img_feat, const float *K, const float *pose,

@@ -7,7 +7,9 @@
 //   feat      [B,C,N]  f32  channel-major; read ONCE per episode by k_feat_compact
 //   workspace: M[B] i32 | seg[B,G] i32 (exclusive prefix of overlap counts per 128 points) |
 //              pix[B,ncap] u16/i32 (pixel id of the m-th predicted-overlap point, rewritten
-//              every observe) | featT[B,N,C] f32 (rows of the predicted-overlap points, point-major)
+//              every observe) | order[B,ncap] u32 + boff[B,392] i32 (per-observe CSR of the visible
+//              points by 32-pixel bucket) | featT[B,N,C] f32 (rows of the predicted-overlap points,
+//              point-major)
 //   obs3d     [B,5,N]  f32 ; obs2d [B,2C,H,W] f32
 #pragma once
 #include "common.cuh"
@@ -19,7 +21,7 @@ constexpr int kTilePix = 128;   // pixels per k_tile_scatter CTA
 constexpr int kMaxC = 256;
 
 struct WsLayout {
-    size_t off_m, off_seg, off_pix, off_feat, total;
+    size_t off_m, off_seg, off_pix, off_order, off_boff, off_feat, total;
     int groups, ncap;
     bool pix16;
 };
@@ -36,6 +38,10 @@ inline WsLayout ws_layout(int B, int N, int C, int P) {
     o = round_up(o + sizeof(int) * (size_t)B * L.groups, 256);
     L.off_pix = o;
     o = round_up(o + sizeof(int) * (size_t)B * L.ncap, 256);
+    L.off_order = o;   // CSR of the visible predicted-overlap points by 32-pixel bucket (scatter_kernels.cuh)
+    o = round_up(o + sizeof(unsigned) * (size_t)B * L.ncap, 256);
+    L.off_boff = o;
+    o = round_up(o + sizeof(int) * (size_t)B * 392, 256);
     L.off_feat = o;
     o = round_up(o + sizeof(float) * (size_t)B * N * C, 256);
     L.total = o;

@@ -93,7 +93,7 @@ CMR_API int cmr_observe(const float *pc, const uint8_t *overlap, const float *im
 CMR_API int cmr_project(const float *pc, const uint8_t *overlap, const float *K, const float *pose, const float *mean,
                         void *workspace, int B, int N, int C, int H, int W, float *obs3d, int32_t *pix_out,
                         int32_t *mvis_out, const float *img_feat, float *obs2d, int *image_copied, void *stream);
-CMR_API int cmr_tile_scatter(const float *img_feat, const float *K, const void *workspace, int B, int N, int C, int H,
+CMR_API int cmr_tile_scatter(const float *img_feat, const float *K, void *workspace, int B, int N, int C, int H,
                              int W, int copy_image, float *obs2d, void *stream);
 
 /* to_disentangled - environment.py:15-21.  poses [B,4,4] in place: t <- (t - m) + R m. */
