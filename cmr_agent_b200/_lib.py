@@ -31,6 +31,7 @@ SIGNATURES = {
     "cmr_tile_scatter": (_c_int, [_c_vp] * 3 + [_c_int] * 6 + [_c_vp] * 2),
     "cmr_to_disentangled": (_c_int, [_c_vp, _c_vp, _c_int, _c_vp]),
     "cmr_step": (_c_int, [_c_vp] * 5 + [_c_int] * 3 + [_c_vp]),
+    "cmr_expert": (_c_int, [_c_vp] * 4 + [_c_int] * 3 + [_c_vp] * 3),
     "cmr_reward_scratch_bytes": (_c_sz, [_c_int]),
     "cmr_reward": (_c_int, [_c_vp] * 6 + [_c_int] * 3 + [_c_vp] * 4),
     "cmr_square_distance": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_vp, _c_vp]),

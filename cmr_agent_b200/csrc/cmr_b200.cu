@@ -377,6 +377,14 @@ int cmr_step(float *pose, const int64_t *action_r, const int64_t *action_t, cons
     return after_launch();
 }
 
+int cmr_expert(const float *pose_source, const float *pose_target, const double *r_steps, const double *t_steps,
+               int nbins, int dof6, int B, int64_t *action_r, int64_t *action_t, void *stream) {
+    CMR_REQUIRE(pose_source && pose_target && r_steps && t_steps && action_r && action_t && nbins > 0 && B > 0, CMR_EINVAL);
+    k_expert<<<ceil_div(B, 64), 64, 0, S_(stream)>>>(pose_source, pose_target, r_steps, t_steps, nbins, dof6 ? 1 : 0, B,
+                                                     action_r, action_t);
+    return after_launch();
+}
+
 size_t cmr_reward_scratch_bytes(int B) { return B > 0 ? (size_t)B * kRewardSlotBytes : 0; }
 
 int cmr_reward(const float *target, const float *pc, const uint8_t *mask, const float *mean, const float *pose,

@@ -783,6 +783,102 @@ __global__ void k_step(float *__restrict__ pose, const int64_t *__restrict__ ar,
 }
 
 // -------------------------------------------------------------------------------------------------
+// expert (environment.py:143-176) on the device: no D2H -> scipy -> H2D round trip per step.
+//   delta_R = target_R @ source_R^T in fp32 (3x3 bmm, plain regime); then, in fp64 like scipy:
+//   matrix -> unit quaternion (scipy Rotation.from_matrix: largest of trace / diagonal) -> extrinsic
+//   xyz Euler angles (scipy as_euler('xyz'), the half-sum / half-difference form), the reference's
+//   ">3 rad" fix-ups (:153-159), and the first-minimum argmin over the float64 step tables.
+__global__ void k_expert(const float *__restrict__ src, const float *__restrict__ tgt, const double *__restrict__ r_steps,
+                         const double *__restrict__ t_steps, int nbins, int dof6, int B, int64_t *__restrict__ a_r,
+                         int64_t *__restrict__ a_t) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const float *S = src + (size_t)b * 16, *T = tgt + (size_t)b * 16;
+    double Mx[3][3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c)   // (T_R @ S_R^T)[r][c] = sum_k T[r][k] * S[c][k]
+            Mx[r][c] = (double)dot3_plain(T[4 * r], T[4 * r + 1], T[4 * r + 2], S[4 * c], S[4 * c + 1], S[4 * c + 2]);
+    const double tr = Mx[0][0] + Mx[1][1] + Mx[2][2];
+    double q[4];   // x, y, z, w
+    int choice;   // numpy argmax over (d0, d1, d2, trace): the first maximum
+    if (Mx[0][0] >= Mx[1][1] && Mx[0][0] >= Mx[2][2] && Mx[0][0] >= tr) choice = 0;
+    else if (Mx[1][1] >= Mx[2][2] && Mx[1][1] >= tr && Mx[1][1] > Mx[0][0]) choice = 1;
+    else if (Mx[2][2] >= tr && Mx[2][2] > Mx[0][0] && Mx[2][2] > Mx[1][1]) choice = 2;
+    else choice = 3;
+    if (choice != 3) {
+        const int i = choice, j = (i + 1) % 3, k = (j + 1) % 3;
+        q[i] = 1.0 - tr + 2.0 * Mx[i][i];
+        q[j] = Mx[j][i] + Mx[i][j];
+        q[k] = Mx[k][i] + Mx[i][k];
+        q[3] = Mx[k][j] - Mx[j][k];
+    } else {
+        q[0] = Mx[2][1] - Mx[1][2];
+        q[1] = Mx[0][2] - Mx[2][0];
+        q[2] = Mx[1][0] - Mx[0][1];
+        q[3] = 1.0 + tr;
+    }
+    const double nq = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) q[i] /= nq;
+    // extrinsic 'xyz' (i, j, k = 0, 1, 2; not symmetric; Levi-Civita sign +1)
+    const double kPi = 3.14159265358979323846;
+    const double a = q[3] - q[1], bb = q[0] + q[2], c = q[1] + q[3], d = q[2] - q[0];
+    double ang[3];
+    ang[1] = 2.0 * atan2(hypot(c, d), hypot(a, bb));
+    const double eps = 1e-7;
+    const int gimbal = fabs(ang[1]) <= eps ? 1 : (fabs(ang[1] - kPi) <= eps ? 2 : 0);
+    const double half_sum = atan2(bb, a), half_diff = atan2(d, c);
+    if (gimbal == 0) {
+        ang[0] = half_sum - half_diff;
+        ang[2] = half_sum + half_diff;
+    } else {   // gimbal lock: third angle set to zero (scipy warns and does the same)
+        ang[2] = 0.0;
+        ang[0] = gimbal == 1 ? 2.0 * half_sum : -2.0 * half_diff;
+    }
+    ang[1] -= kPi / 2.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        if (ang[i] < -kPi) ang[i] += 2.0 * kPi;
+        else if (ang[i] > kPi) ang[i] -= 2.0 * kPi;
+    }
+    // :153-159
+    if (ang[0] > 3.0) {
+        ang[0] = 0.0;
+        ang[2] = 0.0;
+        if (ang[1] > 0.0) ang[1] = kPi - ang[1];
+        else if (ang[1] < 0.0) ang[1] = -1.0 * kPi - ang[1];
+    }
+    double dt[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) dt[i] = (double)__fsub_rn(T[4 * i + 3], S[4 * i + 3]);   // :148 in fp32, promoted at :169
+    auto argmin = [nbins](double v, const double *tab) {
+        int arg = 0;
+        double e0 = fabs(v - tab[0]);
+        for (int i = 1; i < nbins; ++i) {
+            double e = fabs(v - tab[i]);
+            if (e < e0) {
+                e0 = e;
+                arg = i;
+            }
+        }
+        return (int64_t)arg;
+    };
+    if (dof6) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            a_r[b * 3 + i] = argmin(ang[i], r_steps);
+            a_t[b * 3 + i] = argmin(dt[i], t_steps);
+        }
+    } else {   // :172-174
+        a_r[b] = argmin(ang[1], r_steps);
+        a_t[b * 2] = argmin(dt[0], t_steps);
+        a_t[b * 2 + 1] = argmin(dt[2], t_steps);
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
 // reward (environment.py:263-302).  grid (chunks, B): every CTA reduces a slab of points to one fp64
 // partial; the last CTA of an episode to finish adds the partials in slab order (deterministic) and
 // writes distance and reward.  scratch per episode: [counter u32, pad][kRewardChunks x {sum f64, n i64}].

@@ -48,15 +48,25 @@ __global__ void __launch_bounds__(kBinThreads) k_bin(const PixT *pix, const int 
     const int beg = warp * per_warp, end = min(beg + per_warp, m_total);
     int *myhist = hist + warp * T;
 
-    // pass A: per-warp histogram over buckets
-    for (int m0 = beg; m0 < end; m0 += 32) {
-        const int m = m0 + lane;
-        unsigned id = 0xffffffffu;
-        if (m < end) id = (unsigned)pw[m];
-        const unsigned key = id < (unsigned)P ? id / kBucketPix : 0xffffffffu;   // H*W (dump bin) and padding drop out
-        const unsigned same = __match_any_sync(kFull, key);
-        if (key != 0xffffffffu && (__ffs(same) - 1) == lane) myhist[key] += __popc(same);
-        __syncwarp();
+    // pass A: per-warp histogram over buckets.  kBinBatch steps of 32 ids are loaded before the first one
+    // is ranked (the loop is otherwise a chain of dependent L2 round trips).
+    constexpr int kBinBatch = 8;
+    for (int m0 = beg; m0 < end; m0 += 32 * kBinBatch) {
+        unsigned ids[kBinBatch];
+#pragma unroll
+        for (int s2 = 0; s2 < kBinBatch; ++s2) {
+            const int m = m0 + s2 * 32 + lane;
+            ids[s2] = m < end ? (unsigned)pw[m] : 0xffffffffu;
+        }
+#pragma unroll
+        for (int s2 = 0; s2 < kBinBatch; ++s2) {
+            if (m0 + s2 * 32 >= end) break;
+            const unsigned id = ids[s2];
+            const unsigned key = id < (unsigned)P ? id / kBucketPix : 0xffffffffu;   // H*W (dump bin) drops out
+            const unsigned same = __match_any_sync(kFull, key);
+            if (key != 0xffffffffu && (__ffs(same) - 1) == lane) myhist[key] += __popc(same);
+            __syncwarp();
+        }
     }
     __syncthreads();
     // exclusive prefix over warps for every bucket, bucket totals
@@ -101,20 +111,29 @@ __global__ void __launch_bounds__(kBinThreads) k_bin(const PixT *pix, const int 
     __syncthreads();
     // pass B: stable placement
     unsigned *out = order + (size_t)b * ncap;
-    for (int m0 = beg; m0 < end; m0 += 32) {
-        const int m = m0 + lane;
-        unsigned id = 0xffffffffu;
-        if (m < end) id = (unsigned)pw[m];
-        const unsigned key = id < (unsigned)P ? id / kBucketPix : 0xffffffffu;
-        const unsigned same = __match_any_sync(kFull, key);
-        int basepos = 0;
-        if (key != 0xffffffffu) basepos = tot[key] + myhist[key];
-        __syncwarp();
-        if (key != 0xffffffffu) {
-            out[basepos + __popc(same & ((1u << lane) - 1))] = ((unsigned)m << 7) | (id & (kGatherTile - 1));
-            if ((__ffs(same) - 1) == lane) myhist[key] += __popc(same);
+    for (int m0 = beg; m0 < end; m0 += 32 * kBinBatch) {
+        unsigned ids[kBinBatch];
+#pragma unroll
+        for (int s2 = 0; s2 < kBinBatch; ++s2) {
+            const int m = m0 + s2 * 32 + lane;
+            ids[s2] = m < end ? (unsigned)pw[m] : 0xffffffffu;
         }
-        __syncwarp();
+#pragma unroll
+        for (int s2 = 0; s2 < kBinBatch; ++s2) {
+            if (m0 + s2 * 32 >= end) break;
+            const int m = m0 + s2 * 32 + lane;
+            const unsigned id = ids[s2];
+            const unsigned key = id < (unsigned)P ? id / kBucketPix : 0xffffffffu;
+            const unsigned same = __match_any_sync(kFull, key);
+            int basepos = 0;
+            if (key != 0xffffffffu) basepos = tot[key] + myhist[key];
+            __syncwarp();
+            if (key != 0xffffffffu) {
+                out[basepos + __popc(same & ((1u << lane) - 1))] = ((unsigned)m << 7) | (id & (kGatherTile - 1));
+                if ((__ffs(same) - 1) == lane) myhist[key] += __popc(same);
+            }
+            __syncwarp();
+        }
     }
 }
 
@@ -154,14 +173,7 @@ __global__ void __launch_bounds__(256, CQ2 <= 1 ? 4 : 2) k_tile_gather(const uns
     const int T = (P + kBucketPix - 1) / kBucketPix;
     const int bk0 = min(4 * t, T), bk4 = min(4 * t + 4, T);
 
-    // accumulator clear does not depend on the binning: do it before waiting for k_bin
-    {
-        float4 *a4 = reinterpret_cast<float4 *>(acc);
-        const int n4 = (kGatherTile * stride + kGatherTile) / 4;   // acc + cnt are contiguous
-        for (int i = tid; i < n4; i += 256) a4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    pdl_wait();
-
+    pdl_wait();   // the CSR is written by k_bin
     const int *bo = boff + (size_t)b * kBoffStride;
     const int tile_cnt = ld_cg_s32(bo + bk4) - ld_cg_s32(bo + bk0);
     const bool heavy = tile_cnt > kHeavyTile;
@@ -176,6 +188,12 @@ __global__ void __launch_bounds__(256, CQ2 <= 1 ? 4 : 2) k_tile_gather(const uns
     const unsigned *ord = order + (size_t)b * ncap;
     const float *rows = featT + (size_t)b * N * C;
     float *out = obs2d + (size_t)b * 2 * C * P;
+    {
+        float4 *a4 = reinterpret_cast<float4 *>(acc);
+        const int n4 = (width * stride + 3) / 4;
+        for (int i = tid; i < n4; i += 256) a4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tid < kGatherTile) cnt[tid] = 0;
+    }
     __syncthreads();
 
     if (copy_image) {   // image half when k_project could not carry it as TMA traffic

@@ -118,6 +118,13 @@ CMR_API int cmr_reward(const float *target, const float *pc, const uint8_t *mask
                const float *prev, int mode, int B, int N, void *scratch, float *reward, float *dist,
                void *stream);
 
+/* expert - environment.py:143-176 on the device (no D2H / scipy / H2D round trip per step).
+ *   delta_R in fp32, then fp64: scipy's Rotation.from_matrix -> as_euler('xyz') algorithm, the reference's
+ *   ">3 rad" fix-ups and a first-minimum argmin over r_steps / t_steps [nbins] f64 (device).
+ *   action_r [B,1] (3-DoF) or [B,3], action_t [B,2] or [B,3], i64. */
+CMR_API int cmr_expert(const float *pose_source, const float *pose_target, const double *r_steps, const double *t_steps,
+                       int nbins, int dof6, int B, int64_t *action_r, int64_t *action_t, void *stream);
+
 /* ------------------------------------------------------------------ pointnet_util ---- */
 
 /* square_distance - pointnet_util.py:19-33. src [B,S,3], dst [B,N,3] (any strides, in floats) ->

@@ -329,3 +329,44 @@ def test_ten_iteration_rollout_matches_oracle_port(cuda):
         env.step(a_r[it].to(cuda), a_t[it].to(cuda), pose_d, cfg_d)
         eo.step(a_r[it], a_t[it], pose_h, cfg_h)
         assert torch.equal(pose_d.cpu(), pose_h)
+
+
+@pytest.mark.parametrize("dof6", [False, True])
+def test_expert_on_device_matches_scipy_oracle(cuda, dof6):
+    """environment.py:143-176: the device kernel restates scipy's from_matrix/as_euler in fp64; the chosen
+    bins must equal the oracle's (scipy) on random pose pairs, including large y-rotations (the >3 rad
+    fix-up branch) and near-identity deltas."""
+    env = _env()
+    g = torch.Generator().manual_seed(5 + int(dof6))
+    B = 512
+    cfg_h = synth.StepConfig(is_6_DoF=dof6)
+    cfg_d = synth.StepConfig(device=cuda, is_6_DoF=dof6)
+
+    def poses(scale):
+        ang = (torch.rand(B, 3, generator=g) * 2 - 1) * scale
+        if not dof6:
+            ang[:, 0] = 0
+            ang[:, 2] = 0
+        p = torch.eye(4).repeat(B, 1, 1)
+        p[:, :3, :3] = eo.euler_angles_to_matrix(ang, "XYZ")
+        p[:, :3, 3] = torch.randn(B, 3, generator=g) * 6
+        return p
+
+    for scale in (3.14, 0.3, 0.01):
+        src, tgt = poses(scale), poses(scale)
+        want_r, want_t = eo.expert(src, tgt, cfg_h)
+        got_r, got_t = env.expert(src.to(cuda), tgt.to(cuda), cfg_d, None)
+        assert got_r.dtype == torch.int64 and got_r.shape == want_r.shape and got_t.shape == want_t.shape
+        assert torch.equal(got_t.cpu(), want_t)
+        bad = (got_r.cpu() != want_r).sum().item()
+        assert bad == 0, f"{bad} of {want_r.numel()} rotation bins differ (scale {scale})"
+    # one full expert-driven rollout: the device expert steers the pose to the target like the oracle's
+    src, tgt = torch.eye(4).repeat(B, 1, 1), poses(1.0)
+    sd, td = src.to(cuda), tgt.to(cuda)
+    for _ in range(10):
+        a_r, a_t = env.expert(sd, td, cfg_d, None)
+        h_r, h_t = eo.expert(src, tgt, cfg_h)
+        assert torch.equal(a_r.cpu(), h_r) and torch.equal(a_t.cpu(), h_t)
+        env.step(a_r, a_t, sd, cfg_d)
+        eo.step(h_r, h_t, src, cfg_h)
+        assert torch.equal(sd.cpu(), src)
