@@ -12,7 +12,8 @@ data-path collective ("weak" scaling: 32 episodes per GPU).
   e2e    : the same rollout through the reference-facing drop-in API (cmr_agent_b200.environment)
            from pinned HOST tensors: H2D of every input of the rollout and D2H of the per-iteration
            reward/distance and the final poses are inside the timed region.
-  roofline: k_tile_scatter (the dominant kernel), timed live with CUDA events on the launch stream.
+  roofline: the slower of the two observe stages (k_project | k_bin + k_tile_gather), timed live with CUDA
+           events on the launch stream inside the timed region; the other one is roofline_secondary.
   cpu_baseline: the oracle's torch-CPU port of the reference path (oracle/env_oracle.py) on this
            box's host cores, bounded sample.
 `--impl reference` times that CPU port alone (the reference is pure Python and cannot travel to the
@@ -377,7 +378,8 @@ def run_b200_arm(args, rank, world, local):
     # longer is reported as "roofline" (the dominant kernel), the other as "roofline_secondary".
     # Algorithmic bytes: observe = 33N + 4*C*M_vis + 12*C*P per episode, split as
     #   k_project      33N (pc, overlap -> obs3d) + 8*C*P (image half of obs2d, carried as TMA traffic)
-    #   k_tile_scatter 4*C*M_vis (feature rows of the visible points) + 4*C*P (projected half of obs2d)
+    #   k_bin + k_tile_gather (cmr_tile_scatter)  4*C*M_vis (feature rows of the visible points) + 4*C*P
+    #                  (projected half of obs2d)
     _, N, C, H, W = roll.dims
     P = H * W
     proj_s = statistics.mean(e[0].elapsed_time(e[1]) for ev in events for e in ev) / 1e3
@@ -395,7 +397,7 @@ def run_b200_arm(args, rank, world, local):
                 "algorithmic_bytes_per_launch": nbytes, "avg_launch_us": sec * 1e6,
                 "share_of_step": sec * iters * args.steps / dt, "peak_source": peak_src}
 
-    r_proj, r_scat = roof("k_project", bytes_proj, proj_s), roof("k_tile_scatter", bytes_scat, scat_s)
+    r_proj, r_scat = roof("k_project", bytes_proj, proj_s), roof("k_bin+k_tile_gather", bytes_scat, scat_s)
     roofline, roofline2 = (r_proj, r_scat) if proj_s >= scat_s else (r_scat, r_proj)
     roofline["m_vis_per_episode"] = mvis / B
     roofline["observe_frac"] = (bytes_proj + bytes_scat) / (proj_s + scat_s) / 1e9 / peak

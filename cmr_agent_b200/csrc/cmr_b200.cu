@@ -134,8 +134,27 @@ static int launch_bin_gather(const WsLayout &L, const char *ws, const float *img
     size_t smem_bin = sizeof(int) * 32 * (size_t)T;
     int rc = allow_smem(k_bin<PixT>, smem_bin);
     if (rc) return rc;
-    rc = launch_pdl(k_bin<PixT>, dim3(B), dim3(kBinThreads), smem_bin, st, pix, M, N, L.ncap, P, order, boff);
-    if (rc) return rc;
+    {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(B * kBinCluster);
+        cfg.blockDim = dim3(kBinThreads);
+        cfg.dynamicSmemBytes = smem_bin;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        attr[1].id = cudaLaunchAttributeClusterDimension;
+        attr[1].val.clusterDim.x = kBinCluster;
+        attr[1].val.clusterDim.y = 1;
+        attr[1].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 2;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, k_bin<PixT>, pix, M, N, L.ncap, P, order, boff);
+        ++g_launches;
+        if (e != cudaSuccess) return (int)e;
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return (int)e;
+    }
     const int tiles = ceil_div(P, kGatherTile);
     size_t smem = sizeof(float) * kGatherTile * (C + 2) + sizeof(int) * kGatherTile + sizeof(unsigned) * kChunk +
                   sizeof(unsigned) * 8 * kOwnCap;

@@ -15,10 +15,13 @@
 // Used when the grid has at most kBinMaxBuckets 32-pixel buckets (H*W <= 12288; KITTI is 5120, NuScenes
 // 3200); larger grids take the search-based k_tile_scatter of env_kernels.cuh.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace cmr {
 
+constexpr int kBinCluster = 4;          // CTAs (SMs) that share the counting sort of one episode
 constexpr int kBucketPix = 32;          // pixels per bucket (power of two)
 constexpr int kBinMaxBuckets = 384;     // per episode
 constexpr int kBoffStride = kBinMaxBuckets + 8;
@@ -28,14 +31,22 @@ constexpr int kHeavyTile = 160;         // a tile with more points than this is 
 constexpr int kChunk = 1024;            // CSR entries staged per round
 constexpr int kOwnCap = 256;            // private (owned) entries per warp between flushes
 
+// One thread-block CLUSTER of kBinCluster CTAs per episode: every CTA ranks a contiguous quarter of the id
+// list (the sort is instruction-bound on one SM otherwise), the per-bucket totals of the CTAs are exchanged
+// through distributed shared memory, and every CTA derives its own write offsets.
 template <typename PixT>
 __global__ void __launch_bounds__(kBinThreads) k_bin(const PixT *pix, const int *M, int N, int ncap, int P,
                                                       unsigned *__restrict__ order, int *__restrict__ boff) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
     pdl_launch_dependents();
-    extern __shared__ int hist[];          // [32 warps][T] -> exclusive prefix over warps, then running counters
-    __shared__ int tot[kBinMaxBuckets];    // points per bucket -> exclusive prefix over buckets
+    extern __shared__ int hist[];            // [32 warps][T] -> exclusive prefix over warps, then running counters
+    __shared__ int tot[kBinMaxBuckets];      // points per bucket found by THIS CTA (read by the peers)
+    __shared__ int cbase[kBinMaxBuckets];    // points per bucket found by the CTAs before this one
+    __shared__ int goff[kBinMaxBuckets];     // exclusive prefix over buckets of the episode totals
     __shared__ int wsum[32];
-    const int b = blockIdx.x;
+    const int rank = (int)cluster.block_rank(), csz = (int)cluster.num_blocks();
+    const int b = blockIdx.x / csz;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int T = (P + kBucketPix - 1) / kBucketPix;
     for (int i = tid; i < 32 * T; i += kBinThreads) hist[i] = 0;
@@ -44,8 +55,8 @@ __global__ void __launch_bounds__(kBinThreads) k_bin(const PixT *pix, const int 
     pdl_wait();   // the id list is written by k_project
     const int m_total = min(ld_cg_s32(M + b), N);
     const PixT *pw = pix + (size_t)b * ncap;
-    const int per_warp = ((m_total + 31) / 32 + 31) / 32 * 32;   // contiguous slice per warp, whole steps of 32
-    const int beg = warp * per_warp, end = min(beg + per_warp, m_total);
+    const int per_warp = ((m_total + 32 * csz - 1) / (32 * csz) + 31) / 32 * 32;   // whole steps of 32 ids
+    const int beg = min((rank * 32 + warp) * per_warp, m_total), end = min(beg + per_warp, m_total);
     int *myhist = hist + warp * T;
 
     // pass A: per-warp histogram over buckets.  kBinBatch steps of 32 ids are loaded before the first one
@@ -69,7 +80,7 @@ __global__ void __launch_bounds__(kBinThreads) k_bin(const PixT *pix, const int 
         }
     }
     __syncthreads();
-    // exclusive prefix over warps for every bucket, bucket totals
+    // exclusive prefix over warps for every bucket, CTA totals
     for (int t = tid; t < T; t += kBinThreads) {
         int run = 0;
         for (int w = 0; w < 32; ++w) {
@@ -79,10 +90,19 @@ __global__ void __launch_bounds__(kBinThreads) k_bin(const PixT *pix, const int 
         }
         tot[t] = run;
     }
-    __syncthreads();
-    // exclusive prefix over buckets (T <= 384: one value per thread of the first 12 warps)
+    cluster.sync();   // every CTA's totals are visible cluster-wide
+    int v = 0;
+    if (tid < T) {
+        int before = 0;
+        for (int c = 0; c < csz; ++c) {
+            const int x = *cluster.map_shared_rank(&tot[tid], c);
+            if (c < rank) before += x;
+            v += x;
+        }
+        cbase[tid] = before;
+    }
+    // exclusive prefix over buckets of the episode totals (T <= 384: one value per thread of the first 12 warps)
     {
-        int v = tid < T ? tot[tid] : 0;
         int inc = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -103,12 +123,12 @@ __global__ void __launch_bounds__(kBinThreads) k_bin(const PixT *pix, const int 
         __syncthreads();
         const int excl = wsum[warp] + inc - v;
         if (tid < T) {
-            tot[tid] = excl;
-            boff[(size_t)b * kBoffStride + tid] = excl;
+            goff[tid] = excl;
+            if (rank == 0) boff[(size_t)b * kBoffStride + tid] = excl;
         }
-        if (tid == T - 1) boff[(size_t)b * kBoffStride + T] = excl + v;
+        if (tid == T - 1 && rank == 0) boff[(size_t)b * kBoffStride + T] = excl + v;
     }
-    __syncthreads();
+    cluster.sync();   // peers have finished reading tot[]; goff/cbase are complete
     // pass B: stable placement
     unsigned *out = order + (size_t)b * ncap;
     for (int m0 = beg; m0 < end; m0 += 32 * kBinBatch) {
@@ -126,7 +146,7 @@ __global__ void __launch_bounds__(kBinThreads) k_bin(const PixT *pix, const int 
             const unsigned key = id < (unsigned)P ? id / kBucketPix : 0xffffffffu;
             const unsigned same = __match_any_sync(kFull, key);
             int basepos = 0;
-            if (key != 0xffffffffu) basepos = tot[key] + myhist[key];
+            if (key != 0xffffffffu) basepos = goff[key] + cbase[key] + myhist[key];
             __syncwarp();
             if (key != 0xffffffffu) {
                 out[basepos + __popc(same & ((1u << lane) - 1))] = ((unsigned)m << 7) | (id & (kGatherTile - 1));
