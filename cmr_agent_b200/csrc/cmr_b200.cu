@@ -505,4 +505,11 @@ int cmr_query_ball_point(const float *query, const float *ref, float radius2, in
     return after_launch();
 }
 
+#ifdef CMR_DBG_TIMING
+__attribute__((visibility("default"))) int cmr_debug_read(void *dst, size_t bytes) {
+    cudaDeviceSynchronize();
+    return (int)cudaMemcpyFromSymbol(dst, g_dbg, bytes);
+}
+#endif
+
 }  // extern "C"

@@ -148,4 +148,23 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// ---- optional per-CTA timing instrumentation (debug builds only: -DCMR_DBG_TIMING) ---------------------
+#ifdef CMR_DBG_TIMING
+__device__ unsigned long long g_dbg[16 * 8192];
+__device__ __forceinline__ unsigned long long dbg_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define DBG_MARK(slot)                                                                          \
+    do {                                                                                        \
+        if (threadIdx.x == 0) {                                                                 \
+            int _id = blockIdx.y * gridDim.x + blockIdx.x;                                      \
+            if (_id < 8192) g_dbg[_id * 16 + (slot)] = dbg_now();                                \
+        }                                                                                       \
+    } while (0)
+#else
+#define DBG_MARK(slot) do { } while (0)
+#endif
+
 }  // namespace cmr

@@ -984,23 +984,29 @@ __global__ void __launch_bounds__(256) k_reward(const float *__restrict__ target
         last = (done == (unsigned)nchunks - 1);
     }
     __syncthreads();
-    if (last && threadIdx.x == 0) {
+    if (last && warp == 0) {
+        // one partial per lane (<= 32 slabs), then a fixed shuffle tree: deterministic, one L2 round trip
         __threadfence();
         double t = 0.0;
         long long c = 0;
-        for (int k = 0; k < nchunks; ++k) {
-            t += *((volatile double *)&sums[k]);
-            c += *((volatile long long *)&cnts[k]);
+        if (lane < nchunks) {
+            t = *((volatile double *)&sums[lane]);
+            c = *((volatile long long *)&cnts[lane]);
         }
-        float d = (float)(t / (double)c);   // empty mask: 0/0 = NaN like torch's mean of an empty tensor (:289)
-        dist[b] = d;
-        float r = 0.f;
-        if (prev) {                                                                                  // :294-299
-            float pd = prev[b];
-            r = (d < pd ? 0.5f : 0.f) - (d > pd ? 0.5f : 0.f);
+        t = warp_sum(t);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(kFull, c, o);
+        if (lane == 0) {
+            float d = (float)(t / (double)c);   // empty mask: 0/0 = NaN like torch's mean of an empty tensor (:289)
+            dist[b] = d;
+            float r = 0.f;
+            if (prev) {                                                                                  // :294-299
+                float pd = prev[b];
+                r = (d < pd ? 0.5f : 0.f) - (d > pd ? 0.5f : 0.f);
+            }
+            reward[b] = r;
+            *counter = 0;   // self-resetting for the next call
         }
-        reward[b] = r;
-        *counter = 0;   // self-resetting for the next call
     }
 }
 

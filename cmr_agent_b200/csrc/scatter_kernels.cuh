@@ -21,7 +21,7 @@
 
 namespace cmr {
 
-constexpr int kBinCluster = 4;          // CTAs (SMs) that share the counting sort of one episode
+constexpr int kBinCluster = 8;          // CTAs (SMs) that share the counting sort of one episode
 constexpr int kBucketPix = 32;          // pixels per bucket (power of two)
 constexpr int kBinMaxBuckets = 384;     // per episode
 constexpr int kBoffStride = kBinMaxBuckets + 8;
@@ -193,7 +193,9 @@ __global__ void __launch_bounds__(256, CQ2 <= 1 ? 4 : 2) k_tile_gather(const uns
     const int T = (P + kBucketPix - 1) / kBucketPix;
     const int bk0 = min(4 * t, T), bk4 = min(4 * t + 4, T);
 
+    DBG_MARK(0);
     pdl_wait();   // the CSR is written by k_bin
+    DBG_MARK(1);
     const int *bo = boff + (size_t)b * kBoffStride;
     const int tile_cnt = ld_cg_s32(bo + bk4) - ld_cg_s32(bo + bk0);
     const bool heavy = tile_cnt > kHeavyTile;
@@ -224,6 +226,7 @@ __global__ void __launch_bounds__(256, CQ2 <= 1 ? 4 : 2) k_tile_gather(const uns
         }
     }
 
+    DBG_MARK(2);
     unsigned *mine_list = own + warp * kOwnCap;
     constexpr int kBatch = CQ2 <= 1 ? 16 : 8;
     for (int r0 = e0; r0 < e1; r0 += kChunk) {
@@ -236,12 +239,17 @@ __global__ void __launch_bounds__(256, CQ2 <= 1 ? 4 : 2) k_tile_gather(const uns
             for (int q = 0; q < C; q += 32) prefetch_l2(row + q);
         }
         __syncthreads();
+        DBG_MARK(8);
         // every warp walks the round in point order, keeps the entries of ITS pixels, and whenever its
         // private list is (nearly) full - and at the end - adds those rows in order
         int n_own = 0;
         for (int i0 = 0; i0 < n_round + 32; i0 += 32) {   // the last pass (i0 >= n_round) only flushes
             if (i0 >= n_round || n_own > kOwnCap - 32) {
                 __syncwarp();
+                DBG_MARK(9);
+#ifdef CMR_DBG_TIMING
+                if (threadIdx.x == 0) { int _id = blockIdx.y * gridDim.x + blockIdx.x; if (_id < 8192) g_dbg[_id * 16 + 11] = n_own; }
+#endif
                 for (int j0 = 0; j0 < n_own; j0 += kBatch) {
                     float2 v[kBatch][CQ2];
 #pragma unroll
@@ -253,22 +261,45 @@ __global__ void __launch_bounds__(256, CQ2 <= 1 ? 4 : 2) k_tile_gather(const uns
                                 if (q * 64 + 2 * lane < C) v[k][q] = __ldg(reinterpret_cast<const float2 *>(row + q * 64));
                         }
                     }
+                    // add pass: consecutive entries of the same pixel keep their running sum in registers, so
+                    // a hot pixel (hundreds of far points on the vanishing point) is a chain of FADDs instead
+                    // of a chain of shared-memory round trips
+                    int cur = -1;
+                    float2 run[CQ2];
 #pragma unroll
                     for (int k = 0; k < kBatch; ++k) {
                         if (j0 + k < n_own) {
-                            float *a = acc + ((mine_list[j0 + k] & 127u) - poff) * stride + 2 * lane;
+                            const int pl = (int)(mine_list[j0 + k] & 127u) - poff;
+                            if (pl != cur) {   // warp-uniform
+                                if (cur >= 0) {
+#pragma unroll
+                                    for (int q = 0; q < CQ2; ++q)
+                                        if (q * 64 + 2 * lane < C)
+                                            *reinterpret_cast<float2 *>(acc + cur * stride + 2 * lane + q * 64) = run[q];
+                                }
+                                cur = pl;
+#pragma unroll
+                                for (int q = 0; q < CQ2; ++q)
+                                    if (q * 64 + 2 * lane < C)
+                                        run[q] = *reinterpret_cast<const float2 *>(acc + cur * stride + 2 * lane + q * 64);
+                            }
 #pragma unroll
                             for (int q = 0; q < CQ2; ++q) {
                                 if (q * 64 + 2 * lane < C) {
-                                    float2 s2 = *reinterpret_cast<float2 *>(a + q * 64);
-                                    s2.x = __fadd_rn(s2.x, v[k][q].x);
-                                    s2.y = __fadd_rn(s2.y, v[k][q].y);
-                                    *reinterpret_cast<float2 *>(a + q * 64) = s2;
+                                    run[q].x = __fadd_rn(run[q].x, v[k][q].x);
+                                    run[q].y = __fadd_rn(run[q].y, v[k][q].y);
                                 }
                             }
                         }
                     }
+                    if (cur >= 0) {
+#pragma unroll
+                        for (int q = 0; q < CQ2; ++q)
+                            if (q * 64 + 2 * lane < C)
+                                *reinterpret_cast<float2 *>(acc + cur * stride + 2 * lane + q * 64) = run[q];
+                    }
                 }
+                DBG_MARK(10);
                 n_own = 0;
                 __syncwarp();
             }
@@ -287,6 +318,7 @@ __global__ void __launch_bounds__(256, CQ2 <= 1 ? 4 : 2) k_tile_gather(const uns
     }
     __syncthreads();
 
+    DBG_MARK(3);
     // mean + channel-major store: obs2d[b, C + c, p0 + p].  lane <-> pixel; the divisor is per pixel, so it
     // is classified once: n <= 1 and powers of two scale exactly by a multiplication, anything else needs
     // the IEEE division.
@@ -312,6 +344,19 @@ __global__ void __launch_bounds__(256, CQ2 <= 1 ? 4 : 2) k_tile_gather(const uns
             }
         }
     }
+    DBG_MARK(4);
+#ifdef CMR_DBG_TIMING
+    if (threadIdx.x == 0) {
+        int _id = blockIdx.y * gridDim.x + blockIdx.x;
+        if (_id < 8192) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+            g_dbg[_id * 16 + 5] = smid;
+            g_dbg[_id * 16 + 6] = (unsigned long long)p0;
+            g_dbg[_id * 16 + 7] = (unsigned long long)(e1 - e0);
+        }
+    }
+#endif
 }
 
 }  // namespace cmr
