@@ -231,15 +231,15 @@ static int launch_index_points(const void *points, const int64_t *idx, int B, in
     return after_launch();
 }
 
-template <int PPT>
+template <int PPT, int MINB>
 static int launch_fps(const float *xyz, const int64_t *start, int B, int N, int npoint, int64_t *out, int cs,
                       cudaStream_t st) {
     constexpr int THREADS = 512;
     size_t smem = sizeof(float) * 3 * THREADS * PPT;
-    int rc = allow_smem(k_fps<PPT, THREADS>, smem);
+    int rc = allow_smem(k_fps<PPT, THREADS, MINB>, smem);
     if (rc) return rc;
     if (cs > 8) {
-        cudaError_t e = cudaFuncSetAttribute(k_fps<PPT, THREADS>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        cudaError_t e = cudaFuncSetAttribute(k_fps<PPT, THREADS, MINB>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         if (e != cudaSuccess) return (int)e;
     }
     cudaLaunchConfig_t cfg{};
@@ -254,7 +254,7 @@ static int launch_fps(const float *xyz, const int64_t *start, int B, int N, int 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, k_fps<PPT, THREADS>, xyz, start, N, npoint, out);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k_fps<PPT, THREADS, MINB>, xyz, start, N, npoint, out);
     ++g_launches;
     if (e != cudaSuccess) return (int)e;
     e = cudaGetLastError();
@@ -466,8 +466,10 @@ int cmr_farthest_point_sample(const float *xyz, const int64_t *start, int B, int
                               void *stream) {
     CMR_REQUIRE(xyz && start && out && B > 0 && N > 0 && npoint > 0, CMR_EINVAL);
     constexpr int THREADS = 512, kMaxPpt = 24;
-    // smallest cluster that holds the cloud in registers, widened while the whole batch still fits
-    // on the chip in one wave (fewer points per thread = shorter rounds; FPS is latency-bound)
+    // smallest cluster that holds the cloud in registers, widened while the whole batch still fits on the
+    // chip in one wave (fewer points per thread = shorter rounds; FPS is latency-bound).  Measured on B200
+    // (config 4, 128 clouds of 40960): clusters of 4 x 20 points/thread, one CTA per SM: 7.1 ms; clusters of
+    // 8 x 10 points/thread with two CTAs per SM: 9.8 ms (the 8-CTA barrier costs more than it hides).
     int cs = 1;
     while (cs < 16 && (long long)cs * THREADS * kMaxPpt < N) cs *= 2;
     CMR_REQUIRE((long long)cs * THREADS * kMaxPpt >= N, CMR_ERANGE);
@@ -475,12 +477,12 @@ int cmr_farthest_point_sample(const float *xyz, const int64_t *start, int B, int
     while (cs < 8 && (long long)B * cs * 2 <= sms && (long long)cs * THREADS * 4 < N) cs *= 2;
     int ppt = ceil_div(N, cs * THREADS);
     cudaStream_t st = S_(stream);
-    if (ppt <= 4) return launch_fps<4>(xyz, start, B, N, npoint, out, cs, st);
-    if (ppt <= 8) return launch_fps<8>(xyz, start, B, N, npoint, out, cs, st);
-    if (ppt <= 12) return launch_fps<12>(xyz, start, B, N, npoint, out, cs, st);
-    if (ppt <= 16) return launch_fps<16>(xyz, start, B, N, npoint, out, cs, st);
-    if (ppt <= 20) return launch_fps<20>(xyz, start, B, N, npoint, out, cs, st);
-    return launch_fps<24>(xyz, start, B, N, npoint, out, cs, st);
+    if (ppt <= 4) return launch_fps<4, 1>(xyz, start, B, N, npoint, out, cs, st);
+    if (ppt <= 8) return launch_fps<8, 1>(xyz, start, B, N, npoint, out, cs, st);
+    if (ppt <= 12) return launch_fps<12, 1>(xyz, start, B, N, npoint, out, cs, st);
+    if (ppt <= 16) return launch_fps<16, 1>(xyz, start, B, N, npoint, out, cs, st);
+    if (ppt <= 20) return launch_fps<20, 1>(xyz, start, B, N, npoint, out, cs, st);
+    return launch_fps<24, 1>(xyz, start, B, N, npoint, out, cs, st);
 }
 
 int cmr_knn(const float *query, const float *ref, int B, int S, int N, int k, int64_t *out, void *stream) {

@@ -111,8 +111,8 @@ struct alignas(16) FpsRec {
     unsigned pad[3];
 };
 
-template <int PPT, int THREADS>
-__global__ void __launch_bounds__(THREADS, 1) k_fps(const float *__restrict__ xyz, const int64_t *__restrict__ start,
+template <int PPT, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) k_fps(const float *__restrict__ xyz, const int64_t *__restrict__ start,
                                                      int N, int npoint, int64_t *__restrict__ out) {
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned cs = cluster.num_blocks();
