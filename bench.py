@@ -247,22 +247,24 @@ class DeviceRollout:
         self.mvis = torch.zeros(iters, B, dtype=torch.int32, device=dev)
         self.rew = torch.empty(iters, B, device=dev)
         self.dist = torch.empty(iters, B, device=dev)
-        self.mean = None
+        self.mean = torch.empty(B, 3, device=dev)
         self.copied = ctypes.c_int(0)
 
-    def run(self, events=None):
+    def run(self, events=None, count_visible=True):
         """events: per iteration (e0, e1, e2) recorded before cmr_project, between the two observe kernels
-        and after cmr_tile_scatter, on the launch stream."""
+        and after cmr_tile_scatter, on the launch stream.  count_visible: also count the visible
+        predicted-overlap points per episode (M_vis of the roofline; one memset + a few atomics per step)."""
         L, p, st = self.lib, self.lib.ptr, self.lib.stream()
         B, N, C, H, W = self.dims
-        self.mean = self.pc.mean(dim=2).contiguous()                 # environment.py:46 - once per episode
+        L.call("cmr_cloud_mean", p(self.pc), B, N, p(self.mean), st)    # environment.py:46 - once per episode
         L.call("cmr_episode_prepare", p(self.overlap), p(self.feat), B, N, C, p(self.ws), st)
         self.pose.copy_(self.eye)                                    # env.init
         for it in range(self.iters):
             if events is not None:
                 events[it][0].record()
             L.call("cmr_project", p(self.pc), p(self.overlap), p(self.K), p(self.pose), p(self.mean), p(self.ws),
-                   B, N, C, H, W, p(self.obs3d), None, p(self.mvis[it]), p(self.img_feat), p(self.obs2d),
+                   B, N, C, H, W, p(self.obs3d), None, p(self.mvis[it]) if count_visible else None, p(self.img_feat),
+                   p(self.obs2d),
                    ctypes.byref(self.copied), st)
             if events is not None:
                 events[it][1].record()
@@ -352,11 +354,11 @@ def run_b200_arm(args, rank, world, local):
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
-        roll.run()
+        roll.run(count_visible=False)
     torch.cuda.current_stream().wait_stream(side)
     launches0 = _lib.launch_count()
     with torch.cuda.graph(graph):
-        roll.run()
+        roll.run(count_visible=False)     # M_vis is counted in the instrumented eager pass below
     launches_per_step = _lib.launch_count() - launches0
     for _ in range(max(args.warmup, 3)):
         graph.replay()

@@ -1,5 +1,12 @@
+"""Per-CTA timing of the scatter stage (debug builds only).
+
+Build a library with -DCMR_DBG_TIMING (common.cuh: %globaltimer marks per CTA written to g_dbg), e.g.
+    nvcc <flags of cmr_agent_b200/build.py> -DCMR_DBG_TIMING -o /tmp/lib_timing.so cmr_agent_b200/csrc/cmr_b200.cu
+and run   CMR_B200_LIB=/tmp/lib_timing.so python benchmarks/debug/cta_timing.py
+It prints the kernel span, the distribution of CTA durations and the slowest CTAs of cmr_tile_scatter.
+"""
 import sys, os, ctypes
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from cmr_agent_b200 import _lib, synth, environment as env
 dev = torch.device('cuda:0'); B, N = 32, 40960

@@ -300,7 +300,7 @@ size_t cmr_workspace_bytes(int B, int N, int C, int P) {
 
 int cmr_cloud_mean(const float *pc, int B, int N, float *mean, void *stream) {
     CMR_REQUIRE(pc && mean && B > 0 && N > 0, CMR_EINVAL);
-    k_cloud_mean<<<dim3(3, B), 512, 0, S_(stream)>>>(pc, N, mean);
+    k_cloud_mean<<<dim3(3, B), 1024, 0, S_(stream)>>>(pc, N, (N % 4 == 0) && aligned(pc, 16), mean);
     return after_launch();
 }
 

@@ -51,18 +51,26 @@ inline WsLayout ws_layout(int B, int N, int C, int P) {
 // -------------------------------------------------------------------------------------------------
 // pc.mean(dim=2)  (environment.py:46,91,274).  One CTA per (coordinate row, episode); fp64 sum in a
 // fixed order => deterministic.
-__global__ void __launch_bounds__(512) k_cloud_mean(const float *__restrict__ pc, int N, float *__restrict__ mean) {
+__global__ void __launch_bounds__(1024) k_cloud_mean(const float *__restrict__ pc, int N, bool vec,
+                                                      float *__restrict__ mean) {
     const float *row = pc + ((size_t)blockIdx.y * 3 + blockIdx.x) * N;
     double acc = 0.0;
-    for (int j = threadIdx.x; j < N; j += blockDim.x) acc += (double)row[j];
-    __shared__ double part[16];
+    if (vec) {   // N % 4 == 0 and 16-byte aligned rows: all loads of a thread are issued back to back
+        for (int j = threadIdx.x * 4; j < N; j += blockDim.x * 4) {
+            const float4 v = ldg_stream4(row + j);
+            acc += ((double)v.x + (double)v.y) + ((double)v.z + (double)v.w);
+        }
+    } else {
+        for (int j = threadIdx.x; j < N; j += blockDim.x) acc += (double)row[j];
+    }
+    __shared__ double part[32];
     acc = warp_sum(acc);
     if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        double s = 0.0;
-        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += part[w];
-        mean[blockIdx.y * 3 + blockIdx.x] = (float)(s / (double)N);
+    if (threadIdx.x < 32) {
+        double s = threadIdx.x < (blockDim.x >> 5) ? part[threadIdx.x] : 0.0;
+        s = warp_sum(s);
+        if (threadIdx.x == 0) mean[blockIdx.y * 3 + blockIdx.x] = (float)(s / (double)N);
     }
 }
 

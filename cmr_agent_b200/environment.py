@@ -7,10 +7,10 @@ return shapes as /root/reference/environment/environment.py
 so ``Train_Agent.py`` / ``Test_Agent.py`` / ``CMRAgent.py`` run unchanged after
 ``cmr_agent_b200.install()``.  All arithmetic on the path runs in the
 hand-written sm_100a kernels of libcmr_b200.so (include/cmr_b200.h) on the
-current CUDA stream, with no host synchronisation; PyTorch allocates memory,
-hands over the stream, and evaluates ``pc.mean(dim=2)`` once per episode batch
-(the reference's own expression, so the mean has the bits the reference would
-see on this device - see DESIGN.md "cloud mean").
+current CUDA stream, with no host synchronisation; PyTorch allocates memory and
+hands over the stream.  The cloud mean (``pc.mean(dim=2)`` in the reference) is
+computed once per episode batch by cmr_cloud_mean in fp64 - see DESIGN.md
+"cloud mean" for why torch's own fp32 mean is not used by default.
 
 Differences that are deliberate and documented:
   * CUDA only.  CPU tensors where the reference expects device tensors raise.
@@ -35,7 +35,7 @@ _WS_KEY = "_cmr_b200_episode"
 _RW_KEY = "_cmr_b200_reward"
 
 _reward_mode = "shipped"
-_mean_provider = "torch"
+_mean_provider = "kernel"
 
 
 def set_reward_mode(mode):
@@ -48,8 +48,10 @@ def set_reward_mode(mode):
 
 
 def set_mean_provider(name):
-    """"torch" (default): ``pc.mean(dim=2)`` on the device, the reference's own expression.
-    "kernel": cmr_cloud_mean (deterministic fp64 accumulation) for hosts without torch semantics."""
+    """"kernel" (default): cmr_cloud_mean - fp64 accumulation in a fixed order: correctly rounded,
+    deterministic, and independent of the batch shape (so sharding episodes over GPUs cannot change it).
+    "torch": ``pc.mean(dim=2)`` on the device - the reference's own expression, but torch's fp32 mean is
+    neither correctly rounded nor shape invariant (the same cloud gives different bits at B=2 and B=16)."""
     global _mean_provider
     if name not in ("torch", "kernel"):
         raise ValueError(name)
@@ -69,6 +71,7 @@ def cloud_mean(pc):
     """[B,3,N] -> [B,3] with the selected provider."""
     if _mean_provider == "torch":
         return pc.mean(dim=2).contiguous()
+    pc = pc if pc.is_contiguous() else pc.contiguous()
     B, _, N = pc.shape
     out = torch.empty(B, 3, device=pc.device, dtype=torch.float32)
     _lib.call("cmr_cloud_mean", _lib.ptr(pc), B, N, _lib.ptr(out), _lib.stream())
