@@ -12,7 +12,7 @@ data-path collective ("weak" scaling: 32 episodes per GPU).
   e2e    : the same rollout through the reference-facing drop-in API (cmr_agent_b200.environment)
            from pinned HOST tensors: H2D of every input of the rollout and D2H of the per-iteration
            reward/distance and the final poses are inside the timed region.
-  roofline: the slower of the two observe stages (k_project | k_bin + k_tile_gather), timed live with CUDA
+  roofline: the slower of the two observe stages (k_project | k_tile_gather), timed live with CUDA
            events on the launch stream inside the timed region; the other one is roofline_secondary.
   cpu_baseline: the oracle's torch-CPU port of the reference path (oracle/env_oracle.py) on this
            box's host cores, bounded sample.
@@ -262,15 +262,17 @@ class DeviceRollout:
         for it in range(self.iters):
             if events is not None:
                 events[it][0].record()
-            L.call("cmr_project", p(self.pc), p(self.overlap), p(self.K), p(self.pose), p(self.mean), p(self.ws),
-                   B, N, C, H, W, p(self.obs3d), None, p(self.mvis[it]) if count_visible else None, p(self.img_feat),
-                   p(self.obs2d),
-                   ctypes.byref(self.copied), st)
-            if events is not None:
+            mv = p(self.mvis[it]) if count_visible else None
+            if events is None:   # the product call
+                L.call("cmr_observe", p(self.pc), p(self.overlap), p(self.img_feat), p(self.K), p(self.pose), p(self.mean),
+                       p(self.ws), B, N, C, H, W, p(self.obs2d), p(self.obs3d), None, mv, st)
+            else:                # the same two launches with an event between them
+                L.call("cmr_project", p(self.pc), p(self.overlap), p(self.K), p(self.pose), p(self.mean), p(self.ws),
+                       B, N, C, H, W, p(self.obs3d), None, mv, p(self.img_feat), p(self.obs2d),
+                       ctypes.byref(self.copied), 1, st)   # 1 = CMR_PROJECT_PAIRED
                 events[it][1].record()
-            L.call("cmr_tile_scatter", p(self.img_feat), p(self.K), p(self.ws), B, N, C, H, W,
-                   0 if self.copied.value else 1, p(self.obs2d), st)
-            if events is not None:
+                L.call("cmr_tile_scatter", p(self.img_feat), p(self.K), p(self.ws), B, N, C, H, W,
+                       0 if self.copied.value else 1, p(self.obs2d), st)
                 events[it][2].record()
             L.call("cmr_step", p(self.pose), p(self.a_r[it]), p(self.a_t[it]), p(self.rot), p(self.tt), self.nbins,
                    0, B, st)
@@ -400,7 +402,7 @@ def run_b200_arm(args, rank, world, local):
     # longer is reported as "roofline" (the dominant kernel), the other as "roofline_secondary".
     # Algorithmic bytes: observe = 33N + 4*C*M_vis + 12*C*P per episode, split as
     #   k_project      33N (pc, overlap -> obs3d) + 8*C*P (image half of obs2d, carried as TMA traffic)
-    #   k_bin + k_tile_gather (cmr_tile_scatter)  4*C*M_vis (feature rows of the visible points) + 4*C*P
+    #   k_tile_gather (cmr_tile_scatter)           4*C*M_vis (feature rows of the visible points) + 4*C*P
     #                  (projected half of obs2d)
     _, N, C, H, W = roll.dims
     P = H * W
@@ -419,7 +421,7 @@ def run_b200_arm(args, rank, world, local):
                 "algorithmic_bytes_per_launch": nbytes, "avg_launch_us": sec * 1e6,
                 "share_of_step": sec * iters * esteps / dt_eager, "peak_source": peak_src}
 
-    r_proj, r_scat = roof("k_project", bytes_proj, proj_s), roof("k_bin+k_tile_gather", bytes_scat, scat_s)
+    r_proj, r_scat = roof("k_project", bytes_proj, proj_s), roof("k_tile_gather", bytes_scat, scat_s)
     roofline, roofline2 = (r_proj, r_scat) if proj_s >= scat_s else (r_scat, r_proj)
     roofline["m_vis_per_episode"] = mvis / B
     roofline["observe_frac"] = (bytes_proj + bytes_scat) / (proj_s + scat_s) / 1e9 / peak

@@ -42,6 +42,20 @@ def time_cuda(fn, warm=3, reps=10):
     return t[len(t) // 2] / 1e3
 
 
+def time_pair(fa, fb, warm=3, reps=10):
+    """fa(); fb() back to back, an event between them: median seconds of each half."""
+    for _ in range(warm):
+        fa(); fb()
+    torch.cuda.synchronize()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(reps)]
+    for e in ev:
+        e[0].record(); fa(); e[1].record(); fb(); e[2].record()
+    torch.cuda.synchronize()
+    ta = sorted(e[0].elapsed_time(e[1]) for e in ev)
+    tb = sorted(e[1].elapsed_time(e[2]) for e in ev)
+    return ta[len(ta) // 2] / 1e3, tb[len(tb) // 2] / 1e3
+
+
 def frontend(args):
     dev = torch.device("cuda:0")
     B, N, S, K = args.batch, 40960, 1280, 64
@@ -100,12 +114,12 @@ def sweep(args):
 
             def proj():
                 _lib.call("cmr_project", p(ep.pc), p(ep.overlap), p(ep.K), p(pose), p(ep.mean), p(ep.ws), B, N, 64, 40,
-                          128, p(obs3d), None, None, p(ep.img_feat), p(obs2d), None, st())
+                          128, p(obs3d), None, None, p(ep.img_feat), p(obs2d), None, 1, st())
 
             def scat():
                 _lib.call("cmr_tile_scatter", p(ep.img_feat), p(ep.K), p(ep.ws), B, N, 64, 40, 128, 0, p(obs2d), st())
 
-            t_p, t_s = time_cuda(proj), time_cuda(scat)
+            t_p, t_s = time_pair(proj, scat)   # a scatter consumes what ONE project left
             bytes_p = 33.0 * N * B + 8.0 * 64 * 5120 * B     # obs3d stream + image half of obs2d (TMA)
             bytes_s = 4.0 * 64 * mvis + 4.0 * 64 * 5120 * B  # feature rows + projected half of obs2d
             print(json.dumps({
@@ -147,11 +161,14 @@ def env_kernels(args):
     M = float(cpu["pc_overlap_pred"].sum())
     rec("prepare", lambda: _lib.call("cmr_episode_prepare", p(ep.overlap), p(feat), B, N, 64, p(ep.ws), st()),
         B * N * (1 + 256.0) + M * 256.0)
-    rec("project", lambda: _lib.call("cmr_project", p(ep.pc), p(ep.overlap), p(ep.K), p(pose), p(ep.mean), p(ep.ws), B,
-                                     N, 64, 40, 128, p(obs3d), None, None, p(ep.img_feat), p(obs2d), None, st()),
-        33.0 * N * B + 8.0 * 64 * 5120 * B)
-    rec("scatter", lambda: _lib.call("cmr_tile_scatter", p(ep.img_feat), p(ep.K), p(ep.ws), B, N, 64, 40, 128, 0, p(obs2d), st()),
-        256.0 * mvis + 4.0 * 64 * 5120 * B)
+    t_p, t_s = time_pair(
+        lambda: _lib.call("cmr_project", p(ep.pc), p(ep.overlap), p(ep.K), p(pose), p(ep.mean), p(ep.ws), B,
+                          N, 64, 40, 128, p(obs3d), None, None, p(ep.img_feat), p(obs2d), None, 1, st()),
+        lambda: _lib.call("cmr_tile_scatter", p(ep.img_feat), p(ep.K), p(ep.ws), B, N, 64, 40, 128, 0, p(obs2d), st()),
+        reps=20)
+    for name, t, nbytes in (("project", t_p, 33.0 * N * B + 8.0 * 64 * 5120 * B),
+                            ("scatter", t_s, 256.0 * mvis + 4.0 * 64 * 5120 * B)):
+        res[name + "_us"], res[name + "_gbs"], res[name + "_frac"] = t * 1e6, nbytes / t / 1e9, nbytes / t / 1e9 / PEAK
     rec("step", lambda: env.step(a_r, a_t, pose, cfg), 64.0 * B)
     env.reward(pose, data, None)
     rec("reward", lambda: env.reward(pose, data, None), 25.0 * N * B)

@@ -27,7 +27,7 @@ SIGNATURES = {
     "cmr_cloud_mean": (_c_int, [_c_vp, _c_int, _c_int, _c_vp, _c_vp]),
     "cmr_episode_prepare": (_c_int, [_c_vp, _c_vp, _c_int, _c_int, _c_int, _c_vp, _c_vp]),
     "cmr_observe": (_c_int, [_c_vp] * 7 + [_c_int] * 5 + [_c_vp] * 5),
-    "cmr_project": (_c_int, [_c_vp] * 6 + [_c_int] * 5 + [_c_vp] * 7),
+    "cmr_project": (_c_int, [_c_vp] * 6 + [_c_int] * 5 + [_c_vp] * 6 + [_c_int, _c_vp]),
     "cmr_tile_scatter": (_c_int, [_c_vp] * 3 + [_c_int] * 6 + [_c_vp] * 2),
     "cmr_to_disentangled": (_c_int, [_c_vp, _c_vp, _c_int, _c_vp]),
     "cmr_step": (_c_int, [_c_vp] * 5 + [_c_int] * 3 + [_c_vp]),
@@ -63,7 +63,7 @@ def load():
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
-        if lib.cmr_abi_version() != 1:
+        if lib.cmr_abi_version() != 2:
             raise CmrError("libcmr_b200.so ABI version mismatch; rebuild it")
         _lib = lib
     return _lib

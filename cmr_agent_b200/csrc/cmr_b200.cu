@@ -100,8 +100,6 @@ static int launch_tile_scatter(const WsLayout &L, const char *ws, const float *i
     return e == cudaSuccess ? CMR_OK : (int)e;
 }
 
-static_assert(kBoffStride == 392, "ws_layout reserves 392 ints per episode for the bucket offsets");
-
 template <typename Kern, typename... Args>
 static int launch_pdl(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
     cudaLaunchConfig_t cfg{};
@@ -121,60 +119,27 @@ static int launch_pdl(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStream_
     return e == cudaSuccess ? CMR_OK : (int)e;
 }
 
-// projected half of obs2d through the CSR path: k_bin + k_tile_gather (scatter_kernels.cuh)
-template <typename PixT>
-static int launch_bin_gather(const WsLayout &L, const char *ws, const float *img_feat, const float *K, int W, int B,
-                             int N, int C, int P, bool copy_image, float *obs2d, cudaStream_t st) {
-    const PixT *pix = reinterpret_cast<const PixT *>(ws + L.off_pix);
+// true when the projected half of obs2d goes through the bucket buffers k_project fills (scatter_kernels.cuh)
+static bool bucket_path(const WsLayout &L, int C) {
+    return L.buckets > 0 && kHeavyCtas + ceil_div(L.buckets * ceil_div(C, kSlab), kGatherWarps) <= 65535;
+}
+
+// projected half of obs2d from the bucket buffers: k_tile_gather (scatter_kernels.cuh)
+static int launch_gather(const WsLayout &L, const char *ws, const float *img_feat, int B, int N, int C, int P,
+                         bool copy_image, float *obs2d, cudaStream_t st) {
+    int *bcnt = reinterpret_cast<int *>(const_cast<char *>(ws) + L.off_bcnt);
+    const unsigned *bbuf = reinterpret_cast<const unsigned *>(ws + L.off_bbuf);
+    const void *pix = ws + L.off_pix;
     const int *M = reinterpret_cast<const int *>(ws + L.off_m);
     const float *featT = reinterpret_cast<const float *>(ws + L.off_feat);
-    unsigned *order = reinterpret_cast<unsigned *>(const_cast<char *>(ws) + L.off_order);
-    int *boff = reinterpret_cast<int *>(const_cast<char *>(ws) + L.off_boff);
-    const int T = ceil_div(P, kBucketPix);
-    size_t smem_bin = sizeof(int) * 32 * (size_t)T;
-    int rc = allow_smem(k_bin<PixT>, smem_bin);
+    const int *hq = reinterpret_cast<const int *>(ws + L.off_hq);
+    const bool vec = (P % 4 == 0) && aligned(obs2d, 16);
+    // x = episode, y = kHeavyCtas bucket CTAs (the long work starts first), then 4 (bucket, slab) units per CTA
+    const int light = ceil_div(L.buckets * ceil_div(C, kSlab), kGatherWarps);
+    int rc = allow_smem(k_tile_gather, kGatherSmem);
     if (rc) return rc;
-    {
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(B * kBinCluster);
-        cfg.blockDim = dim3(kBinThreads);
-        cfg.dynamicSmemBytes = smem_bin;
-        cfg.stream = st;
-        cudaLaunchAttribute attr[2];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = 1;
-        attr[1].id = cudaLaunchAttributeClusterDimension;
-        attr[1].val.clusterDim.x = kBinCluster;
-        attr[1].val.clusterDim.y = 1;
-        attr[1].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 2;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, k_bin<PixT>, pix, M, N, L.ncap, P, order, boff);
-        ++g_launches;
-        if (e != cudaSuccess) return (int)e;
-        e = cudaGetLastError();
-        if (e != cudaSuccess) return (int)e;
-    }
-    const int tiles = ceil_div(P, kGatherTile);
-    size_t smem = sizeof(float) * kGatherTile * (C + 2) + sizeof(int) * kGatherTile + sizeof(unsigned) * kChunk +
-                  sizeof(unsigned) * 8 * kOwnCap;
-    dim3 grid(B, 4 * tiles);
-    if (C <= 64) {
-        rc = allow_smem(k_tile_gather<1>, smem);
-        if (rc) return rc;
-        return launch_pdl(k_tile_gather<1>, grid, dim3(256), smem, st, (const unsigned *)order, (const int *)boff, featT,
-                          img_feat, K, W, N, L.ncap, C, P, tiles, copy_image, obs2d);
-    }
-    if (C <= 128) {
-        rc = allow_smem(k_tile_gather<2>, smem);
-        if (rc) return rc;
-        return launch_pdl(k_tile_gather<2>, grid, dim3(256), smem, st, (const unsigned *)order, (const int *)boff, featT,
-                          img_feat, K, W, N, L.ncap, C, P, tiles, copy_image, obs2d);
-    }
-    rc = allow_smem(k_tile_gather<4>, smem);
-    if (rc) return rc;
-    return launch_pdl(k_tile_gather<4>, grid, dim3(256), smem, st, (const unsigned *)order, (const int *)boff, featT,
-                      img_feat, K, W, N, L.ncap, C, P, tiles, copy_image, obs2d);
+    return launch_pdl(k_tile_gather, dim3(B, kHeavyCtas + light), dim3(kGatherThreads), kGatherSmem, st, bcnt, bbuf,
+                      L.buckets, hq, pix, L.pix16 ? 1 : 0, M, featT, img_feat, N, L.ncap, C, P, copy_image, vec, obs2d);
 }
 
 // true when the image half of obs2d can travel as tiled TMA boxes inside k_project
@@ -191,7 +156,7 @@ template <typename PixT>
 static int launch_project(const WsLayout &L, char *ws, const float *pc, const uint8_t *overlap, const float *K,
                           const float *pose, const float *mean, int B, int N, int C, int H, int W, float *obs3d,
                           int32_t *pix_out, int32_t *mvis_out, bool img_tma, const CUtensorMap &map_img,
-                          const CUtensorMap &map_out, cudaStream_t st) {
+                          const CUtensorMap &map_out, bool clear_counters, cudaStream_t st) {
     PixT *pix = reinterpret_cast<PixT *>(ws + L.off_pix);
     const int *seg = reinterpret_cast<const int *>(ws + L.off_seg);
     const int *Mws = reinterpret_cast<const int *>(ws + L.off_m);
@@ -205,9 +170,22 @@ static int launch_project(const WsLayout &L, char *ws, const float *pc, const ui
     const size_t smem = img_tma ? sizeof(float) * kTilePix * C : 0;
     int rc = allow_smem(k_project<PixT>, smem);
     if (rc) return rc;
+    int *bcnt = nullptr;
+    unsigned *bbuf = nullptr;
+    int *hq = nullptr;
+    if (bucket_path(L, C)) {
+        hq = reinterpret_cast<int *>(ws + L.off_hq);
+        bcnt = reinterpret_cast<int *>(ws + L.off_bcnt);
+        bbuf = reinterpret_cast<unsigned *>(ws + L.off_bbuf);
+        if (clear_counters) {   // cmr_observe relies on k_tile_gather having cleared them instead
+            cudaError_t e = cudaMemsetAsync(bcnt, 0, L.bcnt_bytes, st);
+            if (e != cudaSuccess) return (int)e;
+        }
+    }
     k_project<PixT><<<dim3(ceil_div(L.groups, 8), B), 256, smem, st>>>(pc, overlap, K, pose, mean, seg, Mws, N, L.ncap,
                                                                       L.groups, H, W, vec, pix, obs3d, pix_out, mvis_out,
-                                                                      img_tiles, C, map_img, map_out);
+                                                                      bcnt, bbuf, L.buckets, bcnt ? bcnt + (size_t)B * kBucketStride : nullptr, hq, img_tiles, C,
+                                                                      map_img, map_out);
     return after_launch();
 }
 
@@ -315,6 +293,9 @@ int cmr_episode_prepare(const uint8_t *overlap, const float *feat, int B, int N,
     int *seg = reinterpret_cast<int *>(ws + L.off_seg);
     float *featT = reinterpret_cast<float *>(ws + L.off_feat);
     const bool vec = (N % 4 == 0) && aligned(overlap, 4);
+    // bucket counters + ticket of the scatter stage start at zero; k_tile_gather leaves them at zero
+    cudaError_t me = cudaMemsetAsync(ws + L.off_bcnt, 0, L.bcnt_bytes, S_(stream));
+    if (me != cudaSuccess) return (int)me;
     k_overlap_scan<<<B, 1024, 0, S_(stream)>>>(overlap, N, L.groups, vec, seg, M);
     int rc = after_launch();
     if (rc) return rc;
@@ -332,9 +313,10 @@ static int check_observe_dims(int B, int N, int C, int H, int W) {
     return CMR_OK;
 }
 
-int cmr_project(const float *pc, const uint8_t *overlap, const float *K, const float *pose, const float *mean,
-                void *workspace, int B, int N, int C, int H, int W, float *obs3d, int32_t *pix_out, int32_t *mvis_out,
-                const float *img_feat, float *obs2d, int *image_copied, void *stream) {
+static int project_impl(const float *pc, const uint8_t *overlap, const float *K, const float *pose, const float *mean,
+                        void *workspace, int B, int N, int C, int H, int W, float *obs3d, int32_t *pix_out,
+                        int32_t *mvis_out, const float *img_feat, float *obs2d, int *image_copied, bool clear_counters,
+                        void *stream) {
     CMR_REQUIRE(pc && overlap && K && pose && mean && workspace && obs3d, CMR_EINVAL);
     int rc = check_observe_dims(B, N, C, H, W);
     if (rc) return rc;
@@ -346,9 +328,18 @@ int cmr_project(const float *pc, const uint8_t *overlap, const float *K, const f
     if (image_copied) *image_copied = img_tma ? 1 : 0;
     if (L.pix16)
         return launch_project<uint16_t>(L, ws, pc, overlap, K, pose, mean, B, N, C, H, W, obs3d, pix_out, mvis_out, img_tma,
-                                        map_img, map_out, S_(stream));
+                                        map_img, map_out, clear_counters, S_(stream));
     return launch_project<int32_t>(L, ws, pc, overlap, K, pose, mean, B, N, C, H, W, obs3d, pix_out, mvis_out, img_tma,
-                                   map_img, map_out, S_(stream));
+                                   map_img, map_out, clear_counters, S_(stream));
+}
+
+// Stand-alone stage 1.  Unless the caller promises the project/scatter pairing, the bucket counters are
+// cleared first, so that the call may be repeated; a cmr_tile_scatter consumes what ONE cmr_project left.
+int cmr_project(const float *pc, const uint8_t *overlap, const float *K, const float *pose, const float *mean,
+                void *workspace, int B, int N, int C, int H, int W, float *obs3d, int32_t *pix_out, int32_t *mvis_out,
+                const float *img_feat, float *obs2d, int *image_copied, int flags, void *stream) {
+    return project_impl(pc, overlap, K, pose, mean, workspace, B, N, C, H, W, obs3d, pix_out, mvis_out, img_feat, obs2d,
+                        image_copied, !(flags & CMR_PROJECT_PAIRED), stream);
 }
 
 int cmr_tile_scatter(const float *img_feat, const float *K, void *workspace, int B, int N, int C, int H, int W,
@@ -361,24 +352,23 @@ int cmr_tile_scatter(const float *img_feat, const float *K, void *workspace, int
     WsLayout L = ws_layout(B, N, C, H * W);
     const char *ws = static_cast<const char *>(workspace);
     const int P = H * W;
-    if (ceil_div(P, kBucketPix) <= kBinMaxBuckets && 4 * ceil_div(P, kGatherTile) <= 65535) {
-        // binned path: counting sort by 32-pixel bucket + one CTA per tile that reads only its own points
-        if (L.pix16) return launch_bin_gather<uint16_t>(L, ws, img_feat, K, W, B, N, C, P, copy_image != 0, obs2d, S_(stream));
-        return launch_bin_gather<int32_t>(L, ws, img_feat, K, W, B, N, C, P, copy_image != 0, obs2d, S_(stream));
-    }
+    if (bucket_path(L, C))   // the visible points were bucketed by k_project: every unit reads only its own
+        return launch_gather(L, ws, img_feat, B, N, C, P, copy_image != 0, obs2d, S_(stream));
     // large grids: every tile CTA searches the episode's id list itself
     if (L.pix16)
         return launch_scatter<uint16_t>(L, ws, img_feat, K, W, B, N, C, P, copy_image != 0, obs2d, S_(stream));
     return launch_scatter<int32_t>(L, ws, img_feat, K, W, B, N, C, P, copy_image != 0, obs2d, S_(stream));
 }
 
+// The hot path: stage 1 + stage 2.  The bucket counters are zero on entry (cmr_episode_prepare) and zero again
+// on exit (the last CTA of k_tile_gather clears them), so no memset sits between the steps of a rollout.
 int cmr_observe(const float *pc, const uint8_t *overlap, const float *img_feat, const float *K, const float *pose,
                 const float *mean, void *workspace, int B, int N, int C, int H, int W, float *obs2d, float *obs3d,
                 int32_t *pix_out, int32_t *mvis_out, void *stream) {
     CMR_REQUIRE(img_feat && obs2d, CMR_EINVAL);
     int copied = 0;
-    int rc = cmr_project(pc, overlap, K, pose, mean, workspace, B, N, C, H, W, obs3d, pix_out, mvis_out, img_feat, obs2d,
-                         &copied, stream);
+    int rc = project_impl(pc, overlap, K, pose, mean, workspace, B, N, C, H, W, obs3d, pix_out, mvis_out, img_feat, obs2d,
+                          &copied, false, stream);
     if (rc) return rc;
     return cmr_tile_scatter(img_feat, K, workspace, B, N, C, H, W, copied ? 0 : 1, obs2d, stream);
 }

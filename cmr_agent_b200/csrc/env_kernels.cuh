@@ -7,9 +7,9 @@
 //   feat      [B,C,N]  f32  channel-major; read ONCE per episode by k_feat_compact
 //   workspace: M[B] i32 | seg[B,G] i32 (exclusive prefix of overlap counts per 128 points) |
 //              pix[B,ncap] u16/i32 (pixel id of the m-th predicted-overlap point, rewritten
-//              every observe) | order[B,ncap] u32 + boff[B,392] i32 (per-observe CSR of the visible
-//              points by 32-pixel bucket) | featT[B,N,C] f32 (rows of the predicted-overlap points,
-//              point-major)
+//              every observe) | bcnt[B,384] i32 (points per 32-pixel bucket, per observe) |
+//              featT[B,N,C] f32 (rows of the predicted-overlap points, point-major) |
+//              bbuf[B,buckets,1024] u32 (per observe: the visible points of every bucket, unordered)
 //   obs3d     [B,5,N]  f32 ; obs2d [B,2C,H,W] f32
 #pragma once
 #include "common.cuh"
@@ -19,9 +19,17 @@ namespace cmr {
 constexpr int kGroup = 128;     // points per compaction group = 32 lanes x 4 points
 constexpr int kTilePix = 128;   // pixels per k_tile_scatter CTA
 constexpr int kMaxC = 256;
+constexpr int kBucketPix = 32;      // pixels per scatter bucket (scatter_kernels.cuh)
+constexpr int kBucketMaxBuckets = 384;  // buckets per episode the bucket path supports (H*W <= 12288)
+constexpr int kBucketStride = 384;      // ints per episode in bcnt
+constexpr int kBucketHdr = 64;          // ints after the counters: [0] heavy-queue length, [1] ticket of k_tile_gather
+constexpr int kLightMax = 64;           // a bucket that receives more visible points than this is queued as heavy
+constexpr int kBucketCap = 1024;    // entries a bucket's buffer holds; fuller buckets are re-read from the id list
 
 struct WsLayout {
-    size_t off_m, off_seg, off_pix, off_order, off_boff, off_feat, total;
+    size_t off_m, off_seg, off_pix, off_bcnt, off_hq, off_feat, off_bbuf, total;
+    size_t bcnt_bytes;   // counters + header: what has to be zero before a k_project
+    int buckets;   // 32-pixel buckets per episode for (this) P, 0 when the bucket path is not used
     int groups, ncap;
     bool pix16;
 };
@@ -38,12 +46,18 @@ inline WsLayout ws_layout(int B, int N, int C, int P) {
     o = round_up(o + sizeof(int) * (size_t)B * L.groups, 256);
     L.off_pix = o;
     o = round_up(o + sizeof(int) * (size_t)B * L.ncap, 256);
-    L.off_order = o;   // CSR of the visible predicted-overlap points by 32-pixel bucket (scatter_kernels.cuh)
-    o = round_up(o + sizeof(unsigned) * (size_t)B * L.ncap, 256);
-    L.off_boff = o;
-    o = round_up(o + sizeof(int) * (size_t)B * 392, 256);
+    L.off_bcnt = o;    // points per 32-pixel bucket, rewritten every observe (scatter_kernels.cuh), + header
+    L.bcnt_bytes = sizeof(int) * ((size_t)B * kBucketStride + kBucketHdr);
+    o = round_up(o + L.bcnt_bytes, 256);
+    L.off_hq = o;      // queue of the heavy buckets of the whole batch (episode << 16 | bucket), per observe
+    o = round_up(o + sizeof(int) * (size_t)B * kBucketMaxBuckets, 256);
     L.off_feat = o;
     o = round_up(o + sizeof(float) * (size_t)B * N * C, 256);
+    // bucket buffers come LAST: their size depends on P, nothing before them does (cmr_episode_prepare
+    // lays the workspace out without knowing P)
+    L.buckets = ceil_div(P, kBucketPix) <= kBucketMaxBuckets ? ceil_div(P, kBucketPix) : 0;
+    L.off_bbuf = o;
+    o = round_up(o + sizeof(unsigned) * (size_t)B * L.buckets * kBucketCap, 256);
     L.total = o;
     return L;
 }
@@ -256,6 +270,8 @@ __global__ void __launch_bounds__(256) k_project(const float *__restrict__ pc, c
                                                   bool vec,
                                                   PixT *__restrict__ pix, float *__restrict__ obs3d,
                                                   int32_t *__restrict__ pix_out, int32_t *__restrict__ mvis,
+                                                  int *__restrict__ bcnt, unsigned *__restrict__ bbuf, int buckets,
+                                                  int *__restrict__ hq_len, int *__restrict__ hq,
                                                   int img_tiles, int C, const __grid_constant__ CUtensorMap map_img,
                                                   const __grid_constant__ CUtensorMap map_out) {
     pdl_launch_dependents();   // k_tile_scatter may start its pose-independent preamble now
@@ -359,9 +375,31 @@ __global__ void __launch_bounds__(256) k_project(const float *__restrict__ pc, c
     }
     int pos = __ldg(seg + (size_t)b * groups + g) + incl - mine;
     PixT *pw = pix + (size_t)b * ncap;
+    const int pos0 = pos;
 #pragma unroll
     for (int i = 0; i < 4; ++i)
         if (flags >> i & 1) pw[pos++] = (PixT)id2[i];
+    if (bcnt && (flags & cam2)) {
+        // visible predicted-overlap points go to the 32-pixel bucket of their pixel (integer atomics: the SET
+        // of entries of a bucket is deterministic, k_tile_gather restores point order by sorting).  The four
+        // atomics of a lane are independent: issued together, their round trips overlap.
+        int slot[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if ((flags & cam2) >> i & 1) slot[i] = atomicAdd(bcnt + (size_t)b * kBucketStride + id2[i] / kBucketPix, 1);
+        int p = pos0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if ((flags & cam2) >> i & 1) {
+                if (slot[i] < kBucketCap)
+                    bbuf[((size_t)b * buckets + id2[i] / kBucketPix) * kBucketCap + slot[i]] =
+                        ((unsigned)p << 7) | ((unsigned)id2[i] & 127u);
+                // exactly one point per bucket sees the counter cross kLightMax: it queues the bucket as heavy
+                if (slot[i] == kLightMax) hq[atomicAdd(hq_len, 1)] = (b << 16) | (id2[i] / kBucketPix);
+            }
+            p += flags >> i & 1;
+        }
+    }
     // k_tile_scatter reads the list in 16-byte words: the warp of the last group pads the ids between
     // M and the next word boundary with all-ones (never inside a tile)
     if (g == groups - 1 && lane == 31) {

@@ -33,7 +33,7 @@ extern "C" {
 #define CMR_API
 #endif
 
-#define CMR_ABI_VERSION 1
+#define CMR_ABI_VERSION 2
 
 #define CMR_OK 0
 #define CMR_EINVAL (-1)      /* null pointer, non-positive size */
@@ -76,8 +76,9 @@ CMR_API int cmr_episode_prepare(const uint8_t *overlap, const float *feat, int B
  *   pix_out (optional, may be NULL) [B,N] i32: v*W+u of every point, H*W when out of frustum -
  *   the integer by-product of :67-72, exported for parity checks.
  *   mvis_out (optional) [B] i32: predicted-overlap points that landed inside the frustum.
- * Sums run in point order per pixel (deterministic, no atomics).  The workspace's pixel-id scratch is
- * rewritten by every call: do not run two observes on one workspace concurrently. */
+ * Sums run in point order per pixel (deterministic, no floating-point atomics).  The workspace's pixel-id
+ * scratch and bucket buffers are rewritten by every call: do not run two observes on one workspace
+ * concurrently. */
 CMR_API int cmr_observe(const float *pc, const uint8_t *overlap, const float *img_feat, const float *K,
                 const float *pose, const float *mean, void *workspace, int B, int N, int C, int H,
                 int W, float *obs2d, float *obs3d, int32_t *pix_out, int32_t *mvis_out, void *stream);
@@ -88,11 +89,19 @@ CMR_API int cmr_observe(const float *pc, const uint8_t *overlap, const float *im
  *                    half of obs2d (obs2d[:, 0:C] = img_feat, :83) as tiled TMA traffic, if their layout
  *                    allows (16-byte aligned, H*W % 4 == 0, H*W >= 128); *image_copied (host, optional)
  *                    reports whether it did.
- *   cmr_tile_scatter environment.py:74-86: the projected half obs2d[:, C:2C] from the pixel ids the last
- *                    cmr_project left; with copy_image != 0 it also copies the image half itself. */
+ *                    It also APPENDS the visible predicted-overlap points to the workspace's per-bucket
+ *                    buffers, which the next cmr_tile_scatter consumes and clears.  By default the bucket
+ *                    counters are cleared first (one memset), so the call may be repeated freely; pass
+ *                    CMR_PROJECT_PAIRED in `flags` when every cmr_project on this workspace is followed by
+ *                    exactly one cmr_tile_scatter - what cmr_observe does - to skip that memset.
+ *   cmr_tile_scatter environment.py:74-86: the projected half obs2d[:, C:2C] from what the last
+ *                    cmr_project left (once per cmr_project); with copy_image != 0 it also copies the
+ *                    image half itself. */
+#define CMR_PROJECT_PAIRED 1
 CMR_API int cmr_project(const float *pc, const uint8_t *overlap, const float *K, const float *pose, const float *mean,
                         void *workspace, int B, int N, int C, int H, int W, float *obs3d, int32_t *pix_out,
-                        int32_t *mvis_out, const float *img_feat, float *obs2d, int *image_copied, void *stream);
+                        int32_t *mvis_out, const float *img_feat, float *obs2d, int *image_copied, int flags,
+                        void *stream);
 CMR_API int cmr_tile_scatter(const float *img_feat, const float *K, void *workspace, int B, int N, int C, int H,
                              int W, int copy_image, float *obs2d, void *stream);
 

@@ -4,6 +4,8 @@ module) against the golden fixtures produced by the real reference and against t
 Bars (BASELINE.json north_star / SURVEY.md A.7): pixel ids, frustum masks, obs3d, poses after
 step: BIT-EXACT.  obs2d, reward distance: <= 1e-5 relative (we additionally observe bit-equality
 for obs2d because the kernel sums in the oracle's point order)."""
+import ctypes
+
 import numpy as np
 import pytest
 import torch
@@ -233,6 +235,62 @@ def test_observe_edge_cases(cuda, case):
         # the oracle itself is pinned; also spell the expected roundings out (half-to-even, inclusive borders)
         assert pix[0, 2].item() == 0 * W + 0 and pix[0, 3].item() == 2 * W + 2 and pix[0, 4].item() == 14 * W + 2
         assert pix[0, 5].item() == H * W and pix[0, 7].item() == H * W and pix[0, 8].item() == H * W
+
+
+@pytest.mark.parametrize("spread", [1, 3, 40])
+def test_observe_dense_buckets(cuda, spread):
+    """Thousands of predicted-overlap points on a few pixels: buckets above kLightMax (64) go to the bucket
+    CTAs, buckets above kBucketCap (1024) are rebuilt from the pixel-id list in several chunks; sums stay
+    sequential in point order (bit-identical to the oracle).  Repeated observes on one workspace agree
+    (the bucket counters are cleared by the kernel itself)."""
+    env = _env()
+    N, H, W = 8192, 16, 64
+    data_cpu = synth.make_batch(2, seed=77, num_pt=N, img_h=64, img_w=256)
+    g = torch.Generator().manual_seed(spread)
+    data_cpu["K"][:] = torch.eye(3)
+    # episode 0: all points on `spread` neighbouring pixels of one row; episode 1: half of them spread out
+    px = torch.randint(0, spread, (2, N), generator=g).float() + 20.0
+    py = torch.full((2, N), 7.0)
+    px[1, N // 2:] = torch.randint(0, W, (N - N // 2,), generator=g).float()
+    py[1, N // 2:] = torch.randint(0, H, (N - N // 2,), generator=g).float()
+    data_cpu["pc"][:, 0], data_cpu["pc"][:, 1], data_cpu["pc"][:, 2] = px, py, 1.0
+    data_cpu["pc_overlap_pred"][:] = torch.rand(2, N, generator=g) < 0.9
+    pose = torch.eye(4).repeat(2, 1, 1)
+    data = hp.to_device(data_cpu, cuda)
+    data["_cmr_b200_mean_override"] = torch.zeros(2, 3)     # u = x, v = y exactly
+    o2, o3, pix, mvis = _observe(env, data, pose, cuda)
+    wpix, winc, wproj = _oracle_obs(data_cpu, pose, torch.zeros(2, 3), H, W)
+    assert torch.equal(pix, wpix) and torch.equal(o3[:, 4], winc.float())
+    assert int(mvis[0]) == int(data_cpu["pc_overlap_pred"][0].sum())
+    assert torch.equal(o2[:, 64:], wproj)
+    for _ in range(3):
+        again = _observe(env, data, pose, cuda)[0]
+        assert torch.equal(again, o2)
+
+
+def test_standalone_project_may_repeat_before_one_scatter(cuda):
+    """cmr_project clears the bucket counters unless CMR_PROJECT_PAIRED is passed: calling it twice and then
+    cmr_tile_scatter once gives the observation of the LAST pose."""
+    from cmr_agent_b200 import _lib
+    env = _env()
+    data_cpu = synth.make_batch(2, seed=5, num_pt=4096, img_h=64, img_w=256)
+    data = hp.to_device(data_cpu, cuda)
+    poses = [_random_poses(2, s, scale_t=1.0).to(cuda) for s in (1, 2)]
+    want = env.observation_from_a_pose(data, poses[1])[0]
+    ep = data["_cmr_b200_episode"][1]
+    p = _lib.ptr
+    obs2d = torch.zeros_like(want)
+    obs3d = torch.empty(2, 5, 4096, device=cuda)
+    copied = ctypes.c_int(0)
+    for pose in poses:
+        _lib.call("cmr_project", p(ep.pc), p(ep.overlap), p(ep.K), p(pose), p(ep.mean), p(ep.ws), 2, 4096, 64, 16, 64,
+                  p(obs3d), None, None, p(ep.img_feat), p(obs2d), ctypes.byref(copied), 0, _lib.stream())
+    _lib.call("cmr_tile_scatter", p(ep.img_feat), p(ep.K), p(ep.ws), 2, 4096, 64, 16, 64, 0 if copied.value else 1,
+              p(obs2d), _lib.stream())
+    assert torch.equal(obs2d, want)
+    # and the workspace is ready for the paired hot path again
+    assert torch.equal(env.observation_from_a_pose(data, poses[0])[0], env.observation_from_a_pose(data, poses[0])[0])
+    assert torch.equal(env.observation_from_a_pose(data, poses[1])[0], want)
 
 
 @pytest.mark.parametrize("C,img_h,img_w", [(32, 64, 256), (128, 64, 128), (64, 1024, 1024)])
