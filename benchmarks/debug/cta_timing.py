@@ -33,7 +33,7 @@ for rep in range(3):   # a scatter consumes what ONE project left
 torch.cuda.synchronize()
 buf = np.zeros(16 * 8192, np.uint64)
 rc = lib.cmr_debug_read(buf.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(buf.nbytes)); assert rc == 0, rc
-nct = min(8192, (HEAVY + 40) * B)
+nct = min(8192, (HEAVY + 20) * B)
 d = buf.reshape(8192, 16)[:nct].astype(np.int64)
 role = (np.arange(nct) // B) < HEAVY
 t0 = d[:, 1].min()     # first CTA released by griddepcontrol.wait
@@ -48,7 +48,7 @@ for name, m in (('light', ~role), ('bucket', role)):
         ok = x[:, 7] > 0
         ph = lambda a, b_, mm: ((x[mm, a] - x[mm, b_]) / 1e3).mean()
         ok = (x[:, 7] > 0) & (x[:, 7] <= 64)
-        print('   warp-0 unit with entries (%d): loads %.2f  order %.2f  add %.2f  store %.2f  wait-for-other-warps %.2f' % (ok.sum(), ph(2, 1, ok), ph(8, 2, ok), ph(3, 8, ok), ph(4, 3, ok), ph(5, 4, ok)))
+        print('   warp-0 unit with entries (%d): loads %.2f  order+flags %.2f  add+means %.2f  store %.2f  other warps still busy %.2f' % (ok.sum(), ph(2, 1, ok), ph(8, 2, ok), ph(3, 8, ok), ph(4, 3, ok), ph(5, 4, ok)))
         for lo, hi in ((1, 8), (9, 16), (17, 32), (33, 48), (49, 64)):
             mm = (x[:, 7] >= lo) & (x[:, 7] <= hi)
             if mm.sum(): print('      %d-%d entries (%d units): order %.2f  add %.2f' % (lo, hi, mm.sum(), ph(8, 2, mm), ph(3, 8, mm)))
@@ -58,9 +58,12 @@ for name, m in (('light', ~role), ('bucket', role)):
         busy = x[:, 6] > HEAVY * 0 + 0
         one = x[:, 6] == 1
         ph = lambda a, b_: ((x[one, a] - x[one, b_]) / 1e3).mean()
-        print('   CTAs with one item (%d, %.0f entries): queue read %.2f  entries staged %.2f  bin+sort %.2f  add %.2f  mean+store %.2f' % (one.sum(), x[one, 7].mean(), ph(2, 1), ph(8, 2), ph(9, 8), ph(10, 9), ph(11, 10)))
+        print('   CTAs with one item (%d, %.0f entries): queue read %.2f  entries staged %.2f  bin+sort+flags %.2f  zero+add %.2f  mean+store %.2f' % (one.sum(), x[one, 7].mean(), ph(2, 1), ph(8, 2), ph(9, 8), ph(10, 9), ph(11, 10)))
     order = np.argsort(-dur)[:6]
     for i in order:
-        print('     cta', i, 'entries', x[i, 7], 'items', x[i, 6], 'released %.1f dur %.1f' % (rel[i], dur[i]))
+        extra = ''
+        if name == 'bucket':
+            extra = '  phases: queue %.2f stage %.2f sort %.2f add %.2f mean+store %.2f' % tuple((x[i, a] - x[i, b_]) / 1e3 for a, b_ in ((2, 1), (8, 2), (9, 8), (10, 9), (11, 10)))
+        print('     cta', i, 'entries', x[i, 7], 'items', x[i, 6], 'released %.1f dur %.1f' % (rel[i], dur[i]), extra)
 hist, edges = np.histogram((d[:, 5] - t0) / 1e3, bins=10)
 print('end-time histogram us:', hist.tolist(), edges.round(1).tolist())

@@ -40,7 +40,8 @@ static EncodeTiledFn encode_tiled() {
     return fn;
 }
 // fp32 tensor [d2][d1][d0] (d0 contiguous), boxes of [1][b1][b0]
-static bool make_map3d(CUtensorMap *m, const float *base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1) {
+static bool make_map3d(CUtensorMap *m, const float *base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1,
+                       CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_NONE) {
     EncodeTiledFn fn = encode_tiled();
     if (!fn) return false;
     cuuint64_t dims[3] = {d0, d1, d2};
@@ -48,7 +49,7 @@ static bool make_map3d(CUtensorMap *m, const float *base, uint64_t d0, uint64_t 
     cuuint32_t box[3] = {b0, b1, 1};
     cuuint32_t es[3] = {1, 1, 1};
     return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(base), dims, strides, box, es,
-              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -121,7 +122,7 @@ static int launch_pdl(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStream_
 
 // true when the projected half of obs2d goes through the bucket buffers k_project fills (scatter_kernels.cuh)
 static bool bucket_path(const WsLayout &L, int C) {
-    return L.buckets > 0 && kHeavyCtas + ceil_div(L.buckets * ceil_div(C, kSlab), kGatherWarps) <= 65535;
+    return L.buckets > 0 && kHeavyCtas + ceil_div(L.buckets, kGatherWarps) <= 65535;
 }
 
 // projected half of obs2d from the bucket buffers: k_tile_gather (scatter_kernels.cuh)
@@ -134,12 +135,17 @@ static int launch_gather(const WsLayout &L, const char *ws, const float *img_fea
     const float *featT = reinterpret_cast<const float *>(ws + L.off_feat);
     const int *hq = reinterpret_cast<const int *>(ws + L.off_hq);
     const bool vec = (P % 4 == 0) && aligned(obs2d, 16);
-    // x = episode, y = kHeavyCtas bucket CTAs (the long work starts first), then 4 (bucket, slab) units per CTA
-    const int light = ceil_div(L.buckets * ceil_div(C, kSlab), kGatherWarps);
+    // result tiles (32 pixels x 64 channels, 128-byte rows, 128B-swizzled in shared memory) leave as ONE tiled TMA store
+    alignas(64) CUtensorMap map_proj;
+    memset(&map_proj, 0, sizeof(map_proj));
+    const bool tma = vec && P >= kBucketPix &&
+                     make_map3d(&map_proj, obs2d, P, 2 * (uint64_t)C, B, kBucketPix, kSlab, CU_TENSOR_MAP_SWIZZLE_128B);
+    // x = episode, y = kHeavyCtas bucket CTAs (the long work starts first), then 4 buckets per CTA
+    const int light = ceil_div(L.buckets, kGatherWarps);
     int rc = allow_smem(k_tile_gather, kGatherSmem);
     if (rc) return rc;
     return launch_pdl(k_tile_gather, dim3(B, kHeavyCtas + light), dim3(kGatherThreads), kGatherSmem, st, bcnt, bbuf,
-                      L.buckets, hq, pix, L.pix16 ? 1 : 0, M, featT, img_feat, N, L.ncap, C, P, copy_image, vec, obs2d);
+                      L.buckets, hq, pix, L.pix16 ? 1 : 0, M, featT, img_feat, N, L.ncap, C, P, copy_image, vec, tma, obs2d, map_proj);
 }
 
 // true when the image half of obs2d can travel as tiled TMA boxes inside k_project
@@ -184,7 +190,7 @@ static int launch_project(const WsLayout &L, char *ws, const float *pc, const ui
     }
     k_project<PixT><<<dim3(ceil_div(L.groups, 8), B), 256, smem, st>>>(pc, overlap, K, pose, mean, seg, Mws, N, L.ncap,
                                                                       L.groups, H, W, vec, pix, obs3d, pix_out, mvis_out,
-                                                                      bcnt, bbuf, L.buckets, bcnt ? bcnt + (size_t)B * kBucketStride : nullptr, hq, img_tiles, C,
+                                                                      bcnt, bbuf, L.buckets, bcnt ? bcnt + 2 * (size_t)B * kBucketStride : nullptr, hq, img_tiles, C,
                                                                       map_img, map_out);
     return after_launch();
 }

@@ -47,7 +47,8 @@ inline WsLayout ws_layout(int B, int N, int C, int P) {
     L.off_pix = o;
     o = round_up(o + sizeof(int) * (size_t)B * L.ncap, 256);
     L.off_bcnt = o;    // points per 32-pixel bucket, rewritten every observe (scatter_kernels.cuh), + header
-    L.bcnt_bytes = sizeof(int) * ((size_t)B * kBucketStride + kBucketHdr);
+    // points per bucket | points beyond kLightMax per bucket | header
+    L.bcnt_bytes = sizeof(int) * (2 * (size_t)B * kBucketStride + kBucketHdr);
     o = round_up(o + L.bcnt_bytes, 256);
     L.off_hq = o;      // queue of the heavy buckets of the whole batch (episode << 16 | bucket), per observe
     o = round_up(o + sizeof(int) * (size_t)B * kBucketMaxBuckets, 256);
@@ -271,7 +272,7 @@ __global__ void __launch_bounds__(256) k_project(const float *__restrict__ pc, c
                                                   PixT *__restrict__ pix, float *__restrict__ obs3d,
                                                   int32_t *__restrict__ pix_out, int32_t *__restrict__ mvis,
                                                   int *__restrict__ bcnt, unsigned *__restrict__ bbuf, int buckets,
-                                                  int *__restrict__ hq_len, int *__restrict__ hq,
+                                                  int *__restrict__ hdr, int *__restrict__ hq,
                                                   int img_tiles, int C, const __grid_constant__ CUtensorMap map_img,
                                                   const __grid_constant__ CUtensorMap map_out) {
     pdl_launch_dependents();   // k_tile_scatter may start its pose-independent preamble now
@@ -380,13 +381,15 @@ __global__ void __launch_bounds__(256) k_project(const float *__restrict__ pc, c
     for (int i = 0; i < 4; ++i)
         if (flags >> i & 1) pw[pos++] = (PixT)id2[i];
     if (bcnt && (flags & cam2)) {
+        int *bc = bcnt + (size_t)b * kBucketStride;
+        int *hc = bc + (size_t)gridDim.y * kBucketStride;   // overflow counters: points beyond kLightMax
         // visible predicted-overlap points go to the 32-pixel bucket of their pixel (integer atomics: the SET
         // of entries of a bucket is deterministic, k_tile_gather restores point order by sorting).  The four
         // atomics of a lane are independent: issued together, their round trips overlap.
         int slot[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-            if ((flags & cam2) >> i & 1) slot[i] = atomicAdd(bcnt + (size_t)b * kBucketStride + id2[i] / kBucketPix, 1);
+            if ((flags & cam2) >> i & 1) slot[i] = atomicAdd(bc + id2[i] / kBucketPix, 1);
         int p = pos0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -394,8 +397,12 @@ __global__ void __launch_bounds__(256) k_project(const float *__restrict__ pc, c
                 if (slot[i] < kBucketCap)
                     bbuf[((size_t)b * buckets + id2[i] / kBucketPix) * kBucketCap + slot[i]] =
                         ((unsigned)p << 7) | ((unsigned)id2[i] & 127u);
-                // exactly one point per bucket sees the counter cross kLightMax: it queues the bucket as heavy
-                if (slot[i] == kLightMax) hq[atomicAdd(hq_len, 1)] = (b << 16) | (id2[i] / kBucketPix);
+                // a heavy bucket: its points beyond kLightMax are counted a second time (the counter the bucket
+                // CTA reads), and the one that saw the counter cross kLightMax queues the bucket
+                if (slot[i] >= kLightMax) {
+                    atomicAdd(hc + id2[i] / kBucketPix, 1);
+                    if (slot[i] == kLightMax) hq[atomicAdd(hdr, 1)] = (b << 16) | (id2[i] / kBucketPix);
+                }
             }
             p += flags >> i & 1;
         }

@@ -9,9 +9,11 @@
 //   k_tile_gather restores the order and adds the rows; per pixel the sum is sequential in point order
 //   exactly like the reference's CPU scatter_add_ (deterministic, bit-identical, no floating-point atomics),
 //   then divided by max(count, 1) and written to obs2d[b, C + c, pixel] channel-major.  The unit of work is
-//   a (bucket, 64-channel slab) pair: 32 pixels x 64 channels of output, two channels per lane, a feature
-//   row = one 256-byte warp load.  The kernel is bound by instruction issue, not by memory latency (measured
-//   with %globaltimer marks per CTA, benchmarks/debug/cta_timing.py): loops run for the entries a unit HAS.
+//   a bucket: 32 pixels, done in slabs of 64 channels (two channels per lane, a feature row = one 256-byte
+//   warp load; the order is established once and reused for every slab).  What bounds the kernel is the
+//   latency of a warp's dependent instructions, not memory (measured with %globaltimer marks per CTA,
+//   benchmarks/debug/cta_timing.py, and ncu's stall reasons): the add loop is branch-free - the sorted keys
+//   carry first-of-pixel / last-of-pixel flags - and runs in batches whose loads are all in flight.
 //     * light units - ONE WARP each, four per CTA, no CTA-wide barrier on the way.  The count and the (at
 //       most kLightMax = 64) entries arrive in one L2 round trip (the entry loads are speculative), two keys
 //       per lane.  Keys (pixel, point) are unique: a key's place in the order is the number of smaller keys,
@@ -25,7 +27,10 @@
 //       by point (rank = number of smaller points IN THE PIXEL), and splits the sorted list at pixel
 //       boundaries into four nearly equal parts, one per warp.  A bucket that overflowed its buffer (more than
 //       kBucketCap points) is rebuilt from the episode's pixel-id list in chunks of kBucketCap, in point order.
-//   The last CTA of the grid to finish resets the counters and the queue for the next observe.
+//   Every counter has exactly one reader, which clears it for the next observe: the light unit reads (and
+//   clears) its bucket's counter, the bucket CTA the bucket's overflow counter (points beyond kLightMax, counted
+//   by k_project in a second array); the last bucket CTA to finish clears the queue length.  No memset between
+//   observes, no grid-wide pass, no word that every CTA reads.
 //
 // Used when the grid has at most kBucketMaxBuckets 32-pixel buckets (H*W <= 12288; KITTI is 5120, NuScenes
 // 3200); larger grids take the search-based k_tile_scatter of env_kernels.cuh.
@@ -36,15 +41,18 @@
 namespace cmr {
 
 constexpr int kHeavyCtas = 16;          // bucket CTAs per episode of the batch
-constexpr int kGatherThreads = 128;     // 4 warps = 4 light units
+constexpr int kGatherThreads = 256;     // 8 warps = 8 light units
 constexpr int kGatherWarps = kGatherThreads / 32;
-constexpr int kSlab = 64;               // channels per unit: two per lane
-constexpr int kTileStride = 36;         // floats per channel row of a 32-pixel result tile: 16-byte aligned rows
-constexpr int kTileFloats = kSlab * kTileStride;
+constexpr int kSlab = 64;               // channels per pass: two per lane
+constexpr int kTileFloats = kSlab * kBucketPix;   // result tile [64 channels][32 pixels]: 128-byte rows, laid out as
+                                                  // TMA's 128-byte swizzle wants them (16-byte chunk ^= row % 8)
+constexpr int kRowBatch = 8;            // rows per batch; a warp keeps two batches going
+constexpr unsigned kKeyFirst = 1u << 31, kKeyLast = 1u << 30;   // flags of a sorted key: pixel << 24 | point
+constexpr unsigned kPadKey = 0;   // no flags, point 0: loaded, added to a run that is never stored
 static_assert(kBucketPix == 32 && kLightMax == 64, "one lane per pixel / two keys per lane");
 static_assert(kBucketCap % kGatherThreads == 0, "whole entries per thread");
 
-constexpr size_t kGatherSmemLight = kGatherWarps * (sizeof(float) * kTileFloats + sizeof(unsigned) * kLightMax);
+constexpr size_t kGatherSmemLight = kGatherWarps * (sizeof(float) * kTileFloats + sizeof(unsigned) * (kLightMax + 32));
 constexpr size_t kGatherSmemHeavy = sizeof(float) * kTileFloats + sizeof(unsigned) * 3 * kBucketCap + sizeof(int) * 128;
 constexpr size_t kGatherSmem = kGatherSmemLight > kGatherSmemHeavy ? kGatherSmemLight : kGatherSmemHeavy;
 
@@ -65,23 +73,49 @@ __device__ __forceinline__ float2 mean2(float2 s, int n) {
     return make_float2(__fdiv_rn(s.x, nf), __fdiv_rn(s.y, nf));
 }
 
-// tile [64 channels][kTileStride] (pixel minor) -> proj[(c0 + r) * P + p0 + pixel], by NT threads (t = 0..NT-1)
+// float offset of (channel row r, pixel px) in the swizzled tile: the 16-byte chunk px / 4 is XORed with r % 8
+__device__ __forceinline__ int tile_off(int r, int px) { return r * kBucketPix + (px ^ ((r & 7) << 2)); }
+
+// A lane's two channel rows (2 * lane, 2 * lane + 1): row 2 * lane + 1 sits 32 floats further with chunk bit 0 flipped
+struct LaneRows {
+    float *row;   // tile + 2 * lane * 32
+    int xs;       // ((2 * lane) & 7) << 2
+    __device__ __forceinline__ int off(int px) const { return px ^ xs; }
+    __device__ __forceinline__ float2 get(int px) const {
+        const int o = off(px);
+        return make_float2(row[o], row[kBucketPix + (o ^ 4)]);
+    }
+    __device__ __forceinline__ void put(int px, float2 v) const {
+        const int o = off(px);
+        row[o] = v.x;
+        row[kBucketPix + (o ^ 4)] = v.y;
+    }
+};
+__device__ __forceinline__ LaneRows lane_rows(float *tile, int lane) { return LaneRows{tile + 2 * lane * kBucketPix, ((2 * lane) & 7) << 2}; }
+
+// tile -> proj[(c0 + r) * P + p0 + pixel].  tma: one tiled TMA store by the calling thread (all writers have
+// fenced and synchronised; returns when the tile has been read).  Otherwise NT threads copy it (t = 0..NT-1).
+__device__ __forceinline__ void store_tile_tma(const float *tile, const CUtensorMap *map, int c0, int C, int p0, int b) {
+    tma_store_3d(map, p0, C + c0, b, tile);
+    bulk_commit();
+    bulk_wait_read_all();
+}
 template <int NT>
-__device__ __forceinline__ void store_tile(const float *tile, int c0, int C, int p0, int P, bool vec,
-                                           float *__restrict__ proj, int t) {
+__device__ __forceinline__ void store_tile(const float *tile, int c0, int C, int p0, int P, float *__restrict__ proj, int t) {
+    const int px = t & 31;
+    for (int r = t >> 5; r < kSlab && c0 + r < C; r += NT >> 5)
+        if (p0 + px < P) proj[(size_t)(c0 + r) * P + p0 + px] = tile[tile_off(r, px)];
+}
+
+// zeros for an empty bucket, all channels, by one warp
+__device__ __forceinline__ void store_zeros(int C, int p0, int P, bool vec, float *__restrict__ proj, int lane) {
     if (vec && p0 + kBucketPix <= P) {
-        const int p4 = t & 7;
-        float *dst = proj + (size_t)c0 * P + p0 + 4 * p4;
+        float *dst = proj + p0 + 4 * (lane & 7);
 #pragma unroll 4
-        for (int k = 0; k < kSlab * 8 / NT; ++k) {
-            const int r = (t >> 3) + k * (NT >> 3);
-            if (c0 + r < C)
-                stg_stream4(dst + (size_t)r * P, *reinterpret_cast<const float4 *>(tile + r * kTileStride + 4 * p4));
-        }
+        for (int r = lane >> 3; r < C; r += 4) stg_stream4(dst + (size_t)r * P, make_float4(0.f, 0.f, 0.f, 0.f));
     } else {
-        const int px = t & 31;
-        for (int r = t >> 5; r < kSlab && c0 + r < C; r += NT >> 5)
-            if (p0 + px < P) proj[(size_t)(c0 + r) * P + p0 + px] = tile[r * kTileStride + px];
+        for (int r = 0; r < C; ++r)
+            if (p0 + lane < P) proj[(size_t)r * P + p0 + lane] = 0.f;
     }
 }
 
@@ -89,115 +123,148 @@ template <int NT>
 __device__ __forceinline__ void zero_tile(float *tile, int t) {
     float4 *t4 = reinterpret_cast<float4 *>(tile);
 #pragma unroll
-    for (int k = 0; k < (kTileFloats / 4 + NT - 1) / NT; ++k)
-        if (t + k * NT < kTileFloats / 4) t4[t + k * NT] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < kTileFloats / 4 / NT; ++k) t4[t + k * NT] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+static_assert(kTileFloats % (4 * kGatherThreads) == 0, "zero_tile covers the tile");
+
+// One entry of the flagged sorted list, without a branch: a run (the entries of one pixel, in point order)
+// starts from zero (kFromTile: from what earlier chunks left in the tile) and is written when it ends.
+template <bool kFromTile>
+__device__ __forceinline__ void add_entry(unsigned key, float2 v, float2 &run, const LaneRows &tl) {
+    const int pl = (int)((key >> 24) & 31u);
+    const bool first = key & kKeyFirst, last = key & kKeyLast;   // warp-uniform
+    float2 base = run;
+    if (first) base = kFromTile ? tl.get(pl) : make_float2(0.f, 0.f);
+    run.x = __fadd_rn(base.x, v.x);
+    run.y = __fadd_rn(base.y, v.y);
+    if (last) tl.put(pl, run);
 }
 
-// Adds the rows of sorted keys [jb, je) (pixel << 24 | point, ordered by pixel then point) to the per-pixel
-// sums in `tile`, sixteen rows in flight.  kMeans: every pixel of the range is complete (its count is the
-// length of its run), so the mean is formed at once; otherwise the sums are left in the tile.
-constexpr int kRowBatch = 8;   // rows a warp loads before it adds them (registers: 2 floats + an address each)
-constexpr unsigned kPadKey = 32u << 24;   // pixel 32 = the padding column of the tile, point 0: a harmless entry
-
-// One entry of the sorted list: its row v is added to the running sum of its pixel; when the pixel changes
-// the finished sum (kMeans: the mean, the run is the pixel's whole list) goes to the tile.
-template <bool kMeans>
-__device__ __forceinline__ void add_entry(unsigned key, float2 v, int &cur, int &cnt, float2 &run, float *tile_lane) {
-    const int pl = (int)(key >> 24);
-    if (pl != cur) {   // warp-uniform
-        if (kMeans && cnt > 1) run = mean2(run, cnt);
-        tile_lane[cur] = run.x;
-        tile_lane[kTileStride + cur] = run.y;
-        cur = pl;
-        cnt = 0;
-        run = kMeans ? make_float2(0.f, 0.f) : make_float2(tile_lane[cur], tile_lane[kTileStride + cur]);
-    }
-    run.x = __fadd_rn(run.x, v.x);
-    run.y = __fadd_rn(run.y, v.y);
-    ++cnt;
-}
-
-// Adds the rows of sorted keys [jb, je) (pixel << 24 | point, ordered by pixel then point) to the per-pixel
-// sums in the tile, kRowBatch rows in flight.  `rows` already points at this lane's two channels of row 0;
-// tile_lane at this lane's first channel row.  kMeans: every pixel of the range is complete (its count is
-// the length of its run), so the mean is formed at once; otherwise the sums are left in the tile.
-template <bool kMeans>
-__device__ __forceinline__ void add_rows(const unsigned *skeys, int jb, int je, const float *__restrict__ rows,
-                                         unsigned C, float *tile_lane) {
-    int cur = 32, cnt = 0;   // starts on the padding column: the first real entry "finishes" an empty run there
-    float2 run = make_float2(0.f, 0.f);
-    int j0 = jb;
-    for (; j0 + kRowBatch <= je; j0 += kRowBatch) {
-        unsigned k[kRowBatch];
-        float2 v[kRowBatch];
+// Adds the rows of the flagged sorted keys [jb, je) to the per-pixel sums of the tile.  Two batches of
+// kRowBatch rows alternate: while one is added the other is in flight (a pixel on the vanishing point holds
+// hundreds of rows that one warp must add in order - what it costs is the exposed load latency per batch).
+// `rows` points at this lane's two channels of row 0.
+__device__ __forceinline__ void load_batch(unsigned (&k)[kRowBatch], float2 (&v)[kRowBatch], const unsigned *skeys, int j0,
+                                           int je, const float *__restrict__ rows, unsigned C) {
+    if (j0 + kRowBatch <= je) {   // warp-uniform
 #pragma unroll
         for (int i = 0; i < kRowBatch; ++i) {
             k[i] = skeys[j0 + i];
             v[i] = ldg_f2(rows + (k[i] & 0xffffffu) * C);
         }
+    } else {
 #pragma unroll
-        for (int i = 0; i < kRowBatch; ++i) add_entry<kMeans>(k[i], v[i], cur, cnt, run, tile_lane);
+        for (int i = 0; i < kRowBatch; ++i) {
+            // past the end: a harmless entry (row 0, no flags: added to a run that is never stored)
+            k[i] = j0 + i < je ? skeys[j0 + i] : kPadKey;
+            v[i] = ldg_f2(rows + (k[i] & 0xffffffu) * C);
+        }
     }
-    for (; j0 < je; ++j0) {
-        const unsigned k = skeys[j0];
-        add_entry<kMeans>(k, ldg_f2(rows + (k & 0xffffffu) * C), cur, cnt, run, tile_lane);
+}
+template <bool kFromTile>
+__device__ __forceinline__ void add_batch(const unsigned (&k)[kRowBatch], const float2 (&v)[kRowBatch], float2 &run,
+                                          const LaneRows &tl) {
+    unsigned flags = 0;
+#pragma unroll
+    for (int i = 0; i < kRowBatch; ++i) flags |= k[i];
+    if (!(flags & (kKeyFirst | kKeyLast))) {
+        // the middle of a long run (hundreds of far points share the pixel of the vanishing point): nothing
+        // but the additions, in order
+#pragma unroll
+        for (int i = 0; i < kRowBatch; ++i) {
+            run.x = __fadd_rn(run.x, v[i].x);
+            run.y = __fadd_rn(run.y, v[i].y);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < kRowBatch; ++i) add_entry<kFromTile>(k[i], v[i], run, tl);
     }
-    if (kMeans && cnt > 1) run = mean2(run, cnt);
-    tile_lane[cur] = run.x;
-    tile_lane[kTileStride + cur] = run.y;
+}
+template <bool kFromTile>
+__device__ __forceinline__ void add_rows(const unsigned *skeys, int jb, int je, const float *__restrict__ rows,
+                                         unsigned C, const LaneRows &tl) {
+    float2 run = make_float2(0.f, 0.f);
+    unsigned ka[kRowBatch], kb[kRowBatch];
+    float2 va[kRowBatch], vb[kRowBatch];
+    load_batch(ka, va, skeys, jb, je, rows, C);
+    for (int j0 = jb; j0 < je; j0 += 2 * kRowBatch) {
+        // loads past the end fetch row 0 (in L1 after the first time): no branches around the batches
+        load_batch(kb, vb, skeys, j0 + kRowBatch, je, rows, C);
+        add_batch<kFromTile>(ka, va, run, tl);
+        load_batch(ka, va, skeys, j0 + 2 * kRowBatch, je, rows, C);
+        add_batch<kFromTile>(kb, vb, run, tl);
+    }
 }
 
-__global__ void __launch_bounds__(kGatherThreads, 5)
+// sums -> means for the pixels of `mask` (bit p: pixel p has more than one point); cnt_of_lane = points of
+// pixel `lane`.  One warp.
+__device__ __forceinline__ void mean_pass(unsigned mask, int cnt_of_lane, const LaneRows &tl) {
+    while (mask) {   // warp-uniform
+        const int pl = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const int n = __shfl_sync(kFull, cnt_of_lane, pl);
+        tl.put(pl, mean2(tl.get(pl), n));
+    }
+}
+
+__global__ void __launch_bounds__(kGatherThreads, 3)
     k_tile_gather(int *bcnt, const unsigned *bbuf, int buckets, const int *hq, const void *pix, int pix16, const int *M,
                   const float *__restrict__ featT, const float *__restrict__ img_feat, int N, int ncap, int C, int P,
-                  bool copy_image, bool vec, float *__restrict__ obs2d) {
-    extern __shared__ __align__(16) float smem_g[];
+                  bool copy_image, bool vec, bool tma, float *__restrict__ obs2d,
+                  const __grid_constant__ CUtensorMap map_proj) {
+    extern __shared__ __align__(1024) float smem_g[];   // the tiles come first: 1024-byte aligned for the swizzle
     const int B = (int)gridDim.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int T = buckets;
     const int slabs = (C + kSlab - 1) / kSlab;
-    int *hdr = bcnt + (size_t)B * kBucketStride;   // [0] heavy-queue length, [1] ticket
+    int *hcnt = bcnt + (size_t)B * kBucketStride;        // points beyond kLightMax of every bucket
+    int *hdr = hcnt + (size_t)B * kBucketStride;         // [0] heavy-queue length, [1] ticket of the bucket CTAs
+    DBG_MARK(0);
+    pdl_wait();   // counters, bucket buffers and queue are written by k_project
+    DBG_MARK(1);
 
     if ((int)blockIdx.y >= kHeavyCtas) {
-        // ------------------------------------------------------------------ light units: one warp each
+        // ------------------------------------------------------------------ light units: one warp per bucket
         const int b = blockIdx.x;
-        const int u = ((int)blockIdx.y - kHeavyCtas) * kGatherWarps + warp;
-        const int bk = u / slabs, slab = u - bk * slabs;
+        const int bk = ((int)blockIdx.y - kHeavyCtas) * kGatherWarps + warp;
         float *tile = smem_g + warp * kTileFloats;
-        unsigned *sk = reinterpret_cast<unsigned *>(smem_g + kGatherWarps * kTileFloats) + warp * kLightMax;
+        unsigned *sk = reinterpret_cast<unsigned *>(smem_g + kGatherWarps * kTileFloats) + warp * (kLightMax + 32);
+        int *pc = reinterpret_cast<int *>(sk + kLightMax);   // [32] points per pixel
         const int p0 = bk * kBucketPix;
-        const int c0 = kSlab * slab;
-        // lanes beyond C read channel 0 instead (their rows of the tile are never stored)
-        const float *rows = featT + (size_t)b * N * C + (c0 + 2 * lane < C ? c0 + 2 * lane : 0);
         float *out = obs2d + (size_t)b * 2 * C * P;
         float *proj = out + (size_t)C * P;
-        DBG_MARK(0);
-        pdl_wait();   // counters and bucket buffers are written by k_project
-        DBG_MARK(1);
         if (bk < T) {
             const unsigned *src = bbuf + ((size_t)b * buckets + bk) * kBucketCap;
             const unsigned e0 = ld_cg_u32(src + lane), e1 = ld_cg_u32(src + 32 + lane);   // speculative
-            const int n = ld_cg_s32(bcnt + (size_t)b * kBucketStride + bk);
+            int *cb = bcnt + (size_t)b * kBucketStride + bk;
+            const int n = ld_cg_s32(cb);
+            if (lane == 0 && n != 0) *cb = 0;   // this warp is the counter's only reader
+            if (n > 0 && n <= kLightMax) {
+                // all the rows this unit will add: on their way to L2 before the first one is needed
+                if (lane < n)
+                    for (int q = 0; q < C; q += 32) prefetch_l2(featT + ((size_t)b * N + (e0 >> 7)) * C + q);
+                if (lane + 32 < n)
+                    for (int q = 0; q < C; q += 32) prefetch_l2(featT + ((size_t)b * N + (e1 >> 7)) * C + q);
+            }
 #ifdef CMR_DBG_TIMING
             if (threadIdx.x == 0) g_dbg[(blockIdx.y * gridDim.x + blockIdx.x) * 16 + 7] = (unsigned long long)(n + (e0 & 0) + (e1 & 0));
             DBG_MARK(2);
 #endif
             if (copy_image) {   // image half when k_project could not carry it as TMA traffic
                 const float *img = img_feat + (size_t)b * C * P;
-                for (int r = 0; r < kSlab && c0 + r < C; ++r)
-                    if (p0 + lane < P) out[(size_t)(c0 + r) * P + p0 + lane] = img[(size_t)(c0 + r) * P + p0 + lane];
+                for (int r = 0; r < C; ++r)
+                    if (p0 + lane < P) out[(size_t)r * P + p0 + lane] = img[(size_t)r * P + p0 + lane];
             }
             if (n == 0) {
-                if (vec && p0 + kBucketPix <= P) {
-                    float *dst = proj + (size_t)c0 * P + p0 + 4 * (lane & 7);
-#pragma unroll
-                    for (int k = 0; k < kSlab / 4; ++k) {
-                        const int r = (lane >> 3) + 4 * k;
-                        if (c0 + r < C) stg_stream4(dst + (size_t)r * P, make_float4(0.f, 0.f, 0.f, 0.f));
-                    }
+                if (tma) {   // zeros leave through the same door: the warp's own tile, cleared
+                    zero_tile<32>(tile, lane);
+                    fence_async_proxy();
+                    __syncwarp();
+                    if (lane == 0)
+                        for (int slab = 0; slab < slabs; ++slab) store_tile_tma(tile, &map_proj, kSlab * slab, C, p0, b);
+                    __syncwarp();
                 } else {
-                    for (int r = 0; r < kSlab && c0 + r < C; ++r)
-                        if (p0 + lane < P) proj[(size_t)(c0 + r) * P + p0 + lane] = 0.f;
+                    store_zeros(C, p0, P, vec, proj, lane);
                 }
             } else if (n > 0 && n <= kLightMax) {   // otherwise the bucket CTAs own the bucket
                 // key = pixel % 32 << 24 | point (unique); empty slots are all-ones (never smaller than a key)
@@ -215,60 +282,89 @@ __global__ void __launch_bounds__(kGatherThreads, 5)
                     r0 += kj < k0;
                     r1 += kj < k1;
                 }
-                // padded to whole batches with harmless entries: they sort last and land in the padding column
-                const int npad = (n + kRowBatch - 1) / kRowBatch * kRowBatch;
                 if (lane < n) sk[r0] = k0;
-                else if (lane < npad) sk[lane] = kPadKey;
                 if (lane + 32 < n) sk[r1] = k1;
-                else if (lane + 32 < npad) sk[lane + 32] = kPadKey;
-                zero_tile<32>(tile, lane);
+                pc[lane] = 0;
                 __syncwarp();
+                // flags: first / last entry of its pixel; points per pixel
+                {
+                    const unsigned a = lane < n ? sk[lane] : 0u, a2 = lane + 32 < n ? sk[lane + 32] : 0u;
+                    const unsigned ap = lane > 0 ? sk[lane - 1] : 0xffffffffu, an = lane + 1 < n ? sk[lane + 1] : 0xffffffffu;
+                    const unsigned a2p = sk[lane + 31], a2n = lane + 33 < n ? sk[lane + 33] : 0xffffffffu;
+                    if (lane < n) atomicAdd(&pc[a >> 24], 1);
+                    if (lane + 32 < n) atomicAdd(&pc[a2 >> 24], 1);
+                    __syncwarp();
+                    if (lane < n)
+                        sk[lane] = a | ((a >> 24) != (ap >> 24) ? kKeyFirst : 0u) | ((a >> 24) != (an >> 24) ? kKeyLast : 0u);
+                    if (lane + 32 < n)
+                        sk[lane + 32] = a2 | ((a2 >> 24) != (a2p >> 24) ? kKeyFirst : 0u) | ((a2 >> 24) != (a2n >> 24) ? kKeyLast : 0u);
+                }
+                __syncwarp();
+                const int my_cnt = pc[lane];
+                const unsigned multi = __ballot_sync(kFull, my_cnt > 1);
+                const LaneRows tl = lane_rows(tile, lane);
                 DBG_MARK(8);
-                add_rows<true>(sk, 0, npad, rows, (unsigned)C, tile + 2 * lane * kTileStride);
-                __syncwarp();
-                DBG_MARK(3);
-                store_tile<32>(tile, c0, C, p0, P, vec, proj, lane);
+                for (int slab = 0; slab < slabs; ++slab) {
+                    const int c0 = kSlab * slab;
+                    // lanes beyond C read channel 0 instead (their rows of the tile are never stored)
+                    const float *rows = featT + (size_t)b * N * C + (c0 + 2 * lane < C ? c0 + 2 * lane : 0);
+                    zero_tile<32>(tile, lane);
+                    __syncwarp();
+                    add_rows<false>(sk, 0, n, rows, (unsigned)C, tl);
+                    mean_pass(multi, my_cnt, tl);
+                    DBG_MARK(3);
+                    if (tma) {
+                        fence_async_proxy();
+                        __syncwarp();
+                        if (lane == 0) store_tile_tma(tile, &map_proj, c0, C, p0, b);
+                    } else {
+                        __syncwarp();
+                        store_tile<32>(tile, c0, C, p0, P, proj, lane);
+                    }
+                    __syncwarp();
+                }
             }
         }
         DBG_MARK(4);
+        DBG_MARK(5);
     } else {
         // ------------------------------------------------------------------ bucket CTA
-        float *tile = smem_g;                                             // [64][kTileStride] sums, then means
+        float *tile = smem_g;                                             // [64][32] swizzled: sums, then means
         unsigned *ent = reinterpret_cast<unsigned *>(tile + kTileFloats);  // [kBucketCap] pixel << 24 | point, as they arrive
         unsigned *ulist = ent + kBucketCap;                               // [kBucketCap] points, grouped by pixel
-        unsigned *slist = ulist + kBucketCap;                             // [kBucketCap] keys, sorted
+        unsigned *slist = ulist + kBucketCap;                             // [kBucketCap] keys, sorted, flagged
         int *pcnt = reinterpret_cast<int *>(slist + kBucketCap);          // [32] entries per pixel of this chunk
         int *pstart = pcnt + 32;                                          // [33] exclusive prefix
         int *ptotal = pstart + 33;                                        // [32] entries per pixel, all chunks
-        int *misc = ptotal + 32;                                          // [4]
-        DBG_MARK(0);
-        pdl_wait();
-        DBG_MARK(1);
-        const int items = min(ld_cg_s32(hdr), B * kBucketMaxBuckets) * slabs;
+        int *misc = ptotal + 32;                                          // [8]
+        const int first_item = (int)(blockIdx.y * gridDim.x + blockIdx.x);
+        int qe = ld_cg_s32(hq + first_item);   // speculative: valid iff first_item < items
+        const int items = min(ld_cg_s32(hdr), B * kBucketMaxBuckets);
 #ifdef CMR_DBG_TIMING
         if (threadIdx.x == 0) {
             g_dbg[(blockIdx.y * gridDim.x + blockIdx.x) * 16 + 7] = 0;
             g_dbg[(blockIdx.y * gridDim.x + blockIdx.x) * 16 + 6] = 0;
         }
 #endif
-        for (int item = (int)(blockIdx.y * gridDim.x + blockIdx.x); item < items; item += kHeavyCtas * B) {
-            const int hr = item / slabs, slab = item - hr * slabs;
-            const int qe = ld_cg_s32(hq + hr);
+        for (int item = first_item; item < items; item += kHeavyCtas * B) {
+            if (item != first_item) qe = ld_cg_s32(hq + item);
             const int b = qe >> 16, bk = qe & 0xffff;
-            const int c = ld_cg_s32(bcnt + (size_t)b * kBucketStride + bk);
+            int *hc = hcnt + (size_t)b * kBucketStride + bk;
+            const int c = ld_cg_s32(hc) + kLightMax;
+            __syncthreads();   // every thread has read the overflow counter
+            if (tid == 0) *hc = 0;
             const int p0 = bk * kBucketPix;
-            const int c0 = kSlab * slab;
-            const float *rows = featT + (size_t)b * N * C + (c0 + 2 * lane < C ? c0 + 2 * lane : 0);
             float *proj = obs2d + (size_t)b * 2 * C * P + (size_t)C * P;
+            const bool chunked = c < 0 || c > kBucketCap;
             DBG_MARK(2);
-            zero_tile<kGatherThreads>(tile, tid);
             if (tid < 32) {
                 pcnt[tid] = 0;
                 ptotal[tid] = 0;
             }
             __syncthreads();
-            // orders the n entries of `ent` (wcnt counted in pcnt) and adds their rows to the per-pixel sums
-            auto accumulate = [&](int n) {
+            // orders the n entries of `ent` (counted per pixel in pcnt): slist = keys sorted by (pixel, point)
+            // with first / last flags, ptotal += points per pixel
+            auto order_chunk = [&](int n) {
                 __syncthreads();   // ent and pcnt are complete
                 if (warp == 0) {
                     const int cp = pcnt[lane];
@@ -281,9 +377,8 @@ __global__ void __launch_bounds__(kGatherThreads, 5)
                     pstart[lane] = inc - cp;
                     if (lane == 31) pstart[32] = inc;
                     ptotal[lane] += cp;
+                    pcnt[lane] = 0;   // reused as the fill level while placing
                 }
-                __syncthreads();
-                if (tid < 32) pcnt[tid] = 0;   // reused as the fill level while placing
                 __syncthreads();
                 for (int i = tid; i < n; i += kGatherThreads) {
                     const unsigned e = ent[i];
@@ -297,78 +392,104 @@ __global__ void __launch_bounds__(kGatherThreads, 5)
                     const unsigned pt = e & 0xffffffu;
                     const int s0 = pstart[pl], s1 = pstart[pl + 1];
                     int r = 0;
+#pragma unroll 8
                     for (int j = s0; j < s1; ++j) r += ulist[j] < pt;
-                    slist[s0 + r] = e;
+                    slist[s0 + r] = e | (r == 0 ? kKeyFirst : 0u) | (r == s1 - s0 - 1 ? kKeyLast : 0u);
                 }
                 if (tid < 32) pcnt[tid] = 0;   // ready for the next chunk's counts
                 __syncthreads();
-                DBG_MARK(9);
-                // split at pixel boundaries into four nearly equal parts: warp w takes the pixels whose first
-                // entry lies in [w * n / 4, (w + 1) * n / 4)
+            };
+            // adds the rows of slist[0, n) for one slab: split at pixel boundaries into eight nearly equal
+            // parts, warp w takes the pixels whose first entry lies in [w * n / 8, (w + 1) * n / 8)
+            auto add_chunk = [&](int n, int c0) {
+                const float *rows = featT + (size_t)b * N * C + (c0 + 2 * lane < C ? c0 + 2 * lane : 0);
                 const int ps = pstart[lane];
-                const int lo = (warp * n + 3) >> 2, hi = ((warp + 1) * n + 3) >> 2;
-                const int pb = __popc(__ballot_sync(kFull, ps < lo)), pe = warp == kGatherWarps - 1 ? 32 : __popc(__ballot_sync(kFull, ps < hi));
+                const int lo = (warp * n + kGatherWarps - 1) / kGatherWarps, hi = ((warp + 1) * n + kGatherWarps - 1) / kGatherWarps;
+                const int pb = __popc(__ballot_sync(kFull, ps < lo));
+                const int pe = warp == kGatherWarps - 1 ? 32 : __popc(__ballot_sync(kFull, ps < hi));
                 const int jb = pb < 32 ? pstart[pb] : n, je = pe < 32 ? pstart[pe] : n;
-                add_rows<false>(slist, jb, je, rows, (unsigned)C, tile + 2 * lane * kTileStride);
+                add_rows<true>(slist, jb, je, rows, (unsigned)C, lane_rows(tile, lane));
+            };
+            auto finish_slab = [&](int c0) {
+                __syncthreads();
+                // sums -> means: warp w takes the pixels p % 8 == w
+                const int my_cnt = ptotal[lane];
+                const unsigned multi = __ballot_sync(kFull, my_cnt > 1) & (0x01010101u << warp);
+                mean_pass(multi, my_cnt, lane_rows(tile, lane));
+                if (tma) {
+                    fence_async_proxy();
+                    __syncthreads();
+                    if (tid == 0) store_tile_tma(tile, &map_proj, c0, C, p0, b);
+                } else {
+                    __syncthreads();
+                    store_tile<kGatherThreads>(tile, c0, C, p0, P, proj, tid);
+                }
                 __syncthreads();
             };
-            if (c >= 0 && c <= kBucketCap) {
+            if (!chunked) {
                 const unsigned *src = bbuf + ((size_t)b * buckets + bk) * kBucketCap;
                 for (int i = tid; i < c; i += kGatherThreads) {
                     const unsigned e = ld_cg_u32(src + i);
                     const unsigned pl = e & 31u;
+                    for (int q = 0; q < C; q += 32) prefetch_l2(featT + ((size_t)b * N + (e >> 7)) * C + q);
                     ent[i] = (pl << 24) | (e >> 7);
                     atomicAdd(&pcnt[pl], 1);
                 }
                 DBG_MARK(8);
-                accumulate(c);
+                order_chunk(c);
+                DBG_MARK(9);
+                for (int slab = 0; slab < slabs; ++slab) {
+                    zero_tile<kGatherThreads>(tile, tid);
+                    __syncthreads();
+                    add_chunk(c, kSlab * slab);
+                    DBG_MARK(10);
+                    finish_slab(kSlab * slab);
+                }
             } else {
                 // the bucket overflowed its buffer: rebuild it from the episode's pixel-id list, kBucketCap
-                // points at a time, in point order (a chunk's points all precede the next chunk's)
+                // points at a time, in point order (a chunk's points all precede the next chunk's); per slab
                 const int m_total = min(ld_cg_s32(M + b), N);
-                int fill = 0;
-                for (int m0 = 0; m0 < m_total; m0 += kGatherThreads) {
-                    const int m = m0 + tid;
-                    int id = -1;
-                    if (m < m_total)
-                        id = pix16 ? (int)static_cast<const uint16_t *>(pix)[(size_t)b * ncap + m]
-                                   : static_cast<const int32_t *>(pix)[(size_t)b * ncap + m];
-                    const bool hit = id >= p0 && id < p0 + kBucketPix && id < P;
-                    const unsigned bal = __ballot_sync(kFull, hit);
-                    if (lane == 0) misc[warp] = __popc(bal);
+                for (int slab = 0; slab < slabs; ++slab) {
+                    zero_tile<kGatherThreads>(tile, tid);
+                    if (tid < 32) ptotal[tid] = 0;
                     __syncthreads();
-                    int before = 0, total = 0;
-                    for (int w = 0; w < kGatherWarps; ++w) {
-                        if (w < warp) before += misc[w];
-                        total += misc[w];
+                    int fill = 0;
+                    for (int m0 = 0; m0 < m_total; m0 += kGatherThreads) {
+                        const int m = m0 + tid;
+                        int id = -1;
+                        if (m < m_total)
+                            id = pix16 ? (int)static_cast<const uint16_t *>(pix)[(size_t)b * ncap + m]
+                                       : static_cast<const int32_t *>(pix)[(size_t)b * ncap + m];
+                        const bool hit = id >= p0 && id < p0 + kBucketPix && id < P;
+                        const unsigned bal = __ballot_sync(kFull, hit);
+                        if (lane == 0) misc[warp] = __popc(bal);
+                        __syncthreads();
+                        int before = 0, total = 0;
+                        for (int w = 0; w < kGatherWarps; ++w) {
+                            if (w < warp) before += misc[w];
+                            total += misc[w];
+                        }
+                        if (fill + total > kBucketCap) {   // uniform
+                            order_chunk(fill);
+                            add_chunk(fill, kSlab * slab);
+                            fill = 0;
+                            __syncthreads();
+                        }
+                        if (hit) {
+                            const unsigned pl = (unsigned)(id - p0);
+                            ent[fill + before + __popc(bal & ((1u << lane) - 1))] = (pl << 24) | (unsigned)m;
+                            atomicAdd(&pcnt[pl], 1);
+                        }
+                        fill += total;
+                        __syncthreads();
                     }
-                    if (fill + total > kBucketCap) {   // uniform
-                        accumulate(fill);
-                        fill = 0;
+                    if (fill > 0) {
+                        order_chunk(fill);
+                        add_chunk(fill, kSlab * slab);
                     }
-                    if (hit) {
-                        const unsigned pl = (unsigned)(id - p0);
-                        ent[fill + before + __popc(bal & ((1u << lane) - 1))] = (pl << 24) | (unsigned)m;
-                        atomicAdd(&pcnt[pl], 1);
-                    }
-                    fill += total;
-                    __syncthreads();
+                    finish_slab(kSlab * slab);
                 }
-                if (fill > 0) accumulate(fill);
             }
-            DBG_MARK(10);
-            // sums -> means: warp w takes the pixels p % 4 == w
-#pragma unroll 1
-            for (int pl = warp; pl < 32; pl += kGatherWarps) {
-                const int n = ptotal[pl];
-                if (n > 1) {
-                    const float2 m = mean2(make_float2(tile[(2 * lane) * kTileStride + pl], tile[(2 * lane + 1) * kTileStride + pl]), n);
-                    tile[(2 * lane) * kTileStride + pl] = m.x;
-                    tile[(2 * lane + 1) * kTileStride + pl] = m.y;
-                }
-            }
-            __syncthreads();
-            store_tile<kGatherThreads>(tile, c0, C, p0, P, vec, proj, tid);
             DBG_MARK(11);
 #ifdef CMR_DBG_TIMING
             if (threadIdx.x == 0) {
@@ -376,24 +497,17 @@ __global__ void __launch_bounds__(kGatherThreads, 5)
                 g_dbg[(blockIdx.y * gridDim.x + blockIdx.x) * 16 + 6] += 1;
             }
 #endif
-            __syncthreads();
         }
         DBG_MARK(4);
+        DBG_MARK(5);
     }
-    // the last CTA of the grid to get here clears the counters and the queue for the next observe: every
-    // CTA has read what it needed from them before it takes its ticket
-    __shared__ int s_last;
-    __syncthreads();
-    if (tid == 0) {
+    // the last bucket CTA to get here clears the queue length for the next observe (they are its only readers)
+    if ((int)blockIdx.y < kHeavyCtas && tid == 0) {
         __threadfence();
-        s_last = atomicAdd(hdr + 1, 1) == (int)(gridDim.x * gridDim.y) - 1;
-    }
-    __syncthreads();
-    DBG_MARK(5);
-    if (s_last) {
-        for (int e = 0; e < B; ++e)
-            for (int t = tid; t < T; t += kGatherThreads) bcnt[(size_t)e * kBucketStride + t] = 0;
-        if (tid < 2) hdr[tid] = 0;
+        if (atomicAdd(hdr + 1, 1) == kHeavyCtas * B - 1) {
+            hdr[0] = 0;
+            hdr[1] = 0;
+        }
     }
 }
 
