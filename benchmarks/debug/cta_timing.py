@@ -63,7 +63,7 @@ for name, m in (('light', ~role), ('bucket', role)):
     for i in order:
         extra = ''
         if name == 'bucket':
-            extra = '  phases: queue %.2f stage %.2f sort %.2f add %.2f mean+store %.2f' % tuple((x[i, a] - x[i, b_]) / 1e3 for a, b_ in ((2, 1), (8, 2), (9, 8), (10, 9), (11, 10)))
+            extra = '  phases: queue %.2f stage %.2f sort %.2f add %.2f [rows landed %.2f, warp0 (%d entries) added %.2f, all warps %.2f] mean+store %.2f' % ((x[i, 2] - x[i, 1]) / 1e3, (x[i, 8] - x[i, 2]) / 1e3, (x[i, 9] - x[i, 8]) / 1e3, (x[i, 10] - x[i, 9]) / 1e3, (x[i, 12] - x[i, 9]) / 1e3, x[i, 15], (x[i, 13] - x[i, 12]) / 1e3, (x[i, 14] - x[i, 13]) / 1e3, (x[i, 11] - x[i, 10]) / 1e3)
         print('     cta', i, 'entries', x[i, 7], 'items', x[i, 6], 'released %.1f dur %.1f' % (rel[i], dur[i]), extra)
 hist, edges = np.histogram((d[:, 5] - t0) / 1e3, bins=10)
 print('end-time histogram us:', hist.tolist(), edges.round(1).tolist())

@@ -153,9 +153,9 @@ static bool image_copy_by_tma(const float *img_feat, const float *obs2d, int B, 
                               CUtensorMap *map_out) {
     memset(map_img, 0, sizeof(*map_img));
     memset(map_out, 0, sizeof(*map_out));
-    return img_feat && obs2d && (P % 4 == 0) && P >= kTilePix && aligned(img_feat, 16) && aligned(obs2d, 16) &&
-           make_map3d(map_img, img_feat, P, C, B, kTilePix, C) &&
-           make_map3d(map_out, obs2d, P, 2 * (uint64_t)C, B, kTilePix, C);
+    return img_feat && obs2d && (P % 4 == 0) && P >= kProjBoxPix && aligned(img_feat, 16) && aligned(obs2d, 16) &&
+           make_map3d(map_img, img_feat, P, C, B, kProjBoxPix, C) &&
+           make_map3d(map_out, obs2d, P, 2 * (uint64_t)C, B, kProjBoxPix, C);
 }
 
 template <typename PixT>
@@ -172,8 +172,8 @@ static int launch_project(const WsLayout &L, char *ws, const float *pc, const ui
         cudaError_t e = cudaMemsetAsync(mvis_out, 0, sizeof(int32_t) * B, st);
         if (e != cudaSuccess) return (int)e;
     }
-    const int img_tiles = img_tma ? ceil_div(H * W, kTilePix) : 0;
-    const size_t smem = img_tma ? sizeof(float) * kTilePix * C : 0;
+    const int img_tiles = img_tma ? ceil_div(H * W, kProjBoxPix) : 0;
+    const size_t smem = img_tma ? sizeof(float) * kProjBoxPix * C : 0;
     int rc = allow_smem(k_project<PixT>, smem);
     if (rc) return rc;
     int *bcnt = nullptr;
@@ -188,9 +188,9 @@ static int launch_project(const WsLayout &L, char *ws, const float *pc, const ui
             if (e != cudaSuccess) return (int)e;
         }
     }
-    k_project<PixT><<<dim3(ceil_div(L.groups, 8), B), 256, smem, st>>>(pc, overlap, K, pose, mean, seg, Mws, N, L.ncap,
+    k_project<PixT><<<dim3(ceil_div(L.groups, kProjWarps), B), 32 * kProjWarps, smem, st>>>(pc, overlap, K, pose, mean, seg, Mws, N, L.ncap,
                                                                       L.groups, H, W, vec, pix, obs3d, pix_out, mvis_out,
-                                                                      bcnt, bbuf, L.buckets, bcnt ? bcnt + 2 * (size_t)B * kBucketStride : nullptr, hq, img_tiles, C,
+                                                                      bcnt, bbuf, L.buckets, bcnt ? bcnt + (size_t)B * kBucketStride : nullptr, hq, img_tiles, C,
                                                                       map_img, map_out);
     return after_launch();
 }

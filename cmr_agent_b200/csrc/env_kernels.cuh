@@ -18,12 +18,18 @@ namespace cmr {
 
 constexpr int kGroup = 128;     // points per compaction group = 32 lanes x 4 points
 constexpr int kTilePix = 128;   // pixels per k_tile_scatter CTA
+#ifndef CMR_PROJ_WARPS
+#define CMR_PROJ_WARPS 8
+#endif
+constexpr int kProjWarps = CMR_PROJ_WARPS;      // warps (128-point groups) per k_project CTA
+constexpr int kProjBoxPix = 16 * kProjWarps;    // pixels of the image box a k_project CTA carries by TMA
 constexpr int kMaxC = 256;
 constexpr int kBucketPix = 32;      // pixels per scatter bucket (scatter_kernels.cuh)
 constexpr int kBucketMaxBuckets = 384;  // buckets per episode the bucket path supports (H*W <= 12288)
 constexpr int kBucketStride = 384;      // ints per episode in bcnt
 constexpr int kBucketHdr = 64;          // ints after the counters: [0] heavy-queue length, [1] ticket of k_tile_gather
 constexpr int kLightMax = 64;           // a bucket that receives more visible points than this is queued as heavy
+constexpr int kCountSeen = 1 << 24;     // added to a heavy bucket's counter by the first of its two readers
 constexpr int kBucketCap = 1024;    // entries a bucket's buffer holds; fuller buckets are re-read from the id list
 
 struct WsLayout {
@@ -47,8 +53,8 @@ inline WsLayout ws_layout(int B, int N, int C, int P) {
     L.off_pix = o;
     o = round_up(o + sizeof(int) * (size_t)B * L.ncap, 256);
     L.off_bcnt = o;    // points per 32-pixel bucket, rewritten every observe (scatter_kernels.cuh), + header
-    // points per bucket | points beyond kLightMax per bucket | header
-    L.bcnt_bytes = sizeof(int) * (2 * (size_t)B * kBucketStride + kBucketHdr);
+    // points per bucket | header
+    L.bcnt_bytes = sizeof(int) * ((size_t)B * kBucketStride + kBucketHdr);
     o = round_up(o + L.bcnt_bytes, 256);
     L.off_hq = o;      // queue of the heavy buckets of the whole batch (episode << 16 | bucket), per observe
     o = round_up(o + sizeof(int) * (size_t)B * kBucketMaxBuckets, 256);
@@ -264,7 +270,7 @@ __device__ __forceinline__ int project_point(const PoseK &s, float x, float y, f
 // episode; writes obs3d (environment.py:88-124) and the pixel id of each predicted-overlap point at
 // its compacted position (input of k_tile_scatter).  One warp = one 128-point group, 4 points/lane.
 template <typename PixT>
-__global__ void __launch_bounds__(256) k_project(const float *__restrict__ pc, const uint8_t *__restrict__ overlap,
+__global__ void __launch_bounds__(32 * kProjWarps) k_project(const float *__restrict__ pc, const uint8_t *__restrict__ overlap,
                                                   const float *__restrict__ K, const float *__restrict__ pose,
                                                   const float *__restrict__ mean, const int *__restrict__ seg,
                                                   const int *__restrict__ M, int N, int ncap, int groups, int H, int W,
@@ -278,7 +284,7 @@ __global__ void __launch_bounds__(256) k_project(const float *__restrict__ pc, c
     pdl_launch_dependents();   // k_tile_scatter may start its pose-independent preamble now
     const int b = blockIdx.y;
     const int lane = threadIdx.x & 31;
-    const int g = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int g = blockIdx.x * kProjWarps + (threadIdx.x >> 5);
     // The image half of obs2d (obs2d[b, 0:C] = img_geo_feat[b], environment.py:83) is a pure copy that does
     // not depend on the pose.  It rides along here as tiled TMA traffic: thread 0 of every CTA moves
     // [C][128-pixel] boxes global -> shared -> global while the CTA's threads do the projection maths -
@@ -291,8 +297,8 @@ __global__ void __launch_bounds__(256) k_project(const float *__restrict__ pc, c
         mbar_init(&img_bar, 1);
         fence_async_proxy();
         if (tile < img_tiles) {
-            mbar_arrive_expect_tx(&img_bar, (unsigned)(C * kTilePix * sizeof(float)));
-            tma_load_3d(img_stage, &map_img, tile * kTilePix, 0, b, &img_bar);
+            mbar_arrive_expect_tx(&img_bar, (unsigned)(C * kProjBoxPix * sizeof(float)));
+            tma_load_3d(img_stage, &map_img, tile * kProjBoxPix, 0, b, &img_bar);
         }
     }
     if (g >= groups) return;
@@ -380,9 +386,12 @@ __global__ void __launch_bounds__(256) k_project(const float *__restrict__ pc, c
 #pragma unroll
     for (int i = 0; i < 4; ++i)
         if (flags >> i & 1) pw[pos++] = (PixT)id2[i];
+#ifdef CMR_DBG_NO_APPEND
+    if (false) {
+#else
     if (bcnt && (flags & cam2)) {
+#endif
         int *bc = bcnt + (size_t)b * kBucketStride;
-        int *hc = bc + (size_t)gridDim.y * kBucketStride;   // overflow counters: points beyond kLightMax
         // visible predicted-overlap points go to the 32-pixel bucket of their pixel (integer atomics: the SET
         // of entries of a bucket is deterministic, k_tile_gather restores point order by sorting).  The four
         // atomics of a lane are independent: issued together, their round trips overlap.
@@ -397,12 +406,8 @@ __global__ void __launch_bounds__(256) k_project(const float *__restrict__ pc, c
                 if (slot[i] < kBucketCap)
                     bbuf[((size_t)b * buckets + id2[i] / kBucketPix) * kBucketCap + slot[i]] =
                         ((unsigned)p << 7) | ((unsigned)id2[i] & 127u);
-                // a heavy bucket: its points beyond kLightMax are counted a second time (the counter the bucket
-                // CTA reads), and the one that saw the counter cross kLightMax queues the bucket
-                if (slot[i] >= kLightMax) {
-                    atomicAdd(hc + id2[i] / kBucketPix, 1);
-                    if (slot[i] == kLightMax) hq[atomicAdd(hdr, 1)] = (b << 16) | (id2[i] / kBucketPix);
-                }
+                // exactly one point per bucket sees the counter cross kLightMax: it queues the bucket as heavy
+                if (slot[i] == kLightMax) hq[atomicAdd(hdr, 1)] = (b << 16) | (id2[i] / kBucketPix);
             }
             p += flags >> i & 1;
         }
@@ -422,13 +427,13 @@ __global__ void __launch_bounds__(256) k_project(const float *__restrict__ pc, c
         while (tile < img_tiles) {
             mbar_wait(&img_bar, parity);
             parity ^= 1;
-            tma_store_3d(&map_out, tile * kTilePix, 0, b, img_stage);
+            tma_store_3d(&map_out, tile * kProjBoxPix, 0, b, img_stage);
             bulk_commit();
             bulk_wait_read_all();   // the box has been read out of shared memory: the stage may be reused / freed
             tile += gridDim.x;
             if (tile < img_tiles) {
-                mbar_arrive_expect_tx(&img_bar, (unsigned)(C * kTilePix * sizeof(float)));
-                tma_load_3d(img_stage, &map_img, tile * kTilePix, 0, b, &img_bar);
+                mbar_arrive_expect_tx(&img_bar, (unsigned)(C * kProjBoxPix * sizeof(float)));
+                tma_load_3d(img_stage, &map_img, tile * kProjBoxPix, 0, b, &img_bar);
             }
         }
     }

@@ -27,10 +27,10 @@
 //       by point (rank = number of smaller points IN THE PIXEL), and splits the sorted list at pixel
 //       boundaries into four nearly equal parts, one per warp.  A bucket that overflowed its buffer (more than
 //       kBucketCap points) is rebuilt from the episode's pixel-id list in chunks of kBucketCap, in point order.
-//   Every counter has exactly one reader, which clears it for the next observe: the light unit reads (and
-//   clears) its bucket's counter, the bucket CTA the bucket's overflow counter (points beyond kLightMax, counted
-//   by k_project in a second array); the last bucket CTA to finish clears the queue length.  No memset between
-//   observes, no grid-wide pass, no word that every CTA reads.
+//   Counters are cleared by their readers: a light bucket's counter has one reader (its warp), a heavy bucket's
+//   two (its warp, which only learns that the bucket is heavy, and the bucket CTA) - each adds kCountSeen, and
+//   the one that finds it already there clears the counter; the last bucket CTA to finish clears the queue
+//   length.  No memset between observes, no grid-wide pass, no word that every CTA reads.
 //
 // Used when the grid has at most kBucketMaxBuckets 32-pixel buckets (H*W <= 12288; KITTI is 5120, NuScenes
 // 3200); larger grids take the search-based k_tile_scatter of env_kernels.cuh.
@@ -55,6 +55,9 @@ static_assert(kBucketCap % kGatherThreads == 0, "whole entries per thread");
 constexpr size_t kGatherSmemLight = kGatherWarps * (sizeof(float) * kTileFloats + sizeof(unsigned) * (kLightMax + 32));
 constexpr size_t kGatherSmemHeavy = sizeof(float) * kTileFloats + sizeof(unsigned) * 3 * kBucketCap + sizeof(int) * 128;
 constexpr size_t kGatherSmem = kGatherSmemLight > kGatherSmemHeavy ? kGatherSmemLight : kGatherSmemHeavy;
+// what a bucket CTA does not need of the light units' tiles stages feature rows: kSlab floats per row
+constexpr int kStageRows = (int)((kGatherSmem - kGatherSmemHeavy) / (sizeof(float) * kSlab));
+static_assert(kStageRows >= 64, "a bucket CTA stages at least 64 rows at a time");
 
 __device__ __forceinline__ unsigned ld_cg_u32(const unsigned *p) {
     unsigned v;
@@ -62,6 +65,12 @@ __device__ __forceinline__ unsigned ld_cg_u32(const unsigned *p) {
     return v;
 }
 __device__ __forceinline__ float2 ldg_f2(const float *p) { return __ldg(reinterpret_cast<const float2 *>(p)); }
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
 
 // sum / count exactly as torch's true_divide (n >= 2): powers of two scale by the exact reciprocal
 __device__ __forceinline__ float2 mean2(float2 s, int n) {
@@ -186,13 +195,13 @@ __device__ __forceinline__ void add_rows(const unsigned *skeys, int jb, int je, 
     float2 run = make_float2(0.f, 0.f);
     unsigned ka[kRowBatch], kb[kRowBatch];
     float2 va[kRowBatch], vb[kRowBatch];
-    load_batch(ka, va, skeys, jb, je, rows, C);
+    if (jb < je) load_batch(ka, va, skeys, jb, je, rows, C);
     for (int j0 = jb; j0 < je; j0 += 2 * kRowBatch) {
-        // loads past the end fetch row 0 (in L1 after the first time): no branches around the batches
-        load_batch(kb, vb, skeys, j0 + kRowBatch, je, rows, C);
+        const bool more = j0 + kRowBatch < je;   // warp-uniform
+        if (more) load_batch(kb, vb, skeys, j0 + kRowBatch, je, rows, C);
         add_batch<kFromTile>(ka, va, run, tl);
-        load_batch(ka, va, skeys, j0 + 2 * kRowBatch, je, rows, C);
-        add_batch<kFromTile>(kb, vb, run, tl);
+        if (j0 + 2 * kRowBatch < je) load_batch(ka, va, skeys, j0 + 2 * kRowBatch, je, rows, C);
+        if (more) add_batch<kFromTile>(kb, vb, run, tl);
     }
 }
 
@@ -217,8 +226,7 @@ __global__ void __launch_bounds__(kGatherThreads, 3)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int T = buckets;
     const int slabs = (C + kSlab - 1) / kSlab;
-    int *hcnt = bcnt + (size_t)B * kBucketStride;        // points beyond kLightMax of every bucket
-    int *hdr = hcnt + (size_t)B * kBucketStride;         // [0] heavy-queue length, [1] ticket of the bucket CTAs
+    int *hdr = bcnt + (size_t)B * kBucketStride;         // [0] heavy-queue length, [1] ticket of the bucket CTAs
     DBG_MARK(0);
     pdl_wait();   // counters, bucket buffers and queue are written by k_project
     DBG_MARK(1);
@@ -237,8 +245,11 @@ __global__ void __launch_bounds__(kGatherThreads, 3)
             const unsigned *src = bbuf + ((size_t)b * buckets + bk) * kBucketCap;
             const unsigned e0 = ld_cg_u32(src + lane), e1 = ld_cg_u32(src + 32 + lane);   // speculative
             int *cb = bcnt + (size_t)b * kBucketStride + bk;
-            const int n = ld_cg_s32(cb);
-            if (lane == 0 && n != 0) *cb = 0;   // this warp is the counter's only reader
+            const int n = ld_cg_s32(cb) & (kCountSeen - 1);
+            if (lane == 0 && n != 0) {
+                if (n <= kLightMax) *cb = 0;   // this warp is the counter's only reader
+                else if (atomicAdd(cb, kCountSeen) >= kCountSeen) *cb = 0;   // the bucket CTA has been here
+            }
             if (n > 0 && n <= kLightMax) {
                 // all the rows this unit will add: on their way to L2 before the first one is needed
                 if (lane < n)
@@ -337,6 +348,7 @@ __global__ void __launch_bounds__(kGatherThreads, 3)
         int *pstart = pcnt + 32;                                          // [33] exclusive prefix
         int *ptotal = pstart + 33;                                        // [32] entries per pixel, all chunks
         int *misc = ptotal + 32;                                          // [8]
+        float *stage = smem_g + kGatherSmemHeavy / sizeof(float);         // [kStageRows][kSlab] staged feature rows
         const int first_item = (int)(blockIdx.y * gridDim.x + blockIdx.x);
         int qe = ld_cg_s32(hq + first_item);   // speculative: valid iff first_item < items
         const int items = min(ld_cg_s32(hdr), B * kBucketMaxBuckets);
@@ -349,10 +361,8 @@ __global__ void __launch_bounds__(kGatherThreads, 3)
         for (int item = first_item; item < items; item += kHeavyCtas * B) {
             if (item != first_item) qe = ld_cg_s32(hq + item);
             const int b = qe >> 16, bk = qe & 0xffff;
-            int *hc = hcnt + (size_t)b * kBucketStride + bk;
-            const int c = ld_cg_s32(hc) + kLightMax;
-            __syncthreads();   // every thread has read the overflow counter
-            if (tid == 0) *hc = 0;
+            int *cb = bcnt + (size_t)b * kBucketStride + bk;
+            const int c = ld_cg_s32(cb) & (kCountSeen - 1);
             const int p0 = bk * kBucketPix;
             float *proj = obs2d + (size_t)b * 2 * C * P + (size_t)C * P;
             const bool chunked = c < 0 || c > kBucketCap;
@@ -362,8 +372,8 @@ __global__ void __launch_bounds__(kGatherThreads, 3)
                 ptotal[tid] = 0;
             }
             __syncthreads();
-            // orders the n entries of `ent` (counted per pixel in pcnt): slist = keys sorted by (pixel, point)
-            // with first / last flags, ptotal += points per pixel
+            // orders the n entries of `ent` (counted per pixel in pcnt): slist = keys sorted by (pixel, point),
+            // pstart = where every pixel's run begins, ptotal += points per pixel
             auto order_chunk = [&](int n) {
                 __syncthreads();   // ent and pcnt are complete
                 if (warp == 0) {
@@ -394,21 +404,58 @@ __global__ void __launch_bounds__(kGatherThreads, 3)
                     int r = 0;
 #pragma unroll 8
                     for (int j = s0; j < s1; ++j) r += ulist[j] < pt;
-                    slist[s0 + r] = e | (r == 0 ? kKeyFirst : 0u) | (r == s1 - s0 - 1 ? kKeyLast : 0u);
+                    slist[s0 + r] = e;
                 }
                 if (tid < 32) pcnt[tid] = 0;   // ready for the next chunk's counts
                 __syncthreads();
             };
-            // adds the rows of slist[0, n) for one slab: split at pixel boundaries into eight nearly equal
-            // parts, warp w takes the pixels whose first entry lies in [w * n / 8, (w + 1) * n / 8)
+            // adds the rows of slist[0, n) for one slab.  The sorted list is split at pixel boundaries into eight
+            // nearly equal parts, warp w takes the pixels whose first entry lies in [w * n / 8, (w + 1) * n / 8).
+            // The rows come through shared memory: the whole CTA fetches kStageRows of them at a time with
+            // cp.async, in sorted order - ONE round trip for a typical bucket instead of one per batch of a warp -
+            // and a pixel's rows are then consecutive: the inner loop is a load and two additions per row.
             auto add_chunk = [&](int n, int c0) {
-                const float *rows = featT + (size_t)b * N * C + (c0 + 2 * lane < C ? c0 + 2 * lane : 0);
+                const float *rbase = featT + (size_t)b * N * C + c0;
+                const int pieces = min(kSlab, C - c0) >> 2;   // 16-byte pieces of a row in this slab
                 const int ps = pstart[lane];
                 const int lo = (warp * n + kGatherWarps - 1) / kGatherWarps, hi = ((warp + 1) * n + kGatherWarps - 1) / kGatherWarps;
                 const int pb = __popc(__ballot_sync(kFull, ps < lo));
                 const int pe = warp == kGatherWarps - 1 ? 32 : __popc(__ballot_sync(kFull, ps < hi));
-                const int jb = pb < 32 ? pstart[pb] : n, je = pe < 32 ? pstart[pe] : n;
-                add_rows<true>(slist, jb, je, rows, (unsigned)C, lane_rows(tile, lane));
+                const LaneRows tl = lane_rows(tile, lane);
+                for (int r0 = 0; r0 < n; r0 += kStageRows) {
+                    const int nr = min(kStageRows, n - r0);
+                    for (int i = tid; i < nr * (kSlab / 4); i += kGatherThreads) {
+                        const int r = i / (kSlab / 4), piece = i % (kSlab / 4);
+                        if (piece < pieces)
+                            cp_async16(stage + r * kSlab + 4 * piece, rbase + (size_t)(slist[r0 + r] & 0xffffffu) * C + 4 * piece);
+                    }
+                    cp_async_wait_all();
+                    __syncthreads();
+#ifdef CMR_DBG_TIMING
+                    if (r0 == 0) DBG_MARK(12);
+#endif
+                    for (int pl = pb; pl < pe; ++pl) {   // this warp's pixels; their sums so far are in the tile
+                        const int js = max(pstart[pl], r0) - r0, jn = min(pstart[pl + 1], r0 + nr) - r0;
+                        if (js >= jn) continue;          // warp-uniform
+                        float2 acc = tl.get(pl);
+                        const float *src = stage + js * kSlab + 2 * lane;
+#pragma unroll 8
+                        for (int j = js; j < jn; ++j, src += kSlab) {
+                            const float2 v = *reinterpret_cast<const float2 *>(src);
+                            acc.x = __fadd_rn(acc.x, v.x);
+                            acc.y = __fadd_rn(acc.y, v.y);
+                        }
+                        tl.put(pl, acc);
+                    }
+#ifdef CMR_DBG_TIMING
+                    if (r0 == 0) DBG_MARK(13);
+#endif
+                    __syncthreads();   // the stage is refilled / the tile is read
+#ifdef CMR_DBG_TIMING
+                    if (r0 == 0) DBG_MARK(14);
+                    if (threadIdx.x == 0) g_dbg[(blockIdx.y * gridDim.x + blockIdx.x) * 16 + 15] = (unsigned long long)(pstart[pe < 32 ? pe : 32] - pstart[pb < 32 ? pb : 32]);
+#endif
+                }
             };
             auto finish_slab = [&](int c0) {
                 __syncthreads();
@@ -490,6 +537,8 @@ __global__ void __launch_bounds__(kGatherThreads, 3)
                     finish_slab(kSlab * slab);
                 }
             }
+            // (barriers since: every thread has read the counter) the second of its two readers clears it
+            if (tid == 0 && atomicAdd(cb, kCountSeen) >= kCountSeen) *cb = 0;
             DBG_MARK(11);
 #ifdef CMR_DBG_TIMING
             if (threadIdx.x == 0) {
