@@ -9,6 +9,7 @@
 #include "env_kernels.cuh"
 #include "pointnet_kernels.cuh"
 #include "scatter_kernels.cuh"
+#include "dataset_kernels.cuh"
 
 namespace cmr {
 
@@ -500,6 +501,28 @@ int cmr_query_ball_point(const float *query, const float *ref, float radius2, in
     CMR_REQUIRE(query && ref && out && nsample > 0 && B > 0 && S > 0 && N > 0, CMR_EINVAL);
     CMR_REQUIRE(B <= 65535, CMR_ERANGE);
     k_ball_query<<<dim3(ceil_div(S, 8), B), 256, 0, S_(stream)>>>(query, ref, radius2, nsample, S, N, out);
+    return after_launch();
+}
+
+// ------------------------------------------------------------------------------ dataset side ----
+
+int cmr_fps_f64(const double *pts, const int64_t *start, int B, int M, int k, int64_t *out_idx, double *out_pts,
+                void *stream) {
+    CMR_REQUIRE(pts && start && out_idx && B > 0 && M > 0 && k > 0, CMR_EINVAL);
+    CMR_REQUIRE(k <= M && (long long)M <= (long long)kFps64Threads * kFps64MaxPpt, CMR_ERANGE);
+    const int ppt = ceil_div(M, kFps64Threads);
+    cudaStream_t st = S_(stream);
+    if (ppt <= 4) k_fps_f64<4><<<B, kFps64Threads, 0, st>>>(pts, start, M, k, out_idx, out_pts);
+    else if (ppt <= 8) k_fps_f64<8><<<B, kFps64Threads, 0, st>>>(pts, start, M, k, out_idx, out_pts);
+    else if (ppt <= 12) k_fps_f64<12><<<B, kFps64Threads, 0, st>>>(pts, start, M, k, out_idx, out_pts);
+    else k_fps_f64<16><<<B, kFps64Threads, 0, st>>>(pts, start, M, k, out_idx, out_pts);
+    return after_launch();
+}
+
+int cmr_nearest_f64(const double *query, const double *ref, int B, int N, int S, int64_t *out, void *stream) {
+    CMR_REQUIRE(query && ref && out && B > 0 && N > 0 && S > 0, CMR_EINVAL);
+    CMR_REQUIRE(B <= 65535, CMR_ERANGE);
+    k_nearest_f64<<<dim3(ceil_div(N, 256), B), 256, 0, S_(stream)>>>(query, ref, N, S, out);
     return after_launch();
 }
 

@@ -172,6 +172,20 @@ CMR_API int cmr_group_points(const float *xyz, const float *points, const float 
  * synchronises `stream`.  0 = none. */
 CMR_API int cmr_take_fault(void *stream);
 
+/* ------------------------------------------------------------------ dataset side ---- */
+
+/* FarthestSampler.sample - dataset/KittiDataset.py:107-126 (= dataset/NuScenesDataset.py:25-44), float64 like
+ * the numpy original.  pts [B,3,M] f64 channel-major (numpy's [3, M] per sample), start [B] i64 (init_idx of
+ * :118, drawn by the host) -> out_idx [B,k] i64 and, if out_pts is not NULL, out_pts [B,3,k] f64.
+ * np.argmax semantics: the first maximum wins.  M <= 16384, k <= M. */
+CMR_API int cmr_fps_f64(const double *pts, const int64_t *start, int B, int M, int k, int64_t *out_idx,
+                        double *out_pts, void *stream);
+
+/* cKDTree(ref.T).query(query.T, k=1)[1] - dataset/KittiDataset.py:365-366: the nearest reference point (node) of
+ * every query point, exact, float64.  query [B,3,N], ref [B,3,S] f64 channel-major -> out [B,N] i64.
+ * Lowest index on exact ties (scipy leaves ties unspecified). */
+CMR_API int cmr_nearest_f64(const double *query, const double *ref, int B, int N, int S, int64_t *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

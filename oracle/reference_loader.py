@@ -41,3 +41,25 @@ def pointnet_util():
     if "pn" not in _cache:
         _cache["pn"] = _load("_cmr_reference_pointnet_util", "models/pointnet_util.py")
     return _cache["pn"]
+
+
+def kitti_dataset():
+    """The module at /root/reference/dataset/KittiDataset.py (FarthestSampler lives there).  It imports plotting
+    and logging packages this image lacks; they are never called by the code under test and are stubbed."""
+    if "kitti" not in _cache:
+        import types
+        for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.image", "tensorboardX", "torchvision",
+                     "torchvision.transforms"):
+            try:
+                __import__(name)
+            except Exception:
+                sys.modules[name] = types.ModuleType(name)
+        if not hasattr(sys.modules["matplotlib"], "pyplot"):
+            sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+            sys.modules["matplotlib"].image = sys.modules["matplotlib.image"]
+        if not hasattr(sys.modules["torchvision"], "transforms"):
+            sys.modules["torchvision"].transforms = sys.modules["torchvision.transforms"]
+        if REFERENCE_ROOT not in sys.path:
+            sys.path.insert(0, REFERENCE_ROOT)
+        _cache["kitti"] = _load("_cmr_reference_kitti_dataset", "dataset/KittiDataset.py")
+    return _cache["kitti"]

@@ -150,7 +150,52 @@ def pointnet_case():
     print("pointnet", {k: getattr(v, "shape", v) for k, v in out.items()})
 
 
+def dataset_inputs(case):
+    """Seeded float64 inputs of the dataset-side cases (regenerated identically by tests/test_dataset_ops.py)."""
+    rng = np.random.RandomState(SEED + {"kitti": 0, "small": 1, "ties": 2}[case])
+    if case == "kitti":      # KittiDataset.py:359-360: 10240 of the cloud's points -> 1280 nodes; 40960 points
+        pc = rng.uniform(-40.0, 40.0, size=(3, 40960))
+        return pc, pc[:, rng.choice(40960, 1280 * 8, replace=False)], 1280
+    if case == "small":
+        pc = rng.randn(3, 3001) * 10.0
+        return pc, pc[:, rng.choice(3001, 777, replace=False)], 50
+    pc = np.round(rng.randn(3, 2048) * 2.0)      # integer coordinates: many exact distance ties and duplicates
+    return pc, pc[:, :1500], 64
+
+
+def dataset_case():
+    """FarthestSampler.sample of the REAL reference class + scipy's cKDTree nearest node (KittiDataset.py:107-126,
+    :365-366) on seeded inputs."""
+    from scipy.spatial import cKDTree
+    kd = reference_loader.kitti_dataset()
+    out = {}
+    for case in ("kitti", "small", "ties"):
+        pc, sub, k = dataset_inputs(case)
+        state = np.random.get_state()
+        np.random.seed(SEED)
+        init_idx = np.random.randint(len(sub))          # what :118 is about to draw
+        np.random.seed(SEED)
+        node, idx = kd.FarthestSampler().sample(sub, k)
+        np.random.set_state(state)
+        assert idx[0] == init_idx
+        out[case + "_init"] = np.int64(init_idx)
+        out[case + "_fps_idx"] = idx
+        out[case + "_fps_pts"] = node
+        if case != "ties":                              # scipy leaves exact ties unspecified
+            out[case + "_nearest"] = cKDTree(node.T).query(pc.T, k=1)[1].astype(np.int64)
+        h = hashlib.sha256()
+        h.update(np.ascontiguousarray(pc).tobytes())
+        h.update(np.ascontiguousarray(sub).tobytes())
+        out[case + "_sha"] = np.frombuffer(h.hexdigest().encode(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(HERE, "dataset.npz"), **out)
+    print("dataset.npz", {k: getattr(v, "shape", ()) for k, v in out.items()})
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "dataset":   # only the dataset-side fixture
+        assert reference_loader.available(), "needs /root/reference"
+        dataset_case()
+        sys.exit(0)
     assert reference_loader.available(), "needs /root/reference"
     torch.set_num_threads(1)
     for name, (b, shape, iters, full) in ENV_CASES.items():
@@ -160,3 +205,4 @@ if __name__ == "__main__":
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
+    dataset_case()
