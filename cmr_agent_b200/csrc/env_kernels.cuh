@@ -30,7 +30,7 @@ constexpr int kBucketStride = 384;      // ints per episode in bcnt
 constexpr int kBucketHdr = 64;          // ints after the counters: [0] heavy-queue length, [1] ticket of k_tile_gather
 constexpr int kLightMax = 64;           // a bucket that receives more visible points than this is queued as heavy
 constexpr int kCountSeen = 1 << 24;     // added to a heavy bucket's counter by the first of its two readers
-constexpr int kBucketCap = 1024;    // entries a bucket's buffer holds; fuller buckets are re-read from the id list
+constexpr int kBucketCap = 2048;    // entries a bucket's buffer holds; fuller buckets are re-read from the id list
 
 struct WsLayout {
     size_t off_m, off_seg, off_pix, off_bcnt, off_hq, off_feat, off_bbuf, total;

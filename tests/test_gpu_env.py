@@ -240,7 +240,7 @@ def test_observe_edge_cases(cuda, case):
 @pytest.mark.parametrize("spread", [1, 3, 40])
 def test_observe_dense_buckets(cuda, spread):
     """Thousands of predicted-overlap points on a few pixels: buckets above kLightMax (64) go to the bucket
-    CTAs, buckets above kBucketCap (1024) are rebuilt from the pixel-id list in several chunks; sums stay
+    CTAs, buckets above kBucketCap (2048) are rebuilt from the pixel-id list in several chunks; sums stay
     sequential in point order (bit-identical to the oracle).  Repeated observes on one workspace agree
     (the bucket counters are cleared by the kernel itself)."""
     env = _env()
