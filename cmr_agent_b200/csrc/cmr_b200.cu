@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "env_kernels.cuh"
@@ -104,6 +105,7 @@ static int launch_tile_scatter(const WsLayout &L, const char *ws, const float *i
 
 template <typename Kern, typename... Args>
 static int launch_pdl(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    static const bool chain = [] { const char *e = getenv("CMR_B200_PDL"); return !(e && e[0] == '0'); }();
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;
     cfg.blockDim = block;
@@ -113,7 +115,7 @@ static int launch_pdl(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStream_
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = chain ? 1 : 0;   // CMR_B200_PDL=0: plain stream order (the kernels' griddepcontrol.wait is then a no-op)
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, args...);
     ++g_launches;
     if (e != cudaSuccess) return (int)e;
@@ -189,11 +191,9 @@ static int launch_project(const WsLayout &L, char *ws, const float *pc, const ui
             if (e != cudaSuccess) return (int)e;
         }
     }
-    k_project<PixT><<<dim3(ceil_div(L.groups, kProjWarps), B), 32 * kProjWarps, smem, st>>>(pc, overlap, K, pose, mean, seg, Mws, N, L.ncap,
-                                                                      L.groups, H, W, vec, pix, obs3d, pix_out, mvis_out,
-                                                                      bcnt, bbuf, L.buckets, bcnt ? bcnt + (size_t)B * kBucketStride : nullptr, hq, img_tiles, C,
-                                                                      map_img, map_out);
-    return after_launch();
+    return launch_pdl(k_project<PixT>, dim3(ceil_div(L.groups, kProjWarps), B), dim3(32 * kProjWarps), smem, st, pc, overlap, K,
+                      pose, mean, seg, Mws, N, L.ncap, L.groups, H, W, vec, pix, obs3d, pix_out, mvis_out, bcnt, bbuf,
+                      L.buckets, bcnt ? bcnt + (size_t)B * kBucketStride : (int *)nullptr, hq, img_tiles, C, map_img, map_out);
 }
 
 template <typename PixT>
@@ -389,8 +389,8 @@ int cmr_to_disentangled(float *poses, const float *mean, int B, void *stream) {
 int cmr_step(float *pose, const int64_t *action_r, const int64_t *action_t, const float *rot_tab, const float *t_tab,
              int nbins, int dof6, int B, void *stream) {
     CMR_REQUIRE(pose && action_r && action_t && rot_tab && t_tab && nbins > 0 && B > 0, CMR_EINVAL);
-    k_step<<<ceil_div(B, 128), 128, 0, S_(stream)>>>(pose, action_r, action_t, rot_tab, t_tab, nbins, dof6 ? 1 : 0, B);
-    return after_launch();
+    return launch_pdl(k_step, dim3(ceil_div(B, 128)), dim3(128), 0, S_(stream), pose, action_r, action_t, rot_tab, t_tab, nbins,
+                      dof6 ? 1 : 0, B);
 }
 
 int cmr_expert(const float *pose_source, const float *pose_target, const double *r_steps, const double *t_steps,
@@ -413,9 +413,8 @@ int cmr_reward(const float *target, const float *pc, const uint8_t *mask, const 
     int per_chunk = (int)round_up((size_t)ceil_div(N, nchunks), 1024);
     nchunks = ceil_div(N, per_chunk);
     const bool vec = (N % 4 == 0) && aligned(mask, 4);
-    k_reward<<<dim3(nchunks, B), 256, 0, S_(stream)>>>(target, pc, mask, mean, pose, prev, mode, N, per_chunk, vec,
-                                                       static_cast<unsigned char *>(scratch), reward, dist);
-    return after_launch();
+    return launch_pdl(k_reward, dim3(nchunks, B), dim3(256), 0, S_(stream), target, pc, mask, mean, pose, prev, mode, N,
+                      per_chunk, vec, static_cast<unsigned char *>(scratch), reward, dist);
 }
 
 // ---------------------------------------------------------------------------- pointnet_util ----

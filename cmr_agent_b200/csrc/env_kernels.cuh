@@ -281,7 +281,8 @@ __global__ void __launch_bounds__(32 * kProjWarps) k_project(const float *__rest
                                                   int *__restrict__ hdr, int *__restrict__ hq,
                                                   int img_tiles, int C, const __grid_constant__ CUtensorMap map_img,
                                                   const __grid_constant__ CUtensorMap map_out) {
-    pdl_launch_dependents();   // k_tile_scatter may start its pose-independent preamble now
+    pdl_launch_dependents();   // k_tile_gather may become resident now
+    pdl_wait();                // the pose comes from a k_step, the counters from the previous k_tile_gather
     const int b = blockIdx.y;
     const int lane = threadIdx.x & 31;
     const int g = blockIdx.x * kProjWarps + (threadIdx.x >> 5);
@@ -793,6 +794,10 @@ __device__ __forceinline__ void mat3_plain(const float *A, const float *Bm, floa
 // per-axis matrices for every bin plus, at index nbins, the matrix of angle 0.0 (3-DoF x/z axes).
 __global__ void k_step(float *__restrict__ pose, const int64_t *__restrict__ ar, const int64_t *__restrict__ at,
                        const float *__restrict__ rot_tab, const float *__restrict__ t_tab, int nbins, int dof6, int B) {
+    // programmatic dependent launch: resident while the previous kernel of the stream drains, and the next one
+    // may become resident while this one runs; nothing is read or written before the wait
+    pdl_launch_dependents();
+    pdl_wait();
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     // torch indexing wraps negative indices once (r_steps[-1] is the last bin)
@@ -948,6 +953,8 @@ __global__ void __launch_bounds__(256) k_reward(const float *__restrict__ target
                                                  const float *__restrict__ pose, const float *__restrict__ prev,
                                                  int mode, int N, int per_chunk, bool vec, unsigned char *scratch,
                                                  float *__restrict__ reward, float *__restrict__ dist) {
+    pdl_launch_dependents();
+    pdl_wait();   // the pose may come from the k_step right before
     const int b = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     PoseK s;
@@ -972,28 +979,8 @@ __global__ void __launch_bounds__(256) k_reward(const float *__restrict__ target
     const bool chain = N >= kBmmChainMinCols;
     double acc = 0.0;
     int n = 0;
-    for (int j0 = beg + threadIdx.x * 4; j0 < end; j0 += 256 * 4) {
-        const unsigned f = load_flags4(mk, j0, end, vec);
-        float p[3][4], t[3][4];
-        if (vec && j0 + 3 < end) {
-            // ~20 % of the points are masked in at random: nearly every 32-byte sector is needed, so
-            // load whole rows coalesced and unconditionally (six 16-byte loads in flight per thread)
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                float4 a = ldg_stream4(px + (size_t)r * N + j0), c = ldg_stream4(tx + (size_t)r * N + j0);
-                p[r][0] = a.x; p[r][1] = a.y; p[r][2] = a.z; p[r][3] = a.w;
-                t[r][0] = c.x; t[r][1] = c.y; t[r][2] = c.z; t[r][3] = c.w;
-            }
-        } else {
-#pragma unroll
-            for (int r = 0; r < 3; ++r)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    bool ok = (f >> i & 1) && j0 + i < end;
-                    p[r][i] = ok ? px[(size_t)r * N + j0 + i] : 0.f;
-                    t[r][i] = ok ? tx[(size_t)r * N + j0 + i] : 0.f;
-                }
-        }
+    // four points: their squared distances, in point order, into the fp64 accumulator
+    auto accumulate = [&](unsigned f, const float (&p)[3][4], const float (&t)[3][4]) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             if (!(f >> i & 1)) continue;
@@ -1012,6 +999,48 @@ __global__ void __launch_bounds__(256) k_reward(const float *__restrict__ target
             }
             acc += (double)sqdist3(t[0][i], t[1][i], t[2][i], bx, by, bz);                                       // :287-288
             ++n;
+        }
+    };
+    // ~20 % of the points are masked in at random: nearly every 32-byte sector is needed, so whole rows are
+    // loaded coalesced and unconditionally
+    auto load_vec = [&](int j0, float (&p)[3][4], float (&t)[3][4]) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            float4 a = ldg_stream4(px + (size_t)r * N + j0), c = ldg_stream4(tx + (size_t)r * N + j0);
+            p[r][0] = a.x; p[r][1] = a.y; p[r][2] = a.z; p[r][3] = a.w;
+            t[r][0] = c.x; t[r][1] = c.y; t[r][2] = c.z; t[r][3] = c.w;
+        }
+    };
+    auto one_slice = [&](int j0) {
+        const unsigned f = load_flags4(mk, j0, end, vec);
+        float p[3][4], t[3][4];
+        if (vec && j0 + 3 < end) {
+            load_vec(j0, p, t);
+        } else {
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    bool ok = (f >> i & 1) && j0 + i < end;
+                    p[r][i] = ok ? px[(size_t)r * N + j0 + i] : 0.f;
+                    t[r][i] = ok ? tx[(size_t)r * N + j0 + i] : 0.f;
+                }
+        }
+        accumulate(f, p, t);
+    };
+    for (int j0 = beg + threadIdx.x * 4; j0 < end; j0 += 2 * 256 * 4) {
+        const int j1 = j0 + 256 * 4;
+        if (vec && j1 + 3 < end) {
+            // two slices per round: twelve 16-byte loads and both flag words in flight before the first use
+            const unsigned f0 = load_flags4(mk, j0, end, vec), f1 = load_flags4(mk, j1, end, vec);
+            float p0[3][4], t0[3][4], p1[3][4], t1[3][4];
+            load_vec(j0, p0, t0);
+            load_vec(j1, p1, t1);
+            accumulate(f0, p0, t0);
+            accumulate(f1, p1, t1);
+        } else {
+            one_slice(j0);
+            if (j1 < end) one_slice(j1);
         }
     }
     __shared__ double psum[8];

@@ -227,6 +227,7 @@ __global__ void __launch_bounds__(kGatherThreads, 3)
     const int T = buckets;
     const int slabs = (C + kSlab - 1) / kSlab;
     int *hdr = bcnt + (size_t)B * kBucketStride;         // [0] heavy-queue length, [1] ticket of the bucket CTAs
+    pdl_launch_dependents();
     DBG_MARK(0);
     pdl_wait();   // counters, bucket buffers and queue are written by k_project
     DBG_MARK(1);
