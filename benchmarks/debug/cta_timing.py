@@ -35,7 +35,8 @@ buf = np.zeros(16 * 8192, np.uint64)
 rc = lib.cmr_debug_read(buf.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(buf.nbytes)); assert rc == 0, rc
 nct = min(8192, (HEAVY + 20) * B)
 d = buf.reshape(8192, 16)[:nct].astype(np.int64)
-role = (np.arange(nct) // B) < HEAVY
+yy = np.arange(nct) // B
+role = (yy < 2 * HEAVY) & (yy % 2 == 0)     # bucket CTAs alternate with light CTAs for the first 2 * HEAVY rows
 t0 = d[:, 1].min()     # first CTA released by griddepcontrol.wait
 print('CTAs seen', nct, ' span from first wait-return to last end us', (d[:, 5].max() - t0) / 1e3)
 for name, m in (('light', ~role), ('bucket', role)):

@@ -125,7 +125,7 @@ static int launch_pdl(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStream_
 
 // true when the projected half of obs2d goes through the bucket buffers k_project fills (scatter_kernels.cuh)
 static bool bucket_path(const WsLayout &L, int C) {
-    return L.buckets > 0 && kHeavyCtas + ceil_div(L.buckets, kGatherWarps) <= 65535;
+    return L.buckets > 0 && kHeavyCtas + std::max(ceil_div(L.buckets, kGatherWarps), kHeavyCtas) <= 65535;
 }
 
 // projected half of obs2d from the bucket buffers: k_tile_gather (scatter_kernels.cuh)
@@ -143,8 +143,8 @@ static int launch_gather(const WsLayout &L, const char *ws, const float *img_fea
     memset(&map_proj, 0, sizeof(map_proj));
     const bool tma = vec && P >= kBucketPix &&
                      make_map3d(&map_proj, obs2d, P, 2 * (uint64_t)C, B, kBucketPix, kSlab, CU_TENSOR_MAP_SWIZZLE_128B);
-    // x = episode, y = kHeavyCtas bucket CTAs (the long work starts first), then 4 buckets per CTA
-    const int light = ceil_div(L.buckets, kGatherWarps);
+    // x = episode, y = kHeavyCtas bucket CTAs interleaved with the first light CTAs (8 buckets each), then the rest
+    const int light = std::max(ceil_div(L.buckets, kGatherWarps), kHeavyCtas);
     int rc = allow_smem(k_tile_gather, kGatherSmem);
     if (rc) return rc;
     return launch_pdl(k_tile_gather, dim3(B, kHeavyCtas + light), dim3(kGatherThreads), kGatherSmem, st, bcnt, bbuf,

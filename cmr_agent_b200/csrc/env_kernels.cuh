@@ -7,9 +7,10 @@
 //   feat      [B,C,N]  f32  channel-major; read ONCE per episode by k_feat_compact
 //   workspace: M[B] i32 | seg[B,G] i32 (exclusive prefix of overlap counts per 128 points) |
 //              pix[B,ncap] u16/i32 (pixel id of the m-th predicted-overlap point, rewritten
-//              every observe) | bcnt[B,384] i32 (points per 32-pixel bucket, per observe) |
+//              every observe) | bcnt[B,384] i32 (visible points per 32-pixel bucket, per observe) + header
+//              (length and ticket of the heavy-bucket queue) | hq[B*384] i32 (the queue) |
 //              featT[B,N,C] f32 (rows of the predicted-overlap points, point-major) |
-//              bbuf[B,buckets,1024] u32 (per observe: the visible points of every bucket, unordered)
+//              bbuf[B,buckets,2048] u32 (per observe: the visible points of every bucket, unordered)
 //   obs3d     [B,5,N]  f32 ; obs2d [B,2C,H,W] f32
 #pragma once
 #include "common.cuh"

@@ -55,8 +55,10 @@ static_assert(kBucketCap % kGatherThreads == 0, "whole entries per thread");
 constexpr size_t kGatherSmemLight = kGatherWarps * (sizeof(float) * kTileFloats + sizeof(unsigned) * (kLightMax + 32));
 constexpr size_t kGatherSmemHeavy = sizeof(float) * kTileFloats + sizeof(unsigned) * 3 * kBucketCap + sizeof(int) * 128;
 constexpr size_t kGatherSmem = kGatherSmemLight > kGatherSmemHeavy ? kGatherSmemLight : kGatherSmemHeavy;
-// what a bucket CTA does not need of the light units' tiles stages feature rows: kSlab floats per row
-constexpr int kStageRows = (int)((kGatherSmem - kGatherSmemHeavy) / (sizeof(float) * kSlab));
+// what a bucket CTA does not need of the light units' tiles stages feature rows (kSlab floats per row), together
+// with the two lists that are dead once the entries are sorted
+constexpr size_t kGatherSmemHeavyLive = sizeof(float) * kTileFloats + sizeof(unsigned) * kBucketCap + sizeof(int) * 128;
+constexpr int kStageRows = (int)((kGatherSmem - kGatherSmemHeavyLive) / (sizeof(float) * kSlab));
 static_assert(kStageRows >= 64, "a bucket CTA stages at least 64 rows at a time");
 
 __device__ __forceinline__ unsigned ld_cg_u32(const unsigned *p) {
@@ -232,10 +234,15 @@ __global__ void __launch_bounds__(kGatherThreads, 3)
     pdl_wait();   // counters, bucket buffers and queue are written by k_project
     DBG_MARK(1);
 
-    if ((int)blockIdx.y >= kHeavyCtas) {
+    // roles in launch order (x fastest, then y): bucket CTAs and light CTAs alternate for the first
+    // 2 * kHeavyCtas rows, so that the (mostly idle) bucket CTAs do not fill the first wave alone
+    const int y = (int)blockIdx.y;
+    const bool bucket_role = y < 2 * kHeavyCtas && !(y & 1);
+    const int role_idx = y < 2 * kHeavyCtas ? y >> 1 : y - kHeavyCtas;
+    if (!bucket_role) {
         // ------------------------------------------------------------------ light units: one warp per bucket
         const int b = blockIdx.x;
-        const int bk = ((int)blockIdx.y - kHeavyCtas) * kGatherWarps + warp;
+        const int bk = role_idx * kGatherWarps + warp;
         float *tile = smem_g + warp * kTileFloats;
         unsigned *sk = reinterpret_cast<unsigned *>(smem_g + kGatherWarps * kTileFloats) + warp * (kLightMax + 32);
         int *pc = reinterpret_cast<int *>(sk + kLightMax);   // [32] points per pixel
@@ -342,15 +349,16 @@ __global__ void __launch_bounds__(kGatherThreads, 3)
     } else {
         // ------------------------------------------------------------------ bucket CTA
         float *tile = smem_g;                                             // [64][32] swizzled: sums, then means
-        unsigned *ent = reinterpret_cast<unsigned *>(tile + kTileFloats);  // [kBucketCap] pixel << 24 | point, as they arrive
-        unsigned *ulist = ent + kBucketCap;                               // [kBucketCap] points, grouped by pixel
-        unsigned *slist = ulist + kBucketCap;                             // [kBucketCap] keys, sorted, flagged
+        unsigned *slist = reinterpret_cast<unsigned *>(tile + kTileFloats);   // [kBucketCap] keys, sorted
         int *pcnt = reinterpret_cast<int *>(slist + kBucketCap);          // [32] entries per pixel of this chunk
         int *pstart = pcnt + 32;                                          // [33] exclusive prefix
         int *ptotal = pstart + 33;                                        // [32] entries per pixel, all chunks
         int *misc = ptotal + 32;                                          // [8]
-        float *stage = smem_g + kGatherSmemHeavy / sizeof(float);         // [kStageRows][kSlab] staged feature rows
-        const int first_item = (int)(blockIdx.y * gridDim.x + blockIdx.x);
+        unsigned *ent = reinterpret_cast<unsigned *>(smem_g + kGatherSmemHeavyLive / sizeof(float));   // [kBucketCap] pixel << 24 | point, as they arrive
+        unsigned *ulist = ent + kBucketCap;                               // [kBucketCap] points, grouped by pixel
+        // [kStageRows][kSlab] staged feature rows: over ent and ulist, which are dead once slist is complete
+        float *stage = reinterpret_cast<float *>(ent);
+        const int first_item = (int)(role_idx * gridDim.x + blockIdx.x);
         int qe = ld_cg_s32(hq + first_item);   // speculative: valid iff first_item < items
         const int items = min(ld_cg_s32(hdr), B * kBucketMaxBuckets);
 #ifdef CMR_DBG_TIMING
@@ -552,7 +560,7 @@ __global__ void __launch_bounds__(kGatherThreads, 3)
         DBG_MARK(5);
     }
     // the last bucket CTA to get here clears the queue length for the next observe (they are its only readers)
-    if ((int)blockIdx.y < kHeavyCtas && tid == 0) {
+    if (bucket_role && tid == 0) {
         __threadfence();
         if (atomicAdd(hdr + 1, 1) == kHeavyCtas * B - 1) {
             hdr[0] = 0;
