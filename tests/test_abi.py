@@ -74,3 +74,9 @@ def test_cpu_tensors_are_rejected_not_computed():
         pointnet_util.farthest_point_sample(torch.zeros(1, 8, 3), 2)
     with pytest.raises(_lib.CmrError):
         pointnet_util.square_distance(torch.zeros(1, 8, 3), torch.zeros(1, 8, 3))
+
+
+def test_graft_entry_build_runs_on_a_cpu_box():
+    """The driver's "does it build" check: compiles (or finds) the library and the oracle, checks the ABI version."""
+    import __graft_entry__ as g
+    g.build()
