@@ -151,6 +151,7 @@ def _random_poses(B, seed, scale_t=6.0):
     (dict(num_pt=16384, img_h=160, img_w=512), 2),
     (dict(num_pt=131072, img_h=160, img_w=512), 1),                                  # sweep upper end
     (dict(num_pt=1001, img_h=44, img_w=68), 3),                                      # ragged: N%4, P%128
+    (dict(num_pt=3000, img_h=40, img_w=72), 2),                                      # P=180: P%4==0, P%32!=0 (TMA clips the last tile)
     (dict(num_pt=44, img_h=160, img_w=512), 2),                                      # plain-bmm regime
     (dict(num_pt=45, img_h=160, img_w=512), 2),
     (dict(num_pt=5, img_h=160, img_w=512), 1),
@@ -293,7 +294,7 @@ def test_standalone_project_may_repeat_before_one_scatter(cuda):
     assert torch.equal(env.observation_from_a_pose(data, poses[1])[0], want)
 
 
-@pytest.mark.parametrize("C,img_h,img_w", [(32, 64, 256), (128, 64, 128), (64, 1024, 1024)])
+@pytest.mark.parametrize("C,img_h,img_w", [(32, 64, 256), (128, 64, 128), (64, 1024, 1024), (96, 40, 72), (256, 64, 128), (4, 64, 128)])
 def test_observe_other_channel_counts_and_32bit_pixels(cuda, C, img_h, img_w):
     """The reference hard-codes 64 channels (environment.py:79); the kernel is generic in C and switches
     to 32-bit pixel ids when H*W >= 65535 (here 256x256)."""
