@@ -14,19 +14,23 @@
 //   latency of a warp's dependent instructions, not memory (measured with %globaltimer marks per CTA,
 //   benchmarks/debug/cta_timing.py, and ncu's stall reasons): the add loop is branch-free - the sorted keys
 //   carry first-of-pixel / last-of-pixel flags - and runs in batches whose loads are all in flight.
-//     * light units - ONE WARP each, four per CTA, no CTA-wide barrier on the way.  The count and the (at
+//     * light units - ONE WARP each, eight per CTA, no CTA-wide barrier on the way.  The count and the (at
 //       most kLightMax = 64) entries arrive in one L2 round trip (the entry loads are speculative), two keys
-//       per lane.  Keys (pixel, point) are unique: a key's place in the order is the number of smaller keys,
-//       counted with n shuffles; the sorted keys go through 256 bytes of shared memory.  Sixteen rows are
-//       loaded together and added to a register-carried running sum per pixel.  The 32 x 64 result tile is
-//       transposed through the warp's private shared memory and stored as float4.
-//     * bucket CTAs (the first kHeavyCtas * B CTAs) - buckets with more than kLightMax points: far points
-//       pile up on the horizon row.  Work item i = (queue[i / slabs], slab i % slabs), strided over the bucket
-//       CTAs of the whole batch (an episode looking down a road has ten times the heavy buckets of one facing
-//       a wall).  The CTA bins the entries by pixel in shared memory (32 counters), orders every pixel's list
-//       by point (rank = number of smaller points IN THE PIXEL), and splits the sorted list at pixel
-//       boundaries into four nearly equal parts, one per warp.  A bucket that overflowed its buffer (more than
-//       kBucketCap points) is rebuilt from the episode's pixel-id list in chunks of kBucketCap, in point order.
+//       per lane; every lane at once starts the rows of its entries towards L2.  Keys (pixel, point) are
+//       unique: a key's place in the order is the number of smaller keys, counted with n shuffles; the sorted
+//       keys go through 256 bytes of shared memory.  Two batches of eight rows alternate in registers and are
+//       added to a register-carried running sum per pixel.  The 32 x 64 result tile is built in the warp's
+//       private shared memory in the layout of TMA's 128-byte swizzle and leaves as ONE tiled TMA store.
+//     * bucket CTAs (kHeavyCtas * B of them, alternating with light CTAs in launch order) - buckets with more
+//       than kLightMax points: far points pile up on the horizon row.  Work item i = queue[i], strided over
+//       the bucket CTAs of the whole batch (an episode looking down a road has ten times the heavy buckets of
+//       one facing a wall).  The CTA bins the entries by pixel in shared memory (32 counters), orders every
+//       pixel's list by point (rank = number of smaller points IN THE PIXEL), fetches the rows with cp.async
+//       in sorted order into the shared memory the light units would use for their tiles (about 200 rows per
+//       round trip), and splits the sorted list at pixel boundaries into eight nearly equal parts, one per
+//       warp: a pixel's rows are then consecutive, the inner loop is a load and two additions per row.
+//       A bucket that overflowed its buffer (more than kBucketCap points) is rebuilt from the episode's
+//       pixel-id list in chunks of kBucketCap, in point order.
 //   Counters are cleared by their readers: a light bucket's counter has one reader (its warp), a heavy bucket's
 //   two (its warp, which only learns that the bucket is heavy, and the bucket CTA) - each adds kCountSeen, and
 //   the one that finds it already there clears the counter; the last bucket CTA to finish clears the queue
