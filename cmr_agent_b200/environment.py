@@ -154,7 +154,7 @@ def observation_from_a_pose(data, RT, return_pixels=False):
 def init(data):
     """environment.py:129-140: identity source poses, ground-truth target pose on the device."""
     B = data["pc"].shape[0]
-    pose_target = data["P"].to(DEVICE)
+    pose_target = data["P"].to(DEVICE, non_blocking=True)    # pinned sources copy asynchronously (graph-capturable)
     pose_source = torch.eye(4, device=DEVICE).repeat(B, 1, 1)
     return pose_source, pose_target
 
