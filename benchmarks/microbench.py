@@ -6,6 +6,7 @@ warm-up, inputs resident in HBM.
   python benchmarks/microbench.py frontend [--batch 128]   FPS 40960->1280 + kNN k=64 + grouping
   python benchmarks/microbench.py sweep                    observe (project + tile scatter), 16K-128K points
   python benchmarks/microbench.py env [--batch 32]         per-kernel times of one rollout iteration
+  python benchmarks/microbench.py cost_volume              IterModel's 729-pose warp of one KITTI cloud
 """
 import argparse
 import json
@@ -176,11 +177,38 @@ def env_kernels(args):
     print(json.dumps(res), flush=True)
 
 
+def cost_volume_bench(args):
+    """models/IterModel.py:272-351 at the reference's sizes: one KITTI cloud, 9^3 = 729 candidate poses."""
+    import time
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_cost_volume import _case
+    from cmr_agent_b200 import cost_volume
+    from oracle import cost_volume_oracle as cvo
+    dev = torch.device("cuda:0")
+    nlabel = 9
+    data, mask, poses, scores = _case(1, 40960, 160, 512, nlabel, 3)
+    H, W, Kp = 40, 128, nlabel ** 3
+    dargs = (data["pc"].to(dev), mask.to(dev), poses.to(dev), data["K"], data["pc_geo_feat"].to(dev), scores.to(dev), H, W)
+    t = time_cuda(lambda: cost_volume.warp(*dargs), warm=2, reps=5)
+    wf, occ = cost_volume.warp(*dargs)
+    vis = float((occ > 0).sum()) / Kp
+    M = int(mask.sum())
+    out_bytes = Kp * 68.0 * H * W * 4
+    # CPU: the reference's own chunking (200 poses at a time), here 27 poses timed and scaled
+    t0 = time.time()
+    cvo.warp(data["pc"], mask, poses[:, :27], data["K"], data["pc_geo_feat"], scores, H, W)
+    t_cpu = (time.time() - t0) * Kp / 27
+    print(json.dumps({"bench": "cost_volume", "poses": Kp, "N": 40960, "masked_points": M, "occupied_pixels_per_pose": vis,
+                      "warp_ms": t * 1e3, "poses_per_s": Kp / t, "output_gbs": out_bytes / t / 1e9,
+                      "output_frac_of_hbm": out_bytes / t / 1e9 / PEAK, "cpu_port_ms_scaled_from_27_poses": t_cpu * 1e3,
+                      "cpu_threads": torch.get_num_threads()}), flush=True)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("which", choices=["frontend", "sweep", "env"])
+    ap.add_argument("which", choices=["frontend", "sweep", "env", "cost_volume"])
     ap.add_argument("--batch", type=int, default=None)
     a = ap.parse_args()
     if a.batch is None:
         a.batch = 128 if a.which == "frontend" else 32
-    {"frontend": frontend, "sweep": sweep, "env": env_kernels}[a.which](a)
+    {"frontend": frontend, "sweep": sweep, "env": env_kernels, "cost_volume": cost_volume_bench}[a.which](a)

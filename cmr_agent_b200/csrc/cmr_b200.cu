@@ -129,8 +129,13 @@ static bool bucket_path(const WsLayout &L, int C) {
 }
 
 // projected half of obs2d from the bucket buffers: k_tile_gather (scatter_kernels.cuh)
+// share / out_rows / row0 / mean_channels: see k_tile_gather.  The observation writes the projected half of
+// obs2d [B, 2C, P] (out_rows = 2C, row0 = C); a cost volume writes [E, C, P] (out_rows = C, row0 = 0).
 static int launch_gather(const WsLayout &L, const char *ws, const float *img_feat, int B, int N, int C, int P,
-                         bool copy_image, float *obs2d, cudaStream_t st) {
+                         bool copy_image, float *obs2d, cudaStream_t st, int share = 1, int out_rows = 0, int row0 = -1,
+                         int mean_channels = 1 << 30) {
+    if (out_rows <= 0) out_rows = 2 * C;
+    if (row0 < 0) row0 = C;
     int *bcnt = reinterpret_cast<int *>(const_cast<char *>(ws) + L.off_bcnt);
     const unsigned *bbuf = reinterpret_cast<const unsigned *>(ws + L.off_bbuf);
     const void *pix = ws + L.off_pix;
@@ -142,13 +147,14 @@ static int launch_gather(const WsLayout &L, const char *ws, const float *img_fea
     alignas(64) CUtensorMap map_proj;
     memset(&map_proj, 0, sizeof(map_proj));
     const bool tma = vec && P >= kBucketPix &&
-                     make_map3d(&map_proj, obs2d, P, 2 * (uint64_t)C, B, kBucketPix, kSlab, CU_TENSOR_MAP_SWIZZLE_128B);
+                     make_map3d(&map_proj, obs2d, P, (uint64_t)out_rows, B, kBucketPix, kSlab, CU_TENSOR_MAP_SWIZZLE_128B);
     // x = episode, y = kHeavyCtas bucket CTAs interleaved with the first light CTAs (8 buckets each), then the rest
     const int light = std::max(ceil_div(L.buckets, kGatherWarps), kHeavyCtas);
     int rc = allow_smem(k_tile_gather, kGatherSmem);
     if (rc) return rc;
     return launch_pdl(k_tile_gather, dim3(B, kHeavyCtas + light), dim3(kGatherThreads), kGatherSmem, st, bcnt, bbuf,
-                      L.buckets, hq, pix, L.pix16 ? 1 : 0, M, featT, img_feat, N, L.ncap, C, P, copy_image, vec, tma, obs2d, map_proj);
+                      L.buckets, hq, pix, L.pix16 ? 1 : 0, M, featT, img_feat, N, L.ncap, C, P, copy_image, vec, tma, obs2d, map_proj,
+                      share, (long long)out_rows * P, (long long)row0 * P, row0, mean_channels);
 }
 
 // true when the image half of obs2d can travel as tiled TMA boxes inside k_project
@@ -165,7 +171,7 @@ template <typename PixT>
 static int launch_project(const WsLayout &L, char *ws, const float *pc, const uint8_t *overlap, const float *K,
                           const float *pose, const float *mean, int B, int N, int C, int H, int W, float *obs3d,
                           int32_t *pix_out, int32_t *mvis_out, bool img_tma, const CUtensorMap &map_img,
-                          const CUtensorMap &map_out, bool clear_counters, cudaStream_t st) {
+                          const CUtensorMap &map_out, bool clear_counters, cudaStream_t st, int share = 1) {
     PixT *pix = reinterpret_cast<PixT *>(ws + L.off_pix);
     const int *seg = reinterpret_cast<const int *>(ws + L.off_seg);
     const int *Mws = reinterpret_cast<const int *>(ws + L.off_m);
@@ -193,7 +199,7 @@ static int launch_project(const WsLayout &L, char *ws, const float *pc, const ui
     }
     return launch_pdl(k_project<PixT>, dim3(ceil_div(L.groups, kProjWarps), B), dim3(32 * kProjWarps), smem, st, pc, overlap, K,
                       pose, mean, seg, Mws, N, L.ncap, L.groups, H, W, vec, pix, obs3d, pix_out, mvis_out, bcnt, bbuf,
-                      L.buckets, bcnt ? bcnt + (size_t)B * kBucketStride : (int *)nullptr, hq, img_tiles, C, map_img, map_out);
+                      L.buckets, bcnt ? bcnt + (size_t)B * kBucketStride : (int *)nullptr, hq, share, img_tiles, C, map_img, map_out);
 }
 
 template <typename PixT>
@@ -501,6 +507,66 @@ int cmr_query_ball_point(const float *query, const float *ref, float radius2, in
     CMR_REQUIRE(B <= 65535, CMR_ERANGE);
     k_ball_query<<<dim3(ceil_div(S, 8), B), 256, 0, S_(stream)>>>(query, ref, radius2, nsample, S, N, out);
     return after_launch();
+}
+
+// ------------------------------------------------------------------------------ cost volume ----
+// models/IterModel.py:272-351: the same project -> scatter kernels, K candidate poses per cloud.
+
+size_t cmr_cost_volume_workspace_bytes(int B, int K, int N, int C, int P) {
+    if (B <= 0 || K <= 0 || N <= 0 || C <= 0 || P <= 0 || (long long)B * K > 65535) return 0;
+    return ws_layout(B * K, N, C, P, B).total;
+}
+
+int cmr_cost_volume_prepare(const uint8_t *mask, const float *feat, int B, int K, int N, int C, void *workspace,
+                            void *stream) {
+    CMR_REQUIRE(mask && feat && workspace && B > 0 && K > 0 && N > 0 && C > 0, CMR_EINVAL);
+    CMR_REQUIRE(C <= kMaxC && (C % 4) == 0 && N < (1 << 24) && (long long)B * K <= 65535, CMR_ERANGE);
+    CMR_REQUIRE(aligned(workspace, 256), CMR_EALIGN);
+    WsLayout L = ws_layout(B * K, N, C, 1, B);
+    char *ws = static_cast<char *>(workspace);
+    cudaStream_t st = S_(stream);
+    cudaError_t me = cudaMemsetAsync(ws + L.off_bcnt, 0, L.bcnt_bytes, st);
+    if (me == cudaSuccess) me = cudaMemsetAsync(ws + L.off_zero, 0, sizeof(float) * 3 * (size_t)B * K, st);
+    if (me != cudaSuccess) return (int)me;
+    int *M = reinterpret_cast<int *>(ws + L.off_m);
+    int *seg = reinterpret_cast<int *>(ws + L.off_seg);
+    float *featT = reinterpret_cast<float *>(ws + L.off_feat);
+    k_overlap_scan<<<B, 1024, 0, st>>>(mask, N, L.groups, (N % 4 == 0) && aligned(mask, 4), seg, M);
+    int rc = after_launch();
+    if (rc) return rc;
+    size_t smem = sizeof(float) * kGroup * (C + 1);
+    rc = allow_smem(k_feat_compact<256>, smem);
+    if (rc) return rc;
+    k_feat_compact<256><<<dim3(L.groups, B), 256, smem, st>>>(mask, feat, N, C, L.groups,
+                                                              (N % 4 == 0) && aligned(feat, 16), seg, featT);
+    return after_launch();
+}
+
+int cmr_cost_volume_warp(const float *pc, const uint8_t *mask, const float *Kmat, const float *poses, void *workspace,
+                         int B, int K, int N, int C, int H, int W, int mean_channels, float *out, void *stream) {
+    CMR_REQUIRE(pc && mask && Kmat && poses && workspace && out && K > 0, CMR_EINVAL);
+    int rc = check_observe_dims(B, N, C, H, W);
+    if (rc) return rc;
+    CMR_REQUIRE((long long)B * K <= 65535, CMR_ERANGE);
+    CMR_REQUIRE(mean_channels >= C || mean_channels % kSlab == 0, CMR_EUNSUPPORTED);   // whole slabs are means or sums
+    CMR_REQUIRE(aligned(workspace, 256), CMR_EALIGN);
+    const int E = B * K, P = H * W;
+    WsLayout L = ws_layout(E, N, C, P, B);
+    CMR_REQUIRE(bucket_path(L, C), CMR_EUNSUPPORTED);   // grids of up to 12288 pixels
+    char *ws = static_cast<char *>(workspace);
+    const float *zero_mean = reinterpret_cast<const float *>(ws + L.off_zero);   // X = R p + t: nothing is subtracted
+    alignas(64) CUtensorMap none_a, none_b;
+    memset(&none_a, 0, sizeof(none_a));
+    memset(&none_b, 0, sizeof(none_b));
+    cudaStream_t st = S_(stream);
+    if (L.pix16)
+        rc = launch_project<uint16_t>(L, ws, pc, mask, Kmat, poses, zero_mean, E, N, C, H, W, nullptr, nullptr, nullptr, false,
+                                      none_a, none_b, false, st, K);
+    else
+        rc = launch_project<int32_t>(L, ws, pc, mask, Kmat, poses, zero_mean, E, N, C, H, W, nullptr, nullptr, nullptr, false,
+                                     none_a, none_b, false, st, K);
+    if (rc) return rc;
+    return launch_gather(L, ws, nullptr, E, N, C, P, false, out, st, K, C, 0, mean_channels);
 }
 
 // ------------------------------------------------------------------------------ dataset side ----

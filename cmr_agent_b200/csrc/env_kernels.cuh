@@ -34,23 +34,25 @@ constexpr int kCountSeen = 1 << 24;     // added to a heavy bucket's counter by 
 constexpr int kBucketCap = 2048;    // entries a bucket's buffer holds; fuller buckets are re-read from the id list
 
 struct WsLayout {
-    size_t off_m, off_seg, off_pix, off_bcnt, off_hq, off_feat, off_bbuf, total;
+    size_t off_m, off_seg, off_pix, off_bcnt, off_hq, off_zero, off_feat, off_bbuf, total;
     size_t bcnt_bytes;   // counters + header: what has to be zero before a k_project
     int buckets;   // 32-pixel buckets per episode for (this) P, 0 when the bucket path is not used
     int groups, ncap;
     bool pix16;
 };
 
-inline WsLayout ws_layout(int B, int N, int C, int P) {
+// B episodes (poses); Bf clouds (B / Bf consecutive episodes share a cloud, its overlap prefix and its feature rows)
+inline WsLayout ws_layout(int B, int N, int C, int P, int Bf = 0) {
     WsLayout L;
+    if (Bf <= 0) Bf = B;
     L.groups = ceil_div(N, kGroup);
     L.ncap = (int)round_up((size_t)N, 8);
     L.pix16 = P < 65535;
     size_t o = 0;
     L.off_m = o;
-    o = round_up(o + sizeof(int) * (size_t)B, 256);
+    o = round_up(o + sizeof(int) * (size_t)Bf, 256);
     L.off_seg = o;
-    o = round_up(o + sizeof(int) * (size_t)B * L.groups, 256);
+    o = round_up(o + sizeof(int) * (size_t)Bf * L.groups, 256);
     L.off_pix = o;
     o = round_up(o + sizeof(int) * (size_t)B * L.ncap, 256);
     L.off_bcnt = o;    // points per 32-pixel bucket, rewritten every observe (scatter_kernels.cuh), + header
@@ -59,8 +61,10 @@ inline WsLayout ws_layout(int B, int N, int C, int P) {
     o = round_up(o + L.bcnt_bytes, 256);
     L.off_hq = o;      // queue of the heavy buckets of the whole batch (episode << 16 | bucket), per observe
     o = round_up(o + sizeof(int) * (size_t)B * kBucketMaxBuckets, 256);
+    L.off_zero = o;    // B x 3 zeros: the "cloud mean" of a transform that is not disentangled (cost volumes)
+    o = round_up(o + sizeof(float) * (size_t)B * 3, 256);
     L.off_feat = o;
-    o = round_up(o + sizeof(float) * (size_t)B * N * C, 256);
+    o = round_up(o + sizeof(float) * (size_t)Bf * N * C, 256);
     // bucket buffers come LAST: their size depends on P, nothing before them does (cmr_episode_prepare
     // lays the workspace out without knowing P)
     L.buckets = ceil_div(P, kBucketPix) <= kBucketMaxBuckets ? ceil_div(P, kBucketPix) : 0;
@@ -236,7 +240,7 @@ struct PoseK {
 };
 
 __device__ __forceinline__ void load_posek(PoseK &s, const float *__restrict__ pose, const float *__restrict__ K,
-                                           const float *__restrict__ mean, int b) {
+                                           const float *__restrict__ mean, int b, int bk) {
     const float *P = pose + (size_t)b * 16;
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
@@ -246,7 +250,7 @@ __device__ __forceinline__ void load_posek(PoseK &s, const float *__restrict__ p
         s.m[r] = __ldg(mean + (size_t)b * 3 + r);
     }
 #pragma unroll
-    for (int i = 0; i < 9; ++i) s.K[i] = __ldg(K + (size_t)b * 9 + i);
+    for (int i = 0; i < 9; ++i) s.K[i] = __ldg(K + (size_t)bk * 9 + i);   // bk: the cloud this pose looks at
 }
 
 // environment.py:54-72 for one point.  Returns the pixel id (H*W when outside the frustum).
@@ -279,12 +283,15 @@ __global__ void __launch_bounds__(32 * kProjWarps) k_project(const float *__rest
                                                   PixT *__restrict__ pix, float *__restrict__ obs3d,
                                                   int32_t *__restrict__ pix_out, int32_t *__restrict__ mvis,
                                                   int *__restrict__ bcnt, unsigned *__restrict__ bbuf, int buckets,
-                                                  int *__restrict__ hdr, int *__restrict__ hq,
+                                                  int *__restrict__ hdr, int *__restrict__ hq, int share,
                                                   int img_tiles, int C, const __grid_constant__ CUtensorMap map_img,
                                                   const __grid_constant__ CUtensorMap map_out) {
     pdl_launch_dependents();   // k_tile_gather may become resident now
     pdl_wait();                // the pose comes from a k_step, the counters from the previous k_tile_gather
     const int b = blockIdx.y;
+    // `share` consecutive poses look at the same cloud (cost volumes: hundreds of candidate poses per cloud,
+    // SURVEY 8f rank 4); everything that belongs to the cloud is indexed by bs, what belongs to the pose by b
+    const int bs = b / share;
     const int lane = threadIdx.x & 31;
     const int g = blockIdx.x * kProjWarps + (threadIdx.x >> 5);
     // The image half of obs2d (obs2d[b, 0:C] = img_geo_feat[b], environment.py:83) is a pure copy that does
@@ -306,10 +313,10 @@ __global__ void __launch_bounds__(32 * kProjWarps) k_project(const float *__rest
     if (g >= groups) return;
     const int j0 = g * kGroup + lane * 4;
     PoseK s;
-    load_posek(s, pose, K, mean, b);
+    load_posek(s, pose, K, mean, b, bs);
     const int P = H * W;
     const float wmax = (float)(W - 1), hmax = (float)(H - 1);
-    const float *px = pc + (size_t)b * 3 * N, *py = px + N, *pz = py + N;
+    const float *px = pc + (size_t)bs * 3 * N, *py = px + N, *pz = py + N;
     float x[4], y[4], z[4];
     if (vec && j0 + 3 < N) {
         float4 a = ldg_stream4(px + j0), c = ldg_stream4(py + j0), d = ldg_stream4(pz + j0);
@@ -325,11 +332,12 @@ __global__ void __launch_bounds__(32 * kProjWarps) k_project(const float *__rest
             z[i] = ok ? pz[j0 + i] : 0.f;
         }
     }
-    const unsigned flags = load_flags4(overlap + (size_t)b * N, j0, N, vec);
+    const unsigned flags = load_flags4(overlap + (size_t)bs * N, j0, N, vec);
     // The 3-D branch multiplies all N columns at once (:93,95), the 2-D branch only the M predicted-
     // overlap columns (:55,58): each follows the bmm regime of its own column count.
     const bool chain3d = N >= kBmmChainMinCols;
-    const bool chain2d = __ldg(M + b) >= kBmmChainMinCols;
+    // (a cost volume - no obs3d - projects all N columns before it masks, models/IterModel.py:281-307)
+    const bool chain2d = obs3d ? __ldg(M + bs) >= kBmmChainMinCols : chain3d;
     int id[4], id2[4];
     unsigned cam = 0, cam2 = 0;
 #pragma unroll
@@ -353,7 +361,9 @@ __global__ void __launch_bounds__(32 * kProjWarps) k_project(const float *__rest
     }
     // ---- obs3d = cat(pc, overlap.float(), in_cam.float())  (:121-124)
     float *o = obs3d + (size_t)b * 5 * N;
-    if (vec && j0 + 3 < N) {
+    if (!obs3d) {
+        // cost volumes need only the 2-D branch
+    } else if (vec && j0 + 3 < N) {
         stg_stream4(o + j0, make_float4(x[0], x[1], x[2], x[3]));
         stg_stream4(o + (size_t)N + j0, make_float4(y[0], y[1], y[2], y[3]));
         stg_stream4(o + 2 * (size_t)N + j0, make_float4(z[0], z[1], z[2], z[3]));
@@ -382,7 +392,7 @@ __global__ void __launch_bounds__(32 * kProjWarps) k_project(const float *__rest
         int t = __shfl_up_sync(kFull, incl, o2);
         if (lane >= o2) incl += t;
     }
-    int pos = __ldg(seg + (size_t)b * groups + g) + incl - mine;
+    int pos = __ldg(seg + (size_t)bs * groups + g) + incl - mine;
     PixT *pw = pix + (size_t)b * ncap;
     const int pos0 = pos;
 #pragma unroll

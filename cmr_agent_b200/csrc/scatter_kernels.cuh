@@ -110,8 +110,8 @@ __device__ __forceinline__ LaneRows lane_rows(float *tile, int lane) { return La
 
 // tile -> proj[(c0 + r) * P + p0 + pixel].  tma: one tiled TMA store by the calling thread (all writers have
 // fenced and synchronised; returns when the tile has been read).  Otherwise NT threads copy it (t = 0..NT-1).
-__device__ __forceinline__ void store_tile_tma(const float *tile, const CUtensorMap *map, int c0, int C, int p0, int b) {
-    tma_store_3d(map, p0, C + c0, b, tile);
+__device__ __forceinline__ void store_tile_tma(const float *tile, const CUtensorMap *map, int y, int p0, int b) {
+    tma_store_3d(map, p0, y, b, tile);
     bulk_commit();
     bulk_wait_read_all();
 }
@@ -226,7 +226,11 @@ __global__ void __launch_bounds__(kGatherThreads, 3)
     k_tile_gather(int *bcnt, const unsigned *bbuf, int buckets, const int *hq, const void *pix, int pix16, const int *M,
                   const float *__restrict__ featT, const float *__restrict__ img_feat, int N, int ncap, int C, int P,
                   bool copy_image, bool vec, bool tma, float *__restrict__ obs2d,
-                  const __grid_constant__ CUtensorMap map_proj) {
+                  const __grid_constant__ CUtensorMap map_proj, int share, long long out_estride, long long proj_off,
+                  int tma_y0, int mean_channels) {
+    // share: consecutive episodes (poses) that look at the same cloud, i.e. the same feature rows.
+    // Output of episode e: obs2d + e * out_estride + proj_off, rows of P floats; the tensor map's row of channel c
+    // is tma_y0 + c.  Channels >= mean_channels are SUMS, not means (the occupancy row of a cost volume).
     extern __shared__ __align__(1024) float smem_g[];   // the tiles come first: 1024-byte aligned for the swizzle
     const int B = (int)gridDim.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -251,8 +255,9 @@ __global__ void __launch_bounds__(kGatherThreads, 3)
         unsigned *sk = reinterpret_cast<unsigned *>(smem_g + kGatherWarps * kTileFloats) + warp * (kLightMax + 32);
         int *pc = reinterpret_cast<int *>(sk + kLightMax);   // [32] points per pixel
         const int p0 = bk * kBucketPix;
-        float *out = obs2d + (size_t)b * 2 * C * P;
-        float *proj = out + (size_t)C * P;
+        float *out = obs2d + (size_t)b * out_estride;
+        float *proj = out + proj_off;
+        const int bs = b / share;
         if (bk < T) {
             const unsigned *src = bbuf + ((size_t)b * buckets + bk) * kBucketCap;
             const unsigned e0 = ld_cg_u32(src + lane), e1 = ld_cg_u32(src + 32 + lane);   // speculative
@@ -265,9 +270,9 @@ __global__ void __launch_bounds__(kGatherThreads, 3)
             if (n > 0 && n <= kLightMax) {
                 // all the rows this unit will add: on their way to L2 before the first one is needed
                 if (lane < n)
-                    for (int q = 0; q < C; q += 32) prefetch_l2(featT + ((size_t)b * N + (e0 >> 7)) * C + q);
+                    for (int q = 0; q < C; q += 32) prefetch_l2(featT + ((size_t)bs * N + (e0 >> 7)) * C + q);
                 if (lane + 32 < n)
-                    for (int q = 0; q < C; q += 32) prefetch_l2(featT + ((size_t)b * N + (e1 >> 7)) * C + q);
+                    for (int q = 0; q < C; q += 32) prefetch_l2(featT + ((size_t)bs * N + (e1 >> 7)) * C + q);
             }
 #ifdef CMR_DBG_TIMING
             if (threadIdx.x == 0) g_dbg[(blockIdx.y * gridDim.x + blockIdx.x) * 16 + 7] = (unsigned long long)(n + (e0 & 0) + (e1 & 0));
@@ -284,7 +289,7 @@ __global__ void __launch_bounds__(kGatherThreads, 3)
                     fence_async_proxy();
                     __syncwarp();
                     if (lane == 0)
-                        for (int slab = 0; slab < slabs; ++slab) store_tile_tma(tile, &map_proj, kSlab * slab, C, p0, b);
+                        for (int slab = 0; slab < slabs; ++slab) store_tile_tma(tile, &map_proj, tma_y0 + kSlab * slab, p0, b);
                     __syncwarp();
                 } else {
                     store_zeros(C, p0, P, vec, proj, lane);
@@ -330,16 +335,16 @@ __global__ void __launch_bounds__(kGatherThreads, 3)
                 for (int slab = 0; slab < slabs; ++slab) {
                     const int c0 = kSlab * slab;
                     // lanes beyond C read channel 0 instead (their rows of the tile are never stored)
-                    const float *rows = featT + (size_t)b * N * C + (c0 + 2 * lane < C ? c0 + 2 * lane : 0);
+                    const float *rows = featT + (size_t)bs * N * C + (c0 + 2 * lane < C ? c0 + 2 * lane : 0);
                     zero_tile<32>(tile, lane);
                     __syncwarp();
                     add_rows<false>(sk, 0, n, rows, (unsigned)C, tl);
-                    mean_pass(multi, my_cnt, tl);
+                    if (c0 < mean_channels) mean_pass(multi, my_cnt, tl);
                     DBG_MARK(3);
                     if (tma) {
                         fence_async_proxy();
                         __syncwarp();
-                        if (lane == 0) store_tile_tma(tile, &map_proj, c0, C, p0, b);
+                        if (lane == 0) store_tile_tma(tile, &map_proj, tma_y0 + c0, p0, b);
                     } else {
                         __syncwarp();
                         store_tile<32>(tile, c0, C, p0, P, proj, lane);
@@ -377,7 +382,8 @@ __global__ void __launch_bounds__(kGatherThreads, 3)
             int *cb = bcnt + (size_t)b * kBucketStride + bk;
             const int c = ld_cg_s32(cb) & (kCountSeen - 1);
             const int p0 = bk * kBucketPix;
-            float *proj = obs2d + (size_t)b * 2 * C * P + (size_t)C * P;
+            float *proj = obs2d + (size_t)b * out_estride + proj_off;
+            const int bs = b / share;
             const bool chunked = c < 0 || c > kBucketCap;
             DBG_MARK(2);
             if (tid < 32) {
@@ -428,7 +434,7 @@ __global__ void __launch_bounds__(kGatherThreads, 3)
             // cp.async, in sorted order - ONE round trip for a typical bucket instead of one per batch of a warp -
             // and a pixel's rows are then consecutive: the inner loop is a load and two additions per row.
             auto add_chunk = [&](int n, int c0) {
-                const float *rbase = featT + (size_t)b * N * C + c0;
+                const float *rbase = featT + (size_t)bs * N * C + c0;
                 const int pieces = min(kSlab, C - c0) >> 2;   // 16-byte pieces of a row in this slab
                 const int ps = pstart[lane];
                 const int lo = (warp * n + kGatherWarps - 1) / kGatherWarps, hi = ((warp + 1) * n + kGatherWarps - 1) / kGatherWarps;
@@ -475,11 +481,11 @@ __global__ void __launch_bounds__(kGatherThreads, 3)
                 // sums -> means: warp w takes the pixels p % 8 == w
                 const int my_cnt = ptotal[lane];
                 const unsigned multi = __ballot_sync(kFull, my_cnt > 1) & (0x01010101u << warp);
-                mean_pass(multi, my_cnt, lane_rows(tile, lane));
+                if (c0 < mean_channels) mean_pass(multi, my_cnt, lane_rows(tile, lane));
                 if (tma) {
                     fence_async_proxy();
                     __syncthreads();
-                    if (tid == 0) store_tile_tma(tile, &map_proj, c0, C, p0, b);
+                    if (tid == 0) store_tile_tma(tile, &map_proj, tma_y0 + c0, p0, b);
                 } else {
                     __syncthreads();
                     store_tile<kGatherThreads>(tile, c0, C, p0, P, proj, tid);
@@ -491,7 +497,7 @@ __global__ void __launch_bounds__(kGatherThreads, 3)
                 for (int i = tid; i < c; i += kGatherThreads) {
                     const unsigned e = ld_cg_u32(src + i);
                     const unsigned pl = e & 31u;
-                    for (int q = 0; q < C; q += 32) prefetch_l2(featT + ((size_t)b * N + (e >> 7)) * C + q);
+                    for (int q = 0; q < C; q += 32) prefetch_l2(featT + ((size_t)bs * N + (e >> 7)) * C + q);
                     ent[i] = (pl << 24) | (e >> 7);
                     atomicAdd(&pcnt[pl], 1);
                 }
@@ -508,7 +514,7 @@ __global__ void __launch_bounds__(kGatherThreads, 3)
             } else {
                 // the bucket overflowed its buffer: rebuild it from the episode's pixel-id list, kBucketCap
                 // points at a time, in point order (a chunk's points all precede the next chunk's); per slab
-                const int m_total = min(ld_cg_s32(M + b), N);
+                const int m_total = min(ld_cg_s32(M + bs), N);
                 for (int slab = 0; slab < slabs; ++slab) {
                     zero_tile<kGatherThreads>(tile, tid);
                     if (tid < 32) ptotal[tid] = 0;

@@ -172,6 +172,25 @@ CMR_API int cmr_group_points(const float *xyz, const float *points, const float 
  * synchronises `stream`.  0 = none. */
 CMR_API int cmr_take_fault(void *stream);
 
+/* ------------------------------------------------------------------ cost volume ---- */
+
+/* The pose-sampling cost volume of models/IterModel.py:272-351: the same projection + ordered scatter as the
+ * observation, for K candidate poses per cloud, without the disentangling (X = R p + t) and for all N columns
+ * at once (the reference projects before it masks).
+ *   cmr_cost_volume_prepare  once per batch of clouds: compacts the rows of the masked points.
+ *                            mask [B,N] u8 (IterModel uses pc_overlap_pred[0] for every cloud), feat [B,C,N] f32.
+ *   cmr_cost_volume_warp     pc [B,3,N], Kmat [B,3,3], poses [B*K,4,4] f32 (rows 0..2 = the [3,4] of :276-279)
+ *                            -> out [B*K, C, H*W] f32: channel c < mean_channels = scatter-mean of feat[c] over the
+ *                            masked points that land in the pixel (:341), channel c >= mean_channels = their SUM
+ *                            (:343: pass the in-camera scores as an extra channel).  mean_channels is a multiple of
+ *                            64 or >= C.  Sums run in point order.  B*K <= 65535, H*W <= 12288. */
+CMR_API size_t cmr_cost_volume_workspace_bytes(int B, int K, int N, int C, int P);
+CMR_API int cmr_cost_volume_prepare(const uint8_t *mask, const float *feat, int B, int K, int N, int C,
+                                    void *workspace, void *stream);
+CMR_API int cmr_cost_volume_warp(const float *pc, const uint8_t *mask, const float *Kmat, const float *poses,
+                                 void *workspace, int B, int K, int N, int C, int H, int W, int mean_channels,
+                                 float *out, void *stream);
+
 /* ------------------------------------------------------------------ dataset side ---- */
 
 /* FarthestSampler.sample - dataset/KittiDataset.py:107-126 (= dataset/NuScenesDataset.py:25-44), float64 like

@@ -1,0 +1,90 @@
+"""Cost-volume warp (models/IterModel.py:272-351): the CUDA path (cmr_cost_volume_* through
+cmr_agent_b200.cost_volume.warp) against the CPU restatement of the reference's torch expressions
+(oracle/cost_volume_oracle.py - parity unpinned: the reference cannot run these lines without a GPU).
+Bar: warped features and occupancy BIT-EXACT (ordered sums), which implies identical pixel indices and masks."""
+import math
+
+import pytest
+import torch
+
+from cmr_agent_b200 import synth
+from oracle import cost_volume_oracle as cvo
+
+
+def _poses(B, nlabel, r_amp, t_amp, seed):
+    """delta_RT_inv[:, :, 0:3, :] of IterModel.sample_poses (:133-172): nlabel^3 poses, rotation about y, shifts in x, z."""
+    g = torch.Generator().manual_seed(seed)
+    base = torch.linspace(-(nlabel - 1) / 2, (nlabel - 1) / 2, nlabel)
+    out = torch.zeros(B, nlabel, nlabel, nlabel, 4, 4)
+    for b in range(B):
+        jitter = torch.rand(3, generator=g) * 0.3
+        for i, ry in enumerate(base * (2 * r_amp / (nlabel - 1)) + jitter[0] * 0.01):
+            c, s = math.cos(float(ry)), math.sin(float(ry))
+            R = torch.tensor([[c, 0.0, s], [0.0, 1.0, 0.0], [-s, 0.0, c]])
+            for j, tx in enumerate(base * (2 * t_amp / (nlabel - 1)) + jitter[1]):
+                for k, tz in enumerate(base * (2 * t_amp / (nlabel - 1)) + jitter[2]):
+                    m = torch.eye(4)
+                    m[:3, :3] = R
+                    m[0, 3], m[2, 3] = tx, tz
+                    out[b, i, j, k] = torch.linalg.inv(m)
+    return out.view(B, -1, 4, 4)[:, :, 0:3, :].contiguous()
+
+
+def _case(B, N, img_h, img_w, nlabel, seed, dense=False):
+    data = synth.make_batch(B, seed=seed, num_pt=N, img_h=img_h, img_w=img_w)
+    g = torch.Generator().manual_seed(seed + 1)
+    scores = torch.rand(B, N, generator=g)
+    mask = data["pc_overlap_pred"][0].clone()
+    if dense:
+        mask[:] = True
+    # the sampled poses perturb the GROUND-TRUTH registration, so that the cloud is in view
+    gt = data["P"][:, 0:3, :]
+    d = _poses(B, nlabel, 0.15, 2.0, seed)
+    R = d[:, :, :, 0:3] @ gt[:, None, :, 0:3]
+    t = d[:, :, :, 0:3] @ gt[:, None, :, 3:4] + d[:, :, :, 3:4]
+    poses = torch.cat([R, t], dim=-1).contiguous()
+    return data, mask, poses, scores
+
+
+@pytest.mark.parametrize("B,N,img_h,img_w,nlabel,dense", [
+    (1, 4096, 160, 512, 3, False),        # KITTI grid, 27 poses
+    (2, 3001, 64, 256, 2, False),         # two clouds share the first one's mask; N % 4 != 0
+    (1, 8192, 160, 320, 3, True),         # NuScenes grid, every point masked in: dense buckets
+])
+def test_oracle_shapes_and_occupancy(B, N, img_h, img_w, nlabel, dense):
+    data, mask, poses, scores = _case(B, N, img_h, img_w, nlabel, 3, dense)
+    H, W = img_h // 4, img_w // 4
+    wf, occ = cvo.warp(data["pc"], mask, poses, data["K"], data["pc_geo_feat"], scores, H, W)
+    assert tuple(wf.shape) == (B, nlabel ** 3, 64, H * W) and tuple(occ.shape) == (B, nlabel ** 3, H * W)
+    assert float(occ.sum()) > 0 and float(wf.abs().sum()) > 0          # the cloud is in view
+    assert bool(((occ > 0) == (wf.abs().sum(dim=2) > 0)).all())        # a pixel has features iff it has points
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,N,img_h,img_w,nlabel,dense", [
+    (1, 4096, 160, 512, 3, False),
+    (2, 3001, 64, 256, 2, False),
+    (1, 8192, 160, 320, 3, True),
+    (1, 40960, 160, 512, 3, False),       # the reference's sizes (27 of its 729 poses)
+])
+def test_gpu_matches_oracle(cuda, B, N, img_h, img_w, nlabel, dense):
+    from cmr_agent_b200 import cost_volume
+    data, mask, poses, scores = _case(B, N, img_h, img_w, nlabel, 3, dense)
+    H, W = img_h // 4, img_w // 4
+    want_f, want_o = cvo.warp(data["pc"], mask, poses, data["K"], data["pc_geo_feat"], scores, H, W)
+    got_f, got_o = cost_volume.warp(data["pc"].to(cuda), mask.to(cuda), poses.to(cuda), data["K"],
+                                    data["pc_geo_feat"].to(cuda), scores.to(cuda), H, W)
+    torch.cuda.synchronize()
+    assert torch.equal(got_o.cpu(), want_o), "occupancy (ordered sum of the in-camera scores) differs"
+    assert torch.equal(got_f.cpu(), want_f), "warped features (ordered scatter-mean) differ"
+    # a second call on fresh buffers gives the same bits (the counters are left clean)
+    again_f, again_o = cost_volume.warp(data["pc"].to(cuda), mask.to(cuda), poses.to(cuda), data["K"],
+                                        data["pc_geo_feat"].to(cuda), scores.to(cuda), H, W)
+    assert torch.equal(again_f, got_f) and torch.equal(again_o, got_o)
+
+
+def test_cost_volume_rejects_cpu_tensors():
+    from cmr_agent_b200 import _lib, cost_volume
+    data, mask, poses, scores = _case(1, 256, 64, 64, 2, 1)
+    with pytest.raises(_lib.CmrError):
+        cost_volume.warp(data["pc"], mask, poses, data["K"], data["pc_geo_feat"], scores, 16, 16)
