@@ -55,6 +55,8 @@ def parse_args():
     ap.add_argument("--cpu-episodes", type=int, default=32, help="episodes in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--streams", type=int, default=2, choices=[1, 2],
+                    help="2: step + reward run on a second stream beside the scatter stage (default); 1: one stream")
     return ap.parse_args()
 
 
@@ -249,6 +251,8 @@ class DeviceRollout:
         self.dist = torch.empty(iters, B, device=dev)
         self.mean = torch.empty(B, 3, device=dev)
         self.copied = ctypes.c_int(0)
+        self.two_streams = False
+        self.side = torch.cuda.Stream(dev)
 
     def run(self, events=None, count_visible=True):
         """events: per iteration (e0, e1, e2) recorded before cmr_project, between the two observe kernels
@@ -263,6 +267,30 @@ class DeviceRollout:
             if events is not None:
                 events[it][0].record()
             mv = p(self.mvis[it]) if count_visible else None
+            prev = p(self.dist[it - 1]) if it else None
+            if events is None and self.two_streams:
+                # the scatter stage only needs what k_project left, and step + reward only need k_project to have
+                # READ the pose: the two run side by side (a C-ABI host owns the streams it passes in)
+                main, side = torch.cuda.current_stream(), self.side
+                L.call("cmr_project", p(self.pc), p(self.overlap), p(self.K), p(self.pose), p(self.mean), p(self.ws),
+                       B, N, C, H, W, p(self.obs3d), None, mv, p(self.img_feat), p(self.obs2d),
+                       ctypes.byref(self.copied), 1, st)   # 1 = CMR_PROJECT_PAIRED
+                side.wait_stream(main)
+                L.call("cmr_tile_scatter", p(self.img_feat), p(self.K), p(self.ws), B, N, C, H, W,
+                       0 if self.copied.value else 1, p(self.obs2d), st)
+                sst = ctypes.c_void_p(side.cuda_stream)
+                L.call("cmr_step", p(self.pose), p(self.a_r[it]), p(self.a_t[it]), p(self.rot), p(self.tt), self.nbins,
+                       0, B, sst)
+                stepped = torch.cuda.Event()
+                stepped.record(side)
+                L.call("cmr_reward", p(self.target), p(self.pc), p(self.mask), p(self.mean), p(self.pose), prev, 0, B, N,
+                       p(self.scratch), p(self.rew[it]), p(self.dist[it]), sst)
+                # the next k_project reads the new pose: it waits for the step, not for the reward (which reads the
+                # pose at most, and is followed on its own stream by the next step)
+                main.wait_event(stepped)
+                if it == self.iters - 1:
+                    main.wait_stream(side)
+                continue
             if events is None:   # the product call
                 L.call("cmr_observe", p(self.pc), p(self.overlap), p(self.img_feat), p(self.K), p(self.pose), p(self.mean),
                        p(self.ws), B, N, C, H, W, p(self.obs2d), p(self.obs3d), None, mv, st)
@@ -276,7 +304,6 @@ class DeviceRollout:
                 events[it][2].record()
             L.call("cmr_step", p(self.pose), p(self.a_r[it]), p(self.a_t[it]), p(self.rot), p(self.tt), self.nbins,
                    0, B, st)
-            prev = p(self.dist[it - 1]) if it else None
             L.call("cmr_reward", p(self.target), p(self.pc), p(self.mask), p(self.mean), p(self.pose), prev, 0, B, N,
                    p(self.scratch), p(self.rew[it]), p(self.dist[it]), st)
 
@@ -348,6 +375,9 @@ def run_b200_arm(args, rank, world, local):
     for _ in range(max(args.warmup, 3)):
         roll.run()
     torch.cuda.synchronize(dev)
+    # what one stream, launched eagerly, leaves behind: the timed (graph, possibly two-stream) rollout must leave the same bits
+    want = [t.clone() for t in (roll.pose, roll.rew, roll.dist, roll.obs2d, roll.obs3d)]
+    roll.two_streams = args.streams == 2
 
     sampler = ClockSampler(local)
     # ---- timed region: the rollout captured ONCE into a CUDA graph (kernels, the memset and the two tiny torch
@@ -365,6 +395,11 @@ def run_b200_arm(args, rank, world, local):
     for _ in range(max(args.warmup, 3)):
         graph.replay()
     torch.cuda.synchronize(dev)
+    for name, a, b_ in zip(("pose", "reward", "distance", "obs2d", "obs3d"), want,
+                           (roll.pose, roll.rew, roll.dist, roll.obs2d, roll.obs3d)):
+        if not torch.equal(a, b_):
+            raise SystemExit(f"bench: the timed rollout's {name} differs from the one-stream eager rollout")
+    del want
     sampler.start()
     t_begin = sampler.mark()
     dt = timed(graph.replay, args.steps, dev)
@@ -458,13 +493,16 @@ def run_b200_arm(args, rank, world, local):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "timing": {"value": "K replays of the rollout captured as one CUDA graph, CUDA events, max over ranks",
+            "timing": {"value": "K replays of the rollout captured as one CUDA graph"
+                                + (" (two streams: step + reward run beside the scatter stage and the next projection, which "
+                                   "waits for the step only)" if args.streams == 2 else " (one stream)")
+                                + ", CUDA events, max over ranks; its outputs equal a one-stream eager rollout's bit for bit",
                        "roofline": f"eager pass of {esteps} rollouts, each queued behind a 3 ms spin kernel, CUDA events around "
                                    "the observe stages; share_of_step is relative to an iteration of that pass",
                        "eager_us_per_iteration": iter_s * 1e6},
             "config": {"workload": "kitti_b32x10", "episodes_per_gpu": B, "iterations": iters,
                        "registration_steps_per_bench_step": B * iters * world, "num_pt": N, "image": "160x512",
-                       "grid": f"{H}x{W}", "channels": C, "sharding": f"episodes/{world}gpu, no data-path collective",
+                       "grid": f"{H}x{W}", "channels": C, "sharding": f"episodes/{world}gpu, no data-path collective", "streams": args.streams,
                        "l2": "per-rollout inputs (%.0f MB) exceed the 126 MB L2" %
                              ((roll.feat.numel() + roll.pc.numel() * 2 + roll.img_feat.numel()) * 4 / 1e6)},
             "roofline": roofline, "roofline_secondary": roofline2, "cpu_baseline": cpu_base, "e2e": e2e, "gpu_launches": int(launches),

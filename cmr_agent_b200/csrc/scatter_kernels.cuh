@@ -44,6 +44,9 @@
 
 namespace cmr {
 
+#ifndef CMR_GATHER_MINB
+#define CMR_GATHER_MINB 3
+#endif
 constexpr int kHeavyCtas = 16;          // bucket CTAs per episode of the batch
 constexpr int kGatherThreads = 256;     // 8 warps = 8 light units
 constexpr int kGatherWarps = kGatherThreads / 32;
@@ -222,7 +225,7 @@ __device__ __forceinline__ void mean_pass(unsigned mask, int cnt_of_lane, const 
     }
 }
 
-__global__ void __launch_bounds__(kGatherThreads, 3)
+__global__ void __launch_bounds__(kGatherThreads, CMR_GATHER_MINB)
     k_tile_gather(int *bcnt, const unsigned *bbuf, int buckets, const int *hq, const void *pix, int pix16, const int *M,
                   const float *__restrict__ featT, const float *__restrict__ img_feat, int N, int ncap, int C, int P,
                   bool copy_image, bool vec, bool tma, float *__restrict__ obs2d,
