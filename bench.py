@@ -56,7 +56,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--streams", type=int, default=2, choices=[1, 2],
-                    help="2: step + reward run on a second stream beside the scatter stage (default); 1: one stream")
+                    help="2: the reward runs on a second stream beside the next observation (default); 1: one stream")
     return ap.parse_args()
 
 
@@ -269,25 +269,24 @@ class DeviceRollout:
             mv = p(self.mvis[it]) if count_visible else None
             prev = p(self.dist[it - 1]) if it else None
             if events is None and self.two_streams:
-                # the scatter stage only needs what k_project left, and step + reward only need k_project to have
-                # READ the pose: the two run side by side (a C-ABI host owns the streams it passes in)
+                # the reward is a training signal nothing in the loop waits for: it runs on a second stream beside
+                # the next projection and scatter.  Everything the agent's next action would depend on (observe,
+                # then step) keeps its order on the first stream.  (A C-ABI host owns the streams it passes in.)
                 main, side = torch.cuda.current_stream(), self.side
-                L.call("cmr_project", p(self.pc), p(self.overlap), p(self.K), p(self.pose), p(self.mean), p(self.ws),
-                       B, N, C, H, W, p(self.obs3d), None, mv, p(self.img_feat), p(self.obs2d),
-                       ctypes.byref(self.copied), 1, st)   # 1 = CMR_PROJECT_PAIRED
-                side.wait_stream(main)
-                L.call("cmr_tile_scatter", p(self.img_feat), p(self.K), p(self.ws), B, N, C, H, W,
-                       0 if self.copied.value else 1, p(self.obs2d), st)
                 sst = ctypes.c_void_p(side.cuda_stream)
+                L.call("cmr_observe", p(self.pc), p(self.overlap), p(self.img_feat), p(self.K), p(self.pose), p(self.mean),
+                       p(self.ws), B, N, C, H, W, p(self.obs2d), p(self.obs3d), None, mv, st)
+                if it:
+                    main.wait_event(rewarded)   # the previous reward may still be reading the pose this step rewrites
                 L.call("cmr_step", p(self.pose), p(self.a_r[it]), p(self.a_t[it]), p(self.rot), p(self.tt), self.nbins,
-                       0, B, sst)
+                       0, B, st)
                 stepped = torch.cuda.Event()
-                stepped.record(side)
+                stepped.record(main)
+                side.wait_event(stepped)
                 L.call("cmr_reward", p(self.target), p(self.pc), p(self.mask), p(self.mean), p(self.pose), prev, 0, B, N,
                        p(self.scratch), p(self.rew[it]), p(self.dist[it]), sst)
-                # the next k_project reads the new pose: it waits for the step, not for the reward (which reads the
-                # pose at most, and is followed on its own stream by the next step)
-                main.wait_event(stepped)
+                rewarded = torch.cuda.Event()
+                rewarded.record(side)
                 if it == self.iters - 1:
                     main.wait_stream(side)
                 continue
@@ -494,8 +493,8 @@ def run_b200_arm(args, rank, world, local):
             "warmup": max(args.warmup, 3), "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "timing": {"value": "K replays of the rollout captured as one CUDA graph"
-                                + (" (two streams: step + reward run beside the scatter stage and the next projection, which "
-                                   "waits for the step only)" if args.streams == 2 else " (one stream)")
+                                + (" (two streams: the reward of an iteration runs beside the next iteration's observation; "
+                                   "observe and step keep their order)" if args.streams == 2 else " (one stream)")
                                 + ", CUDA events, max over ranks; its outputs equal a one-stream eager rollout's bit for bit",
                        "roofline": f"eager pass of {esteps} rollouts, each queued behind a 3 ms spin kernel, CUDA events around "
                                    "the observe stages; share_of_step is relative to an iteration of that pass",
