@@ -148,13 +148,18 @@ static int launch_gather(const WsLayout &L, const char *ws, const float *img_fea
     memset(&map_proj, 0, sizeof(map_proj));
     const bool tma = vec && P >= kBucketPix &&
                      make_map3d(&map_proj, obs2d, P, (uint64_t)out_rows, B, kBucketPix, kSlab, CU_TENSOR_MAP_SWIZZLE_128B);
+    // image half of obs2d inside this kernel (cmr_project left it to us): boxes of the same shape, same swizzle
+    alignas(64) CUtensorMap map_img;
+    memset(&map_img, 0, sizeof(map_img));
+    const bool img_tma = copy_image && tma && share == 1 && out_rows == 2 * C && aligned(img_feat, 16) &&
+                         make_map3d(&map_img, img_feat, P, (uint64_t)C, B, kBucketPix, kSlab, CU_TENSOR_MAP_SWIZZLE_128B);
     // x = episode, y = kHeavyCtas bucket CTAs interleaved with the first light CTAs (8 buckets each), then the rest
     const int light = std::max(ceil_div(L.buckets, kGatherWarps), kHeavyCtas);
     int rc = allow_smem(k_tile_gather, kGatherSmem);
     if (rc) return rc;
     return launch_pdl(k_tile_gather, dim3(B, kHeavyCtas + light), dim3(kGatherThreads), kGatherSmem, st, bcnt, bbuf,
                       L.buckets, hq, pix, L.pix16 ? 1 : 0, M, featT, img_feat, N, L.ncap, C, P, copy_image, vec, tma, obs2d, map_proj,
-                      share, (long long)out_rows * P, (long long)row0 * P, row0, mean_channels);
+                      share, (long long)out_rows * P, (long long)row0 * P, row0, mean_channels, img_tma, map_img);
 }
 
 // true when the image half of obs2d can travel as tiled TMA boxes inside k_project
@@ -337,7 +342,15 @@ static int project_impl(const float *pc, const uint8_t *overlap, const float *K,
     WsLayout L = ws_layout(B, N, C, H * W);
     char *ws = static_cast<char *>(workspace);
     alignas(64) CUtensorMap map_img, map_out;
-    const bool img_tma = image_copy_by_tma(img_feat, obs2d, B, C, H * W, &map_img, &map_out);
+    // who carries the image half of obs2d: k_tile_gather (its light warps have an idle tile and idle time while
+    // they wait for k_project; CMR_B200_IMG=gather, the default when the bucket path is taken) or k_project
+    static const bool img_in_gather = [] { const char *e = getenv("CMR_B200_IMG"); return !(e && e[0] == 'p'); }();
+    const bool img_tma = !(img_in_gather && bucket_path(L, C)) &&
+                         image_copy_by_tma(img_feat, obs2d, B, C, H * W, &map_img, &map_out);
+    if (!img_tma) {
+        memset(&map_img, 0, sizeof(map_img));
+        memset(&map_out, 0, sizeof(map_out));
+    }
     if (image_copied) *image_copied = img_tma ? 1 : 0;
     if (L.pix16)
         return launch_project<uint16_t>(L, ws, pc, overlap, K, pose, mean, B, N, C, H, W, obs3d, pix_out, mvis_out, img_tma,

@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(kGatherThreads, CMR_GATHER_MINB)
                   const float *__restrict__ featT, const float *__restrict__ img_feat, int N, int ncap, int C, int P,
                   bool copy_image, bool vec, bool tma, float *__restrict__ obs2d,
                   const __grid_constant__ CUtensorMap map_proj, int share, long long out_estride, long long proj_off,
-                  int tma_y0, int mean_channels) {
+                  int tma_y0, int mean_channels, bool img_tma, const __grid_constant__ CUtensorMap map_img) {
     // share: consecutive episodes (poses) that look at the same cloud, i.e. the same feature rows.
     // Output of episode e: obs2d + e * out_estride + proj_off, rows of P floats; the tensor map's row of channel c
     // is tma_y0 + c.  Channels >= mean_channels are SUMS, not means (the occupancy row of a cost volume).
@@ -242,14 +242,26 @@ __global__ void __launch_bounds__(kGatherThreads, CMR_GATHER_MINB)
     int *hdr = bcnt + (size_t)B * kBucketStride;         // [0] heavy-queue length, [1] ticket of the bucket CTAs
     pdl_launch_dependents();
     DBG_MARK(0);
-    pdl_wait();   // counters, bucket buffers and queue are written by k_project
-    DBG_MARK(1);
-
     // roles in launch order (x fastest, then y): bucket CTAs and light CTAs alternate for the first
     // 2 * kHeavyCtas rows, so that the (mostly idle) bucket CTAs do not fill the first wave alone
     const int y = (int)blockIdx.y;
     const bool bucket_role = y < 2 * kHeavyCtas && !(y & 1);
     const int role_idx = y < 2 * kHeavyCtas ? y >> 1 : y - kHeavyCtas;
+    // The image half of obs2d (obs2d[b, 0:C] = img_geo_feat[b], environment.py:83) does not depend on the pose:
+    // every light warp fetches the [64 channels][32 pixels] box of ITS bucket into its (still unused) result tile
+    // before it waits for k_project, and sends it on to obs2d once it may write there.
+    __shared__ __align__(8) uint64_t img_bar[kGatherWarps];
+    const bool img_here = img_tma && !bucket_role && role_idx * kGatherWarps + warp < T;
+    if (img_here && lane == 0) {
+        mbar_init(&img_bar[warp], 1);
+        fence_async_proxy();
+        mbar_arrive_expect_tx(&img_bar[warp], (unsigned)(kTileFloats * sizeof(float)));
+        tma_load_3d(smem_g + warp * kTileFloats, &map_img, (role_idx * kGatherWarps + warp) * kBucketPix, 0, blockIdx.x,
+                    &img_bar[warp]);
+    }
+    pdl_wait();   // counters, bucket buffers and queue are written by k_project
+    DBG_MARK(1);
+
     if (!bucket_role) {
         // ------------------------------------------------------------------ light units: one warp per bucket
         const int b = blockIdx.x;
@@ -281,7 +293,22 @@ __global__ void __launch_bounds__(kGatherThreads, CMR_GATHER_MINB)
             if (threadIdx.x == 0) g_dbg[(blockIdx.y * gridDim.x + blockIdx.x) * 16 + 7] = (unsigned long long)(n + (e0 & 0) + (e1 & 0));
             DBG_MARK(2);
 #endif
-            if (copy_image) {   // image half when k_project could not carry it as TMA traffic
+            if (img_here) {
+                // slabs beyond the first are fetched and forwarded one after the other (C > 64 only)
+                for (int slab = 0; slab < slabs; ++slab) {
+                    if (lane == 0) {
+                        if (slab) {
+                            mbar_arrive_expect_tx(&img_bar[warp], (unsigned)(kTileFloats * sizeof(float)));
+                            tma_load_3d(tile, &map_img, p0, kSlab * slab, b, &img_bar[warp]);
+                        }
+                        mbar_wait(&img_bar[warp], slab & 1);
+                        tma_store_3d(&map_proj, p0, kSlab * slab, b, tile);   // rows [0, C) of obs2d[b]: the image half
+                        bulk_commit();
+                        bulk_wait_read_all();
+                    }
+                }
+                __syncwarp();
+            } else if (copy_image) {   // image half when neither kernel can carry it as TMA traffic
                 const float *img = img_feat + (size_t)b * C * P;
                 for (int r = 0; r < C; ++r)
                     if (p0 + lane < P) out[(size_t)r * P + p0 + lane] = img[(size_t)r * P + p0 + lane];
