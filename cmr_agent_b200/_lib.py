@@ -32,6 +32,8 @@ SIGNATURES = {
     "cmr_cost_volume_warp": (_c_int, [_c_vp] * 5 + [_c_int] * 7 + [_c_vp, _c_vp]),
     "cmr_fps_f64": (_c_int, [_c_vp, _c_vp, _c_int, _c_int, _c_int, _c_vp, _c_vp, _c_vp]),
     "cmr_nearest_f64": (_c_int, [_c_vp, _c_vp, _c_int, _c_int, _c_int, _c_vp, _c_vp]),
+    "cmr_episode_scan": (_c_int, [_c_vp, _c_int, _c_int, _c_int, _c_vp, _c_vp]),
+    "cmr_episode_compact": (_c_int, [_c_vp, _c_vp, _c_int, _c_int, _c_int, _c_vp, _c_vp]),
     "cmr_project": (_c_int, [_c_vp] * 6 + [_c_int] * 5 + [_c_vp] * 6 + [_c_int, _c_vp]),
     "cmr_tile_scatter": (_c_int, [_c_vp] * 3 + [_c_int] * 6 + [_c_vp] * 2),
     "cmr_to_disentangled": (_c_int, [_c_vp, _c_vp, _c_int, _c_vp]),

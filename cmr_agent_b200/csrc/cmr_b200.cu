@@ -300,29 +300,46 @@ int cmr_cloud_mean(const float *pc, int B, int N, float *mean, void *stream) {
     return after_launch();
 }
 
-int cmr_episode_prepare(const uint8_t *overlap, const float *feat, int B, int N, int C, void *workspace,
-                        void *stream) {
-    CMR_REQUIRE(overlap && feat && workspace && B > 0 && N > 0 && C > 0, CMR_EINVAL);
+// The two halves of cmr_episode_prepare.  cmr_project needs only the first (the prefix of the overlap counts), so a
+// host with two streams can run the second - the big one: it reads all of feat - beside the first projection.
+int cmr_episode_scan(const uint8_t *overlap, int B, int N, int C, void *workspace, void *stream) {
+    CMR_REQUIRE(overlap && workspace && B > 0 && N > 0 && C > 0, CMR_EINVAL);
     CMR_REQUIRE(C <= kMaxC && (C % 4) == 0 && N < (1 << 24) && B <= 65535, CMR_ERANGE);
     CMR_REQUIRE(aligned(workspace, 256), CMR_EALIGN);
     WsLayout L = ws_layout(B, N, C, 1);
     char *ws = static_cast<char *>(workspace);
     int *M = reinterpret_cast<int *>(ws + L.off_m);
     int *seg = reinterpret_cast<int *>(ws + L.off_seg);
-    float *featT = reinterpret_cast<float *>(ws + L.off_feat);
-    const bool vec = (N % 4 == 0) && aligned(overlap, 4);
     // bucket counters + ticket of the scatter stage start at zero; k_tile_gather leaves them at zero
     cudaError_t me = cudaMemsetAsync(ws + L.off_bcnt, 0, L.bcnt_bytes, S_(stream));
     if (me != cudaSuccess) return (int)me;
-    k_overlap_scan<<<B, 1024, 0, S_(stream)>>>(overlap, N, L.groups, vec, seg, M);
-    int rc = after_launch();
-    if (rc) return rc;
+    k_overlap_scan<<<B, 1024, 0, S_(stream)>>>(overlap, N, L.groups, (N % 4 == 0) && aligned(overlap, 4), seg, M);
+    return after_launch();
+}
+
+int cmr_episode_compact(const uint8_t *overlap, const float *feat, int B, int N, int C, void *workspace,
+                        void *stream) {
+    CMR_REQUIRE(overlap && feat && workspace && B > 0 && N > 0 && C > 0, CMR_EINVAL);
+    CMR_REQUIRE(C <= kMaxC && (C % 4) == 0 && N < (1 << 24) && B <= 65535, CMR_ERANGE);
+    CMR_REQUIRE(aligned(workspace, 256), CMR_EALIGN);
+    WsLayout L = ws_layout(B, N, C, 1);
+    char *ws = static_cast<char *>(workspace);
+    const int *seg = reinterpret_cast<const int *>(ws + L.off_seg);
+    float *featT = reinterpret_cast<float *>(ws + L.off_feat);
     size_t smem = sizeof(float) * kGroup * (C + 1);
-    rc = allow_smem(k_feat_compact<256>, smem);
+    int rc = allow_smem(k_feat_compact<256>, smem);
     if (rc) return rc;
     k_feat_compact<256><<<dim3(L.groups, B), 256, smem, S_(stream)>>>(overlap, feat, N, C, L.groups,
                                                                       (N % 4 == 0) && aligned(feat, 16), seg, featT);
     return after_launch();
+}
+
+int cmr_episode_prepare(const uint8_t *overlap, const float *feat, int B, int N, int C, void *workspace,
+                        void *stream) {
+    CMR_REQUIRE(feat, CMR_EINVAL);
+    int rc = cmr_episode_scan(overlap, B, N, C, workspace, stream);
+    if (rc) return rc;
+    return cmr_episode_compact(overlap, feat, B, N, C, workspace, stream);
 }
 
 static int check_observe_dims(int B, int N, int C, int H, int W) {

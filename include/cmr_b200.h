@@ -67,6 +67,12 @@ CMR_API int cmr_cloud_mean(const float *pc, int B, int N, float *mean, void *str
  * C must be a multiple of 4 and <= 256. */
 CMR_API int cmr_episode_prepare(const uint8_t *overlap, const float *feat, int B, int N, int C, void *workspace,
                         void *stream);
+/* The two halves of cmr_episode_prepare, for hosts with a second stream: cmr_project needs only the scan (prefix counts
+ * + cleared bucket counters); the compaction - which reads all of feat - is needed from the first cmr_tile_scatter on
+ * and may run beside the first projection.  cmr_episode_compact must be ordered after cmr_episode_scan. */
+CMR_API int cmr_episode_scan(const uint8_t *overlap, int B, int N, int C, void *workspace, void *stream);
+CMR_API int cmr_episode_compact(const uint8_t *overlap, const float *feat, int B, int N, int C, void *workspace,
+                                void *stream);
 
 /* observation_from_a_pose - environment.py:25-126.
  *   pc [B,3,N] f32, overlap [B,N] u8, img_feat [B,C,H,W] f32, K [B,3,3] f32, pose [B,4,4] f32,
