@@ -8,12 +8,16 @@ compaction, done once per episode like the drop-in does) + 10 x (observation_fro
 reward) = batch*10 registration steps.  Episodes shard across GPUs by rank with no
 data-path collective ("weak" scaling: 32 episodes per GPU).
 
-  value  : registration steps/s with all inputs resident in HBM, kernels called through the C ABI.
+  value  : registration steps/s with all inputs resident in HBM, kernels called through the C ABI; the rollout is
+           captured once as a CUDA graph and replayed.  --streams 2 (default): the reward of an iteration runs on
+           a second stream beside the next observation (observe and step keep their order); the replayed rollout's
+           outputs are compared bit for bit with a one-stream eager rollout before anything is timed.
   e2e    : the same rollout through the reference-facing drop-in API (cmr_agent_b200.environment)
            from pinned HOST tensors: H2D of every input of the rollout and D2H of the per-iteration
            reward/distance and the final poses are inside the timed region.
   roofline: the slower of the two observe stages (k_project | k_tile_gather), timed live with CUDA
-           events on the launch stream inside the timed region; the other one is roofline_secondary.
+           events on the launch stream in an instrumented pass (one stream, every rollout queued behind a spin
+           kernel so that the host's enqueue rate does not show); the other one is roofline_secondary.
   cpu_baseline: the oracle's torch-CPU port of the reference path (oracle/env_oracle.py) on this
            box's host cores, bounded sample.
 `--impl reference` times that CPU port alone (the reference is pure Python and cannot travel to the
