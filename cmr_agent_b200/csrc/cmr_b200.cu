@@ -535,7 +535,8 @@ int cmr_query_ball_point(const float *query, const float *ref, float radius2, in
                          int64_t *out, void *stream) {
     CMR_REQUIRE(query && ref && out && nsample > 0 && B > 0 && S > 0 && N > 0, CMR_EINVAL);
     CMR_REQUIRE(B <= 65535, CMR_ERANGE);
-    k_ball_query<<<dim3(ceil_div(S, 8), B), 256, 0, S_(stream)>>>(query, ref, radius2, nsample, S, N, out);
+    constexpr int kQpw = 4;   // queries per warp
+    k_ball_query<kQpw><<<dim3(ceil_div(S, 8 * kQpw), B), 256, 0, S_(stream)>>>(query, ref, radius2, nsample, S, N, out);
     return after_launch();
 }
 

@@ -347,38 +347,72 @@ __global__ void __launch_bounds__(256) k_knn(const float *__restrict__ query, co
 
 // -------------------------------------------------------------------------------------------------
 // query_ball_point (pointnet_util.py:73-93): the first nsample indices (ascending) with
-// !(d > r2), padded with the first hit, N everywhere when there is none.  One warp per query,
-// ordered ballot append, early exit once nsample are found.
+// !(d > r2), padded with the first hit, N everywhere when there is none.  A warp owns QPW queries; the
+// reference points go through a shared-memory tile that the 8 * QPW queries of the CTA share (most queries
+// of a KITTI-scale cloud find fewer than nsample neighbours and scan everything); ordered ballot append; the
+// CTA stops as soon as all its queries are full.
+template <int QPW>
 __global__ void __launch_bounds__(256) k_ball_query(const float *__restrict__ query, const float *__restrict__ ref,
                                                      float r2, int nsample, int S, int N, int64_t *__restrict__ out) {
+    __shared__ float tx[kKnnTile], ty[kKnnTile], tz[kKnnTile];
     const int b = blockIdx.y;
-    const int lane = threadIdx.x & 31;
-    const int s = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (s >= S) return;
-    const float *q = query + ((size_t)b * S + s) * 3;
-    const float qx = __ldg(q), qy = __ldg(q + 1), qz = __ldg(q + 2);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int q0 = (blockIdx.x * 8 + warp) * QPW;
+    const float *qb = query + (size_t)b * S * 3;
     const float *rb = ref + (size_t)b * N * 3;
-    int64_t *o = out + ((size_t)b * S + s) * nsample;
-    int found = 0;
-    long long first = N;
-    for (int base = 0; base < N && found < nsample; base += 32) {
-        int j = base + lane;
-        bool hit = false;
-        if (j < N) {
-            float dd = sqdist3(qx, qy, qz, __ldg(rb + (size_t)j * 3), __ldg(rb + (size_t)j * 3 + 1),
-                               __ldg(rb + (size_t)j * 3 + 2));
-            hit = !(dd > r2);                                                   // :88
+    float qx[QPW], qy[QPW], qz[QPW];
+    int found[QPW];
+    long long first[QPW];
+#pragma unroll
+    for (int q = 0; q < QPW; ++q) {
+        const int s = min(q0 + q, S - 1);
+        qx[q] = __ldg(qb + (size_t)s * 3);
+        qy[q] = __ldg(qb + (size_t)s * 3 + 1);
+        qz[q] = __ldg(qb + (size_t)s * 3 + 2);
+        found[q] = q0 + q < S ? 0 : nsample;   // queries past the end count as full
+        first[q] = N;
+    }
+    for (int base = 0; base < N; base += kKnnTile) {
+        bool open = false;
+#pragma unroll
+        for (int q = 0; q < QPW; ++q) open |= found[q] < nsample;
+        if (!__syncthreads_or(open)) break;   // (also the barrier before the tile is overwritten)
+        for (int i = tid; i < kKnnTile; i += 256) {
+            const int j = base + i;
+            const bool ok = j < N;
+            tx[i] = ok ? __ldg(rb + (size_t)j * 3) : 0.f;
+            ty[i] = ok ? __ldg(rb + (size_t)j * 3 + 1) : 0.f;
+            tz[i] = ok ? __ldg(rb + (size_t)j * 3 + 2) : 0.f;
         }
-        unsigned m = __ballot_sync(kFull, hit);
-        if (m) {
-            if (found == 0) first = base + __ffs(m) - 1;
-            int pos = found + __popc(m & ((1u << lane) - 1));
-            if (hit && pos < nsample) o[pos] = j;
-            found += __popc(m);
+        __syncthreads();
+        if (!open) continue;
+        const int lim = min(kKnnTile, N - base);
+        for (int c = 0; c < lim; c += 32) {
+            const bool in = c + lane < lim;
+            const float rx = tx[c + lane], ry = ty[c + lane], rz = tz[c + lane];
+            const int j = base + c + lane;
+#pragma unroll
+            for (int q = 0; q < QPW; ++q) {
+                if (found[q] >= nsample) continue;   // warp-uniform
+                const float dd = sqdist3(qx[q], qy[q], qz[q], rx, ry, rz);
+                const bool hit = in && !(dd > r2);                                  // :88
+                const unsigned m = __ballot_sync(kFull, hit);
+                if (m) {
+                    if (found[q] == 0) first[q] = base + c + __ffs(m) - 1;
+                    const int pos = found[q] + __popc(m & ((1u << lane) - 1));
+                    if (hit && pos < nsample) out[((size_t)b * S + q0 + q) * nsample + pos] = j;
+                    found[q] += __popc(m);
+                }
+            }
         }
     }
-    found = min(found, nsample);
-    for (int i = found + lane; i < nsample; i += 32) o[i] = first;             // :90-92
+#pragma unroll
+    for (int q = 0; q < QPW; ++q) {
+        if (q0 + q >= S) continue;
+        int64_t *o = out + ((size_t)b * S + q0 + q) * nsample;
+        const int f = min(found[q], nsample);
+        for (int i = f + lane; i < nsample; i += 32) o[i] = first[q];              // :90-92
+    }
 }
 
 }  // namespace cmr
