@@ -9,6 +9,7 @@ warm-up, inputs resident in HBM.
   python benchmarks/microbench.py cost_volume              IterModel's 729-pose warp of one KITTI cloud
 """
 import argparse
+import ctypes
 import json
 import os
 import sys
@@ -113,18 +114,23 @@ def sweep(args):
             obs3d = torch.empty(B, 5, N, device=dev)
             p = _lib.ptr
 
+            copied = ctypes.c_int(0)   # 1: k_project carried the image half of obs2d, 0: k_tile_gather does
+
             def proj():
                 _lib.call("cmr_project", p(ep.pc), p(ep.overlap), p(ep.K), p(pose), p(ep.mean), p(ep.ws), B, N, 64, 40,
-                          128, p(obs3d), None, None, p(ep.img_feat), p(obs2d), None, 1, st())
+                          128, p(obs3d), None, None, p(ep.img_feat), p(obs2d), ctypes.byref(copied), 1, st())
 
             def scat():
-                _lib.call("cmr_tile_scatter", p(ep.img_feat), p(ep.K), p(ep.ws), B, N, 64, 40, 128, 0, p(obs2d), st())
+                _lib.call("cmr_tile_scatter", p(ep.img_feat), p(ep.K), p(ep.ws), B, N, 64, 40, 128,
+                          0 if copied.value else 1, p(obs2d), st())
 
             t_p, t_s = time_pair(proj, scat)   # a scatter consumes what ONE project left
-            bytes_p = 33.0 * N * B + 8.0 * 64 * 5120 * B     # obs3d stream + image half of obs2d (TMA)
-            bytes_s = 4.0 * 64 * mvis + 4.0 * 64 * 5120 * B  # feature rows + projected half of obs2d
+            img_bytes = 8.0 * 64 * 5120 * B                  # image half of obs2d, in and out (TMA), by whoever carries it
+            bytes_p = 33.0 * N * B + (img_bytes if copied.value else 0.0)                     # obs3d stream (+ image)
+            bytes_s = 4.0 * 64 * mvis + 4.0 * 64 * 5120 * B + (0.0 if copied.value else img_bytes)   # rows + projected half
             print(json.dumps({
                 "bench": "sweep", "N": N, "overlap_frac": frac, "batch": B, "m_vis_per_episode": mvis / B,
+                "image_half_in": "k_project" if copied.value else "k_tile_gather",
                 "project_us": t_p * 1e6, "project_gbs": bytes_p / t_p / 1e9, "project_frac": bytes_p / t_p / 1e9 / PEAK,
                 "scatter_us": t_s * 1e6, "scatter_gbs": bytes_s / t_s / 1e9, "scatter_frac": bytes_s / t_s / 1e9 / PEAK,
                 "observe_steps_per_s": B / (t_p + t_s),
@@ -162,13 +168,17 @@ def env_kernels(args):
     M = float(cpu["pc_overlap_pred"].sum())
     rec("prepare", lambda: _lib.call("cmr_episode_prepare", p(ep.overlap), p(feat), B, N, 64, p(ep.ws), st()),
         B * N * (1 + 256.0) + M * 256.0)
+    copied = ctypes.c_int(0)
     t_p, t_s = time_pair(
         lambda: _lib.call("cmr_project", p(ep.pc), p(ep.overlap), p(ep.K), p(pose), p(ep.mean), p(ep.ws), B,
-                          N, 64, 40, 128, p(obs3d), None, None, p(ep.img_feat), p(obs2d), None, 1, st()),
-        lambda: _lib.call("cmr_tile_scatter", p(ep.img_feat), p(ep.K), p(ep.ws), B, N, 64, 40, 128, 0, p(obs2d), st()),
+                          N, 64, 40, 128, p(obs3d), None, None, p(ep.img_feat), p(obs2d), ctypes.byref(copied), 1, st()),
+        lambda: _lib.call("cmr_tile_scatter", p(ep.img_feat), p(ep.K), p(ep.ws), B, N, 64, 40, 128,
+                          0 if copied.value else 1, p(obs2d), st()),
         reps=20)
-    for name, t, nbytes in (("project", t_p, 33.0 * N * B + 8.0 * 64 * 5120 * B),
-                            ("scatter", t_s, 256.0 * mvis + 4.0 * 64 * 5120 * B)):
+    img_bytes = 8.0 * 64 * 5120 * B
+    res["image_half_in"] = "k_project" if copied.value else "k_tile_gather"
+    for name, t, nbytes in (("project", t_p, 33.0 * N * B + (img_bytes if copied.value else 0.0)),
+                            ("scatter", t_s, 256.0 * mvis + 4.0 * 64 * 5120 * B + (0.0 if copied.value else img_bytes))):
         res[name + "_us"], res[name + "_gbs"], res[name + "_frac"] = t * 1e6, nbytes / t / 1e9, nbytes / t / 1e9 / PEAK
     rec("step", lambda: env.step(a_r, a_t, pose, cfg), 64.0 * B)
     env.reward(pose, data, None)
