@@ -608,10 +608,23 @@ int cmr_fps_f64(const double *pts, const int64_t *start, int B, int M, int k, in
     CMR_REQUIRE(k <= M && (long long)M <= (long long)kFps64Threads * kFps64MaxPpt, CMR_ERANGE);
     const int ppt = ceil_div(M, kFps64Threads);
     cudaStream_t st = S_(stream);
-    if (ppt <= 4) k_fps_f64<4><<<B, kFps64Threads, 0, st>>>(pts, start, M, k, out_idx, out_pts);
-    else if (ppt <= 8) k_fps_f64<8><<<B, kFps64Threads, 0, st>>>(pts, start, M, k, out_idx, out_pts);
-    else if (ppt <= 12) k_fps_f64<12><<<B, kFps64Threads, 0, st>>>(pts, start, M, k, out_idx, out_pts);
-    else k_fps_f64<16><<<B, kFps64Threads, 0, st>>>(pts, start, M, k, out_idx, out_pts);
+    const size_t smem = sizeof(double) * 2 * (size_t)M;   // x and y of the cloud, resident for all rounds
+    const bool stage = smem <= 200 * 1024;
+#define CMR_FPS64_LAUNCH(PPT)                                                                                    \
+    do {                                                                                                         \
+        if (stage) {                                                                                             \
+            int rc = allow_smem(k_fps_f64<PPT, true>, smem);                                                     \
+            if (rc) return rc;                                                                                   \
+            k_fps_f64<PPT, true><<<B, kFps64Threads, smem, st>>>(pts, start, M, k, out_idx, out_pts);            \
+        } else {                                                                                                 \
+            k_fps_f64<PPT, false><<<B, kFps64Threads, 0, st>>>(pts, start, M, k, out_idx, out_pts);              \
+        }                                                                                                        \
+    } while (0)
+    if (ppt <= 4) CMR_FPS64_LAUNCH(4);
+    else if (ppt <= 8) CMR_FPS64_LAUNCH(8);
+    else if (ppt <= 12) CMR_FPS64_LAUNCH(12);
+    else CMR_FPS64_LAUNCH(16);
+#undef CMR_FPS64_LAUNCH
     return after_launch();
 }
 

@@ -21,7 +21,9 @@ __device__ __forceinline__ double sqdist3_f64(double ax, double ay, double az, d
 // [3, M]); start [B] = init_idx of :118.  The running distances (np.minimum of :125) live in registers, the
 // coordinates are re-read every round (they stay in L2; three f64 planes do not fit one SM).  np.argmax of :122
 // returns the FIRST maximum: ties go to the lowest index.  out_idx [B,k] i64, out_pts [B,3,k] f64 (optional).
-template <int PPT>
+// kStage: x and y live in (dynamic) shared memory and z in registers for all rounds - nothing is re-read from L2;
+// needs 16 M bytes of shared memory (M <= 12800 or so), otherwise the coordinates are re-read every round.
+template <int PPT, bool kStage>
 __global__ void __launch_bounds__(kFps64Threads) k_fps_f64(const double *__restrict__ pts, const int64_t *__restrict__ start,
                                                             int M, int k, int64_t *__restrict__ out_idx,
                                                             double *__restrict__ out_pts) {
@@ -31,7 +33,20 @@ __global__ void __launch_bounds__(kFps64Threads) k_fps_f64(const double *__restr
     __shared__ double s_val[32];
     __shared__ int s_idx[32];
     __shared__ int s_win;
-    double dist[PPT];
+    extern __shared__ double s_xy[];   // kStage: [2][M]
+    double dist[PPT], zreg[PPT];
+    if (kStage) {
+#pragma unroll
+        for (int i = 0; i < PPT; ++i) {
+            const int j = i * kFps64Threads + tid;
+            zreg[i] = 0.0;
+            if (j < M) {
+                s_xy[j] = px[j];
+                s_xy[M + j] = py[j];
+                zreg[i] = pz[j];
+            }
+        }
+    }
     int cur = (int)start[b];
     if (cur < 0 || cur >= M) {
         if (tid == 0) atomicExch(&g_fault, 1);
@@ -57,7 +72,8 @@ __global__ void __launch_bounds__(kFps64Threads) k_fps_f64(const double *__restr
         for (int i = 0; i < PPT; ++i) {
             const int j = i * kFps64Threads + tid;
             if (j < M) {
-                const double x = __ldg(px + j), y = __ldg(py + j), z = __ldg(pz + j);
+                const double x = kStage ? s_xy[j] : __ldg(px + j), y = kStage ? s_xy[M + j] : __ldg(py + j),
+                             z = kStage ? zreg[i] : __ldg(pz + j);
                 const double d = sqdist3_f64(cx, cy, cz, x, y, z);
                 // round 1 initialises the distances (:120), later rounds take np.minimum (:125)
                 dist[i] = (r == 1) ? d : fmin(dist[i], d);
