@@ -22,6 +22,11 @@ constexpr int kTilePix = 128;   // pixels per k_tile_scatter CTA
 #ifndef CMR_PROJ_WARPS
 #define CMR_PROJ_WARPS 8
 #endif
+#ifdef CMR_PROJ_MINB
+#define CMR_PROJ_BOUNDS __launch_bounds__(32 * CMR_PROJ_WARPS, CMR_PROJ_MINB)
+#else
+#define CMR_PROJ_BOUNDS __launch_bounds__(32 * CMR_PROJ_WARPS)
+#endif
 constexpr int kProjWarps = CMR_PROJ_WARPS;      // warps (128-point groups) per k_project CTA
 constexpr int kProjBoxPix = 16 * kProjWarps;    // pixels of the image box a k_project CTA carries by TMA
 constexpr int kMaxC = 256;
@@ -275,7 +280,7 @@ __device__ __forceinline__ int project_point(const PoseK &s, float x, float y, f
 // episode; writes obs3d (environment.py:88-124) and the pixel id of each predicted-overlap point at
 // its compacted position (input of k_tile_scatter).  One warp = one 128-point group, 4 points/lane.
 template <typename PixT>
-__global__ void __launch_bounds__(32 * kProjWarps) k_project(const float *__restrict__ pc, const uint8_t *__restrict__ overlap,
+__global__ void CMR_PROJ_BOUNDS k_project(const float *__restrict__ pc, const uint8_t *__restrict__ overlap,
                                                   const float *__restrict__ K, const float *__restrict__ pose,
                                                   const float *__restrict__ mean, const int *__restrict__ seg,
                                                   const int *__restrict__ M, int N, int ncap, int groups, int H, int W,
