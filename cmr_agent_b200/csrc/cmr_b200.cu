@@ -257,6 +257,28 @@ static int launch_fps(const float *xyz, const int64_t *start, int B, int N, int 
     return e == cudaSuccess ? CMR_OK : (int)e;
 }
 
+// rows of the predicted-overlap points, channel-major -> point-major: by TMA boxes when the tensor allows it
+static int launch_feat_compact(const uint8_t *overlap, const float *feat, int B, int N, int C, int groups, const int *seg,
+                               float *featT, cudaStream_t st) {
+    static const bool use_tma = [] { const char *e = getenv("CMR_B200_COMPACT"); return !(e && e[0] == 'l'); }();
+    alignas(64) CUtensorMap map_feat;
+    memset(&map_feat, 0, sizeof(map_feat));
+    if (use_tma && N % 4 == 0 && N >= 32 && C >= 64 && aligned(feat, 16) &&
+        make_map3d(&map_feat, feat, N, (uint64_t)C, B, 32, 64, CU_TENSOR_MAP_SWIZZLE_128B)) {
+        const size_t smem = sizeof(float) * 4 * 64 * 32;
+        int rc = allow_smem(k_feat_compact_tma, smem);
+        if (rc) return rc;
+        k_feat_compact_tma<<<dim3(groups, B), 256, smem, st>>>(overlap, N, C, groups, seg, featT, map_feat);
+        return after_launch();
+    }
+    const size_t smem = sizeof(float) * kGroup * (C + 1);
+    int rc = allow_smem(k_feat_compact<256>, smem);
+    if (rc) return rc;
+    k_feat_compact<256><<<dim3(groups, B), 256, smem, st>>>(overlap, feat, N, C, groups, (N % 4 == 0) && aligned(feat, 16),
+                                                            seg, featT);
+    return after_launch();
+}
+
 extern "C" {
 
 int cmr_abi_version(void) { return CMR_ABI_VERSION; }
@@ -326,12 +348,7 @@ int cmr_episode_compact(const uint8_t *overlap, const float *feat, int B, int N,
     char *ws = static_cast<char *>(workspace);
     const int *seg = reinterpret_cast<const int *>(ws + L.off_seg);
     float *featT = reinterpret_cast<float *>(ws + L.off_feat);
-    size_t smem = sizeof(float) * kGroup * (C + 1);
-    int rc = allow_smem(k_feat_compact<256>, smem);
-    if (rc) return rc;
-    k_feat_compact<256><<<dim3(L.groups, B), 256, smem, S_(stream)>>>(overlap, feat, N, C, L.groups,
-                                                                      (N % 4 == 0) && aligned(feat, 16), seg, featT);
-    return after_launch();
+    return launch_feat_compact(overlap, feat, B, N, C, L.groups, seg, featT, S_(stream));
 }
 
 int cmr_episode_prepare(const uint8_t *overlap, const float *feat, int B, int N, int C, void *workspace,
@@ -565,12 +582,7 @@ int cmr_cost_volume_prepare(const uint8_t *mask, const float *feat, int B, int K
     k_overlap_scan<<<B, 1024, 0, st>>>(mask, N, L.groups, (N % 4 == 0) && aligned(mask, 4), seg, M);
     int rc = after_launch();
     if (rc) return rc;
-    size_t smem = sizeof(float) * kGroup * (C + 1);
-    rc = allow_smem(k_feat_compact<256>, smem);
-    if (rc) return rc;
-    k_feat_compact<256><<<dim3(L.groups, B), 256, smem, st>>>(mask, feat, N, C, L.groups,
-                                                              (N % 4 == 0) && aligned(feat, 16), seg, featT);
-    return after_launch();
+    return launch_feat_compact(mask, feat, B, N, C, L.groups, seg, featT, st);
 }
 
 int cmr_cost_volume_warp(const float *pc, const uint8_t *mask, const float *Kmat, const float *poses, void *workspace,

@@ -238,6 +238,70 @@ __global__ void __launch_bounds__(kThreads) k_feat_compact(const uint8_t *__rest
     }
 }
 
+// The same compaction with the [64 channels][128 points] tile of a group brought in by TMA: four boxes of 32 points
+// (128-byte rows, 128-byte swizzle) per 64-channel slab, one thread issues them, no registers hold data in flight
+// (32 KB per CTA), and the warps only write the rows of the predicted-overlap points.  Needs N % 4 == 0 and a
+// 16-byte aligned tensor (the tensor map); k_feat_compact is the general form.
+__global__ void __launch_bounds__(256) k_feat_compact_tma(const uint8_t *__restrict__ overlap, int N, int C, int groups,
+                                                           const int *__restrict__ seg, float *__restrict__ featT,
+                                                           const __grid_constant__ CUtensorMap map_feat) {
+    extern __shared__ __align__(1024) float box[];   // [4 boxes][64 channels][32 points], swizzled
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ int rank[kGroup];
+    __shared__ int wbase[5];
+    const int g = blockIdx.x, b = blockIdx.y;
+    const int j0 = g * kGroup;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int slabs = (C + 63) >> 6;
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        fence_async_proxy();
+        mbar_arrive_expect_tx(&bar, 4u * 64u * 32u * (unsigned)sizeof(float));
+#pragma unroll
+        for (int q = 0; q < 4; ++q) tma_load_3d(box + q * 2048, &map_feat, j0 + 32 * q, 0, b, &bar);
+    }
+    // ranks of the overlap points inside the group (warps 0..3 cover 32 points each)
+    const uint8_t *ov = overlap + (size_t)b * N;
+    if (warp < 4) {
+        const int j = j0 + warp * 32 + lane;
+        const bool f = j < N && ov[j];
+        const unsigned m = __ballot_sync(kFull, f);
+        rank[warp * 32 + lane] = f ? __popc(m & ((1u << lane) - 1)) : -1;
+        if (lane == 0) wbase[warp + 1] = __popc(m);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        wbase[0] = 0;
+        for (int w = 1; w <= 4; ++w) wbase[w] += wbase[w - 1];
+    }
+    __syncthreads();
+    float *dst = featT + ((size_t)b * N + seg[(size_t)b * groups + g]) * C;
+    for (int slab = 0; slab < slabs; ++slab) {
+        mbar_wait(&bar, slab & 1);
+        // one warp per row: lane reads channels lane and lane + 32 of the slab (element (c, p) of box p / 32 sits
+        // at c * 32 + ((p % 32) ^ ((c % 8) << 2)))
+        for (int p = warp; p < kGroup; p += 8) {
+            const int rk = rank[p];
+            if (rk < 0) continue;   // warp-uniform
+            const int pos = wbase[p >> 5] + rk;
+            const float *bx = box + (p >> 5) * 2048;
+            const int pp = p & 31;
+            const int c = lane, c2 = lane + 32;
+            float *row = dst + (size_t)pos * C + 64 * slab;
+            if (64 * slab + c < C) row[c] = bx[c * 32 + (pp ^ ((c & 7) << 2))];
+            if (64 * slab + c2 < C) row[c2] = bx[c2 * 32 + (pp ^ ((c2 & 7) << 2))];
+        }
+        if (slab + 1 < slabs) {
+            __syncthreads();   // the boxes have been read
+            if (tid == 0) {
+                mbar_arrive_expect_tx(&bar, 4u * 64u * 32u * (unsigned)sizeof(float));
+#pragma unroll
+                for (int q = 0; q < 4; ++q) tma_load_3d(box + q * 2048, &map_feat, j0 + 32 * q, 64 * (slab + 1), b, &bar);
+            }
+        }
+    }
+}
+
 // -------------------------------------------------------------------------------------------------
 // Per-episode constants of one observe call, staged once per CTA.
 struct PoseK {
