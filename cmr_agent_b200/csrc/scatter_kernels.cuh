@@ -47,7 +47,10 @@ namespace cmr {
 #ifndef CMR_GATHER_MINB
 #define CMR_GATHER_MINB 3
 #endif
-constexpr int kHeavyCtas = 16;          // bucket CTAs per episode of the batch
+#ifndef CMR_HEAVY_CTAS
+#define CMR_HEAVY_CTAS 16
+#endif
+constexpr int kHeavyCtas = CMR_HEAVY_CTAS;          // bucket CTAs per episode of the batch
 constexpr int kGatherThreads = 256;     // 8 warps = 8 light units
 constexpr int kGatherWarps = kGatherThreads / 32;
 constexpr int kSlab = 64;               // channels per pass: two per lane
