@@ -135,3 +135,21 @@ def test_world_size_2_gloo_sharding_and_allreduce(tmp_path):
     assert res["world"] == 2 and res["slow"] == 2.0
     for k, v in ref.items():
         assert abs(res["summary"][k] - v) < 1e-9, k
+
+
+def test_reference_arm_of_the_bench_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU path the driver times beside ours) runs without a GPU and prints one JSON
+    line with the contract's keys; a small sample keeps it to a few seconds."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0", "--cpu-episodes", "2", "--iters", "2"], capture_output=True, text=True,
+                         timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "steps/s" and line["value"] > 0
+    for key in ("metric", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
