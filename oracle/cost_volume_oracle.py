@@ -1,9 +1,11 @@
 """CPU restatement of the cost-volume warp of models/IterModel.py:272-351 (TEST INFRASTRUCTURE ONLY).
 
-The reference evaluates these lines inline in ``IterModel.forward`` with hard-coded ``.cuda()`` calls, so they cannot
-be executed as they are in a container without a GPU and there is no callable boundary to import: PARITY UNPINNED -
-this file restates the same torch expressions, line by line, on the CPU (torch_scatter through oracle/shims.py, the
-same stand-in that is pinned for the environment path).  Differences from the reference text: tensors stay where
+The reference evaluates these lines inline in ``IterModel.forward`` with hard-coded ``.cuda()`` calls and there is no
+callable boundary to import; this file restates the same torch expressions, line by line, on the CPU (torch_scatter
+through oracle/shims.py, the same stand-in that is pinned for the environment path).  PINNED by
+tests/golden/cost_volume.npz: the outputs of the reference's own statements (taken from its syntax tree and run on the
+CPU with ``Tensor.cuda`` as the identity by tests/golden/make_golden.py), reproduced bit for bit by ``warp`` below
+(tests/test_cost_volume.py::test_oracle_matches_reference_golden).  Differences from the reference text: tensors stay where
 they are; the dump bin is H*W instead of the literal 5120 (:311, equal for KITTI's 40 x 128); poses are processed in
 one piece instead of chunks of 200 (:324-346; the chunks are independent).
 """

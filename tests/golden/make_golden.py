@@ -191,7 +191,106 @@ def dataset_case():
     print("dataset.npz", {k: getattr(v, "shape", ()) for k, v in out.items()})
 
 
+COST_VOLUME_CASES = {
+    # name: (clouds, points, nlabel, R_amplitude, T_amplitude, every point masked in)
+    # the reference hard-codes the 40 x 128 grid (dump bin 5120, IterModel.py:311) and 64 channels (:341)
+    "sparse": (1, 4096, 3, 0.15, 2.0, False),
+    "shared": (2, 3001, 3, 0.3, 3.0, False),      # two clouds, the first one's mask selects for both (:272); nlabel is odd (:29)
+    "dense": (1, 8192, 3, 0.1, 1.0, True),
+}
+
+
+def cost_volume_inputs(case):
+    """Seeded inputs of a cost-volume case: the batch, the cloud AT THE CURRENT POSE (data_batch['pc_i']; here
+    the ground-truth registration, so that the sampled poses keep it in view), the mask and the scores."""
+    B, N, nlabel, r_amp, t_amp, dense = COST_VOLUME_CASES[case]
+    data = synth.make_batch(B, seed=SEED + 11, num_pt=N, img_h=160, img_w=512)
+    g = torch.Generator().manual_seed(SEED + 12)
+    scores = torch.rand(B, N, generator=g)
+    mask = data["pc_overlap_pred"].clone()
+    if dense:
+        mask[:] = True
+    P = data["P"][:, 0:3, :]
+    pc_i = P[:, :, 0:3] @ data["pc"] + P[:, :, 3:4]
+    amp = (torch.full((B, 1), r_amp), torch.full((B, 1), t_amp))
+    return data, pc_i, mask, scores, nlabel, amp
+
+
+def _reference_iter_model_pieces():
+    """The statements of models/IterModel.py that make up the cost-volume warp, taken from the reference's OWN
+    source through its syntax tree and compiled as they stand: the methods ``angle2matrix`` and ``sample_poses``
+    (:96-172) and the part of ``forward`` from the mask selection to the cropped outputs (:272-351).  The module
+    itself cannot be imported (cv2, the networks) and ``forward`` runs the whole model around these lines."""
+    import ast
+    path = os.path.join(reference_loader.REFERENCE_ROOT, "models", "IterModel.py")
+    tree = ast.parse(open(path).read(), path)
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "IterModel")
+    fn = {n.name: n for n in cls.body if isinstance(n, ast.FunctionDef)}
+
+    def assigns(node, name):
+        return isinstance(node, ast.Assign) and any(isinstance(t, ast.Name) and t.id == name for t in node.targets)
+
+    body = fn["forward"].body
+    first = next(i for i, n in enumerate(body) if assigns(n, "pc_mask"))
+    # the warp ends where the image features enter (:353); the statement before crops the occupancy (:351)
+    last = next(i for i, n in enumerate(body) if i > first and assigns(n, "img_geo_feat")) - 1
+    assert assigns(body[last], "pc_warped_occupancy")
+    block = ast.Module(body=body[first:last + 1], type_ignores=[])
+    methods = ast.Module(body=[fn["angle2matrix"], fn["sample_poses"]], type_ignores=[])
+    return compile(methods, path, "exec"), compile(block, path, "exec"), (body[first].lineno, body[last].end_lineno)
+
+
+def cost_volume_case():
+    """Run the reference's own lines on the CPU: ``Tensor.cuda`` is the identity while they execute and
+    ``torch_scatter`` is the stand-in of oracle/shims.py (pinned with the environment fixtures)."""
+    import types
+    from oracle import shims
+    methods_code, block_code, lines = _reference_iter_model_pieces()
+    print("cost volume: IterModel.py:%d-%d" % lines)
+    shims.install()
+    import torch_scatter
+    out = {"reference_lines": np.array(lines, dtype=np.int64)}
+    real_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        for case in COST_VOLUME_CASES:
+            data, pc_i, mask, scores, nlabel, (r_amp, t_amp) = cost_volume_inputs(case)
+            ns = {"torch": torch, "np": np, "math": __import__("math")}
+            exec(methods_code, ns)
+            model = types.SimpleNamespace(nlabel=nlabel)
+            half = (nlabel - 1) / 2                                  # IterModel.py:29 for this nlabel
+            model.base = torch.from_numpy(np.array(range(int(-half), int(half) + 1))).unsqueeze(0)
+            model.angle2matrix = types.MethodType(ns["angle2matrix"], model)
+            model.sample_poses = types.MethodType(ns["sample_poses"], model)
+            batch = {"pc_overlap_pred": mask, "pc_overlap_pred_standby": mask, "pc_i": pc_i, "K": data["K"],
+                     "img": data["img"], "pc_geo_feat": data["pc_geo_feat"], "pc_is_in_cam_scores": scores,
+                     "R_amplitude": r_amp, "T_amplitude": t_amp}
+            env = {"torch": torch, "torch_scatter": torch_scatter, "self": model, "data_batch": batch}
+            exec(block_code, env)
+            wf, occ = env["pc_warped_geo_feat"], env["pc_warped_occupancy"]
+            assert tuple(wf.shape) == (pc_i.shape[0], nlabel ** 3, 64, 5120) and float(occ.sum()) > 0
+            out[case + "_poses"] = env["delta_RT"].numpy()           # sample_poses' output, [B, nlabel^3, 3, 4]
+            out[case + "_occupancy"] = occ.numpy()
+            out[case + "_features_sha"] = np.frombuffer(sha(wf).encode(), dtype=np.uint8)
+            # the channels of a few hundred pixels in full (the rest is covered by the hash)
+            flat = wf.permute(0, 1, 3, 2).reshape(-1, 64)
+            rows = torch.nonzero(occ.reshape(-1) > 0)[:, 0][::37][:512]
+            out[case + "_sample_rows"] = rows.numpy()
+            out[case + "_sample_features"] = flat[rows].numpy()
+            out[case + "_inputs_sha"] = np.frombuffer(
+                sha(data["pc"], data["pc_geo_feat"], mask, data["K"], pc_i, scores).encode(), dtype=np.uint8)
+    finally:
+        torch.Tensor.cuda = real_cuda
+    np.savez_compressed(os.path.join(HERE, "cost_volume.npz"), **out)
+    print("cost_volume.npz", {k: getattr(v, "shape", ()) for k, v in out.items()},
+          os.path.getsize(os.path.join(HERE, "cost_volume.npz")) // 1024, "KiB")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "cost_volume":   # only the cost-volume fixture
+        assert reference_loader.available(), "needs /root/reference"
+        cost_volume_case()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "dataset":   # only the dataset-side fixture
         assert reference_loader.available(), "needs /root/reference"
         dataset_case()
@@ -206,3 +305,4 @@ if __name__ == "__main__":
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
     dataset_case()
+    cost_volume_case()

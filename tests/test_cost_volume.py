@@ -1,14 +1,67 @@
 """Cost-volume warp (models/IterModel.py:272-351): the CUDA path (cmr_cost_volume_* through
 cmr_agent_b200.cost_volume.warp) against the CPU restatement of the reference's torch expressions
-(oracle/cost_volume_oracle.py - parity unpinned: the reference cannot run these lines without a GPU).
+(oracle/cost_volume_oracle.py) and against tests/golden/cost_volume.npz - the outputs of the reference's OWN
+statements (IterModel.py:96-172 and :272-351, compiled from its syntax tree by tests/golden/make_golden.py with
+``Tensor.cuda`` as the identity), which is what pins the oracle.
 Bar: warped features and occupancy BIT-EXACT (ordered sums), which implies identical pixel indices and masks."""
+import hashlib
 import math
+import os
+import sys
 
+import numpy as np
 import pytest
 import torch
 
 from cmr_agent_b200 import synth
 from oracle import cost_volume_oracle as cvo
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+import make_golden  # noqa: E402  (its cost_volume_inputs() regenerates the seeded inputs)
+
+GOLDEN = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cost_volume.npz"))
+GOLDEN_CASES = tuple(make_golden.COST_VOLUME_CASES)
+
+
+def _sha(*tensors):
+    h = hashlib.sha256()
+    for t in tensors:
+        h.update(np.ascontiguousarray(t.numpy()).tobytes())
+    return h.hexdigest().encode()
+
+
+def _golden_inputs(case):
+    data, pc_i, mask, scores, nlabel, _ = make_golden.cost_volume_inputs(case)
+    assert _sha(data["pc"], data["pc_geo_feat"], mask, data["K"], pc_i, scores) == \
+        GOLDEN[case + "_inputs_sha"].tobytes(), "seeded inputs differ from the fixture's"
+    return data, pc_i, mask[0], scores, torch.from_numpy(GOLDEN[case + "_poses"])
+
+
+def _check_golden(case, wf, occ):
+    assert torch.equal(occ, torch.from_numpy(GOLDEN[case + "_occupancy"])), "occupancy differs from the reference's"
+    rows = torch.from_numpy(GOLDEN[case + "_sample_rows"])
+    got = wf.permute(0, 1, 3, 2).reshape(-1, wf.shape[2])[rows]
+    assert torch.equal(got, torch.from_numpy(GOLDEN[case + "_sample_features"])), "sampled pixels differ"
+    assert _sha(wf.contiguous()) == GOLDEN[case + "_features_sha"].tobytes(), "warped features differ from the reference's"
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_oracle_matches_reference_golden(case):
+    """Pins the oracle: the restatement reproduces, bit for bit, what the reference's own lines computed."""
+    data, pc_i, mask, scores, poses = _golden_inputs(case)
+    wf, occ = cvo.warp(pc_i, mask, poses, data["K"], data["pc_geo_feat"], scores, 40, 128)
+    _check_golden(case, wf, occ)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_gpu_matches_reference_golden(cuda, case):
+    from cmr_agent_b200 import cost_volume
+    data, pc_i, mask, scores, poses = _golden_inputs(case)
+    wf, occ = cost_volume.warp(pc_i.to(cuda), mask.to(cuda), poses.to(cuda), data["K"], data["pc_geo_feat"].to(cuda),
+                               scores.to(cuda), 40, 128)
+    torch.cuda.synchronize()
+    _check_golden(case, wf.cpu(), occ.cpu())
 
 
 def _poses(B, nlabel, r_amp, t_amp, seed):
