@@ -155,11 +155,14 @@ static int launch_gather(const WsLayout &L, const char *ws, const float *img_fea
                          make_map3d(&map_img, img_feat, P, (uint64_t)C, B, kBucketPix, kSlab, CU_TENSOR_MAP_SWIZZLE_128B);
     // x = episode, y = kHeavyCtas bucket CTAs interleaved with the first light CTAs (8 buckets each), then the rest
     const int light = std::max(ceil_div(L.buckets, kGatherWarps), kHeavyCtas);
+    // four SUMMED channels after whole slabs (features + occupancy of a cost volume): no slab pass of their own
+    static const bool tail_slab = getenv("CMR_B200_TAIL") && !strcmp(getenv("CMR_B200_TAIL"), "slab");
+    const int tail = (!tail_slab && C > kSlab && C % kSlab == 4 && mean_channels <= C - 4) ? 4 : 0;
     int rc = allow_smem(k_tile_gather, kGatherSmem);
     if (rc) return rc;
     return launch_pdl(k_tile_gather, dim3(B, kHeavyCtas + light), dim3(kGatherThreads), kGatherSmem, st, bcnt, bbuf,
                       L.buckets, hq, pix, L.pix16 ? 1 : 0, M, featT, img_feat, N, L.ncap, C, P, copy_image, vec, tma, obs2d, map_proj,
-                      share, (long long)out_rows * P, (long long)row0 * P, row0, mean_channels, img_tma, map_img);
+                      share, (long long)out_rows * P, (long long)row0 * P, row0, mean_channels, img_tma, map_img, tail);
 }
 
 // true when the image half of obs2d can travel as tiled TMA boxes inside k_project

@@ -77,6 +77,7 @@ __device__ __forceinline__ unsigned ld_cg_u32(const unsigned *p) {
     return v;
 }
 __device__ __forceinline__ float2 ldg_f2(const float *p) { return __ldg(reinterpret_cast<const float2 *>(p)); }
+__device__ __forceinline__ float4 ldg_f4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
@@ -233,7 +234,9 @@ __global__ void __launch_bounds__(kGatherThreads, CMR_GATHER_MINB)
                   const float *__restrict__ featT, const float *__restrict__ img_feat, int N, int ncap, int C, int P,
                   bool copy_image, bool vec, bool tma, float *__restrict__ obs2d,
                   const __grid_constant__ CUtensorMap map_proj, int share, long long out_estride, long long proj_off,
-                  int tma_y0, int mean_channels, bool img_tma, const __grid_constant__ CUtensorMap map_img) {
+                  int tma_y0, int mean_channels, bool img_tma, const __grid_constant__ CUtensorMap map_img, int tail) {
+    // tail (0 or 4): the last four channels (a slab of their own, all of them SUMS) are not given a pass over the
+    // rows by the light warps: a lane sums them for ITS pixel, in point order (the occupancy row of a cost volume).
     // share: consecutive episodes (poses) that look at the same cloud, i.e. the same feature rows.
     // Output of episode e: obs2d + e * out_estride + proj_off, rows of P floats; the tensor map's row of channel c
     // is tma_y0 + c.  Channels >= mean_channels are SUMS, not means (the occupancy row of a cost volume).
@@ -328,6 +331,13 @@ __global__ void __launch_bounds__(kGatherThreads, CMR_GATHER_MINB)
                     store_zeros(C, p0, P, vec, proj, lane);
                 }
             } else if (n > 0 && n <= kLightMax) {   // otherwise the bucket CTAs own the bucket
+                // the tail channels of this unit's rows: on their way while the entries are ranked
+                float4 t0 = make_float4(0.f, 0.f, 0.f, 0.f), t1 = t0;
+                if (tail) {
+                    const float *tb = featT + (size_t)bs * N * C + (C - 4);
+                    if (lane < n) t0 = ldg_f4(tb + (size_t)(e0 >> 7) * C);
+                    if (lane + 32 < n) t1 = ldg_f4(tb + (size_t)(e1 >> 7) * C);
+                }
                 // key = pixel % 32 << 24 | point (unique); empty slots are all-ones (never smaller than a key)
                 const unsigned k0 = lane < n ? ((e0 & 31u) << 24) | (e0 >> 7) : 0xffffffffu;
                 const unsigned k1 = lane + 32 < n ? ((e1 & 31u) << 24) | (e1 >> 7) : 0xffffffffu;
@@ -365,7 +375,37 @@ __global__ void __launch_bounds__(kGatherThreads, CMR_GATHER_MINB)
                 const unsigned multi = __ballot_sync(kFull, my_cnt > 1);
                 const LaneRows tl = lane_rows(tile, lane);
                 DBG_MARK(8);
-                for (int slab = 0; slab < slabs; ++slab) {
+                if (tail) {
+                    // sorted entries are grouped by pixel, in point order: lane = pixel walks its own group
+                    float4 *tv = reinterpret_cast<float4 *>(tile);   // the tile is idle until the first slab is zeroed
+                    if (lane < n) tv[r0] = t0;
+                    if (lane + 32 < n) tv[r1] = t1;
+                    int incl = my_cnt;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int up = __shfl_up_sync(kFull, incl, o);
+                        if (lane >= o) incl += up;
+                    }
+                    const int start = incl - my_cnt;
+                    __syncwarp();
+                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int i = 0; i < my_cnt; ++i) {
+                        const float4 v = tv[start + i];
+                        acc.x = __fadd_rn(acc.x, v.x);
+                        acc.y = __fadd_rn(acc.y, v.y);
+                        acc.z = __fadd_rn(acc.z, v.z);
+                        acc.w = __fadd_rn(acc.w, v.w);
+                    }
+                    __syncwarp();
+                    if (p0 + lane < P) {
+                        float *dst = proj + (size_t)(C - 4) * P + p0 + lane;
+                        dst[0] = acc.x;
+                        dst[(size_t)P] = acc.y;
+                        dst[2 * (size_t)P] = acc.z;
+                        dst[3 * (size_t)P] = acc.w;
+                    }
+                }
+                for (int slab = 0; slab < (tail ? slabs - 1 : slabs); ++slab) {
                     const int c0 = kSlab * slab;
                     // lanes beyond C read channel 0 instead (their rows of the tile are never stored)
                     const float *rows = featT + (size_t)bs * N * C + (c0 + 2 * lane < C ? c0 + 2 * lane : 0);

@@ -165,7 +165,11 @@ def test_index_points_backward(cuda):
     (po.index_points(a, idx) * w).sum().backward()
     b = pts.to(cuda).requires_grad_(True)
     (pn.index_points(b, idx.to(cuda)) * w.to(cuda)).sum().backward()
-    assert hp.rel_err(b.grad.cpu(), a.grad) <= 1e-5
+    # a row's gradient is a float32 sum of up to ~10 terms added in atomic (arbitrary) order, here and in torch's own
+    # CUDA backward: the bound is relative to the sum of the terms' magnitudes, not to the (possibly cancelling) result
+    scale = torch.zeros_like(pts).index_put_((torch.arange(2).view(2, 1, 1).expand_as(idx), idx), w.abs(), accumulate=True)
+    assert bool(((b.grad.cpu() - a.grad).abs() <= 2e-6 * scale + 1e-7).all())
+    assert bool((b.grad.cpu()[scale == 0] == 0).all())
 
 
 def test_group_points_and_knn_grouping(cuda):
