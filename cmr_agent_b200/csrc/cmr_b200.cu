@@ -165,6 +165,59 @@ static int launch_gather(const WsLayout &L, const char *ws, const float *img_fea
                       share, (long long)out_rows * P, (long long)row0 * P, row0, mean_channels, img_tma, map_img, tail);
 }
 
+// who carries the image half of obs2d: 'g' k_tile_gather (default), 'p' k_project, 's' k_image_copy on a side stream
+static char image_mode() {
+    static const char mode = [] { const char *e = getenv("CMR_B200_IMG"); return (e && (e[0] == 'p' || e[0] == 's')) ? e[0] : 'g'; }();
+    return mode;
+}
+
+// CMR_B200_IMG=stream: the image half of obs2d does not depend on the pose, so it is copied by k_image_copy on a
+// stream of the library's own that forks from `st` here and is joined by image_copy_join() when the observation's
+// other kernels have been launched.  Returns false when the copy cannot go this way (nothing has been launched).
+struct SideStream {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+static SideStream *side_stream() {
+    static SideStream per_device[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    SideStream &s = per_device[dev];
+    if (!s.stream) {
+        if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) {
+            s.stream = nullptr;
+            return nullptr;
+        }
+    }
+    return &s;
+}
+static bool image_copy_fork(const float *img_feat, float *obs2d, int B, int C, int P, cudaStream_t st) {
+    if (!(P % 4 == 0 && P >= kBucketPix && aligned(img_feat, 16) && aligned(obs2d, 16))) return false;
+    alignas(64) CUtensorMap map_img, map_out;
+    memset(&map_img, 0, sizeof(map_img));
+    memset(&map_out, 0, sizeof(map_out));
+    if (!make_map3d(&map_img, img_feat, P, (uint64_t)C, B, kBucketPix, kSlab, CU_TENSOR_MAP_SWIZZLE_128B) ||
+        !make_map3d(&map_out, obs2d, P, 2 * (uint64_t)C, B, kBucketPix, kSlab, CU_TENSOR_MAP_SWIZZLE_128B))
+        return false;
+    SideStream *s = side_stream();
+    const size_t smem = sizeof(float) * kTileFloats * kCopyStages;
+    if (!s || allow_smem(k_image_copy, smem) != CMR_OK) return false;
+    if (cudaEventRecord(s->fork, st) != cudaSuccess || cudaStreamWaitEvent(s->stream, s->fork, 0) != cudaSuccess) return false;
+    const int boxes_per_row = ceil_div(P, kBucketPix), slabs = ceil_div(C, kSlab), total = B * slabs * boxes_per_row;
+    const int grid = std::min(ceil_div(total, kCopyStages), 2 * sm_count());
+    k_image_copy<<<grid, 32, smem, s->stream>>>(map_img, map_out, boxes_per_row, slabs, total);
+    ++g_launches;
+    cudaEventRecord(s->join, s->stream);
+    return true;
+}
+static int image_copy_join(cudaStream_t st) {
+    SideStream *s = side_stream();
+    cudaError_t e = s ? cudaStreamWaitEvent(st, s->join, 0) : cudaErrorUnknown;
+    return e == cudaSuccess ? CMR_OK : (int)e;
+}
+
 // true when the image half of obs2d can travel as tiled TMA boxes inside k_project
 static bool image_copy_by_tma(const float *img_feat, const float *obs2d, int B, int C, int P, CUtensorMap *map_img,
                               CUtensorMap *map_out) {
@@ -381,7 +434,7 @@ static int project_impl(const float *pc, const uint8_t *overlap, const float *K,
     alignas(64) CUtensorMap map_img, map_out;
     // who carries the image half of obs2d: k_tile_gather (its light warps have an idle tile and idle time while
     // they wait for k_project; CMR_B200_IMG=gather, the default when the bucket path is taken) or k_project
-    static const bool img_in_gather = [] { const char *e = getenv("CMR_B200_IMG"); return !(e && e[0] == 'p'); }();
+    static const bool img_in_gather = image_mode() != 'p';
     const bool img_tma = !(img_in_gather && bucket_path(L, C)) &&
                          image_copy_by_tma(img_feat, obs2d, B, C, H * W, &map_img, &map_out);
     if (!img_tma) {
@@ -430,10 +483,17 @@ int cmr_observe(const float *pc, const uint8_t *overlap, const float *img_feat, 
                 int32_t *pix_out, int32_t *mvis_out, void *stream) {
     CMR_REQUIRE(img_feat && obs2d, CMR_EINVAL);
     int copied = 0;
-    int rc = project_impl(pc, overlap, K, pose, mean, workspace, B, N, C, H, W, obs3d, pix_out, mvis_out, img_feat, obs2d,
-                          &copied, false, stream);
+    int rc = check_observe_dims(B, N, C, H, W);
     if (rc) return rc;
-    return cmr_tile_scatter(img_feat, K, workspace, B, N, C, H, W, copied ? 0 : 1, obs2d, stream);
+    const bool forked = image_mode() == 's' && (C % kSlab) == 0 && image_copy_fork(img_feat, obs2d, B, C, H * W, S_(stream));
+    rc = project_impl(pc, overlap, K, pose, mean, workspace, B, N, C, H, W, obs3d, pix_out, mvis_out, img_feat, obs2d,
+                      &copied, false, stream);
+    if (!rc) rc = cmr_tile_scatter(img_feat, K, workspace, B, N, C, H, W, (copied || forked) ? 0 : 1, obs2d, stream);
+    if (forked) {   // joined whatever happened: a capturing stream must not be left forked
+        const int jrc = image_copy_join(S_(stream));
+        if (!rc) rc = jrc;
+    }
+    return rc;
 }
 
 int cmr_to_disentangled(float *poses, const float *mean, int B, void *stream) {
