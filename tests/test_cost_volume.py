@@ -120,6 +120,7 @@ def test_oracle_shapes_and_occupancy(B, N, img_h, img_w, nlabel, dense):
     (1, 8192, 160, 320, 3, True),
     (1, 40960, 160, 512, 3, False),       # the reference's sizes (27 of its 729 poses)
     (2, 40960, 64, 64, 2, True),          # 8 buckets for thousands of visible points: buffers overflow, shared clouds
+    (1, 2048, 36, 100, 3, True),          # 9 x 25 grid: P % 4 != 0, results leave without TMA
 ])
 def test_gpu_matches_oracle(cuda, B, N, img_h, img_w, nlabel, dense):
     from cmr_agent_b200 import cost_volume
