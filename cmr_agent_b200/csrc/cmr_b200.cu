@@ -665,7 +665,23 @@ int cmr_cost_volume_warp(const float *pc, const uint8_t *mask, const float *Kmat
     memset(&none_a, 0, sizeof(none_a));
     memset(&none_b, 0, sizeof(none_b));
     cudaStream_t st = S_(stream);
-    if (L.pix16)
+    // only the masked points are projected (k_project_masked); CMR_B200_CV_PROJECT=full: k_project over all N points
+    static const bool full_project = [] { const char *e = getenv("CMR_B200_CV_PROJECT"); return e && e[0] == 'f'; }();
+    if (!full_project) {
+        const int *seg = reinterpret_cast<const int *>(ws + L.off_seg);
+        int *bcnt = reinterpret_cast<int *>(ws + L.off_bcnt);
+        unsigned *bbuf = reinterpret_cast<unsigned *>(ws + L.off_bbuf);
+        int *hq = reinterpret_cast<int *>(ws + L.off_hq);
+        int *hdr = bcnt + (size_t)E * kBucketStride;
+        const bool vec = (N % 4 == 0) && aligned(mask, 4);
+        const dim3 grid(ceil_div(L.groups, kProjWarps), E), block(32 * kProjWarps);
+        if (L.pix16)
+            rc = launch_pdl(k_project_masked<uint16_t>, grid, block, 0, st, pc, mask, Kmat, poses, zero_mean, seg, N, L.ncap,
+                            L.groups, H, W, vec, reinterpret_cast<uint16_t *>(ws + L.off_pix), bcnt, bbuf, L.buckets, hdr, hq, K);
+        else
+            rc = launch_pdl(k_project_masked<int32_t>, grid, block, 0, st, pc, mask, Kmat, poses, zero_mean, seg, N, L.ncap,
+                            L.groups, H, W, vec, reinterpret_cast<int32_t *>(ws + L.off_pix), bcnt, bbuf, L.buckets, hdr, hq, K);
+    } else if (L.pix16)
         rc = launch_project<uint16_t>(L, ws, pc, mask, Kmat, poses, zero_mean, E, N, C, H, W, nullptr, nullptr, nullptr, false,
                                       none_a, none_b, false, st, K);
     else

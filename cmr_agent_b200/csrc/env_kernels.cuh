@@ -520,6 +520,75 @@ __global__ void CMR_PROJ_BOUNDS k_project(const float *__restrict__ pc, const ui
     }
 }
 
+// k_project for a cost volume (models/IterModel.py:281-318; no obs3d): only the MASKED points of a pose are used, so
+// only they are projected.  One warp = one 128-point group: the flags are scanned as in k_project, the masked points'
+// offsets are listed in shared memory, and every lane takes one listed point per pass (a group of a 22 % mask is
+// one pass).  Writes the same pixel-id list and bucket entries as k_project does for these points.
+template <typename PixT>
+__global__ void __launch_bounds__(32 * CMR_PROJ_WARPS)
+    k_project_masked(const float *__restrict__ pc, const uint8_t *__restrict__ mask, const float *__restrict__ K,
+                     const float *__restrict__ pose, const float *__restrict__ mean, const int *__restrict__ seg, int N,
+                     int ncap, int groups, int H, int W, bool vec, PixT *__restrict__ pix, int *__restrict__ bcnt,
+                     unsigned *__restrict__ bbuf, int buckets, int *__restrict__ hdr, int *__restrict__ hq, int share) {
+    pdl_launch_dependents();
+    pdl_wait();
+    __shared__ unsigned char list[kProjWarps][kGroup];
+    const int b = blockIdx.y, bs = b / share;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = blockIdx.x * kProjWarps + warp;
+    if (g >= groups) return;
+    const unsigned flags = load_flags4(mask + (size_t)bs * N, g * kGroup + lane * 4, N, vec);
+    const int mine = __popc(flags);
+    int incl = mine;
+#pragma unroll
+    for (int o2 = 1; o2 < 32; o2 <<= 1) {
+        int t = __shfl_up_sync(kFull, incl, o2);
+        if (lane >= o2) incl += t;
+    }
+    int r = incl - mine;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        if (flags >> i & 1) list[warp][r++] = (unsigned char)(lane * 4 + i);
+    const int cnt = __shfl_sync(kFull, incl, 31);
+    __syncwarp();
+    const int base = __ldg(seg + (size_t)bs * groups + g);
+    PixT *pw = pix + (size_t)b * ncap;
+    if (cnt > 0) {
+        PoseK s;
+        load_posek(s, pose, K, mean, b, bs);
+        const int P = H * W;
+        const float wmax = (float)(W - 1), hmax = (float)(H - 1);
+        const float *px = pc + (size_t)bs * 3 * N, *py = px + N, *pz = py + N;
+        // every column of the cloud is multiplied before the mask is applied (:281-302): the regime of N columns
+        const bool chain = N >= kBmmChainMinCols;
+        int *bc = bcnt + (size_t)b * kBucketStride;
+        for (int r0 = 0; r0 < cnt; r0 += 32) {
+            const int k = r0 + lane;
+            if (k < cnt) {
+                const int j = g * kGroup + list[warp][k];
+                const float x = __ldg(px + j), y = __ldg(py + j), z = __ldg(pz + j);
+                bool in_cam;
+                const int id = chain ? project_point<true>(s, x, y, z, wmax, hmax, W, P, in_cam)
+                                     : project_point<false>(s, x, y, z, wmax, hmax, W, P, in_cam);
+                const int pos = base + k;
+                pw[pos] = (PixT)id;
+                if (in_cam) {
+                    const int slot = atomicAdd(bc + id / kBucketPix, 1);
+                    if (slot < kBucketCap)
+                        bbuf[((size_t)b * buckets + id / kBucketPix) * kBucketCap + slot] = ((unsigned)pos << 7) | ((unsigned)id & 127u);
+                    if (slot == kLightMax) hq[atomicAdd(hdr, 1)] = (b << 16) | (id / kBucketPix);
+                }
+            }
+        }
+    }
+    // the id list is read in 16-byte words: all-ones between M and the next word boundary (as k_project does)
+    if (g == groups - 1 && lane == 31) {
+        constexpr int kPer = 16 / sizeof(PixT);
+        const int end = base + cnt;
+        for (int m = end; m < (end + kPer - 1) / kPer * kPer; ++m) pw[m] = (PixT)~(PixT)0;
+    }
+}
+
 // Scatter-mean of the predicted-overlap points' features onto the pixel grid + concat with the image
 // features (environment.py:74-86).  One CTA owns kTilePix consecutive pixels of one episode:
 //   (0) copies the image-feature half of obs2d for its pixels (does not depend on the pose),
