@@ -429,3 +429,21 @@ def test_expert_on_device_matches_scipy_oracle(cuda, dof6):
         env.step(a_r, a_t, sd, cfg_d)
         eo.step(h_r, h_t, src, cfg_h)
         assert torch.equal(sd.cpu(), src)
+
+
+@pytest.mark.parametrize("switch", ["CMR_B200_IMG=stream", "CMR_B200_IMG=project", "CMR_B200_PDL=0"])
+def test_ab_switches_keep_parity(cuda, switch):
+    """The A/B switches of DESIGN.md section 9 (read once per process) select other kernels for the same result: the
+    golden and dense-bucket cases run again in a child process with the switch set."""
+    import os
+    import subprocess
+    import sys
+    name, value = switch.split("=")
+    if os.environ.get("CMR_B200_AB_CHILD"):
+        pytest.skip("already inside the child run")
+    env = dict(os.environ, CMR_B200_AB_CHILD="1", **{name: value})
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_env.py", "-x", "-q", "-m", "gpu", "-k",
+                        "reference_golden or dense_buckets or other_channel_counts", "-p", "no:cacheprovider"],
+                       cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
