@@ -31,6 +31,11 @@
 //       warp: a pixel's rows are then consecutive, the inner loop is a load and two additions per row.
 //       A bucket that overflowed its buffer (more than kBucketCap points) is rebuilt from the episode's
 //       pixel-id list in chunks of kBucketCap, in point order.
+//     * the image half of obs2d (obs2d[b, 0:C] = img_geo_feat[b], environment.py:83) rides along: before it waits
+//       for k_project, every light warp fetches the [64][32] box of its bucket's pixels into its (still idle) tile
+//       with a TMA load and sends it on with a TMA store - no registers, no LSU instructions.
+//     * a cost volume's four tail channels (the summed scores + padding, models/IterModel.py:343) get no slab pass
+//       from the light warps: a lane adds them up for its own pixel (`tail`).
 //   Counters are cleared by their readers: a light bucket's counter has one reader (its warp), a heavy bucket's
 //   two (its warp, which only learns that the bucket is heavy, and the bucket CTA) - each adds kCountSeen, and
 //   the one that finds it already there clears the counter; the last bucket CTA to finish clears the queue
