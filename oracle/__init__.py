@@ -23,6 +23,11 @@ cmr_oracle.c        plain-C restatement of the integer-critical arithmetic
                     (projection, FPS, stable kNN, ball query, scatter-mean)
                     used for full-size bit-exact checks in seconds.
 cref.py             ctypes binding of the compiled cmr_oracle.c.
+dataset_oracle.py   numpy restatement of the datasets' float64 FPS and nearest-node search.
+cost_volume_oracle.py  torch-CPU restatement of IterModel's cost-volume warp (pinned by
+                    tests/golden/cost_volume.npz, made from the reference's own statements).
+tower_oracle.py     the agent's 3-D tower in eval mode (no CUDA path yet: pins the algebra
+                    of a later round's kernel against the reference's modules).
 
 Parity pinning: the reference ships no tests or golden vectors,
 so the pins are (1) the restatement == the real reference on seeded inputs,

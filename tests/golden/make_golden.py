@@ -286,7 +286,62 @@ def cost_volume_case():
           os.path.getsize(os.path.join(HERE, "cost_volume.npz")) // 1024, "KiB")
 
 
+def tower_inputs():
+    """Seeded weights of the four blocks (oracle/tower_oracle.make_state) and an obs3d [2, 5, 4096] made the way the
+    environment makes it: xyz, predicted-overlap flag, in-frustum flag (environment.py:121-124)."""
+    from oracle import tower_oracle
+    states = [tower_oracle.make_state(SEED + 40 + i, cin, cout) for i, (cin, cout) in enumerate(tower_oracle.TOWER)]
+    data = synth.make_batch(2, seed=SEED + 21, num_pt=4096, img_h=160, img_w=512)
+    g = torch.Generator().manual_seed(SEED + 22)
+    in_cam = (torch.rand(2, 4096, generator=g) < 0.3).float()
+    obs3d = torch.cat([data["pc"], data["pc_overlap_pred"].float().unsqueeze(1), in_cam.unsqueeze(1)], dim=1).contiguous()
+    return states, obs3d
+
+
+def reference_tower(states, obs3d):
+    """The reference's own ConvBNReLURes1D modules (models/PointNN.py:260-282) in eval mode, loaded with `states` and
+    composed exactly as CMRAgent.forward does (models/CMRAgent.py:92-101; the module list of :25-29)."""
+    import importlib
+    import types
+    from oracle import shims, tower_oracle
+    shims.install()
+    for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.image", "tensorboardX"):
+        try:
+            __import__(name)
+        except Exception:
+            sys.modules[name] = types.ModuleType(name)
+    if reference_loader.REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, reference_loader.REFERENCE_ROOT)
+    pn = importlib.import_module("models.PointNN")
+    layers = []
+    for sd, (cin, cout) in zip(states, tower_oracle.TOWER):
+        m = pn.ConvBNReLURes1D(cin, cout)
+        m.load_state_dict(sd)
+        layers.append(m.eval())
+    with torch.no_grad():
+        embed_3d = obs3d
+        for step, layer in enumerate(layers):                     # CMRAgent.py:94-100
+            feat_3d = layer(embed_3d)
+            embed_3d = torch.max(feat_3d, dim=2, keepdim=True)[0]
+            if step < len(layers) - 1:
+                embed_3d = embed_3d.repeat(1, 1, feat_3d.shape[2])
+                embed_3d = torch.cat([feat_3d, embed_3d], dim=1)
+        return embed_3d.view(embed_3d.shape[0], -1)               # :101
+
+
+def tower_case():
+    states, obs3d = tower_inputs()
+    want = reference_tower(states, obs3d)
+    np.savez_compressed(os.path.join(HERE, "tower.npz"), embed_3d=want.numpy(),
+                        obs3d_sha=np.frombuffer(sha(obs3d).encode(), dtype=np.uint8))
+    print("tower.npz", tuple(want.shape))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "tower":   # only the tower fixture
+        assert reference_loader.available(), "needs /root/reference"
+        tower_case()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "cost_volume":   # only the cost-volume fixture
         assert reference_loader.available(), "needs /root/reference"
         cost_volume_case()
@@ -306,3 +361,4 @@ if __name__ == "__main__":
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
     dataset_case()
     cost_volume_case()
+    tower_case()
