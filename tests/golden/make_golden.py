@@ -7,6 +7,11 @@ It imports /root/reference/environment/environment.py and models/pointnet_util.p
 cmr_agent_b200.synth, and stores the OUTPUTS (plus the tiny inputs that cannot be regenerated:
 poses, cloud means, FPS start indices).  Bulk inputs are regenerated from the seed at test time and
 verified against the sha256 stored here.  The fixtures travel to the GPU box; the reference does not.
+
+    python tests/golden/make_golden.py dataset | cost_volume | tower     # one fixture only
+dataset.npz: the reference's FarthestSampler class + scipy's cKDTree.  cost_volume.npz: the reference's own statements of
+IterModel.py:96-172 and :272-351, compiled from its syntax tree (the module does not import; forward() runs the whole
+model around them).  tower.npz: the reference's ConvBNReLURes1D modules composed as CMRAgent.forward composes them.
 """
 import hashlib
 import os
