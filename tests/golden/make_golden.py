@@ -10,8 +10,8 @@ verified against the sha256 stored here.  The fixtures travel to the GPU box; th
 
     python tests/golden/make_golden.py dataset | cost_volume | tower     # one fixture only
 dataset.npz: the reference's FarthestSampler class + scipy's cKDTree.  cost_volume.npz: the reference's own statements of
-IterModel.py:96-172 and :272-351, compiled from its syntax tree (the module does not import; forward() runs the whole
-model around them).  tower.npz: the reference's ConvBNReLURes1D modules composed as CMRAgent.forward composes them.
+IterModel.py:96-172 and :272-351, compiled from its syntax tree (the class cannot be constructed without a GPU - __init__ calls
+.cuda(), :29 - and forward() runs the whole model around them).  tower.npz: the reference's ConvBNReLURes1D modules composed as CMRAgent.forward composes them.
 """
 import hashlib
 import os
@@ -224,8 +224,9 @@ def cost_volume_inputs(case):
 def _reference_iter_model_pieces():
     """The statements of models/IterModel.py that make up the cost-volume warp, taken from the reference's OWN
     source through its syntax tree and compiled as they stand: the methods ``angle2matrix`` and ``sample_poses``
-    (:96-172) and the part of ``forward`` from the mask selection to the cropped outputs (:272-351).  The module
-    itself cannot be imported (cv2, the networks) and ``forward`` runs the whole model around these lines."""
+    (:96-172) and the part of ``forward`` from the mask selection to the cropped outputs (:272-351).  The class
+    cannot be constructed without a GPU (``__init__`` calls ``.cuda()``, :29) and ``forward`` runs the whole model
+    around these lines."""
     import ast
     path = os.path.join(reference_loader.REFERENCE_ROOT, "models", "IterModel.py")
     tree = ast.parse(open(path).read(), path)
