@@ -31,20 +31,50 @@ def _i64c(t, name):
     return t if t.is_contiguous() else t.contiguous()
 
 
-def square_distance(src, dst):
-    """pointnet_util.py:19-33: src [B,S,3], dst [B,N,3] (any strides) -> [B,S,N] f32."""
-    _lib.require_cuda(src, "src", torch.float32)
-    _lib.require_cuda(dst, "dst", torch.float32)
+def _square_distance_raw(src, dst):
     B, S, Cs = src.shape
     Bd, N, Cd = dst.shape
     if Cs != 3 or Cd != 3 or B != Bd:
         raise _lib.CmrError("square_distance expects src [B,S,3] and dst [B,N,3]")
     out = torch.empty(B, S, N, device=src.device, dtype=torch.float32)
+    if out.numel() == 0:
+        return out
     ss = (ctypes.c_int64 * 3)(*src.stride())
     ds = (ctypes.c_int64 * 3)(*dst.stride())
     _lib.call("cmr_square_distance", _lib.ptr(src), ctypes.cast(ss, ctypes.c_void_p), _lib.ptr(dst),
               ctypes.cast(ds, ctypes.c_void_p), B, S, N, _lib.ptr(out), _lib.stream())
     return out
+
+
+class _SquareDistance(torch.autograd.Function):
+    """d[s,n] = |src_s - dst_n|^2; d/dsrc_s = 2 sum_n g[s,n] (src_s - dst_n), d/ddst_n = -2 sum_s g[s,n] (src_s - dst_n).
+    The reference differentiates the same expression through broadcasting (pointnet_util.py:33); its callers only
+    ever pass coordinates, so this backward exists for gradient equivalence, not for speed."""
+
+    @staticmethod
+    def forward(ctx, src, dst):
+        ctx.save_for_backward(src, dst)
+        return _square_distance_raw(src, dst)
+
+    @staticmethod
+    def backward(ctx, g):
+        src, dst = ctx.saved_tensors
+        g = g.contiguous()
+        gs = gd = None
+        if ctx.needs_input_grad[0]:
+            gs = 2.0 * (g.sum(dim=2, keepdim=True) * src - torch.bmm(g, dst))
+        if ctx.needs_input_grad[1]:
+            gd = 2.0 * (g.sum(dim=1).unsqueeze(-1) * dst - torch.bmm(g.transpose(1, 2), src))
+        return gs, gd
+
+
+def square_distance(src, dst):
+    """pointnet_util.py:19-33: src [B,S,3], dst [B,N,3] (any strides) -> [B,S,N] f32."""
+    _lib.require_cuda(src, "src", torch.float32)
+    _lib.require_cuda(dst, "dst", torch.float32)
+    if torch.is_grad_enabled() and (src.requires_grad or dst.requires_grad):
+        return _SquareDistance.apply(src, dst)
+    return _square_distance_raw(src, dst)
 
 
 class _IndexPoints(torch.autograd.Function):
@@ -141,23 +171,66 @@ def knn_point(k, xyz, new_xyz):
     return out
 
 
+def _group_points_raw(xyz, points, new_xyz, idx):
+    B, N, _ = xyz.shape
+    _, S, K = idx.shape
+    D = 0 if points is None else points.shape[-1]
+    out = torch.empty(B, S, K, 3 + D, device=xyz.device, dtype=torch.float32)
+    if out.numel():
+        _lib.call("cmr_group_points", _lib.ptr(xyz), _lib.ptr(points), _lib.ptr(new_xyz), _lib.ptr(idx), B, N, S, K,
+                  D, _lib.ptr(out), _lib.stream())
+    return out
+
+
+def _scatter_rows(grad_rows, idx_flat, N):
+    """sum of grad_rows [B,S',C] into rows idx_flat [B,S'] of a zero [B,N,C] (cmr_index_points_backward)."""
+    B, S, C = grad_rows.shape
+    grad = torch.zeros(B, N, C, device=grad_rows.device, dtype=torch.float32)
+    if S and C:
+        _lib.call("cmr_index_points_backward", _lib.ptr(grad_rows.contiguous()), _lib.ptr(idx_flat), B, N, S, C,
+                  _lib.ptr(grad), _lib.stream())
+    return grad
+
+
+class _GroupPoints(torch.autograd.Function):
+    """Gradient of the fused gather - centroid || gather: what autograd gives the reference through
+    index_points, the subtraction and the cat (pointnet_util.py:120-129)."""
+
+    @staticmethod
+    def forward(ctx, xyz, points, new_xyz, idx):
+        ctx.save_for_backward(idx)
+        ctx.n = xyz.shape[1]
+        ctx.has_points = points is not None
+        return _group_points_raw(xyz, points, new_xyz, idx)
+
+    @staticmethod
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        B, S, K = idx.shape
+        flat = idx.reshape(B, S * K)
+        g = g.float()
+        gxyz = gpts = gnew = None
+        if ctx.needs_input_grad[0]:
+            gxyz = _scatter_rows(g[..., :3].reshape(B, S * K, 3), flat, ctx.n)
+        if ctx.has_points and ctx.needs_input_grad[1]:
+            gpts = _scatter_rows(g[..., 3:].reshape(B, S * K, -1), flat, ctx.n)
+        if ctx.needs_input_grad[2]:
+            gnew = -g[..., :3].sum(dim=2)
+        return gxyz, gpts, gnew, None
+
+
 def group_points(xyz, points, new_xyz, idx):
     """Fused tail of sample_and_group (pointnet_util.py:120-129):
     cat(xyz[idx] - new_xyz[:, :, None], points[idx]) -> [B,S,K,3+D]."""
     xyz = _f32c(xyz, "xyz")
     new_xyz = _f32c(new_xyz, "new_xyz")
     idx = _i64c(idx, "idx")
-    B, N, _ = xyz.shape
-    _, S, K = idx.shape
-    D = 0
     if points is not None:
         points = _f32c(points, "points")
-        D = points.shape[-1]
-    out = torch.empty(B, S, K, 3 + D, device=xyz.device, dtype=torch.float32)
-    if out.numel():
-        _lib.call("cmr_group_points", _lib.ptr(xyz), _lib.ptr(points), _lib.ptr(new_xyz), _lib.ptr(idx), B, N, S, K,
-                  D, _lib.ptr(out), _lib.stream())
-    return out
+    if torch.is_grad_enabled() and (xyz.requires_grad or new_xyz.requires_grad or
+                                    (points is not None and points.requires_grad)):
+        return _GroupPoints.apply(xyz, points, new_xyz, idx)
+    return _group_points_raw(xyz, points, new_xyz, idx)
 
 
 def sample_and_group(npoint, radius, nsample, xyz, points, returnfps=False, knn=False):

@@ -35,8 +35,13 @@ def test_step_tables_equal_the_reference_expression():
     assert torch.equal(drop_in.euler_angles_to_matrix(ang, "XYZ"), eo.euler_angles_to_matrix(ang, "XYZ"))
 
 
-def test_install_aliases_the_reference_import_names():
-    code = textwrap.dedent("""
+def _run(code):
+    out = subprocess.run([sys.executable, "-c", textwrap.dedent(code)], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "ok" in out.stdout, (out.stdout[-1000:], out.stderr[-3000:])
+
+
+def test_install_without_a_reference_tree_registers_the_drop_ins():
+    _run("""
         import sys
         sys.path.insert(0, %r)
         import cmr_agent_b200
@@ -54,10 +59,81 @@ def test_install_aliases_the_reference_import_names():
             assert hasattr(pn, f), f
         cmr_agent_b200.uninstall()
         assert "environment.environment" not in sys.modules
+        assert "models.pointnet_util" not in sys.modules
         print("ok")
     """ % ROOT)
-    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
-    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
+def _needs_reference():
+    from oracle import reference_loader as rl
+    if not rl.available():
+        pytest.skip("no reference tree (/root/reference or oracle/_ref)")
+    return rl.REFERENCE_ROOT
+
+
+def test_install_before_the_reference_imports_keeps_its_packages_whole():
+    """INTEGRATION.md section 2 order: install() first, then the reference's own import lines
+    (Train_Agent.py:13-16, models/PointNN.py:7).  environment.buffer must still resolve and the
+    nn.Module classes of models/pointnet_util.py must still be there."""
+    ref = _needs_reference()
+    _run("""
+        import sys
+        sys.path.insert(0, %r)
+        from oracle import reference_loader as rl
+        rl.put_on_path()
+        import cmr_agent_b200
+        from cmr_agent_b200 import environment as drop_env, pointnet_util as drop_pn
+        cmr_agent_b200.install()
+        from config import KittiConfiguration
+        from models import CMRAgent, MultiHeadModel
+        from environment import environment as env
+        from environment.buffer import Buffer
+        import environment as env_pkg, models.PointNN as pnn, models.pointnet_util as pu
+        assert env is drop_env and env_pkg.environment is drop_env
+        assert env_pkg.__file__.startswith(%r)
+        assert Buffer.__module__ == "environment.buffer"
+        assert pu.__file__.startswith(%r)                      # the real module, patched
+        assert pnn.index_points is drop_pn.index_points and pnn.square_distance is drop_pn.square_distance
+        for f in ("farthest_point_sample", "query_ball_point", "sample_and_group", "sample_and_group_all"):
+            assert getattr(pu, f) is getattr(drop_pn, f), f
+        for c in ("PointNetSetAbstraction", "PointNetSetAbstractionMsg", "PointNetFeaturePropagation", "pc_normalize",
+                  "timeit"):
+            assert hasattr(pu, c), c
+        # the classes reach the drop-ins through their module globals
+        assert pu.PointNetSetAbstraction.forward.__globals__["sample_and_group"] is drop_pn.sample_and_group
+        cmr_agent_b200.uninstall()
+        assert "environment.environment" not in sys.modules or sys.modules["environment.environment"] is not drop_env
+        print("ok")
+    """ % (ROOT, ref, ref))
+
+
+def test_install_after_the_reference_imports_repoints_bound_names():
+    ref = _needs_reference()
+    _run("""
+        import sys
+        sys.path.insert(0, %r)
+        from oracle import reference_loader as rl
+        rl.put_on_path()
+        from models import CMRAgent
+        from environment import environment as env
+        from environment.buffer import Buffer
+        import models.PointNN as pnn, models.pointnet_util as pu
+        orig_sq, orig_env = pnn.square_distance, env
+        import types
+        driver = types.ModuleType("fake_driver"); driver.env = env; sys.modules["fake_driver"] = driver
+        import cmr_agent_b200
+        from cmr_agent_b200 import environment as drop_env, pointnet_util as drop_pn
+        cmr_agent_b200.install()
+        import environment as env_pkg
+        assert env_pkg.environment is drop_env and sys.modules["environment.environment"] is drop_env
+        assert driver.env is drop_env                                   # `from environment import environment as env`
+        assert pnn.square_distance is drop_pn.square_distance and pnn.index_points is drop_pn.index_points
+        assert pu.sample_and_group is drop_pn.sample_and_group
+        cmr_agent_b200.uninstall()
+        assert pnn.square_distance is orig_sq and driver.env is orig_env and pu.square_distance is orig_sq
+        assert sys.modules["environment.environment"] is orig_env
+        print("ok")
+    """ % ROOT)
 
 
 def test_signatures_match_the_reference_functions():
