@@ -48,6 +48,10 @@ SIGNATURES = {
     "cmr_knn": (_c_int, [_c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp]),
     "cmr_query_ball_point": (_c_int, [_c_vp, _c_vp, _c_f, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp]),
     "cmr_group_points": (_c_int, [_c_vp] * 4 + [_c_int] * 5 + [_c_vp, _c_vp]),
+    "cmr_tower_blob_bytes": (_c_sz, [_c_int]),
+    "cmr_tower_pack": (_c_int, [_c_int] + [_c_vp] * 8),
+    "cmr_tower_workspace_bytes": (_c_sz, [_c_int, _c_int]),
+    "cmr_tower_forward": (_c_int, [_c_vp] * 6 + [_c_int, _c_int, _c_vp, _c_vp]),
 }
 
 _lib = None

@@ -11,6 +11,7 @@
 #include "pointnet_kernels.cuh"
 #include "scatter_kernels.cuh"
 #include "dataset_kernels.cuh"
+#include "tower_kernels.cuh"
 
 namespace cmr {
 
@@ -52,6 +53,19 @@ static bool make_map3d(CUtensorMap *m, const float *base, uint64_t d0, uint64_t 
     cuuint32_t es[3] = {1, 1, 1};
     return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(base), dims, strides, box, es,
               CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// bf16 feature planes of the 3-D tower: tensor [B][N][64] (128-byte rows), boxes of [1][rows][64], 128B swizzle
+static bool make_plane_map(CUtensorMap *m, const void *base, uint64_t N, uint64_t B, uint32_t rows) {
+    EncodeTiledFn fn = encode_tiled();
+    if (!fn) return false;
+    cuuint64_t dims[3] = {64, N, B};
+    cuuint64_t strides[2] = {128, N * 128};
+    cuuint32_t box[3] = {64, rows, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(base), dims, strides, box, es,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -333,6 +347,31 @@ static int launch_feat_compact(const uint8_t *overlap, const float *feat, int B,
     k_feat_compact<256><<<dim3(groups, B), 256, smem, st>>>(overlap, feat, N, C, groups, (N % 4 == 0) && aligned(feat, 16),
                                                             seg, featT);
     return after_launch();
+}
+
+// workspace: five bf16 planes [B][N][64] + the max keys of the four blocks (64, 64, 64, 128 per episode)
+struct TowerWs {
+    size_t plane, off_keys, keys_bytes, total;
+};
+static TowerWs tower_ws(int B, int N) {
+    TowerWs w;
+    w.plane = round_up((size_t)B * N * 128, 1024);
+    w.off_keys = 5 * w.plane;
+    w.keys_bytes = (size_t)B * (64 * 3 + 128) * sizeof(unsigned);
+    w.total = w.off_keys + round_up(w.keys_bytes, 1024);
+    return w;
+}
+template <bool kLast, int kPlanesOut>
+static int launch_tower_mma(const void *blob, int B, int N, int tiles_per_ep, int box_rows, const CUtensorMap &in_hi, const CUtensorMap &in_lo,
+                            const CUtensorMap &in_lo2, const CUtensorMap &out_hi, const CUtensorMap &out_lo,
+                            const CUtensorMap &out_lo2, const unsigned *prev_keys, unsigned *max_keys, cudaStream_t st) {
+    auto kern = k_tower_mma<kLast, kPlanesOut>;
+    const size_t smem = TowerCfg<kLast>::smem_bytes;
+    int rc = allow_smem(kern, smem);
+    if (rc) return rc;
+    const int grid = std::min(B * tiles_per_ep, sm_count());
+    return launch_pdl(kern, dim3(grid), dim3(kTowerThreads), smem, st, static_cast<const unsigned char *>(blob), B, N, tiles_per_ep, box_rows,
+                      in_hi, in_lo, in_lo2, out_hi, out_lo, out_lo2, prev_keys, max_keys);
 }
 
 extern "C" {
@@ -724,6 +763,69 @@ int cmr_nearest_f64(const double *query, const double *ref, int B, int N, int S,
     CMR_REQUIRE(B <= 65535, CMR_ERANGE);
     k_nearest_f64<<<dim3(ceil_div(N, 256), B), 256, 0, S_(stream)>>>(query, ref, N, S, out);
     return after_launch();
+}
+
+// -------------------------------------------------------------------------------- 3-D tower ----
+// models/CMRAgent.py:25-29,92-101 (eval mode): tower_kernels.cuh
+
+size_t cmr_tower_blob_bytes(int kind) {
+    switch (kind) {
+        case CMR_TOWER_FIRST: return TowerBlobFirst::total;
+        case CMR_TOWER_MID: return TowerBlobMid::total;
+        case CMR_TOWER_LAST: return TowerBlobLast::total;
+        default: return 0;
+    }
+}
+
+int cmr_tower_pack(int kind, const float *W1, const float *b1, const float *W2, const float *b2, const float *Ws,
+                   const float *bs, void *blob, void *stream) {
+    CMR_REQUIRE(kind >= CMR_TOWER_FIRST && kind <= CMR_TOWER_LAST, CMR_EINVAL);
+    CMR_REQUIRE(W1 && b1 && W2 && b2 && blob && (kind == CMR_TOWER_LAST || (Ws && bs)), CMR_EINVAL);
+    CMR_REQUIRE(aligned(blob, 128), CMR_EALIGN);
+    k_tower_pack<<<32, 256, 0, S_(stream)>>>(kind, W1, b1, W2, b2, Ws, bs, static_cast<unsigned char *>(blob));
+    return after_launch();
+}
+
+size_t cmr_tower_workspace_bytes(int B, int N) { return (B > 0 && N > 0) ? tower_ws(B, N).total : 0; }
+
+int cmr_tower_forward(const float *obs3d, const void *blob1, const void *blob2, const void *blob3, const void *blob4,
+                      void *workspace, int B, int N, float *embed, void *stream) {
+    CMR_REQUIRE(obs3d && blob1 && blob2 && blob3 && blob4 && workspace && embed && B > 0 && N > 0, CMR_EINVAL);
+    CMR_REQUIRE(B <= 65535 && N < (1 << 24), CMR_ERANGE);
+    CMR_REQUIRE(aligned(workspace, 1024) && aligned(blob2, 128) && aligned(blob3, 128) && aligned(blob4, 128) && aligned(blob1, 16),
+                CMR_EALIGN);
+    cudaStream_t st = S_(stream);
+    const TowerWs w = tower_ws(B, N);
+    char *ws = static_cast<char *>(workspace);
+    char *plane[5];
+    for (int i = 0; i < 5; ++i) plane[i] = ws + i * w.plane;
+    unsigned *keys1 = reinterpret_cast<unsigned *>(ws + w.off_keys), *keys2 = keys1 + (size_t)B * 64, *keys3 = keys2 + (size_t)B * 64,
+             *keys4 = keys3 + (size_t)B * 64;
+    cudaError_t e = cudaMemsetAsync(keys1, 0, w.keys_bytes, st);
+    if (e != cudaSuccess) return (int)e;
+    const int tiles_per_ep = ceil_div(N, kTowerTile);
+    const uint32_t rows = (uint32_t)std::min(N, kTowerTile);
+    alignas(64) CUtensorMap m[5];
+    for (int i = 0; i < 5; ++i)
+        if (!make_plane_map(&m[i], plane[i], (uint64_t)N, (uint64_t)B, rows)) return CMR_EUNSUPPORTED;
+    // block 1 (fp32 pipes): obs3d -> planes 0,1
+    {
+        const size_t smem = 32768 + TowerBlobFirst::total;
+        int rc = allow_smem(k_tower_first, smem);
+        if (rc) return rc;
+        const int grid = std::min(B * tiles_per_ep, 4 * sm_count());
+        rc = launch_pdl(k_tower_first, dim3(grid), dim3(128), smem, st, obs3d, static_cast<const unsigned char *>(blob1), B, N,
+                        tiles_per_ep, m[0], m[1], keys1);
+        if (rc) return rc;
+    }
+    // block 2: planes 0,1 -> 2,3;  block 3: planes 2,3 -> 0,1,4;  block 4: planes 0,1,4 -> keys
+    int rc = launch_tower_mma<false, 2>(blob2, B, N, tiles_per_ep, (int)rows, m[0], m[1], m[1], m[2], m[3], m[3], keys1, keys2, st);
+    if (rc) return rc;
+    rc = launch_tower_mma<false, 3>(blob3, B, N, tiles_per_ep, (int)rows, m[2], m[3], m[3], m[0], m[1], m[4], keys2, keys3, st);
+    if (rc) return rc;
+    rc = launch_tower_mma<true, 2>(blob4, B, N, tiles_per_ep, (int)rows, m[0], m[1], m[4], m[0], m[1], m[4], keys3, keys4, st);
+    if (rc) return rc;
+    return launch_pdl(k_tower_finish, dim3(ceil_div(B * 128, 256)), dim3(256), 0, st, (const unsigned *)keys4, embed, B * 128);
 }
 
 #ifdef CMR_DBG_TIMING

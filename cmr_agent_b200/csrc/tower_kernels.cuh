@@ -1,0 +1,705 @@
+// tower_kernels.cuh - the agent's 3-D tower on tcgen05 tensor cores + TMEM.
+//
+// Reference: CMRAgent.forward, models/CMRAgent.py:92-101, over state_3d_embed (:25-29): four ConvBNReLURes1D
+// blocks (models/PointNN.py:260-282; 5->64, 128->64, 128->64, 128->128 channels, 1x1 convolutions) with a global
+// max over the N points of an episode between them.  Eval mode: every BatchNorm1d is folded into the convolution
+// before it (host side, cmr_agent_b200/agent_tower.py; algebra pinned by oracle/tower_oracle.py).
+//
+// Algebra (oracle/tower_oracle.py):  the input of blocks 2-4 is cat([feat (64), max_prev.repeat(N) (64)]), so the
+// half of every first-layer product that meets the repeated max is a PER-EPISODE BIAS  W[:, 64:] @ max_prev.
+//   block 1 (k_tower_first, fp32 FMA - K = 5 is no tensor-core shape):
+//       h = lrelu(W1 x + b1) (5 ch);  out = lrelu(W2 h + Ws x + (b2 + bs))              -> feat1 [64]
+//   blocks 2, 3 (k_tower_mma<false>):
+//       h = lrelu(W1a feat + bias1_e)           (128 ch;  bias1_e = b1 + W1b max_prev)
+//       out = lrelu(W2 h + Wsa feat + bias2_e)  ( 64 ch;  bias2_e = b2 + bs + Wsb max_prev)
+//   block 4 (k_tower_mma<true>; identity shortcut = the concatenated input itself):
+//       h as above;  out[c] = lrelu((W2 h)[c] + b2[c] + (c < 64 ? feat[c] : max_prev[c-64]))   (128 ch)
+//   after every block: max over the episode's points per channel -> ordered-uint keys, atomicMax.
+//
+// Precision.  north_star's bar is 1e-5 (read on the output's scale, tests/test_tower_oracle.py); single-pass bf16
+// or tf32 operands are 1e-3 off.  Every GEMM therefore runs as three bf16 passes over split operands
+// (x = hi + lo, hi = bf16(x), lo = bf16(x - hi)):  hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM - measured
+// 4-5e-6 on the output's scale, at 3/2 of the tensor time one tf32 pass would take.
+//
+// Orientation: M = 128 points (TMEM lanes), N = output channels (TMEM columns), K = input channels.
+//   A operand = activations: `feat` tiles arrive by TMA as two bf16 planes [128 pts][64 ch] (128-byte rows,
+//       128B swizzle: exactly the K-major UMMA layout), h is written BACK INTO TMEM by the epilogue as packed bf16
+//       pairs over the accumulator it was read from, and the second GEMM takes its A operand from TMEM.
+//   B operand = weights, pre-split and pre-swizzled once by k_tower_pack, resident in shared memory.
+// Features travel between the blocks as bf16 planes [B][N][64] (hi, lo; a third plane lo2 after block 3, whose
+// consumer adds them back to an exact fp32 for the identity shortcut) - 4 bytes per value, as fp32 would be.
+//
+// Warp roles of k_tower_mma (384 threads): warp 0 = TMA producer, warp 1 = TMEM allocation + MMA issue (one
+// elected lane), warps 4-7 and 8-11 = two epilogue groups working on alternate tiles, each with its own TMEM
+// accumulators (D1/H 128 columns + D2 64|128 columns), so that the tensor pipe works on tile t+1 while tile t is
+// in the epilogue.  A CTA owns a contiguous range of 128-point tiles; when the range crosses into the next
+// episode the epilogue groups flush their running maxima, recompute the per-episode biases and go on.
+#pragma once
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace cmr {
+
+constexpr int kTowerF = 64;            // embed_dim (config/KittiConfig.py:63)
+constexpr int kTowerTile = 128;        // points per tile = UMMA M
+constexpr int kTowerThreads = 384;
+constexpr float kTowerSlope = 0.2f;    // LeakyReLU(negative_slope=0.2), PointNN.py:267,272
+
+// ---- packed weights: byte offsets inside the blob k_tower_pack writes (one blob per block) ------------------------
+// mid block (blocks 2, 3):   W1a hi|lo [128 x 64], W2 hi|lo [64 x 128] as two K-blocks, Wsa hi|lo [64 x 64]
+// last block (block 4):      W1a hi|lo [128 x 64], W2 hi|lo [128 x 128] as two K-blocks
+// then fp32 side arrays (read from global memory when an episode's biases are set up)
+struct TowerBlobMid {
+    static constexpr int w1_hi = 0, w1_lo = 16384, w2_hi = 32768, w2_lo = 49152, ws_hi = 65536, ws_lo = 73728;
+    static constexpr int smem_bytes = 81920;
+    static constexpr int w1bT = smem_bytes;                 // [64][128] f32: W1[:, 64+k] transposed
+    static constexpr int b1 = w1bT + 64 * 128 * 4;          // [128]
+    static constexpr int wsbT = b1 + 128 * 4;               // [64][64]: Ws[:, 64+k] transposed
+    static constexpr int b2 = wsbT + 64 * 64 * 4;           // [64]: b2 + bs
+    static constexpr int total = b2 + 64 * 4;
+};
+struct TowerBlobLast {
+    static constexpr int w1_hi = 0, w1_lo = 16384, w2_hi = 32768, w2_lo = 65536;
+    static constexpr int smem_bytes = 98304;
+    static constexpr int w1bT = smem_bytes;
+    static constexpr int b1 = w1bT + 64 * 128 * 4;
+    static constexpr int b2 = b1 + 128 * 4;                 // [128]
+    static constexpr int total = b2 + 128 * 4;
+};
+// block 1: fp32, per output channel 12 floats {W2 row (5), Ws row (5), b2 + bs, 0}, then W1 [5][5], b1 [5]
+struct TowerBlobFirst {
+    static constexpr int rows = 0;                          // [64][12] f32
+    static constexpr int w1 = 64 * 12 * 4;                  // [5][5]
+    static constexpr int b1 = w1 + 25 * 4;                  // [5]
+    static constexpr int total = ((b1 + 5 * 4 + 15) / 16) * 16;
+};
+
+// ---- order-preserving float <-> uint keys for atomicMax (0 = "no value yet") ---------------------------------------
+__device__ __forceinline__ unsigned f2key(float v) {
+    unsigned b = __float_as_uint(v);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float key2f(unsigned k) {
+    return __uint_as_float((k & 0x80000000u) ? (k ^ 0x80000000u) : ~k);
+}
+__device__ __forceinline__ float lrelu(float v) { return fmaxf(v, __fmul_rn(kTowerSlope, v)); }
+
+// x -> (hi, lo[, lo2]) bf16 pieces of two neighbouring channels, packed little-endian (even channel in the low half)
+__device__ __forceinline__ unsigned pack_bf16x2(float lo_elem, float hi_elem) {
+    unsigned r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+    return r;
+}
+__device__ __forceinline__ float bf16lo_f(unsigned p) { return __uint_as_float(p << 16); }
+__device__ __forceinline__ float bf16hi_f(unsigned p) { return __uint_as_float(p & 0xffff0000u); }
+
+// ---- tcgen05 / TMEM wrappers (inline PTX; SASS: UTCHMMA, LDTM/STTM, UTCBAR) -----------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t *smem_slot, uint32_t cols) {   // one full warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {      // the same warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// all tcgen05.mma issued so far by this thread have completed -> one arrival on `bar`
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]            (kind::f16: bf16 operands, fp32 accumulate)
+__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
+        : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem desc]
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
+        : "memory");
+}
+// shared-memory matrix descriptor: K-major, 128-byte rows, 128B swizzle, 8-row groups 1024 bytes apart
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3ffffu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
+// instruction descriptor: bf16 x bf16 -> fp32, both operands K-major, M = 128, N = n
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+// 32 lanes x 32 columns of fp32: lane = this thread's TMEM lane, r[i] = column i
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,"
+        "%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,"
+        "%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+        "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
+        "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+
+// 2-D tiled TMA through a 3-D tensor map [B][N][64] bf16 (boxes of [1][128][64], 128B swizzle; rows beyond N are
+// zero-filled on load and clipped on store)
+__device__ __forceinline__ void tma_store_3d_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+// per-channel max over the 32 points of a warp: lane l ends up with max_p v_p[l] (31 exchanges instead of 32 x 5)
+__device__ __forceinline__ float warp_transpose_max(float (&v)[32], int lane) {
+#pragma unroll
+    for (int half = 16; half >= 1; half >>= 1) {
+        const bool upper = (lane & half) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const float send = upper ? v[i] : v[i + half];
+            const float keep = upper ? v[i + half] : v[i];
+            v[i] = fmaxf(keep, __shfl_xor_sync(kFull, send, half));
+        }
+    }
+    return v[0];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// k_tower_pack: folded fp32 weights -> the blobs above (once per set of weights).
+//   kind 0 = first block : W1 [5][5], b1 [5], W2 [64][5], b2 [64], Ws [64][5], bs [64]
+//   kind 1 = mid block   : W1 [128][128], b1 [128], W2 [64][128], b2 [64], Ws [64][128], bs [64]
+//   kind 2 = last block  : W1 [128][128], b1 [128], W2 [128][128], b2 [128]
+// A bf16 image of W [rows][K-block of 64]: element (n, k) at n*128 + (((k>>3) ^ (n&7)) << 4) + (k&7)*2 bytes.
+__device__ __forceinline__ void pack_split(unsigned char *img_hi, unsigned char *img_lo, int n, int k, float w) {
+    const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(__fsub_rn(w, __bfloat162float(hi)));
+    const int off = n * 128 + ((((k & 63) >> 3) ^ (n & 7)) << 4) + (k & 7) * 2;
+    *reinterpret_cast<__nv_bfloat16 *>(img_hi + off) = hi;
+    *reinterpret_cast<__nv_bfloat16 *>(img_lo + off) = lo;
+}
+__global__ void k_tower_pack(int kind, const float *__restrict__ W1, const float *__restrict__ b1, const float *__restrict__ W2,
+                             const float *__restrict__ b2, const float *__restrict__ Ws, const float *__restrict__ bs,
+                             unsigned char *__restrict__ blob) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    if (kind == 0) {
+        float *rows = reinterpret_cast<float *>(blob + TowerBlobFirst::rows);
+        for (int i = tid; i < 64 * 12; i += nth) {
+            const int c = i / 12, j = i % 12;
+            rows[i] = j < 5 ? W2[c * 5 + j] : j < 10 ? Ws[c * 5 + j - 5] : j == 10 ? __fadd_rn(b2[c], bs[c]) : 0.f;
+        }
+        float *w1 = reinterpret_cast<float *>(blob + TowerBlobFirst::w1);
+        for (int i = tid; i < 25; i += nth) w1[i] = W1[i];
+        float *bb = reinterpret_cast<float *>(blob + TowerBlobFirst::b1);
+        for (int i = tid; i < 5; i += nth) bb[i] = b1[i];
+        return;
+    }
+    const bool last = kind == 2;
+    const int out2 = last ? 128 : 64;
+    // conv1, feature half: W1[:, :64] -> B operand [128 rows][64 K]
+    for (int i = tid; i < 128 * 64; i += nth) {
+        const int n = i >> 6, k = i & 63;
+        pack_split(blob + TowerBlobMid::w1_hi, blob + TowerBlobMid::w1_lo, n, k, W1[n * 128 + k]);
+    }
+    // conv2: W2 [out2][128] -> two K-blocks of [out2 rows][64 K]
+    const int w2_hi = last ? TowerBlobLast::w2_hi : TowerBlobMid::w2_hi, w2_lo = last ? TowerBlobLast::w2_lo : TowerBlobMid::w2_lo;
+    for (int i = tid; i < out2 * 128; i += nth) {
+        const int n = i >> 7, k = i & 127, kb = k >> 6;
+        pack_split(blob + w2_hi + kb * out2 * 128, blob + w2_lo + kb * out2 * 128, n, k, W2[n * 128 + k]);
+    }
+    float *w1bT = reinterpret_cast<float *>(blob + (last ? TowerBlobLast::w1bT : TowerBlobMid::w1bT));
+    for (int i = tid; i < 64 * 128; i += nth) {
+        const int k = i >> 7, n = i & 127;
+        w1bT[i] = W1[n * 128 + 64 + k];
+    }
+    float *pb1 = reinterpret_cast<float *>(blob + (last ? TowerBlobLast::b1 : TowerBlobMid::b1));
+    for (int i = tid; i < 128; i += nth) pb1[i] = b1[i];
+    if (last) {
+        float *pb2 = reinterpret_cast<float *>(blob + TowerBlobLast::b2);
+        for (int i = tid; i < 128; i += nth) pb2[i] = b2[i];
+    } else {
+        for (int i = tid; i < 64 * 64; i += nth) {
+            const int n = i >> 6, k = i & 63;
+            pack_split(blob + TowerBlobMid::ws_hi, blob + TowerBlobMid::ws_lo, n, k, Ws[n * 128 + k]);
+        }
+        float *wsbT = reinterpret_cast<float *>(blob + TowerBlobMid::wsbT);
+        for (int i = tid; i < 64 * 64; i += nth) {
+            const int k = i >> 6, n = i & 63;
+            wsbT[i] = Ws[n * 128 + 64 + k];
+        }
+        float *pb2 = reinterpret_cast<float *>(blob + TowerBlobMid::b2);
+        for (int i = tid; i < 64; i += nth) pb2[i] = __fadd_rn(b2[i], bs[i]);
+    }
+}
+
+// contiguous share of `total` tiles for CTA `cta` of `nctas`
+__device__ __forceinline__ void tower_tile_range(int total, int cta, int nctas, int &t0, int &t1) {
+    t0 = (int)((long long)total * cta / nctas);
+    t1 = (int)((long long)total * (cta + 1) / nctas);
+}
+
+// stage one output tile: thread = point `p` of the tile, v[32] = channels 32*j .. 32*j+31 -> bf16 pieces into the
+// 128B-swizzled planes (row p = 128 bytes; 16-byte chunk q of the row lives at position q ^ (p & 7))
+template <int kPlanes>
+__device__ __forceinline__ void tower_stage_chunk(unsigned char *planes, int plane_bytes, int p, int j, const float (&v)[32]) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        uint4 hi, lo, lo2;
+        unsigned *ph = &hi.x, *pl = &lo.x, *pl2 = &lo2.x;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float a = v[q * 8 + 2 * e], b = v[q * 8 + 2 * e + 1];
+            const unsigned h = pack_bf16x2(a, b);
+            const float ra = __fsub_rn(a, bf16lo_f(h)), rb = __fsub_rn(b, bf16hi_f(h));
+            const unsigned l = pack_bf16x2(ra, rb);
+            ph[e] = h;
+            pl[e] = l;
+            if (kPlanes == 3) pl2[e] = pack_bf16x2(__fsub_rn(ra, bf16lo_f(l)), __fsub_rn(rb, bf16hi_f(l)));
+        }
+        const int off = p * 128 + (((4 * j + q) ^ (p & 7)) << 4);
+        *reinterpret_cast<uint4 *>(planes + off) = hi;
+        *reinterpret_cast<uint4 *>(planes + plane_bytes + off) = lo;
+        if (kPlanes == 3) *reinterpret_cast<uint4 *>(planes + 2 * plane_bytes + off) = lo2;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// k_tower_first: block 1 on the fp32 pipes.  thread = point; obs3d [B][5][N] -> feat1 planes (hi, lo) + max keys.
+__global__ void __launch_bounds__(128) k_tower_first(const float *__restrict__ obs3d, const unsigned char *__restrict__ blob, int B, int N,
+                                                     int tiles_per_ep, const __grid_constant__ CUtensorMap map_hi,
+                                                     const __grid_constant__ CUtensorMap map_lo, unsigned *__restrict__ max_keys) {
+    extern __shared__ __align__(1024) unsigned char tower_smem[];
+    unsigned char *const smem = tower_smem;
+    unsigned char *planes = smem;                                  // 2 x 16 KB
+    float *wrow = reinterpret_cast<float *>(smem + 32768);         // [64][12]
+    float *w1 = wrow + 64 * 12;                                    // [25] + b1 [5]
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int i = tid; i < TowerBlobFirst::total / 4; i += 128) wrow[i] = reinterpret_cast<const float *>(blob)[i];
+    if (tid == 0) {
+        tma_prefetch_map(&map_hi);
+        tma_prefetch_map(&map_lo);
+    }
+    __syncthreads();
+    pdl_wait();        // obs3d is the previous kernel's output when the tower follows cmr_observe in a stream
+    int t0, t1;
+    tower_tile_range(B * tiles_per_ep, blockIdx.x, gridDim.x, t0, t1);
+    float mx[2] = {-INFINITY, -INFINITY};
+    int cur_ep = -1;
+    for (int t = t0; t < t1; ++t) {
+        const int e = t / tiles_per_ep, n0 = (t - e * tiles_per_ep) * kTowerTile;
+        if (e != cur_ep) {
+            if (cur_ep >= 0) {
+                atomicMax(max_keys + cur_ep * 64 + lane, f2key(mx[0]));
+                atomicMax(max_keys + cur_ep * 64 + 32 + lane, f2key(mx[1]));
+            }
+            mx[0] = mx[1] = -INFINITY;
+            cur_ep = e;
+        }
+        const int n = n0 + tid;
+        const bool valid = n < N;
+        float x[5], h[5];
+#pragma unroll
+        for (int c = 0; c < 5; ++c) x[c] = valid ? __ldg(obs3d + ((size_t)e * 5 + c) * N + n) : 0.f;
+#pragma unroll
+        for (int o = 0; o < 5; ++o) {
+            float a = w1[25 + o];
+#pragma unroll
+            for (int c = 0; c < 5; ++c) a = __fmaf_rn(w1[o * 5 + c], x[c], a);
+            h[o] = lrelu(a);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const float4 *r = reinterpret_cast<const float4 *>(wrow + (32 * j + i) * 12);
+                const float4 r0 = r[0], r1 = r[1], r2 = r[2];
+                float a = r2.z;
+                a = __fmaf_rn(r0.x, h[0], a);
+                a = __fmaf_rn(r0.y, h[1], a);
+                a = __fmaf_rn(r0.z, h[2], a);
+                a = __fmaf_rn(r0.w, h[3], a);
+                a = __fmaf_rn(r1.x, h[4], a);
+                a = __fmaf_rn(r1.y, x[0], a);
+                a = __fmaf_rn(r1.z, x[1], a);
+                a = __fmaf_rn(r1.w, x[2], a);
+                a = __fmaf_rn(r2.x, x[3], a);
+                a = __fmaf_rn(r2.y, x[4], a);
+                v[i] = lrelu(a);
+            }
+            tower_stage_chunk<2>(planes, 16384, tid, j, v);
+            if (!valid) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = -INFINITY;
+            }
+            mx[j] = fmaxf(mx[j], warp_transpose_max(v, lane));
+        }
+        fence_async_proxy();
+        __syncthreads();
+        if (tid == 0) {
+            tma_store_3d(&map_hi, 0, n0, e, planes);
+            tma_store_3d(&map_lo, 0, n0, e, planes + 16384);
+            bulk_commit();
+            tma_store_3d_wait_read();
+        }
+        __syncthreads();
+    }
+    if (cur_ep >= 0) {
+        atomicMax(max_keys + cur_ep * 64 + lane, f2key(mx[0]));
+        atomicMax(max_keys + cur_ep * 64 + 32 + lane, f2key(mx[1]));
+    }
+    pdl_launch_dependents();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// k_tower_mma<kLast, kPlanesOut>: blocks 2-4.
+//   kLast = false: in planes (hi, lo); out planes kPlanesOut (2 after block 2, 3 after block 3); 64 max keys / episode
+//   kLast = true : in planes (hi, lo, lo2); no feature output; 128 max keys / episode
+template <bool kLast>
+struct TowerCfg {
+    static constexpr int kInPlanes = kLast ? 3 : 2;
+    static constexpr int kStageBytes = 49152;                       // room for 3 planes of 16 KB (in, or staged out)
+    static constexpr int kStages = kLast ? 2 : 3;
+    static constexpr int kWeightBytes = kLast ? TowerBlobLast::smem_bytes : TowerBlobMid::smem_bytes;
+    static constexpr int kN2 = kLast ? 128 : 64;                    // channels of the second GEMM
+    static constexpr int kBufCols = 128 + kN2;                      // TMEM columns per epilogue group: D1/H + D2
+    static constexpr int kTmemCols = 512;
+    static constexpr int off_stage = kWeightBytes;
+    static constexpr int off_bias1 = off_stage + kStages * kStageBytes;   // [128] f32
+    static constexpr int off_bias2 = off_bias1 + 512;                      // [128] f32
+    static constexpr int off_maxprev = off_bias2 + 512;                    // [64] f32
+    static constexpr int off_bars = off_maxprev + 256;                     // mbarriers
+    static constexpr int kNumBars = 1 + 2 * kStages + 8;
+    static constexpr int off_tmem_slot = off_bars + kNumBars * 8;
+    static constexpr int smem_bytes = off_tmem_slot + 16;
+};
+
+template <bool kLast, int kPlanesOut>
+__global__ void __launch_bounds__(kTowerThreads, 1)
+k_tower_mma(const unsigned char *__restrict__ blob, int B, int N, int tiles_per_ep, int box_rows, const __grid_constant__ CUtensorMap in_hi,
+            const __grid_constant__ CUtensorMap in_lo, const __grid_constant__ CUtensorMap in_lo2,
+            const __grid_constant__ CUtensorMap out_hi, const __grid_constant__ CUtensorMap out_lo,
+            const __grid_constant__ CUtensorMap out_lo2, const unsigned *__restrict__ prev_keys, unsigned *__restrict__ max_keys) {
+    using Cfg = TowerCfg<kLast>;
+    using Blob = typename std::conditional<kLast, TowerBlobLast, TowerBlobMid>::type;
+    extern __shared__ __align__(1024) unsigned char tower_smem[];
+    unsigned char *const smem = tower_smem;
+    float *bias1 = reinterpret_cast<float *>(smem + Cfg::off_bias1);
+    float *bias2 = reinterpret_cast<float *>(smem + Cfg::off_bias2);
+    float *maxprev = reinterpret_cast<float *>(smem + Cfg::off_maxprev);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + Cfg::off_bars);
+    uint64_t *w_full = bars;
+    uint64_t *x_full = bars + 1, *x_empty = x_full + Cfg::kStages;
+    uint64_t *d1_full = x_empty + Cfg::kStages, *h_full = d1_full + 2, *d2_full = h_full + 2, *t_empty = d2_full + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + Cfg::off_tmem_slot);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    int t0, t1;
+    tower_tile_range(B * tiles_per_ep, blockIdx.x, gridDim.x, t0, t1);
+    const int ntiles = t1 - t0;
+
+    if (tid == 0) {
+        mbar_init(w_full, 1);
+        for (int s = 0; s < Cfg::kStages; ++s) {
+            mbar_init(x_full + s, 1);
+            mbar_init(x_empty + s, kLast ? 128 : 1);
+        }
+        for (int g = 0; g < 2; ++g) {
+            mbar_init(d1_full + g, 1);
+            mbar_init(h_full + g, 128);
+            mbar_init(d2_full + g, 1);
+            mbar_init(t_empty + g, 128);
+        }
+        tma_prefetch_map(&in_hi);
+        tma_prefetch_map(&in_lo);
+        if (kLast) tma_prefetch_map(&in_lo2);
+        if (!kLast) {
+            tma_prefetch_map(&out_hi);
+            tma_prefetch_map(&out_lo);
+            if (kPlanesOut == 3) tma_prefetch_map(&out_lo2);
+        }
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ============================== TMA producer ==============================
+        if (lane == 0) {
+            mbar_arrive_expect_tx(w_full, Cfg::kWeightBytes);          // the weights do not depend on the previous kernel
+            bulk_g2s(smem, blob, Cfg::kWeightBytes, w_full);
+            pdl_wait();                                                // the feature planes do
+            for (int i = 0; i < ntiles; ++i) {
+                const int s = i % Cfg::kStages, use = i / Cfg::kStages;
+                if (use > 0) mbar_wait(x_empty + s, (use - 1) & 1);
+                const int t = t0 + i, e = t / tiles_per_ep, n0 = (t - e * tiles_per_ep) * kTowerTile;
+                unsigned char *st = smem + Cfg::off_stage + s * Cfg::kStageBytes;
+                mbar_arrive_expect_tx(x_full + s, Cfg::kInPlanes * box_rows * 128);   // a box is min(N, 128) rows
+                tma_load_3d(st, &in_hi, 0, n0, e, x_full + s);
+                tma_load_3d(st + 16384, &in_lo, 0, n0, e, x_full + s);
+                if (kLast) tma_load_3d(st + 32768, &in_lo2, 0, n0, e, x_full + s);
+            }
+        }
+    } else if (warp == 1) {
+        // ============================== MMA issuer ==============================
+        if (lane == 0) {
+            const uint32_t sbase = smem_u32(smem);
+            constexpr uint32_t idesc128 = umma_idesc_bf16(128), idesc2 = umma_idesc_bf16(Cfg::kN2);
+            // second GEMM of tile i (its h is in TMEM): D2 (+)= H * W2^T, three passes over 8 K-chunks
+            auto issue_c2 = [&](int i) {
+                const int g = i & 1;
+                mbar_wait(h_full + g, (i >> 1) & 1);
+                tc_fence_after();
+                const uint32_t d1 = tmem_base + g * Cfg::kBufCols, d2 = d1 + 128;
+                bool acc = true;      // D2 already holds the shortcut product (mid) or shortcut + bias (last)
+#pragma unroll
+                for (int pass = 0; pass < 3; ++pass) {
+                    const int a_lo = pass == 2 ? 16 : 0;                         // hi*lo, hi*hi ... see order below
+                    const uint32_t w = sbase + (pass == 1 ? Blob::w2_lo : Blob::w2_hi);
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk) {
+                        const uint32_t a = d1 + 32 * (kk >> 1) + 8 * (kk & 1) + a_lo;
+                        const uint64_t b = umma_desc_sw128(w + (kk >> 2) * (Cfg::kN2 * 128) + (kk & 3) * 32);
+                        mma_ts(d2, a, b, idesc2, acc);
+                        acc = true;
+                    }
+                }
+                tc_commit(d2_full + g);
+            };
+            mbar_wait(w_full, 0);
+            for (int i = 0; i < ntiles; ++i) {
+                const int s = i % Cfg::kStages, g = i & 1;
+                mbar_wait(x_full + s, (i / Cfg::kStages) & 1);
+                if (i >= 2) mbar_wait(t_empty + g, ((i >> 1) - 1) & 1);
+                tc_fence_after();
+                const uint32_t xs = sbase + Cfg::off_stage + s * Cfg::kStageBytes;
+                const uint32_t d1 = tmem_base + g * Cfg::kBufCols, d2 = d1 + 128;
+                // first GEMM: D1 = X * W1a^T (N = 128); mid blocks also start D2 = X * Wsa^T (N = 64)
+#pragma unroll
+                for (int pass = 0; pass < 3; ++pass) {
+                    const uint32_t xa = xs + (pass == 2 ? 16384 : 0);
+                    const uint32_t w1 = sbase + (pass == 1 ? Blob::w1_lo : Blob::w1_hi);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                        mma_ss(d1, umma_desc_sw128(xa + kk * 32), umma_desc_sw128(w1 + kk * 32), idesc128, (pass | kk) != 0);
+                }
+                if (!kLast) {
+#pragma unroll
+                    for (int pass = 0; pass < 3; ++pass) {
+                        const uint32_t xa = xs + (pass == 2 ? 16384 : 0);
+                        const uint32_t ws = sbase + (pass == 1 ? TowerBlobMid::ws_lo : TowerBlobMid::ws_hi);
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk)
+                            mma_ss(d2, umma_desc_sw128(xa + kk * 32), umma_desc_sw128(ws + kk * 32), idesc2, (pass | kk) != 0);
+                    }
+                }
+                tc_commit(d1_full + g);
+                if (i >= 1) issue_c2(i - 1);
+            }
+            if (ntiles > 0) issue_c2(ntiles - 1);
+        }
+    } else if (warp >= 4) {
+        // ============================== epilogue groups ==============================
+        const int g = (warp - 4) >> 2;                  // group 0: warps 4-7, group 1: warps 8-11 -> tiles i = g (mod 2)
+        const int wq = warp & 3;                        // TMEM lane quarter this warp may touch
+        const int p = wq * 32 + lane;                   // point of the tile = TMEM lane
+        const int etid = tid - 128;                     // 0..255 over both groups
+        const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
+        const uint32_t d1 = tmem_base + g * Cfg::kBufCols + lane_addr, d2 = d1 + 128;
+        constexpr int kChunks2 = Cfg::kN2 / 32;
+        float mx[kChunks2];
+#pragma unroll
+        for (int j = 0; j < kChunks2; ++j) mx[j] = -INFINITY;
+        int cur_ep = -1;
+        pdl_wait();                                      // prev_keys are the previous kernel's output
+
+        auto flush = [&]() {
+            if (cur_ep >= 0) {
+#pragma unroll
+                for (int j = 0; j < kChunks2; ++j) atomicMax(max_keys + cur_ep * Cfg::kN2 + 32 * j + lane, f2key(mx[j]));
+            }
+#pragma unroll
+            for (int j = 0; j < kChunks2; ++j) mx[j] = -INFINITY;
+        };
+        // per-episode biases (both groups together: 256 threads, named barrier 1)
+        auto setup_episode = [&](int e) {
+            named_bar_sync(1, 256);                      // everybody is done with the previous episode's biases
+            if (etid < 64) maxprev[etid] = key2f(prev_keys[e * 64 + etid]);
+            named_bar_sync(1, 256);
+            if (etid < 128) {
+                const float *w = reinterpret_cast<const float *>(blob + Blob::w1bT);
+                float a = reinterpret_cast<const float *>(blob + Blob::b1)[etid];
+#pragma unroll 8
+                for (int k = 0; k < 64; ++k) a = __fmaf_rn(__ldg(w + k * 128 + etid), maxprev[k], a);
+                bias1[etid] = a;
+            } else if (!kLast) {
+                if (etid < 192) {
+                    const int c = etid - 128;
+                    const float *w = reinterpret_cast<const float *>(blob + TowerBlobMid::wsbT);
+                    float a = reinterpret_cast<const float *>(blob + TowerBlobMid::b2)[c];
+#pragma unroll 8
+                    for (int k = 0; k < 64; ++k) a = __fmaf_rn(__ldg(w + k * 64 + c), maxprev[k], a);
+                    bias2[c] = a;
+                }
+            } else {
+                const int c = etid - 128;
+                const float b = reinterpret_cast<const float *>(blob + TowerBlobLast::b2)[c];
+                bias2[c] = c >= 64 ? __fadd_rn(b, maxprev[c - 64]) : b;
+            }
+            named_bar_sync(1, 256);
+        };
+
+        // both groups walk the CTA's tile list in the same order so that they meet at episode boundaries
+        for (int i = 0; i < ntiles; ++i) {
+            const int t = t0 + i, e = t / tiles_per_ep, n0 = (t - e * tiles_per_ep) * kTowerTile;
+            if (e != cur_ep) {
+                flush();
+                setup_episode(e);
+                cur_ep = e;
+            }
+            if ((i & 1) != g) continue;
+            const int s = i % Cfg::kStages;
+            const uint32_t par = (i >> 1) & 1;
+            const bool valid = n0 + p < N;
+            unsigned char *stage = smem + Cfg::off_stage + s * Cfg::kStageBytes;
+
+            // ---- E1: D1 -> h = lrelu(D1 + bias1) -> bf16 hi|lo pairs back into the same TMEM columns ----
+            mbar_wait(d1_full + g, par);
+            tc_fence_after();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                uint32_t r[32];
+                tmem_ld32(d1 + 32 * j, r);
+                tc_wait_ld();
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const float2 bb = *reinterpret_cast<const float2 *>(bias1 + 32 * j + 2 * q);
+                    const float a = lrelu(__fadd_rn(__uint_as_float(r[2 * q]), bb.x));
+                    const float b = lrelu(__fadd_rn(__uint_as_float(r[2 * q + 1]), bb.y));
+                    const unsigned h = pack_bf16x2(a, b);
+                    hi[q] = h;
+                    lo[q] = pack_bf16x2(__fsub_rn(a, bf16lo_f(h)), __fsub_rn(b, bf16hi_f(h)));
+                }
+                tmem_st16(d1 + 32 * j, hi);
+                tmem_st16(d1 + 32 * j + 16, lo);
+            }
+            if (kLast) {
+                mbar_wait(x_full + s, (i / Cfg::kStages) & 1);   // observe the TMA's writes ourselves before reading them
+                // D2 starts as bias + identity shortcut: feat (exact: hi + lo + lo2) for c < 64, max_prev for c >= 64
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t r[32];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 b0 = *reinterpret_cast<const float4 *>(bias2 + 32 * j + 8 * q);
+                        const float4 b1 = *reinterpret_cast<const float4 *>(bias2 + 32 * j + 8 * q + 4);
+                        float o[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                        if (j < 2) {
+                            const int off = p * 128 + (((4 * j + q) ^ (p & 7)) << 4);
+                            const uint4 xh = *reinterpret_cast<const uint4 *>(stage + off);
+                            const uint4 xl = *reinterpret_cast<const uint4 *>(stage + 16384 + off);
+                            const uint4 xl2 = *reinterpret_cast<const uint4 *>(stage + 32768 + off);
+                            const unsigned *ph = &xh.x, *pl = &xl.x, *pl2 = &xl2.x;
+#pragma unroll
+                            for (int e2 = 0; e2 < 4; ++e2) {
+                                const float x0 = __fadd_rn(__fadd_rn(bf16lo_f(ph[e2]), bf16lo_f(pl[e2])), bf16lo_f(pl2[e2]));
+                                const float x1 = __fadd_rn(__fadd_rn(bf16hi_f(ph[e2]), bf16hi_f(pl[e2])), bf16hi_f(pl2[e2]));
+                                o[2 * e2] = __fadd_rn(o[2 * e2], x0);
+                                o[2 * e2 + 1] = __fadd_rn(o[2 * e2 + 1], x1);
+                            }
+                        }
+#pragma unroll
+                        for (int e2 = 0; e2 < 8; ++e2) r[8 * q + e2] = __float_as_uint(o[e2]);
+                    }
+                    tmem_st32(d2 + 32 * j, r);
+                }
+            }
+            tc_wait_st();
+            tc_fence_before();
+            mbar_arrive(h_full + g);
+            if (kLast) mbar_arrive(x_empty + s);         // this thread's reads of the input stage are done
+
+            // ---- E2: D2 -> out = lrelu(D2 [+ bias2]) -> running max (+ staged bf16 planes -> TMA store) ----
+            mbar_wait(d2_full + g, par);
+            tc_fence_after();
+#pragma unroll
+            for (int j = 0; j < kChunks2; ++j) {
+                uint32_t r[32];
+                tmem_ld32(d2 + 32 * j, r);
+                tc_wait_ld();
+                float v[32];
+#pragma unroll
+                for (int q = 0; q < 32; ++q) {
+                    const float d = __uint_as_float(r[q]);
+                    v[q] = lrelu(kLast ? d : __fadd_rn(d, bias2[32 * j + q]));
+                }
+                if (!kLast) tower_stage_chunk<kPlanesOut>(stage, 16384, p, j, v);
+                if (!valid) {
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) v[q] = -INFINITY;
+                }
+                mx[j] = fmaxf(mx[j], warp_transpose_max(v, lane));
+            }
+            tc_fence_before();
+            mbar_arrive(t_empty + g);                    // D1/H and D2 of this group may be overwritten
+            if (!kLast) {
+                fence_async_proxy();
+                named_bar_sync(2 + g, 128);
+                if ((tid & 127) == 0) {
+                    tma_store_3d(&out_hi, 0, n0, e, stage);
+                    tma_store_3d(&out_lo, 0, n0, e, stage + 16384);
+                    if (kPlanesOut == 3) tma_store_3d(&out_lo2, 0, n0, e, stage + 32768);
+                    bulk_commit();
+                    tma_store_3d_wait_read();
+                    mbar_arrive(x_empty + s);            // the stage may be refilled
+                }
+            }
+        }
+        flush();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    pdl_launch_dependents();
+}
+
+// keys -> fp32 embedding [B][128]
+__global__ void k_tower_finish(const unsigned *__restrict__ keys, float *__restrict__ out, int n) {
+    pdl_wait();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = key2f(keys[i]);
+}
+
+}  // namespace cmr

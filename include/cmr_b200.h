@@ -197,6 +197,28 @@ CMR_API int cmr_cost_volume_warp(const float *pc, const uint8_t *mask, const flo
                                  void *workspace, int B, int K, int N, int C, int H, int W, int mean_channels,
                                  float *out, void *stream);
 
+/* ------------------------------------------------------------------ agent: 3-D tower ---- */
+
+/* The 3-D state tower of the agent - models/CMRAgent.py:25-29 (state_3d_embed: four ConvBNReLURes1D blocks,
+ * models/PointNN.py:260-282) and its forward loop :92-101 (block, global max over the points, repeat + cat),
+ * EVAL MODE: the caller folds every BatchNorm1d into the 1x1 convolution before it (W' = W g / sqrt(var + eps),
+ * b' = (b - mean) g / sqrt(var + eps) + beta) and hands over plain fp32 matrices.  tcgen05 tensor cores, fp32
+ * accumulation in TMEM, three bf16 passes over split operands per product (1e-5 on the output's scale).
+ *   cmr_tower_pack     once per set of weights and block: folded weights -> device blob (cmr_tower_blob_bytes(kind)).
+ *                      CMR_TOWER_FIRST: W1 [5,5] b1 [5] W2 [64,5] b2 [64] Ws [64,5] bs [64]   (net.0/1, net.3/4, shortcut)
+ *                      CMR_TOWER_MID:   W1 [128,128] b1 [128] W2 [64,128] b2 [64] Ws [64,128] bs [64]
+ *                      CMR_TOWER_LAST:  W1 [128,128] b1 [128] W2 [128,128] b2 [128], Ws = bs = NULL (identity shortcut)
+ *                      all row-major [out, in] f32 on the device; blob 128-byte aligned.
+ *   cmr_tower_forward  obs3d [B,5,N] f32 (observation_3d of cmr_observe) -> embed [B,128] f32 = embed_3d of
+ *                      CMRAgent.py:101.  workspace: cmr_tower_workspace_bytes(B, N), 1024-byte aligned. */
+enum { CMR_TOWER_FIRST = 0, CMR_TOWER_MID = 1, CMR_TOWER_LAST = 2 };
+CMR_API size_t cmr_tower_blob_bytes(int kind);
+CMR_API int cmr_tower_pack(int kind, const float *W1, const float *b1, const float *W2, const float *b2, const float *Ws,
+                           const float *bs, void *blob, void *stream);
+CMR_API size_t cmr_tower_workspace_bytes(int B, int N);
+CMR_API int cmr_tower_forward(const float *obs3d, const void *blob1, const void *blob2, const void *blob3,
+                              const void *blob4, void *workspace, int B, int N, float *embed, void *stream);
+
 /* ------------------------------------------------------------------ dataset side ---- */
 
 /* FarthestSampler.sample - dataset/KittiDataset.py:107-126 (= dataset/NuScenesDataset.py:25-44), float64 like

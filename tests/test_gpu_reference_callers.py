@@ -14,8 +14,8 @@ The comparator is the reference's `environment/environment.py` / `models/pointne
 against itself - cuBLAS rounds the k=3 products differently from the CPU, `pc.mean` differs by an ulp between the
 per-sample and the batched call (environment.py:46 vs :91), the scatter uses float atomics - so the environment
 comparison is made in lock-step (both environments see the drop-in's action sequence) with these bars:
-obs3d rows 0-3 bit-exact; in-frustum flags differ for < 0.05 % of the points; >= 99.9 % of obs2d within 1e-5
-relative; logits within 1e-2; the action equal unless the two best logits are a near-tie; poses within 1e-5.
+obs3d rows 0-3 bit-exact; at most 4 in-frustum flags differ; >= 99.98 % of obs2d within 1e-5
+relative; logits within 1e-4; the action equal unless the two best logits are a near-tie; poses within 1e-5.
 The bit-exact bars stay where they are: against the CPU reference (tests/test_gpu_env.py, golden fixtures).
 """
 import copy
@@ -121,9 +121,10 @@ def test_test_agent_loop_on_the_drop_in_matches_the_reference_environment_on_cud
     with torch.no_grad():
         pose_ref, target_ref = _inference_loop(w["ref_env"], agent, data, config, compare)
     print(f"\n[g1 B={B}] {stats}")
-    assert stats["flag_flips"] <= max(2, int(5e-4 * B * N)), stats
-    assert stats["obs2d_bad"] <= 1e-3, stats
-    assert stats["logit_err"] <= 1e-2, stats
+    # measured on a B200 (round 2): 0 flips, 2.4e-5 of obs2d, logits 6e-7 apart, no near-tie
+    assert stats["flag_flips"] <= 4, stats
+    assert stats["obs2d_bad"] <= 2e-4, stats
+    assert stats["logit_err"] <= 1e-4, stats
     assert stats["pose_err"] <= 1e-5, stats
     assert float((pose_ref - pose_ours).abs().max()) <= 1e-5
     assert float((target_ref - target_ours).abs().max()) <= 1e-4
