@@ -18,7 +18,7 @@ data = dict(cpu)
 for k in ("pc", "pc_overlap_pred", "pc_geo_feat", "img_geo_feat"): data[k] = cpu[k].to(dev)
 pose, _ = env.init(data)
 for _ in range(3): env.observation_from_a_pose(data, pose)
-ep = data["_cmr_b200_episode"][1]; p = _lib.ptr
+ep = env.episode_state(data); p = _lib.ptr
 obs2d = torch.empty(B, 128, 40, 128, device=dev)
 obs3d = torch.empty(B, 5, N, device=dev)
 lib = _lib.load()

@@ -19,9 +19,9 @@ def key2f(k):
     return torch.from_numpy(bits.view(np.float32).copy())
 
 
-def bf16_plane(ws, idx, plane_bytes, B, N):
-    raw = ws[idx * plane_bytes: idx * plane_bytes + B * N * 128].cpu().numpy().view(np.uint16).astype(np.uint32) << 16
-    return torch.from_numpy(raw.view(np.float32).copy()).reshape(B, N, 64)
+def piece_plane(ws, idx, plane_bytes, B, N):
+    raw = ws[idx * plane_bytes: idx * plane_bytes + B * N * 128].cpu().numpy()
+    return torch.from_numpy(raw.view(np.float16).astype(np.float32)).reshape(B, N, 64)      # fp16 pieces (CMR_TOWER_FMT=1)
 
 
 def scaled(got, want):
@@ -52,8 +52,8 @@ def main():
     f3 = to.block(states[2], f2, m2); m3 = f3.max(dim=2)[0]
     f4 = to.block(states[3], f3, m3); m4 = f4.max(dim=2)[0]
     print("max1", scaled(k1, m1), "max2", scaled(k2, m2), "max3", scaled(k3, m3), "max4", scaled(k4, m4))
-    feat2 = bf16_plane(ws, 2, plane_bytes, B, N) + bf16_plane(ws, 3, plane_bytes, B, N)
-    feat3 = bf16_plane(ws, 0, plane_bytes, B, N) + bf16_plane(ws, 1, plane_bytes, B, N) + bf16_plane(ws, 4, plane_bytes, B, N)
+    feat2 = piece_plane(ws, 2, plane_bytes, B, N) + piece_plane(ws, 3, plane_bytes, B, N)
+    feat3 = piece_plane(ws, 0, plane_bytes, B, N) + piece_plane(ws, 1, plane_bytes, B, N) + piece_plane(ws, 4, plane_bytes, B, N)
     print("feat2", scaled(feat2, f2.permute(0, 2, 1)), "feat3", scaled(feat3, f3.permute(0, 2, 1)))
     print("out", scaled(out.cpu(), m4), "finite", bool(torch.isfinite(out).all()))
     bad = (feat2 - f2.permute(0, 2, 1)).abs().max(dim=2)[0]

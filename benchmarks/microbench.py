@@ -7,6 +7,7 @@ warm-up, inputs resident in HBM.
   python benchmarks/microbench.py sweep                    observe (project + tile scatter), 16K-128K points
   python benchmarks/microbench.py env [--batch 32]         per-kernel times of one rollout iteration
   python benchmarks/microbench.py cost_volume              IterModel's 729-pose warp of one KITTI cloud
+  python benchmarks/microbench.py tower [--batch 32]       the agent's 3-D tower (tcgen05) vs the reference's modules on cuDNN
 """
 import argparse
 import ctypes
@@ -108,7 +109,7 @@ def sweep(args):
             pose[:, 2, 3] = 3.0
             o = env.observation_from_a_pose(data, pose, return_pixels=True)
             mvis = int(o[3].sum())
-            ep = data["_cmr_b200_episode"][1]
+            ep = env.episode_state(data)
             st = _lib.stream
             obs2d = torch.empty(B, 128, 40, 128, device=dev)
             obs3d = torch.empty(B, 5, N, device=dev)
@@ -152,7 +153,7 @@ def env_kernels(args):
     pose, _ = env.init(data)
     o = env.observation_from_a_pose(data, pose, return_pixels=True)
     mvis = int(o[3].sum())
-    ep = data["_cmr_b200_episode"][1]
+    ep = env.episode_state(data)
     p, st = _lib.ptr, _lib.stream
     obs2d = torch.empty(B, 128, 40, 128, device=dev)
     obs3d = torch.empty(B, 5, N, device=dev)
@@ -214,11 +215,71 @@ def cost_volume_bench(args):
                       "cpu_threads": torch.get_num_threads()}), flush=True)
 
 
+def tower_bench(args):
+    """models/CMRAgent.py:92-101 at KITTI size: cmr_tower_forward against the reference's own ConvBNReLURes1D modules
+    (oracle/_ref, eager cuDNN/cuBLAS on the same GPU, TF32 on - torch's default - and off).
+    FLOPs counted: the dense products the reference evaluates per point (2 x MACs, full 128-wide first layers)."""
+    from cmr_agent_b200 import agent_tower
+    from oracle import reference_loader as rl, tower_oracle as to
+    dev = torch.device("cuda:0")
+    B, N = args.batch, 40960
+    g = torch.Generator().manual_seed(3)
+    obs3d = torch.cat([(torch.rand(B, 3, N, generator=g) - 0.5) * 160, (torch.rand(B, 2, N, generator=g) < 0.3).float()], 1).to(dev)
+    states = [to.make_state(50 + i, ci, co) for i, (ci, co) in enumerate(to.TOWER)]
+    tower = agent_tower.Tower3D(states, dev)
+    t = time_cuda(lambda: tower(obs3d), warm=3, reps=20)
+    macs_ref = sum(ci * ci + ci * co + (ci * co if ci != co else 0) for ci, co in to.TOWER)       # per point, as the reference computes
+    macs_here = 5 * 5 + 2 * 5 * 64 + 2 * (64 * 128 + 128 * 64 + 64 * 64) + (64 * 128 + 128 * 128)  # the repeated max is a bias
+    res = {"bench": "tower", "B": B, "N": N, "tower_ms": t * 1e3, "points_per_s": B * N / t,
+           "tflops_reference_count": 2.0 * macs_ref * B * N / t / 1e12, "tflops_executed_logical": 2.0 * macs_here * B * N / t / 1e12,
+           "tensor_passes_per_product": 3, "tflops_tensor_pipe": 3 * 2.0 * (macs_here - 665) * B * N / t / 1e12,
+           "hbm_bytes_per_point": 20 + 256 * 2 + 256 + 256 + 384 + 384, }
+    res["hbm_gbs"] = res["hbm_bytes_per_point"] * B * N / t / 1e9
+    res["hbm_frac"] = res["hbm_gbs"] / PEAK
+    try:
+        bf16 = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"])
+        res["tensor_frac_of_bf16_sustained"] = res["tflops_tensor_pipe"] / bf16
+    except Exception:
+        pass
+    if rl.available():
+        rl.put_on_path()
+        import importlib
+        pnn = importlib.import_module("models.PointNN")
+        layers = []
+        for sd, (ci, co) in zip(states, to.TOWER):
+            m = pnn.ConvBNReLURes1D(ci, co)
+            m.load_state_dict(sd)
+            layers.append(m.to(dev).eval())
+
+        def ref():                                            # CMRAgent.py:92-101 verbatim control flow
+            with torch.no_grad():
+                embed_3d = obs3d
+                for step, layer in enumerate(layers):
+                    feat_3d = layer(embed_3d)
+                    embed_3d = torch.max(feat_3d, dim=2, keepdim=True)[0]
+                    if step < len(layers) - 1:
+                        embed_3d = embed_3d.repeat(1, 1, feat_3d.shape[2])
+                        embed_3d = torch.cat([feat_3d, embed_3d], dim=1)
+                return embed_3d.view(embed_3d.shape[0], -1)
+        want64 = None
+        for tf32 in (True, False):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            tr = time_cuda(ref, warm=2, reps=5)
+            out = ref()
+            res[f"reference_eager_ms_tf32_{'on' if tf32 else 'off'}"] = tr * 1e3
+            res[f"speedup_vs_reference_tf32_{'on' if tf32 else 'off'}"] = tr / t
+            got = tower(obs3d)
+            res[f"scaled_err_vs_reference_tf32_{'on' if tf32 else 'off'}"] = float(
+                ((got - out).abs().max(dim=1)[0] / out.abs().max(dim=1)[0]).max())
+    print(json.dumps(res), flush=True)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("which", choices=["frontend", "sweep", "env", "cost_volume"])
+    ap.add_argument("which", choices=["frontend", "sweep", "env", "cost_volume", "tower"])
     ap.add_argument("--batch", type=int, default=None)
     a = ap.parse_args()
     if a.batch is None:
         a.batch = 128 if a.which == "frontend" else 32
-    {"frontend": frontend, "sweep": sweep, "env": env_kernels, "cost_volume": cost_volume_bench}[a.which](a)
+    {"frontend": frontend, "sweep": sweep, "env": env_kernels, "cost_volume": cost_volume_bench, "tower": tower_bench}[a.which](a)

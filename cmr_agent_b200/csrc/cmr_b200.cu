@@ -572,6 +572,39 @@ int cmr_reward(const float *target, const float *pc, const uint8_t *mask, const 
                       per_chunk, vec, static_cast<unsigned char *>(scratch), reward, dist);
 }
 
+int cmr_reward_compare(const float *dist_cached, const float *prev, int B, float *reward, float *dist, void *stream) {
+    CMR_REQUIRE(dist_cached && reward && dist && B > 0, CMR_EINVAL);
+    return launch_pdl(k_reward_compare, dim3(ceil_div(B, 128)), dim3(128), 0, S_(stream), dist_cached, prev, B, reward, dist);
+}
+
+// One agent iteration in one call: step (:179-207) -> reward (:263-302) -> observation of the new pose (:25-126),
+// each part optional.  Nothing here that the separate entry points do not do - it saves a host round trip per part.
+int cmr_iteration(const cmr_iteration_args *a, float *pose, const int64_t *action_r, const int64_t *action_t,
+                  const float *prev, float *reward, float *dist, float *obs2d, float *obs3d, void *stream) {
+    CMR_REQUIRE(a && pose, CMR_EINVAL);
+    int rc = CMR_OK;
+    if (action_r || action_t) {
+        CMR_REQUIRE(action_r && action_t, CMR_EINVAL);
+        rc = cmr_step(pose, action_r, action_t, a->rot_tab, a->t_tab, a->nbins, a->dof6, a->B, stream);
+        if (rc) return rc;
+    }
+    if (reward || dist) {
+        CMR_REQUIRE(reward && dist, CMR_EINVAL);
+        if (a->reward_mode == CMR_REWARD_SHIPPED && a->dist_cached)
+            rc = cmr_reward_compare(a->dist_cached, prev, a->B, reward, dist, stream);
+        else
+            rc = cmr_reward(a->target, a->pc, a->mask, a->mean, pose, prev, a->reward_mode, a->B, a->N, a->reward_scratch, reward,
+                            dist, stream);
+        if (rc) return rc;
+    }
+    if (obs2d || obs3d) {
+        CMR_REQUIRE(obs2d && obs3d, CMR_EINVAL);
+        rc = cmr_observe(a->pc, a->overlap, a->img_feat, a->K, pose, a->mean, a->workspace, a->B, a->N, a->C, a->H, a->W, obs2d,
+                         obs3d, nullptr, nullptr, stream);
+    }
+    return rc;
+}
+
 // ---------------------------------------------------------------------------- pointnet_util ----
 
 int cmr_square_distance(const float *src, const int64_t src_stride[3], const float *dst, const int64_t dst_stride[3],

@@ -1246,4 +1246,22 @@ __global__ void __launch_bounds__(256) k_reward(const float *__restrict__ target
     }
 }
 
+// The shipped reward ignores its pose (environment.py:272-275): its distance is a constant of the episode batch.
+// Later calls on the same batch compare the memoised distance with `prev` (:293-298) and hand out fresh copies.
+__global__ void k_reward_compare(const float *__restrict__ cached, const float *__restrict__ prev, int B,
+                                 float *__restrict__ reward, float *__restrict__ dist) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const float d = cached[b];
+    dist[b] = d;
+    float r = 0.f;
+    if (prev) {
+        const float pd = prev[b];
+        r = (d < pd ? 0.5f : 0.f) - (d > pd ? 0.5f : 0.f);
+    }
+    reward[b] = r;
+}
+
 }  // namespace cmr

@@ -17,16 +17,22 @@
 //   after every block: max over the episode's points per channel -> ordered-uint keys, atomicMax.
 //
 // Precision.  north_star's bar is 1e-5 (read on the output's scale, tests/test_tower_oracle.py); single-pass bf16
-// or tf32 operands are 1e-3 off.  Every GEMM therefore runs as three bf16 passes over split operands
-// (x = hi + lo, hi = bf16(x), lo = bf16(x - hi)):  hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM - measured
-// 4-5e-6 on the output's scale, at 3/2 of the tensor time one tf32 pass would take.
+// or tf32 operands are 1e-3 off.  Every GEMM therefore runs as three 16-bit passes over split operands,
+// x = hi + lo,  hi = fp16(x), lo = fp16(x - hi)  (22 significant bits):  hi*hi + hi*lo + lo*hi, fp32 accumulation in
+// TMEM; the dropped lo*lo term and the representation error are 2^-22 of |x||w| each.
+//   * measured on a B200: bf16 pieces (16-17 bits) give 5e-6 typical but 1.2e-5 worst over 300 episodes -
+//     not enough; kind::f16 rejects an fp16 operand meeting a bf16 one (illegal instruction), so "bf16 hi, fp16 lo"
+//     is not available; fp16 pieces cost the same three passes.
+//   * range: fp16 holds |x| <= 65504; conversions saturate (no inf/NaN), hi + lo then still carries values up to
+//     131008 at reduced precision, and any |activation| > 65504 raises the sticky fault flag (cmr_take_fault() == 3).
+//     The tower's inputs are coordinates in metres and 0/1 flags; CMR_TOWER_FMT=0 builds the bf16 variant.
 //
 // Orientation: M = 128 points (TMEM lanes), N = output channels (TMEM columns), K = input channels.
-//   A operand = activations: `feat` tiles arrive by TMA as two bf16 planes [128 pts][64 ch] (128-byte rows,
+//   A operand = activations: `feat` tiles arrive by TMA as two 16-bit planes [128 pts][64 ch] (128-byte rows,
 //       128B swizzle: exactly the K-major UMMA layout), h is written BACK INTO TMEM by the epilogue as packed bf16
 //       pairs over the accumulator it was read from, and the second GEMM takes its A operand from TMEM.
 //   B operand = weights, pre-split and pre-swizzled once by k_tower_pack, resident in shared memory.
-// Features travel between the blocks as bf16 planes [B][N][64] (hi, lo; a third plane lo2 after block 3, whose
+// Features travel between the blocks as 16-bit planes [B][N][64] (hi, lo; a third plane lo2 after block 3, whose
 // consumer adds them back to an exact fp32 for the identity shortcut) - 4 bytes per value, as fp32 would be.
 //
 // Warp roles of k_tower_mma (384 threads): warp 0 = TMA producer, warp 1 = TMEM allocation + MMA issue (one
@@ -36,6 +42,7 @@
 // episode the epilogue groups flush their running maxima, recompute the per-episode biases and go on.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
@@ -45,6 +52,15 @@ constexpr int kTowerF = 64;            // embed_dim (config/KittiConfig.py:63)
 constexpr int kTowerTile = 128;        // points per tile = UMMA M
 constexpr int kTowerThreads = 384;
 constexpr float kTowerSlope = 0.2f;    // LeakyReLU(negative_slope=0.2), PointNN.py:267,272
+#ifndef CMR_TOWER_PASSES
+#define CMR_TOWER_PASSES 3
+#endif
+#ifndef CMR_TOWER_FMT
+#define CMR_TOWER_FMT 1
+#endif
+constexpr int kTowerPasses = CMR_TOWER_PASSES;   // 3: hh + hl + lh;  4: + ll
+constexpr bool kTowerF16 = CMR_TOWER_FMT == 1;   // pieces are fp16 (1, default) or bf16 (0)
+constexpr float kTowerF16Max = 65504.f;
 
 // ---- packed weights: byte offsets inside the blob k_tower_pack writes (one blob per block) ------------------------
 // mid block (blocks 2, 3):   W1a hi|lo [128 x 64], W2 hi|lo [64 x 128] as two K-blocks, Wsa hi|lo [64 x 64]
@@ -85,14 +101,23 @@ __device__ __forceinline__ float key2f(unsigned k) {
 }
 __device__ __forceinline__ float lrelu(float v) { return fmaxf(v, __fmul_rn(kTowerSlope, v)); }
 
-// x -> (hi, lo[, lo2]) bf16 pieces of two neighbouring channels, packed little-endian (even channel in the low half)
-__device__ __forceinline__ unsigned pack_bf16x2(float lo_elem, float hi_elem) {
+// two neighbouring channels -> one packed 16-bit pair (even channel in the low half), and back to fp32
+__device__ __forceinline__ unsigned pack2(float even, float odd) {
     unsigned r;
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+    if (kTowerF16)
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(odd), "f"(even));
+    else
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(odd), "f"(even));
     return r;
 }
-__device__ __forceinline__ float bf16lo_f(unsigned p) { return __uint_as_float(p << 16); }
-__device__ __forceinline__ float bf16hi_f(unsigned p) { return __uint_as_float(p & 0xffff0000u); }
+__device__ __forceinline__ float2 unpack2(unsigned p) {
+    if (kTowerF16) return __half22float2(*reinterpret_cast<const __half2 *>(&p));
+    return make_float2(__uint_as_float(p << 16), __uint_as_float(p & 0xffff0000u));
+}
+// the sticky fault word of the library (common.cuh): 3 = an activation of the tower left the fp16 range
+__device__ __forceinline__ void tower_range_check(bool out_of_range) {
+    if (kTowerF16 && __any_sync(kFull, out_of_range) && (threadIdx.x & 31) == 0) atomicExch(&g_fault, 3);
+}
 
 // ---- tcgen05 / TMEM wrappers (inline PTX; SASS: UTCHMMA, LDTM/STTM, UTCBAR) -----------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t *smem_slot, uint32_t cols) {   // one full warp
@@ -140,9 +165,15 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     return (uint64_t)((smem_addr & 0x3ffffu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
            ((uint64_t)2 << 61);
 }
-// instruction descriptor: bf16 x bf16 -> fp32, both operands K-major, M = 128, N = n
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+// instruction descriptor: 16-bit x 16-bit -> fp32, both operands K-major, M = 128, N = n; format 0 = f16, 1 = bf16
+__host__ __device__ constexpr uint32_t umma_idesc_16(int n, int a_bf16, int b_bf16) {
+    return (1u << 4) | ((uint32_t)a_bf16 << 7) | ((uint32_t)b_bf16 << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+// pass p of a split product: which piece of A and of B it multiplies (0 = hi, 1 = lo), and the descriptor for it
+__host__ __device__ constexpr int tower_pass_a(int p) { return p >= 2 ? 1 : 0; }   // hh, hl, lh, ll
+__host__ __device__ constexpr int tower_pass_b(int p) { return p & 1; }
+__host__ __device__ constexpr uint32_t tower_idesc(int n, int p) {
+    return umma_idesc_16(n, kTowerF16 ? 0 : 1, kTowerF16 ? 0 : 1);
 }
 // 32 lanes x 32 columns of fp32: lane = this thread's TMEM lane, r[i] = column i
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
@@ -201,11 +232,11 @@ __device__ __forceinline__ float warp_transpose_max(float (&v)[32], int lane) {
 //   kind 2 = last block  : W1 [128][128], b1 [128], W2 [128][128], b2 [128]
 // A bf16 image of W [rows][K-block of 64]: element (n, k) at n*128 + (((k>>3) ^ (n&7)) << 4) + (k&7)*2 bytes.
 __device__ __forceinline__ void pack_split(unsigned char *img_hi, unsigned char *img_lo, int n, int k, float w) {
-    const __nv_bfloat16 hi = __float2bfloat16_rn(w);
-    const __nv_bfloat16 lo = __float2bfloat16_rn(__fsub_rn(w, __bfloat162float(hi)));
     const int off = n * 128 + ((((k & 63) >> 3) ^ (n & 7)) << 4) + (k & 7) * 2;
-    *reinterpret_cast<__nv_bfloat16 *>(img_hi + off) = hi;
-    *reinterpret_cast<__nv_bfloat16 *>(img_lo + off) = lo;
+    const unsigned h = pack2(w, 0.f);
+    const unsigned l = pack2(__fsub_rn(w, unpack2(h).x), 0.f);
+    *reinterpret_cast<unsigned short *>(img_hi + off) = (unsigned short)(h & 0xffffu);
+    *reinterpret_cast<unsigned short *>(img_lo + off) = (unsigned short)(l & 0xffffu);
 }
 __global__ void k_tower_pack(int kind, const float *__restrict__ W1, const float *__restrict__ b1, const float *__restrict__ W2,
                              const float *__restrict__ b2, const float *__restrict__ Ws, const float *__restrict__ bs,
@@ -271,6 +302,7 @@ __device__ __forceinline__ void tower_tile_range(int total, int cta, int nctas, 
 // 128B-swizzled planes (row p = 128 bytes; 16-byte chunk q of the row lives at position q ^ (p & 7))
 template <int kPlanes>
 __device__ __forceinline__ void tower_stage_chunk(unsigned char *planes, int plane_bytes, int p, int j, const float (&v)[32]) {
+    bool big = false;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         uint4 hi, lo, lo2;
@@ -278,18 +310,24 @@ __device__ __forceinline__ void tower_stage_chunk(unsigned char *planes, int pla
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const float a = v[q * 8 + 2 * e], b = v[q * 8 + 2 * e + 1];
-            const unsigned h = pack_bf16x2(a, b);
-            const float ra = __fsub_rn(a, bf16lo_f(h)), rb = __fsub_rn(b, bf16hi_f(h));
-            const unsigned l = pack_bf16x2(ra, rb);
+            big |= fabsf(a) > kTowerF16Max || fabsf(b) > kTowerF16Max;
+            const unsigned h = pack2(a, b);
+            const float2 hf = unpack2(h);
+            const float ra = __fsub_rn(a, hf.x), rb = __fsub_rn(b, hf.y);
+            const unsigned l = pack2(ra, rb);
             ph[e] = h;
             pl[e] = l;
-            if (kPlanes == 3) pl2[e] = pack_bf16x2(__fsub_rn(ra, bf16lo_f(l)), __fsub_rn(rb, bf16hi_f(l)));
+            if (kPlanes == 3) {
+                const float2 lf = unpack2(l);
+                pl2[e] = pack2(__fsub_rn(ra, lf.x), __fsub_rn(rb, lf.y));
+            }
         }
         const int off = p * 128 + (((4 * j + q) ^ (p & 7)) << 4);
         *reinterpret_cast<uint4 *>(planes + off) = hi;
         *reinterpret_cast<uint4 *>(planes + plane_bytes + off) = lo;
         if (kPlanes == 3) *reinterpret_cast<uint4 *>(planes + 2 * plane_bytes + off) = lo2;
     }
+    tower_range_check(big);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -475,7 +513,7 @@ k_tower_mma(const unsigned char *__restrict__ blob, int B, int N, int tiles_per_
         // ============================== MMA issuer ==============================
         if (lane == 0) {
             const uint32_t sbase = smem_u32(smem);
-            constexpr uint32_t idesc128 = umma_idesc_bf16(128), idesc2 = umma_idesc_bf16(Cfg::kN2);
+
             // second GEMM of tile i (its h is in TMEM): D2 (+)= H * W2^T, three passes over 8 K-chunks
             auto issue_c2 = [&](int i) {
                 const int g = i & 1;
@@ -484,14 +522,16 @@ k_tower_mma(const unsigned char *__restrict__ blob, int B, int N, int tiles_per_
                 const uint32_t d1 = tmem_base + g * Cfg::kBufCols, d2 = d1 + 128;
                 bool acc = true;      // D2 already holds the shortcut product (mid) or shortcut + bias (last)
 #pragma unroll
-                for (int pass = 0; pass < 3; ++pass) {
-                    const int a_lo = pass == 2 ? 16 : 0;                         // hi*lo, hi*hi ... see order below
-                    const uint32_t w = sbase + (pass == 1 ? Blob::w2_lo : Blob::w2_hi);
+                for (int pass = 0; pass < kTowerPasses; ++pass) {
+                    const int a_lo = tower_pass_a(pass) ? 16 : 0;               // the lo pairs sit 16 columns after the hi pairs
+                    const uint32_t w = sbase + (tower_pass_b(pass) ? Blob::w2_lo : Blob::w2_hi);
+                    constexpr int n2 = Cfg::kN2;
+                    const uint32_t idesc = tower_idesc(n2, pass);
 #pragma unroll
                     for (int kk = 0; kk < 8; ++kk) {
                         const uint32_t a = d1 + 32 * (kk >> 1) + 8 * (kk & 1) + a_lo;
                         const uint64_t b = umma_desc_sw128(w + (kk >> 2) * (Cfg::kN2 * 128) + (kk & 3) * 32);
-                        mma_ts(d2, a, b, idesc2, acc);
+                        mma_ts(d2, a, b, idesc, acc);
                         acc = true;
                     }
                 }
@@ -507,21 +547,23 @@ k_tower_mma(const unsigned char *__restrict__ blob, int B, int N, int tiles_per_
                 const uint32_t d1 = tmem_base + g * Cfg::kBufCols, d2 = d1 + 128;
                 // first GEMM: D1 = X * W1a^T (N = 128); mid blocks also start D2 = X * Wsa^T (N = 64)
 #pragma unroll
-                for (int pass = 0; pass < 3; ++pass) {
-                    const uint32_t xa = xs + (pass == 2 ? 16384 : 0);
-                    const uint32_t w1 = sbase + (pass == 1 ? Blob::w1_lo : Blob::w1_hi);
+                for (int pass = 0; pass < kTowerPasses; ++pass) {
+                    const uint32_t xa = xs + (tower_pass_a(pass) ? 16384 : 0);
+                    const uint32_t w1 = sbase + (tower_pass_b(pass) ? Blob::w1_lo : Blob::w1_hi);
+                    const uint32_t idesc = tower_idesc(128, pass);
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk)
-                        mma_ss(d1, umma_desc_sw128(xa + kk * 32), umma_desc_sw128(w1 + kk * 32), idesc128, (pass | kk) != 0);
+                        mma_ss(d1, umma_desc_sw128(xa + kk * 32), umma_desc_sw128(w1 + kk * 32), idesc, (pass | kk) != 0);
                 }
                 if (!kLast) {
 #pragma unroll
-                    for (int pass = 0; pass < 3; ++pass) {
-                        const uint32_t xa = xs + (pass == 2 ? 16384 : 0);
-                        const uint32_t ws = sbase + (pass == 1 ? TowerBlobMid::ws_lo : TowerBlobMid::ws_hi);
+                    for (int pass = 0; pass < kTowerPasses; ++pass) {
+                        const uint32_t xa = xs + (tower_pass_a(pass) ? 16384 : 0);
+                        const uint32_t ws = sbase + (tower_pass_b(pass) ? TowerBlobMid::ws_lo : TowerBlobMid::ws_hi);
+                        const uint32_t idesc = tower_idesc(64, pass);
 #pragma unroll
                         for (int kk = 0; kk < 4; ++kk)
-                            mma_ss(d2, umma_desc_sw128(xa + kk * 32), umma_desc_sw128(ws + kk * 32), idesc2, (pass | kk) != 0);
+                            mma_ss(d2, umma_desc_sw128(xa + kk * 32), umma_desc_sw128(ws + kk * 32), idesc, (pass | kk) != 0);
                     }
                 }
                 tc_commit(d1_full + g);
@@ -603,15 +645,19 @@ k_tower_mma(const unsigned char *__restrict__ blob, int B, int N, int tiles_per_
                 tmem_ld32(d1 + 32 * j, r);
                 tc_wait_ld();
                 uint32_t hi[16], lo[16];
+                bool big = false;
 #pragma unroll
                 for (int q = 0; q < 16; ++q) {
                     const float2 bb = *reinterpret_cast<const float2 *>(bias1 + 32 * j + 2 * q);
                     const float a = lrelu(__fadd_rn(__uint_as_float(r[2 * q]), bb.x));
                     const float b = lrelu(__fadd_rn(__uint_as_float(r[2 * q + 1]), bb.y));
-                    const unsigned h = pack_bf16x2(a, b);
+                    big |= fabsf(a) > kTowerF16Max || fabsf(b) > kTowerF16Max;
+                    const unsigned h = pack2(a, b);
+                    const float2 hf = unpack2(h);
                     hi[q] = h;
-                    lo[q] = pack_bf16x2(__fsub_rn(a, bf16lo_f(h)), __fsub_rn(b, bf16hi_f(h)));
+                    lo[q] = pack2(__fsub_rn(a, hf.x), __fsub_rn(b, hf.y));
                 }
+                tower_range_check(big);
                 tmem_st16(d1 + 32 * j, hi);
                 tmem_st16(d1 + 32 * j + 16, lo);
             }
@@ -634,8 +680,9 @@ k_tower_mma(const unsigned char *__restrict__ blob, int B, int N, int tiles_per_
                             const unsigned *ph = &xh.x, *pl = &xl.x, *pl2 = &xl2.x;
 #pragma unroll
                             for (int e2 = 0; e2 < 4; ++e2) {
-                                const float x0 = __fadd_rn(__fadd_rn(bf16lo_f(ph[e2]), bf16lo_f(pl[e2])), bf16lo_f(pl2[e2]));
-                                const float x1 = __fadd_rn(__fadd_rn(bf16hi_f(ph[e2]), bf16hi_f(pl[e2])), bf16hi_f(pl2[e2]));
+                                const float2 hf = unpack2(ph[e2]), lf = unpack2(pl[e2]), l2f = unpack2(pl2[e2]);
+                                const float x0 = __fadd_rn(__fadd_rn(hf.x, lf.x), l2f.x);
+                                const float x1 = __fadd_rn(__fadd_rn(hf.y, lf.y), l2f.y);
                                 o[2 * e2] = __fadd_rn(o[2 * e2], x0);
                                 o[2 * e2 + 1] = __fadd_rn(o[2 * e2 + 1], x1);
                             }
@@ -651,7 +698,7 @@ k_tower_mma(const unsigned char *__restrict__ blob, int B, int N, int tiles_per_
             mbar_arrive(h_full + g);
             if (kLast) mbar_arrive(x_empty + s);         // this thread's reads of the input stage are done
 
-            // ---- E2: D2 -> out = lrelu(D2 [+ bias2]) -> running max (+ staged bf16 planes -> TMA store) ----
+            // ---- E2: D2 -> out = lrelu(D2 [+ bias2]) -> running max (+ staged 16-bit planes -> TMA store) ----
             mbar_wait(d2_full + g, par);
             tc_fence_after();
 #pragma unroll

@@ -140,6 +140,36 @@ CMR_API int cmr_reward(const float *target, const float *pc, const uint8_t *mask
 CMR_API int cmr_expert(const float *pose_source, const float *pose_target, const double *r_steps, const double *t_steps,
                        int nbins, int dof6, int B, int64_t *action_r, int64_t *action_t, void *stream);
 
+/* The shipped reward (environment.py:272-290) ignores its pose: its distance is a constant of the episode batch.
+ * A host that has kept the distance of an earlier cmr_reward call on the same batch (dist_cached [B]) gets the
+ * comparison with `prev` (:293-298) and fresh copies from this call instead of re-reading 25 bytes per point. */
+CMR_API int cmr_reward_compare(const float *dist_cached, const float *prev, int B, float *reward, float *dist,
+                               void *stream);
+
+/* One agent iteration as ONE host call: the loop body of Train_Agent.py:229-248 / Test_Agent.py:154-170 around
+ * the agent's forward pass -  step (environment.py:179-207), reward of the new pose (:263-302), observation of the
+ * new pose (:25-126).  `a` holds everything that is constant over the iterations of an episode batch and is filled
+ * once per batch; the per-iteration arguments choose the parts:
+ *   action_r/action_t NULL -> no step;  reward/dist NULL -> no reward;  obs2d/obs3d NULL -> no observation.
+ * With reward_mode == CMR_REWARD_SHIPPED and dist_cached != NULL the reward is cmr_reward_compare. */
+typedef struct cmr_iteration_args {
+    const float *pc;          /* [B,3,N] */
+    const uint8_t *overlap;   /* [B,N] */
+    const float *img_feat;    /* [B,C,H,W] */
+    const float *K;           /* [B,3,3] */
+    const float *mean;        /* [B,3] */
+    void *workspace;          /* cmr_episode_prepare */
+    const float *rot_tab;     /* step tables, see cmr_step */
+    const float *t_tab;
+    const float *target;      /* reward: pc_in_cam_space [B,3,N] */
+    const uint8_t *mask;      /* reward: pc_mask != 0, [B,N] */
+    void *reward_scratch;     /* cmr_reward_scratch_bytes(B), zeroed once */
+    const float *dist_cached; /* [B] or NULL */
+    int B, N, C, H, W, nbins, dof6, reward_mode;
+} cmr_iteration_args;
+CMR_API int cmr_iteration(const cmr_iteration_args *a, float *pose, const int64_t *action_r, const int64_t *action_t,
+                          const float *prev, float *reward, float *dist, float *obs2d, float *obs3d, void *stream);
+
 /* ------------------------------------------------------------------ pointnet_util ---- */
 
 /* square_distance - pointnet_util.py:19-33. src [B,S,3], dst [B,N,3] (any strides, in floats) ->

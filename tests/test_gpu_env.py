@@ -166,7 +166,7 @@ def test_observe_matches_oracle_with_device_mean(cuda, shape, B):
     for trial in range(3):
         pose = _random_poses(B, 100 + trial, scale_t=2.0 if trial else 0.0)
         o2, o3, pix, mvis = _observe(env, data, pose, cuda)
-        mean = data["_cmr_b200_episode"][1].mean.cpu()
+        mean = env.episode_state(data).mean.cpu()
         wpix, winc, wproj = _oracle_obs(data_cpu, pose, mean, H, W)
         assert torch.equal(pix, wpix), f"{(pix != wpix).sum().item()} of {pix.numel()} pixel ids differ"
         assert torch.equal(o3[:, 4], winc.float())
@@ -224,7 +224,7 @@ def test_observe_edge_cases(cuda, case):
     if case == "exact_edges":
         data["_cmr_b200_mean_override"] = torch.zeros(2, 3)     # keep u = x exact
     o2, o3, pix, mvis = _observe(env, data, pose, cuda)
-    mean = data["_cmr_b200_episode"][1].mean.cpu()
+    mean = env.episode_state(data).mean.cpu()
     wpix, winc, wproj = _oracle_obs(data_cpu, pose, mean, H, W)
     assert torch.equal(pix, wpix) and torch.equal(o3[:, 4], winc.float())
     assert torch.equal(o2[:, 64:], wproj)
@@ -278,7 +278,7 @@ def test_standalone_project_may_repeat_before_one_scatter(cuda):
     data = hp.to_device(data_cpu, cuda)
     poses = [_random_poses(2, s, scale_t=1.0).to(cuda) for s in (1, 2)]
     want = env.observation_from_a_pose(data, poses[1])[0]
-    ep = data["_cmr_b200_episode"][1]
+    ep = env.episode_state(data)
     p = _lib.ptr
     obs2d = torch.zeros_like(want)
     obs3d = torch.empty(2, 5, 4096, device=cuda)
@@ -304,7 +304,7 @@ def test_observe_other_channel_counts_and_32bit_pixels(cuda, C, img_h, img_w):
     data = hp.to_device(data_cpu, cuda)
     pose = _random_poses(1, 3, scale_t=1.0)
     o2, o3, pix, mvis = _observe(env, data, pose, cuda)
-    mean = data["_cmr_b200_episode"][1].mean.cpu()
+    mean = env.episode_state(data).mean.cpu()
     wpix, winc, wproj = _oracle_obs(data_cpu, pose, mean, H, W)
     assert torch.equal(pix, wpix) and torch.equal(o3[:, 4], winc.float())
     assert torch.equal(o2[:, :C], data_cpu["img_geo_feat"])
@@ -321,7 +321,7 @@ def test_reward_modes_against_c_oracle(cuda):
         for mode, flag in (("shipped", 0), ("intended", 1)):
             env.set_reward_mode(mode)
             rew, dist = env.reward(pose, data, None)
-            mean = data["_cmr_b200_reward"][1].mean.cpu()
+            mean = env._reward_state(data).mean.cpu()
             assert float(rew.abs().sum()) == 0.0
             for b in range(2):
                 want = cref.p2p(data_cpu["pc_in_cam_space"][b].numpy(), data_cpu["pc"][b].numpy(),
@@ -351,11 +351,11 @@ def test_fresh_outputs_cache_invalidation_and_cpu_rejection(cuda):
     # buffer.py:105-106 keeps references to the observations: every call must return fresh storage
     assert a2.data_ptr() != b2.data_ptr() and a3.data_ptr() != b3.data_ptr()
     assert torch.equal(a2, b2) and torch.equal(a3, b3)
-    ep = data["_cmr_b200_episode"][1]
-    assert env.observation_from_a_pose(data, pose) is not None and data["_cmr_b200_episode"][1] is ep
+    ep = env.episode_state(data)
+    assert env.observation_from_a_pose(data, pose) is not None and env.episode_state(data) is ep
     data["pc_overlap_pred"].logical_not_()                      # in-place edit bumps the version counter
     c2, c3 = env.observation_from_a_pose(data, pose)
-    assert data["_cmr_b200_episode"][1] is not ep
+    assert env.episode_state(data) is not ep
     assert torch.equal(c3[:, 3], data["pc_overlap_pred"].float())
     with pytest.raises(_lib.CmrError):
         env.observation_from_a_pose(data_cpu, torch.eye(4).repeat(2, 1, 1))
@@ -379,7 +379,7 @@ def test_ten_iteration_rollout_matches_oracle_port(cuda):
     for it in range(10):
         o2, o3, pix, _ = env.observation_from_a_pose(data, pose_d, return_pixels=True)
         if mean is None:
-            mean = data["_cmr_b200_episode"][1].mean.cpu()
+            mean = env.episode_state(data).mean.cpu()
         p2, p3 = eo.observation_from_a_pose(data_cpu, pose_h, mean=mean.unsqueeze(-1))
         wpix, _ = eo.projected_pixels(data_cpu, pose_h, mean=mean.unsqueeze(-1))
         assert torch.equal(pix.cpu(), wpix)
@@ -447,3 +447,104 @@ def test_ab_switches_keep_parity(cuda, switch):
                         "reference_golden or dense_buckets or other_channel_counts", "-p", "no:cacheprovider"],
                        cwd=root, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_cache_never_serves_stale_features_and_leaves_data_alone(cuda):
+    """The per-batch state is keyed on the identity of `data`'s tensors and keeps them alive, so a replaced tensor
+    is seen even if the allocator hands its storage out again; nothing is written into the caller's dict."""
+    env = _env()
+    data_cpu = synth.make_batch(2, seed=21, num_pt=4096, img_h=64, img_w=256)
+    H, W = 16, 64
+    data = hp.to_device(data_cpu, cuda)
+    keys = set(data.keys())
+    pose = _random_poses(2, 5, scale_t=1.0)
+    o2a, _, pix, _ = _observe(env, data, pose, cuda)
+    env.reward(pose.to(cuda), data, None)
+    assert set(data.keys()) == keys and all(torch.is_tensor(v) for v in data.values())
+    # re-run "geo_model": a new feature tensor of the same shape (the old one is dropped; same address is likely)
+    new_feat = torch.nn.functional.normalize(torch.randn(2, 64, 4096, generator=torch.Generator().manual_seed(1)), dim=1)
+    old_ptr = data["pc_geo_feat"].data_ptr()
+    data["pc_geo_feat"] = None
+    data["pc_geo_feat"] = new_feat.to(cuda)
+    o2b, _, pix_b, _ = _observe(env, data, pose, cuda)
+    mean = env.episode_state(data).mean.cpu()
+    cpu2 = dict(data_cpu, pc_geo_feat=new_feat)
+    _, _, wproj = _oracle_obs(cpu2, pose, mean, H, W)
+    assert torch.equal(pix, pix_b)
+    assert torch.equal(o2b[:, 64:], wproj), f"stale features served (old ptr reused: {old_ptr == data['pc_geo_feat'].data_ptr()})"
+    # same for the reward's inputs
+    data["pc_mask"] = torch.zeros_like(data_cpu["pc_mask"])
+    data["pc_mask"][:, :100] = 1
+    _, d2 = env.reward(pose.to(cuda), data, None)
+    for b in range(2):
+        want = cref.p2p(data_cpu["pc_in_cam_space"][b].numpy(), data_cpu["pc"][b].numpy(), data["pc_mask"][b].numpy(),
+                        env._reward_state(data).mean[b].cpu().numpy(), pose[b].numpy(), 0)
+        assert abs(float(d2[b]) - want) <= TOL * abs(want)
+
+
+def test_shipped_reward_is_memoised_bit_identically(cuda):
+    env = _env()
+    from cmr_agent_b200 import _lib
+    data_cpu = synth.make_batch(3, seed=31, num_pt=40960, img_h=160, img_w=512)
+    data = hp.to_device(data_cpu, cuda)
+    pose = _random_poses(3, 2).to(cuda)
+    n0 = _lib.launch_count()
+    r0, d0 = env.reward(pose, data, None)
+    first = _lib.launch_count() - n0
+    kept = d0.clone()
+    d0.mul_(3.0)                                               # the caller owns what it was handed
+    n1 = _lib.launch_count()
+    r1, d1 = env.reward(pose, data, kept)
+    assert _lib.launch_count() - n1 == 1 and first >= 1       # one tiny compare kernel, not a pass over the cloud
+    assert torch.equal(d1, kept) and d1.data_ptr() != kept.data_ptr() and float(r1.abs().sum()) == 0.0
+    r2, d2 = env.reward(pose, data, kept * 2)
+    r3, d3 = env.reward(pose, data, kept * 0.5)
+    assert torch.equal(r2.flatten().cpu(), torch.full((3,), 0.5)) and torch.equal(r3.flatten().cpu(), torch.full((3,), -0.5))
+    assert torch.equal(d2, kept) and torch.equal(d3, kept)
+    # an in-place edit of an input invalidates the memo
+    data["pc"].add_(0.25)
+    _, d4 = env.reward(pose, data, None)
+    assert not torch.equal(d4, kept)
+
+
+@pytest.mark.parametrize("mode", ["shipped", "intended"])
+def test_iterate_equals_the_three_separate_calls(cuda, mode):
+    env = _env()
+    data_cpu = synth.make_batch(3, seed=41, num_pt=8192, img_h=160, img_w=512)
+    cfg = synth.StepConfig(device=cuda)
+    a_r, a_t = synth.make_actions(3, 4, seed=9)
+    env.set_reward_mode(mode)
+    try:
+        da, db = hp.to_device(data_cpu, cuda), hp.to_device(data_cpu, cuda)
+        pa, _ = env.init(da)
+        pb, _ = env.init(db)
+        _, prev_a = env.reward(pa, da, None)
+        _, prev_b = env.reward(pb, db, None)
+        for it in range(4):
+            ar, at = a_r[it].to(cuda), a_t[it].to(cuda)
+            env.step(ar, at, pa, cfg)
+            rew_a, prev_a = env.reward(pa, da, prev_a)
+            o2a, o3a = env.observation_from_a_pose(da, pa)
+            out = env.iterate(db, pb, ar, at, cfg, prev_distance=prev_b)
+            assert out[0] is pb
+            _, rew_b, prev_b, o2b, o3b = out
+            assert torch.equal(pa, pb) and torch.equal(rew_a, rew_b) and torch.equal(prev_a, prev_b)
+            assert torch.equal(o2a, o2b) and torch.equal(o3a, o3b)
+        _, r_none, d_none, o2, o3 = env.iterate(db, pb, None, None, cfg, with_reward=False)
+        assert r_none is None and d_none is None and torch.equal(o2, o2b)
+    finally:
+        env.set_reward_mode("shipped")
+
+
+def test_validation_mode_reports_device_faults(cuda):
+    env = _env()
+    from cmr_agent_b200 import _lib
+    cfg = synth.StepConfig(device=cuda)
+    pose = torch.eye(4, device=cuda).repeat(2, 1, 1)
+    env.set_validation(True)
+    try:
+        with pytest.raises(_lib.CmrError):
+            env.step(torch.tensor([[3], [11]], device=cuda), torch.tensor([[0, 0], [0, 0]], device=cuda), pose, cfg)
+        env.step(torch.tensor([[3], [4]], device=cuda), torch.tensor([[0, 0], [0, 0]], device=cuda), pose, cfg)
+    finally:
+        env.set_validation(False)
