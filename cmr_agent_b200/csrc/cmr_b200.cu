@@ -12,6 +12,7 @@
 #include "scatter_kernels.cuh"
 #include "dataset_kernels.cuh"
 #include "tower_kernels.cuh"
+#include "session.cuh"
 
 namespace cmr {
 
@@ -527,7 +528,14 @@ int cmr_observe(const float *pc, const uint8_t *overlap, const float *img_feat, 
     const bool forked = image_mode() == 's' && (C % kSlab) == 0 && image_copy_fork(img_feat, obs2d, B, C, H * W, S_(stream));
     rc = project_impl(pc, overlap, K, pose, mean, workspace, B, N, C, H, W, obs3d, pix_out, mvis_out, img_feat, obs2d,
                       &copied, false, stream);
+    const bool projected = rc == CMR_OK;
     if (!rc) rc = cmr_tile_scatter(img_feat, K, workspace, B, N, C, H, W, (copied || forked) ? 0 : 1, obs2d, stream);
+    if (rc && projected) {
+        // k_project has filled the bucket counters and nobody will consume them: leave the workspace as the next
+        // cmr_observe expects it (counters and queue header zero) instead of silently wrong results later
+        WsLayout L = ws_layout(B, N, C, H * W);
+        cudaMemsetAsync(static_cast<char *>(workspace) + L.off_bcnt, 0, L.bcnt_bytes, S_(stream));
+    }
     if (forked) {   // joined whatever happened: a capturing stream must not be left forked
         const int jrc = image_copy_join(S_(stream));
         if (!rc) rc = jrc;
@@ -796,6 +804,231 @@ int cmr_nearest_f64(const double *query, const double *ref, int B, int N, int S,
     CMR_REQUIRE(B <= 65535, CMR_ERANGE);
     k_nearest_f64<<<dim3(ceil_div(N, 256), B), 256, 0, S_(stream)>>>(query, ref, N, S, out);
     return after_launch();
+}
+
+// ------------------------------------------------------------------------------ rollout session ----
+
+#define CMR_CUDA(call)                       \
+    do {                                     \
+        cudaError_t e_ = (call);             \
+        if (e_ != cudaSuccess) return (int)e_; \
+    } while (0)
+
+static void session_free(cmr_session *s) {
+    if (!s) return;
+    if (s->slots) {
+        for (int i = 0; i < s->depth; ++i) {
+            SessionSlot &t = s->slots[i];
+            void *dev[] = {t.pc, t.feat, t.img_feat, t.K, t.target_pose, t.pc_in_cam, t.overlap, t.mask_u8, t.mask_i64, t.a_r, t.a_t,
+                           t.mean, t.pose, t.obs2d, t.obs3d, t.rew, t.dist, t.ws, t.scratch};
+            for (void *p : dev)
+                if (p) cudaFree(p);
+            void *host[] = {t.h_rew, t.h_dist, t.h_pose, t.h_target};
+            for (void *p : host)
+                if (p) cudaFreeHost(p);
+            cudaEvent_t ev[] = {t.uploaded, t.done, t.up_begin, t.up_end};
+            for (cudaEvent_t e : ev)
+                if (e) cudaEventDestroy(e);
+        }
+        delete[] s->slots;
+    }
+    if (s->rot_tab) cudaFree(s->rot_tab);
+    if (s->t_tab) cudaFree(s->t_tab);
+    if (s->copy) cudaStreamDestroy(s->copy);
+    if (s->compute) cudaStreamDestroy(s->compute);
+    delete s;
+}
+
+int cmr_session_create(const cmr_session_config *cfg, cmr_session **out) {
+    CMR_REQUIRE(cfg && out && cfg->rot_tab && cfg->t_tab, CMR_EINVAL);
+    CMR_REQUIRE(cfg->iters > 0 && cfg->depth >= 1 && cfg->depth <= 8 && cfg->nbins > 0, CMR_EINVAL);
+    int rc = check_observe_dims(cfg->B, cfg->N, cfg->C, cfg->H, cfg->W);
+    if (rc) return rc;
+    cmr_session *s = new (std::nothrow) cmr_session();
+    CMR_REQUIRE(s, CMR_EINVAL);
+    s->cfg = *cfg;
+    s->cfg.rot_tab = s->cfg.t_tab = nullptr;
+    s->depth = cfg->depth;
+    s->nbins = cfg->nbins;
+    s->slots = new (std::nothrow) SessionSlot[cfg->depth];
+    const size_t B = cfg->B, N = cfg->N, C = cfg->C, P = (size_t)cfg->H * cfg->W, I = cfg->iters;
+    const int nr = cfg->dof6 ? 3 : 1, nt = cfg->dof6 ? 3 : 2;
+    auto fail = [&](int code) {
+        session_free(s);
+        return code;
+    };
+    if (!s->slots) return fail(CMR_EINVAL);
+#define CMR_S(call)                                  \
+    do {                                             \
+        cudaError_t e_ = (call);                     \
+        if (e_ != cudaSuccess) return fail((int)e_); \
+    } while (0)
+    CMR_S(cudaStreamCreateWithFlags(&s->copy, cudaStreamNonBlocking));
+    CMR_S(cudaStreamCreateWithFlags(&s->compute, cudaStreamNonBlocking));
+    const size_t rot_bytes = sizeof(float) * 3 * (cfg->nbins + 1) * 9;
+    CMR_S(cudaMalloc(&s->rot_tab, rot_bytes));
+    CMR_S(cudaMalloc(&s->t_tab, sizeof(float) * cfg->nbins));
+    CMR_S(cudaMemcpy(s->rot_tab, cfg->rot_tab, rot_bytes, cudaMemcpyHostToDevice));
+    CMR_S(cudaMemcpy(s->t_tab, cfg->t_tab, sizeof(float) * cfg->nbins, cudaMemcpyHostToDevice));
+    for (int i = 0; i < s->depth; ++i) {
+        SessionSlot &t = s->slots[i];
+        CMR_S(cudaMalloc(&t.pc, sizeof(float) * B * 3 * N));
+        if (!cfg->features_resident) {
+            CMR_S(cudaMalloc(&t.feat, sizeof(float) * B * C * N));
+            CMR_S(cudaMalloc(&t.img_feat, sizeof(float) * B * C * P));
+        }
+        CMR_S(cudaMalloc(&t.K, sizeof(float) * B * 9));
+        CMR_S(cudaMalloc(&t.target_pose, sizeof(float) * B * 16));
+        CMR_S(cudaMalloc(&t.pc_in_cam, sizeof(float) * B * 3 * N));
+        CMR_S(cudaMalloc(&t.overlap, B * N));
+        CMR_S(cudaMalloc(&t.mask_u8, B * N));
+        CMR_S(cudaMalloc(&t.mask_i64, sizeof(long long) * B * N));
+        CMR_S(cudaMalloc(&t.a_r, sizeof(long long) * I * B * nr));
+        CMR_S(cudaMalloc(&t.a_t, sizeof(long long) * I * B * nt));
+        CMR_S(cudaMalloc(&t.mean, sizeof(float) * B * 3));
+        CMR_S(cudaMalloc(&t.pose, sizeof(float) * B * 16));
+        CMR_S(cudaMalloc(&t.obs2d, sizeof(float) * B * 2 * C * P));
+        CMR_S(cudaMalloc(&t.obs3d, sizeof(float) * B * 5 * N));
+        CMR_S(cudaMalloc(&t.rew, sizeof(float) * I * B));
+        CMR_S(cudaMalloc(&t.dist, sizeof(float) * I * B));
+        CMR_S(cudaMalloc(&t.ws, cmr_workspace_bytes(cfg->B, cfg->N, cfg->C, (int)P)));
+        CMR_S(cudaMalloc(&t.scratch, cmr_reward_scratch_bytes(cfg->B)));
+        CMR_S(cudaMemset(t.scratch, 0, cmr_reward_scratch_bytes(cfg->B)));
+        CMR_S(cudaHostAlloc(&t.h_rew, sizeof(float) * I * B, cudaHostAllocDefault));
+        CMR_S(cudaHostAlloc(&t.h_dist, sizeof(float) * I * B, cudaHostAllocDefault));
+        CMR_S(cudaHostAlloc(&t.h_pose, sizeof(float) * B * 16, cudaHostAllocDefault));
+        CMR_S(cudaHostAlloc(&t.h_target, sizeof(float) * B * 16, cudaHostAllocDefault));
+        CMR_S(cudaEventCreateWithFlags(&t.uploaded, cudaEventDisableTiming));
+        CMR_S(cudaEventCreateWithFlags(&t.done, cudaEventDisableTiming));
+        CMR_S(cudaEventCreate(&t.up_begin));
+        CMR_S(cudaEventCreate(&t.up_end));
+    }
+#undef CMR_S
+    s->bytes_per_upload = sizeof(float) * (B * 3 * N * 2 + B * 9 + B * 16) + B * N + sizeof(long long) * (B * N + I * B * (nr + nt)) +
+                          (cfg->features_resident ? 0 : sizeof(float) * (B * C * N + B * C * P));
+    *out = s;
+    return CMR_OK;
+}
+
+void cmr_session_destroy(cmr_session *s) {
+    if (!s) return;
+    if (s->compute) cudaStreamSynchronize(s->compute);
+    if (s->copy) cudaStreamSynchronize(s->copy);
+    session_free(s);
+}
+
+static void session_account_upload(cmr_session *s, SessionSlot &t) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, t.up_begin, t.up_end) == cudaSuccess && ms > 0.f) {
+        s->h2d_bytes += (double)s->bytes_per_upload;
+        s->h2d_seconds += ms * 1e-3;
+        ++s->timed_uploads;
+    }
+}
+
+int cmr_session_submit(cmr_session *s, const cmr_rollout_inputs *in, long long *ticket) {
+    CMR_REQUIRE(s && in && ticket, CMR_EINVAL);
+    CMR_REQUIRE(in->pc && in->overlap && in->feat && in->img_feat && in->K && in->P && in->pc_in_cam && in->pc_mask && in->action_r &&
+                    in->action_t,
+                CMR_EINVAL);
+    const cmr_session_config &c = s->cfg;
+    const size_t B = c.B, N = c.N, C = c.C, P = (size_t)c.H * c.W, I = c.iters;
+    const int nr = c.dof6 ? 3 : 1, nt = c.dof6 ? 3 : 2;
+    SessionSlot &t = s->slots[s->submitted % s->depth];
+    if (t.in_flight) {   // the slot's previous rollout has not been collected: it must at least be complete
+        CMR_CUDA(cudaEventSynchronize(t.done));
+        session_account_upload(s, t);
+        t.in_flight = false;
+    }
+    // ---- uploads (copy stream).  The slot's buffers are free: its previous rollout is complete (above / wait).
+    CMR_CUDA(cudaEventRecord(t.up_begin, s->copy));
+    const cudaMemcpyKind h2d = cudaMemcpyHostToDevice;
+    CMR_CUDA(cudaMemcpyAsync(t.pc, in->pc, sizeof(float) * B * 3 * N, h2d, s->copy));
+    CMR_CUDA(cudaMemcpyAsync(t.overlap, in->overlap, B * N, h2d, s->copy));
+    CMR_CUDA(cudaMemcpyAsync(t.K, in->K, sizeof(float) * B * 9, h2d, s->copy));
+    CMR_CUDA(cudaMemcpyAsync(t.target_pose, in->P, sizeof(float) * B * 16, h2d, s->copy));
+    CMR_CUDA(cudaMemcpyAsync(t.a_r, in->action_r, sizeof(long long) * I * B * nr, h2d, s->copy));
+    CMR_CUDA(cudaMemcpyAsync(t.a_t, in->action_t, sizeof(long long) * I * B * nt, h2d, s->copy));
+    if (!c.features_resident) {
+        CMR_CUDA(cudaMemcpyAsync(t.feat, in->feat, sizeof(float) * B * C * N, h2d, s->copy));
+        CMR_CUDA(cudaMemcpyAsync(t.img_feat, in->img_feat, sizeof(float) * B * C * P, h2d, s->copy));
+        t.feat_used = t.feat;
+        t.img_used = t.img_feat;
+    } else {
+        t.feat_used = in->feat;
+        t.img_used = in->img_feat;
+    }
+    CMR_CUDA(cudaMemcpyAsync(t.pc_in_cam, in->pc_in_cam, sizeof(float) * B * 3 * N, h2d, s->copy));
+    CMR_CUDA(cudaMemcpyAsync(t.mask_i64, in->pc_mask, sizeof(long long) * B * N, h2d, s->copy));
+    CMR_CUDA(cudaEventRecord(t.up_end, s->copy));
+    CMR_CUDA(cudaEventRecord(t.uploaded, s->copy));
+    // ---- the rollout (compute stream)
+    cudaStream_t st = s->compute;
+    CMR_CUDA(cudaStreamWaitEvent(st, t.uploaded, 0));
+    int rc = cmr_cloud_mean(t.pc, c.B, c.N, t.mean, st);                                  // environment.py:46 - once per episode
+    if (!rc) rc = cmr_episode_prepare(t.overlap, t.feat_used, c.B, c.N, c.C, t.ws, st);
+    if (rc) return rc;
+    k_pose_identity<<<ceil_div(c.B * 16, 256), 256, 0, st>>>(t.pose, c.B);               // env.init (:138)
+    rc = after_launch();
+    if (!rc) rc = cmr_to_disentangled(t.target_pose, t.mean, c.B, st);                    // Test_Agent.py:152
+    if (rc) return rc;
+    k_mask_to_u8<<<std::min<long long>((long long)(B * N + 255) / 256, 4096), 256, 0, st>>>(t.mask_i64, t.mask_u8, B * N);   // :268
+    rc = after_launch();
+    for (int it = 0; it < c.iters && !rc; ++it) {
+        rc = cmr_observe(t.pc, t.overlap, t.img_used, t.K, t.pose, t.mean, t.ws, c.B, c.N, c.C, c.H, c.W, t.obs2d, t.obs3d, nullptr,
+                         nullptr, st);
+        if (!rc) rc = cmr_step(t.pose, (const int64_t *)t.a_r + (size_t)it * B * nr, (const int64_t *)t.a_t + (size_t)it * B * nt,
+                               s->rot_tab, s->t_tab, s->nbins, c.dof6, c.B, st);
+        if (!rc) {
+            const float *prev = it ? t.dist + (size_t)(it - 1) * B : nullptr;
+            if (c.reward_mode == CMR_REWARD_SHIPPED && it > 0)   // the shipped distance is a constant of the batch (:272-275)
+                rc = cmr_reward_compare(t.dist, prev, c.B, t.rew + (size_t)it * B, t.dist + (size_t)it * B, st);
+            else
+                rc = cmr_reward(t.pc_in_cam, t.pc, t.mask_u8, t.mean, t.pose, prev, c.reward_mode, c.B, c.N, t.scratch,
+                                t.rew + (size_t)it * B, t.dist + (size_t)it * B, st);
+        }
+    }
+    if (rc) return rc;
+    const cudaMemcpyKind d2h = cudaMemcpyDeviceToHost;
+    CMR_CUDA(cudaMemcpyAsync(t.h_rew, t.rew, sizeof(float) * I * B, d2h, st));
+    CMR_CUDA(cudaMemcpyAsync(t.h_dist, t.dist, sizeof(float) * I * B, d2h, st));
+    CMR_CUDA(cudaMemcpyAsync(t.h_pose, t.pose, sizeof(float) * B * 16, d2h, st));
+    CMR_CUDA(cudaMemcpyAsync(t.h_target, t.target_pose, sizeof(float) * B * 16, d2h, st));
+    CMR_CUDA(cudaEventRecord(t.done, st));
+    t.in_flight = true;
+    *ticket = s->submitted++;
+    return CMR_OK;
+}
+
+int cmr_session_wait(cmr_session *s, long long ticket, float *rewards, float *dists, float *poses, float *target_poses) {
+    CMR_REQUIRE(s && ticket >= 0 && ticket < s->submitted && ticket >= s->submitted - s->depth, CMR_EINVAL);
+    SessionSlot &t = s->slots[ticket % s->depth];
+    CMR_CUDA(cudaEventSynchronize(t.done));
+    if (t.in_flight) {
+        session_account_upload(s, t);
+        t.in_flight = false;
+    }
+    const size_t B = s->cfg.B, I = s->cfg.iters;
+    if (rewards) memcpy(rewards, t.h_rew, sizeof(float) * I * B);
+    if (dists) memcpy(dists, t.h_dist, sizeof(float) * I * B);
+    if (poses) memcpy(poses, t.h_pose, sizeof(float) * B * 16);
+    if (target_poses) memcpy(target_poses, t.h_target, sizeof(float) * B * 16);
+    return CMR_OK;
+}
+
+int cmr_session_stats(const cmr_session *s, double *h2d_gbs, double *bytes_per_rollout) {
+    CMR_REQUIRE(s, CMR_EINVAL);
+    if (h2d_gbs) *h2d_gbs = s->h2d_seconds > 0 ? s->h2d_bytes / s->h2d_seconds / 1e9 : 0.0;
+    if (bytes_per_rollout) *bytes_per_rollout = (double)s->bytes_per_upload;
+    return CMR_OK;
+}
+
+int cmr_session_peek(cmr_session *s, long long ticket, const float **obs2d, const float **obs3d) {
+    CMR_REQUIRE(s && ticket >= 0 && ticket < s->submitted && ticket >= s->submitted - s->depth, CMR_EINVAL);
+    SessionSlot &t = s->slots[ticket % s->depth];
+    if (obs2d) *obs2d = t.obs2d;
+    if (obs3d) *obs3d = t.obs3d;
+    return CMR_OK;
 }
 
 // -------------------------------------------------------------------------------- 3-D tower ----

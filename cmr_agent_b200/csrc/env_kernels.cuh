@@ -488,7 +488,7 @@ __global__ void CMR_PROJ_BOUNDS k_project(const float *__restrict__ pc, const ui
                     bbuf[((size_t)b * buckets + id2[i] / kBucketPix) * kBucketCap + slot[i]] =
                         ((unsigned)p << 7) | ((unsigned)id2[i] & 127u);
                 // exactly one point per bucket sees the counter cross kLightMax: it queues the bucket as heavy
-                if (slot[i] == kLightMax) hq[atomicAdd(hdr, 1)] = (b << 16) | (id2[i] / kBucketPix);
+                if (slot[i] == kLightMax) hq[atomicAdd(hdr, 1)] = (int)(((unsigned)b << 16) | (unsigned)(id2[i] / kBucketPix));
             }
             p += flags >> i & 1;
         }
@@ -576,7 +576,7 @@ __global__ void __launch_bounds__(32 * CMR_PROJ_WARPS)
                     const int slot = atomicAdd(bc + id / kBucketPix, 1);
                     if (slot < kBucketCap)
                         bbuf[((size_t)b * buckets + id / kBucketPix) * kBucketCap + slot] = ((unsigned)pos << 7) | ((unsigned)id & 127u);
-                    if (slot == kLightMax) hq[atomicAdd(hdr, 1)] = (b << 16) | (id / kBucketPix);
+                    if (slot == kLightMax) hq[atomicAdd(hdr, 1)] = (int)(((unsigned)b << 16) | (unsigned)(id / kBucketPix));
                 }
             }
         }

@@ -487,7 +487,7 @@ __global__ void __launch_bounds__(kGatherThreads, CMR_GATHER_MINB)
 #endif
         for (int item = first_item; item < items; item += kHeavyCtas * B) {
             if (item != first_item) qe = ld_cg_s32(hq + item);
-            const int b = qe >> 16, bk = qe & 0xffff;
+            const int b = (int)((unsigned)qe >> 16), bk = qe & 0xffff;   // episodes up to 65535: the entry is unsigned
             int *cb = bcnt + (size_t)b * kBucketStride + bk;
             const int c = ld_cg_s32(cb) & (kCountSeen - 1);
             const int p0 = bk * kBucketPix;

@@ -170,6 +170,50 @@ typedef struct cmr_iteration_args {
 CMR_API int cmr_iteration(const cmr_iteration_args *a, float *pose, const int64_t *action_r, const int64_t *action_t,
                           const float *prev, float *reward, float *dist, float *obs2d, float *obs3d, void *stream);
 
+/* ------------------------------------------------------------------ rollout session ---- */
+
+/* A whole registration rollout - init (environment.py:129-140), to_disentangled of the target (:15-21), then
+ * `iters` times  observation_from_a_pose -> step -> reward  (Test_Agent.py:154-170 / Train_Agent.py:229-248 with the
+ * actions given) - driven from HOST buffers by one call, pipelined: the session owns `depth` slots of device memory,
+ * a copy stream and a compute stream, and uploads rollout k+1 while the kernels of rollout k run.
+ *   cmr_session_create   allocates everything (device buffers, pinned result staging, streams, events) for batches
+ *                        of the configured shape.  features_resident != 0: `feat` and `img_feat` of cmr_rollout_inputs
+ *                        are DEVICE pointers (where CMR-Agent's feature network leaves them) and are not copied.
+ *   cmr_session_submit   enqueues the uploads and the kernels of one rollout and returns immediately; host buffers
+ *                        must stay valid (and should be pinned) until the matching cmr_session_wait.
+ *                        pc_mask is int64 as the dataset delivers it; actions are [iters, B, 1|3] / [iters, B, 2|3] int64.
+ *   cmr_session_wait     blocks until rollout `ticket` is complete and copies its results to the caller:
+ *                        rewards / dists [iters, B], final poses [B,4,4], disentangled target poses [B,4,4]
+ *                        (any of them may be NULL).
+ *   cmr_session_stats    average host->device rate of the uploads so far (GB/s, CUDA events on the copy stream)
+ *                        and the bytes one rollout uploads. */
+typedef struct cmr_session cmr_session;
+typedef struct cmr_session_config {
+    int B, N, C, H, W, iters, dof6, reward_mode, depth, features_resident, nbins;
+    const float *rot_tab; /* host: step tables, see cmr_step ([3, nbins+1, 3, 3]) */
+    const float *t_tab;   /* host: [nbins] */
+} cmr_session_config;
+typedef struct cmr_rollout_inputs {
+    const float *pc;            /* host [B,3,N] */
+    const uint8_t *overlap;     /* host [B,N] */
+    const float *feat;          /* host (or device, features_resident) [B,C,N] */
+    const float *img_feat;      /* host (or device, features_resident) [B,C,H,W] */
+    const float *K;             /* host [B,3,3] */
+    const float *P;             /* host [B,4,4]: data['P'] */
+    const float *pc_in_cam;     /* host [B,3,N] */
+    const int64_t *pc_mask;     /* host [B,N] */
+    const int64_t *action_r;    /* host [iters,B,1|3] */
+    const int64_t *action_t;    /* host [iters,B,2|3] */
+} cmr_rollout_inputs;
+CMR_API int cmr_session_create(const cmr_session_config *cfg, cmr_session **out);
+CMR_API void cmr_session_destroy(cmr_session *s);
+CMR_API int cmr_session_submit(cmr_session *s, const cmr_rollout_inputs *in, long long *ticket);
+CMR_API int cmr_session_wait(cmr_session *s, long long ticket, float *rewards, float *dists, float *poses,
+                             float *target_poses);
+CMR_API int cmr_session_stats(const cmr_session *s, double *h2d_gbs, double *bytes_per_rollout);
+/* device views of a slot's last observation (tests): obs2d [B,2C,H,W], obs3d [B,5,N] of rollout `ticket` */
+CMR_API int cmr_session_peek(cmr_session *s, long long ticket, const float **obs2d, const float **obs3d);
+
 /* ------------------------------------------------------------------ pointnet_util ---- */
 
 /* square_distance - pointnet_util.py:19-33. src [B,S,3], dst [B,N,3] (any strides, in floats) ->
