@@ -50,6 +50,12 @@ SIGNATURES = {
     "cmr_group_points": (_c_int, [_c_vp] * 4 + [_c_int] * 5 + [_c_vp, _c_vp]),
     "cmr_reward_compare": (_c_int, [_c_vp, _c_vp, _c_int, _c_vp, _c_vp, _c_vp]),
     "cmr_iteration": (_c_int, [_c_vp] * 10),
+    "cmr_session_create": (_c_int, [_c_vp, _c_vp]),
+    "cmr_session_destroy": (None, [_c_vp]),
+    "cmr_session_submit": (_c_int, [_c_vp, _c_vp, _c_vp]),
+    "cmr_session_wait": (_c_int, [_c_vp, ctypes.c_longlong, _c_vp, _c_vp, _c_vp, _c_vp]),
+    "cmr_session_stats": (_c_int, [_c_vp, _c_vp, _c_vp]),
+    "cmr_session_last_observation": (_c_int, [_c_vp, ctypes.c_longlong, _c_vp, _c_vp, _c_vp]),
     "cmr_tower_blob_bytes": (_c_sz, [_c_int]),
     "cmr_tower_pack": (_c_int, [_c_int] + [_c_vp] * 8),
     "cmr_tower_workspace_bytes": (_c_sz, [_c_int, _c_int]),
@@ -113,6 +119,19 @@ def bind(name):
 def fail(rc, what):
     msg = load().cmr_error_string(rc).decode()
     raise CmrError(f"{what} failed: {msg} (code {rc})")
+
+
+class SessionConfig(ctypes.Structure):
+    """cmr_session_config of include/cmr_b200.h."""
+    _fields_ = [(n, ctypes.c_int) for n in ("B", "N", "C", "H", "W", "iters", "dof6", "reward_mode", "depth",
+                                            "features_resident", "nbins")] + \
+               [("rot_tab", ctypes.c_void_p), ("t_tab", ctypes.c_void_p)]
+
+
+class RolloutInputs(ctypes.Structure):
+    """cmr_rollout_inputs of include/cmr_b200.h."""
+    _fields_ = [(n, ctypes.c_void_p) for n in ("pc", "overlap", "feat", "img_feat", "K", "P", "pc_in_cam", "pc_mask",
+                                               "action_r", "action_t")]
 
 
 class IterationArgs(ctypes.Structure):

@@ -1023,11 +1023,13 @@ int cmr_session_stats(const cmr_session *s, double *h2d_gbs, double *bytes_per_r
     return CMR_OK;
 }
 
-int cmr_session_peek(cmr_session *s, long long ticket, const float **obs2d, const float **obs3d) {
+int cmr_session_last_observation(cmr_session *s, long long ticket, float *obs2d, float *obs3d, void *stream) {
     CMR_REQUIRE(s && ticket >= 0 && ticket < s->submitted && ticket >= s->submitted - s->depth, CMR_EINVAL);
     SessionSlot &t = s->slots[ticket % s->depth];
-    if (obs2d) *obs2d = t.obs2d;
-    if (obs3d) *obs3d = t.obs3d;
+    const size_t B = s->cfg.B, N = s->cfg.N, C = s->cfg.C, P = (size_t)s->cfg.H * s->cfg.W;
+    CMR_CUDA(cudaStreamWaitEvent(S_(stream), t.done, 0));
+    if (obs2d) CMR_CUDA(cudaMemcpyAsync(obs2d, t.obs2d, sizeof(float) * B * 2 * C * P, cudaMemcpyDeviceToDevice, S_(stream)));
+    if (obs3d) CMR_CUDA(cudaMemcpyAsync(obs3d, t.obs3d, sizeof(float) * B * 5 * N, cudaMemcpyDeviceToDevice, S_(stream)));
     return CMR_OK;
 }
 

@@ -211,8 +211,9 @@ CMR_API int cmr_session_submit(cmr_session *s, const cmr_rollout_inputs *in, lon
 CMR_API int cmr_session_wait(cmr_session *s, long long ticket, float *rewards, float *dists, float *poses,
                              float *target_poses);
 CMR_API int cmr_session_stats(const cmr_session *s, double *h2d_gbs, double *bytes_per_rollout);
-/* device views of a slot's last observation (tests): obs2d [B,2C,H,W], obs3d [B,5,N] of rollout `ticket` */
-CMR_API int cmr_session_peek(cmr_session *s, long long ticket, const float **obs2d, const float **obs3d);
+/* the observation of the LAST iteration of rollout `ticket` (still in its slot), copied device-to-device into the
+ * caller's obs2d [B,2C,H,W] / obs3d [B,5,N] on `stream` (ordered after the rollout) */
+CMR_API int cmr_session_last_observation(cmr_session *s, long long ticket, float *obs2d, float *obs3d, void *stream);
 
 /* ------------------------------------------------------------------ pointnet_util ---- */
 
