@@ -468,7 +468,7 @@ static int project_impl(const float *pc, const uint8_t *overlap, const float *K,
     CMR_REQUIRE(pc && overlap && K && pose && mean && workspace && obs3d, CMR_EINVAL);
     int rc = check_observe_dims(B, N, C, H, W);
     if (rc) return rc;
-    CMR_REQUIRE(aligned(workspace, 256), CMR_EALIGN);
+    CMR_REQUIRE(aligned(workspace, 256) && aligned(pose, 16), CMR_EALIGN);   // pose rows are read as float4
     WsLayout L = ws_layout(B, N, C, H * W);
     char *ws = static_cast<char *>(workspace);
     alignas(64) CUtensorMap map_img, map_out;
@@ -731,6 +731,7 @@ int cmr_cost_volume_prepare(const uint8_t *mask, const float *feat, int B, int K
 int cmr_cost_volume_warp(const float *pc, const uint8_t *mask, const float *Kmat, const float *poses, void *workspace,
                          int B, int K, int N, int C, int H, int W, int mean_channels, float *out, void *stream) {
     CMR_REQUIRE(pc && mask && Kmat && poses && workspace && out && K > 0, CMR_EINVAL);
+    CMR_REQUIRE(aligned(poses, 16), CMR_EALIGN);
     int rc = check_observe_dims(B, N, C, H, W);
     if (rc) return rc;
     CMR_REQUIRE((long long)B * K <= 65535, CMR_ERANGE);

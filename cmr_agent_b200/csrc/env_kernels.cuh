@@ -310,12 +310,14 @@ struct PoseK {
 
 __device__ __forceinline__ void load_posek(PoseK &s, const float *__restrict__ pose, const float *__restrict__ K,
                                            const float *__restrict__ mean, int b, int bk) {
-    const float *P = pose + (size_t)b * 16;
+    const float4 *P = reinterpret_cast<const float4 *>(pose + (size_t)b * 16);   // a pose is 64 bytes: rows [R | t]
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) s.R[3 * r + c] = __ldg(P + 4 * r + c);
-        s.t[r] = __ldg(P + 4 * r + 3);
+        const float4 row = __ldg(P + r);
+        s.R[3 * r] = row.x;
+        s.R[3 * r + 1] = row.y;
+        s.R[3 * r + 2] = row.z;
+        s.t[r] = row.w;
         s.m[r] = __ldg(mean + (size_t)b * 3 + r);
     }
 #pragma unroll
@@ -360,9 +362,9 @@ __global__ void CMR_PROJ_BOUNDS k_project(const float *__restrict__ pc, const ui
     const int b = blockIdx.y;
     // `share` consecutive poses look at the same cloud (cost volumes: hundreds of candidate poses per cloud,
     // SURVEY 8f rank 4); everything that belongs to the cloud is indexed by bs, what belongs to the pose by b
-    const int bs = b / share;
-    const int lane = threadIdx.x & 31;
-    const int g = blockIdx.x * kProjWarps + (threadIdx.x >> 5);
+    const int bs = share == 1 ? b : b / share;   // (the observation's share is 1: no integer division on its path)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = blockIdx.x * kProjWarps + warp;
     // The image half of obs2d (obs2d[b, 0:C] = img_geo_feat[b], environment.py:83) is a pure copy that does
     // not depend on the pose.  It rides along here as tiled TMA traffic: thread 0 of every CTA moves
     // [C][128-pixel] boxes global -> shared -> global while the CTA's threads do the projection maths -
@@ -467,32 +469,41 @@ __global__ void CMR_PROJ_BOUNDS k_project(const float *__restrict__ pc, const ui
 #pragma unroll
     for (int i = 0; i < 4; ++i)
         if (flags >> i & 1) pw[pos++] = (PixT)id2[i];
-#ifdef CMR_DBG_NO_APPEND
-    if (false) {
-#else
-    if (bcnt && (flags & cam2)) {
-#endif
-        int *bc = bcnt + (size_t)b * kBucketStride;
-        // visible predicted-overlap points go to the 32-pixel bucket of their pixel (integer atomics: the SET
-        // of entries of a bucket is deterministic, k_tile_gather restores point order by sorting).  The four
-        // atomics of a lane are independent: issued together, their round trips overlap.
-        int slot[4];
+#ifndef CMR_DBG_NO_APPEND
+    if (bcnt) {
+        // Visible predicted-overlap points go to the 32-pixel bucket of their pixel (integer atomics: the SET of
+        // entries of a bucket is deterministic, k_tile_gather restores point order by sorting).  A warp holds 128
+        // points of which a handful are visible: they are first compacted into a per-warp list (four ballots give
+        // every lane its offset), then ONE pass with one listed point per lane does the atomics and the stores -
+        // instead of four divergent passes over the lanes' point slots.
+        __shared__ int2 vlist[kProjWarps][kGroup];   // (pixel id, compacted position)
+        const unsigned vis = flags & cam2;
+        const unsigned b0 = __ballot_sync(kFull, vis & 1u), b1 = __ballot_sync(kFull, vis & 2u);
+        const unsigned b2 = __ballot_sync(kFull, vis & 4u), b3 = __ballot_sync(kFull, vis & 8u);
+        const int total = __popc(b0) + __popc(b1) + __popc(b2) + __popc(b3);
+        if (total) {   // warp-uniform
+            const unsigned lt = (1u << lane) - 1u;
+            int r = __popc(b0 & lt) + __popc(b1 & lt) + __popc(b2 & lt) + __popc(b3 & lt);
+            int p = pos0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-            if ((flags & cam2) >> i & 1) slot[i] = atomicAdd(bc + id2[i] / kBucketPix, 1);
-        int p = pos0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            if ((flags & cam2) >> i & 1) {
-                if (slot[i] < kBucketCap)
-                    bbuf[((size_t)b * buckets + id2[i] / kBucketPix) * kBucketCap + slot[i]] =
-                        ((unsigned)p << 7) | ((unsigned)id2[i] & 127u);
-                // exactly one point per bucket sees the counter cross kLightMax: it queues the bucket as heavy
-                if (slot[i] == kLightMax) hq[atomicAdd(hdr, 1)] = (int)(((unsigned)b << 16) | (unsigned)(id2[i] / kBucketPix));
+            for (int i = 0; i < 4; ++i) {
+                if (vis >> i & 1) vlist[warp][r++] = make_int2(id2[i], p);
+                p += flags >> i & 1;
             }
-            p += flags >> i & 1;
+            __syncwarp();
+            int *bc = bcnt + (size_t)b * kBucketStride;
+            for (int k = lane; k < total; k += 32) {
+                const int2 e = vlist[warp][k];
+                const int bucket = e.x / kBucketPix;
+                const int slot = atomicAdd(bc + bucket, 1);
+                if (slot < kBucketCap)
+                    bbuf[((size_t)b * buckets + bucket) * kBucketCap + slot] = ((unsigned)e.y << 7) | ((unsigned)e.x & 127u);
+                // exactly one point per bucket sees the counter cross kLightMax: it queues the bucket as heavy
+                if (slot == kLightMax) hq[atomicAdd(hdr, 1)] = (int)(((unsigned)b << 16) | (unsigned)bucket);
+            }
         }
     }
+#endif
     // k_tile_scatter reads the list in 16-byte words: the warp of the last group pads the ids between
     // M and the next word boundary with all-ones (never inside a tile)
     if (g == groups - 1 && lane == 31) {
