@@ -46,7 +46,10 @@ SIGNATURES = {
     "cmr_index_points_backward": (_c_int, [_c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp]),
     "cmr_farthest_point_sample": (_c_int, [_c_vp, _c_vp, _c_int, _c_int, _c_int, _c_vp, _c_vp]),
     "cmr_knn": (_c_int, [_c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp]),
+    "cmr_knn_grid_workspace_bytes": (_c_sz, [_c_int, _c_int]),
+    "cmr_knn_grid": (_c_int, [_c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp, _c_vp]),
     "cmr_query_ball_point": (_c_int, [_c_vp, _c_vp, _c_f, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp]),
+    "cmr_query_ball_point_grid": (_c_int, [_c_vp, _c_vp, _c_f, _c_f, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp, _c_vp]),
     "cmr_group_points": (_c_int, [_c_vp] * 4 + [_c_int] * 5 + [_c_vp, _c_vp]),
     "cmr_reward_compare": (_c_int, [_c_vp, _c_vp, _c_int, _c_vp, _c_vp, _c_vp]),
     "cmr_iteration": (_c_int, [_c_vp] * 10),

@@ -691,6 +691,57 @@ int cmr_knn(const float *query, const float *ref, int B, int S, int N, int k, in
     return after_launch();
 }
 
+static int build_knn_grid(const float *ref, int B, int N, unsigned char *ws, const KnnGridWs &w, cudaStream_t st) {
+    k_grid_setup<<<B, 256, 0, st>>>(ref, N, ws, w.per_cloud, w.off_start, w.off_fill);
+    int rc = after_launch();
+    if (rc) return rc;
+    k_grid_count<<<dim3(ceil_div(N, 256), B), 256, 0, st>>>(ref, N, ws, w.per_cloud, w.off_start);
+    rc = after_launch();
+    if (rc) return rc;
+    k_grid_scan<<<B, 1024, 0, st>>>(ws, w.per_cloud, w.off_start);
+    rc = after_launch();
+    if (rc) return rc;
+    k_grid_fill<<<dim3(ceil_div(N, 256), B), 256, 0, st>>>(ref, N, ws, w.per_cloud, w.off_start, w.off_fill, w.off_sorted);
+    return after_launch();
+}
+
+size_t cmr_knn_grid_workspace_bytes(int B, int N) { return (B > 0 && N > 0) ? (size_t)B * knn_grid_ws(N).per_cloud : 0; }
+
+int cmr_knn_grid(const float *query, const float *ref, int B, int S, int N, int k, void *workspace, int64_t *out, void *stream) {
+    CMR_REQUIRE(query && ref && out && workspace && B > 0 && S > 0 && N > 0 && k > 0, CMR_EINVAL);
+    CMR_REQUIRE(k <= 128 && k <= N && B <= 65535, CMR_ERANGE);
+    CMR_REQUIRE(aligned(workspace, 256), CMR_EALIGN);
+    const KnnGridWs w = knn_grid_ws(N);
+    unsigned char *ws = static_cast<unsigned char *>(workspace);
+    cudaStream_t st = S_(stream);
+    int rc = build_knn_grid(ref, B, N, ws, w, st);
+    if (rc) return rc;
+    const dim3 grid(ceil_div(S, 8), B);
+    if (k <= 64)
+        k_knn_grid<64><<<grid, 256, 0, st>>>(query, ws, w.per_cloud, w.off_start, w.off_sorted, S, N, k, out);
+    else
+        k_knn_grid<128><<<grid, 256, 0, st>>>(query, ws, w.per_cloud, w.off_start, w.off_sorted, S, N, k, out);
+    return after_launch();
+}
+
+int cmr_query_ball_point_grid(const float *query, const float *ref, float radius2, float radius, int nsample, int B, int S, int N,
+                              void *workspace, int64_t *out, void *stream) {
+    CMR_REQUIRE(query && ref && out && workspace && nsample > 0 && B > 0 && S > 0 && N > 0, CMR_EINVAL);
+    CMR_REQUIRE(B <= 65535 && nsample <= 128 && radius >= 0.f, CMR_ERANGE);
+    CMR_REQUIRE(aligned(workspace, 256), CMR_EALIGN);
+    const KnnGridWs w = knn_grid_ws(N);
+    unsigned char *ws = static_cast<unsigned char *>(workspace);
+    cudaStream_t st = S_(stream);
+    int rc = build_knn_grid(ref, B, N, ws, w, st);
+    if (rc) return rc;
+    const dim3 grid(ceil_div(S, 8), B);
+    if (nsample <= 64)
+        k_ball_grid<64><<<grid, 256, 0, st>>>(query, ws, w.per_cloud, w.off_start, w.off_sorted, radius2, radius, nsample, S, N, out);
+    else
+        k_ball_grid<128><<<grid, 256, 0, st>>>(query, ws, w.per_cloud, w.off_start, w.off_sorted, radius2, radius, nsample, S, N, out);
+    return after_launch();
+}
+
 int cmr_query_ball_point(const float *query, const float *ref, float radius2, int nsample, int B, int S, int N,
                          int64_t *out, void *stream) {
     CMR_REQUIRE(query && ref && out && nsample > 0 && B > 0 && S > 0 && N > 0, CMR_EINVAL);

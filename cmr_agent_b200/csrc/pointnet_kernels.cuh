@@ -415,4 +415,313 @@ __global__ void __launch_bounds__(256) k_ball_query(const float *__restrict__ qu
     }
 }
 
+// -------------------------------------------------------------------------------------------------
+// kNN with a uniform grid over the reference cloud (same result as k_knn, bit for bit: the same distance
+// expression, the same (distance, index) order - only far fewer candidates are evaluated).
+//   k_grid_setup  one CTA per cloud: bounding box, the two axes with the largest extent (a LiDAR cloud is a slab:
+//                 the third axis is not binned), square cells sized for ~16 points each, at most kGridMaxCells.
+//   k_grid_count / k_grid_scan / k_grid_fill   counting sort of the points by cell: sorted[cell-major] = (x, y, z, index).
+//   k_knn_grid    one warp per query: rings of cells around the query's cell, nearest first; every ring is at most
+//                 four contiguous spans of the sorted array.  The search stops when the k-th distance so far is
+//                 STRICTLY below the squared distance to the unexplored region (minus a rounding margin): a point out
+//                 there cannot enter the list, not even on a tie.  Candidates are admitted on d <= tau (points arrive
+//                 in cell order, so a tie may carry a smaller index than the current k-th).
+constexpr int kGridMaxCells = 4096;
+constexpr int kGridTargetPerCell = 16;
+struct KnnGrid {
+    float o0, o1, inv0, inv1, h;
+    int a0, a1, g0, g1, pad0, pad1, pad2;
+};
+struct KnnGridWs {
+    size_t per_cloud, off_start, off_fill, off_sorted;
+};
+inline KnnGridWs knn_grid_ws(int N) {
+    KnnGridWs w;
+    w.off_start = 64;
+    w.off_fill = w.off_start + sizeof(int) * (kGridMaxCells + 1 + 3);
+    w.off_sorted = round_up(w.off_fill + sizeof(int) * kGridMaxCells, 256);
+    w.per_cloud = round_up(w.off_sorted + sizeof(float4) * (size_t)N, 256);
+    return w;
+}
+__device__ __forceinline__ int grid_cell_1d(float v, float o, float inv, int g) {
+    const int c = (int)floorf(__fmul_rn(__fsub_rn(v, o), inv));
+    return min(max(c, 0), g - 1);
+}
+
+__global__ void __launch_bounds__(256) k_grid_setup(const float *__restrict__ ref, int N, unsigned char *__restrict__ ws, size_t per_cloud,
+                                                    size_t off_start, size_t off_fill) {
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const float *rb = ref + (size_t)b * N * 3;
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int j = tid; j < N; j += 256) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float v = __ldg(rb + (size_t)j * 3 + a);
+            lo[a] = fminf(lo[a], v);
+            hi[a] = fmaxf(hi[a], v);
+        }
+    }
+    __shared__ float slo[3][8], shi[3][8];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[a] = fminf(lo[a], __shfl_xor_sync(kFull, lo[a], o));
+            hi[a] = fmaxf(hi[a], __shfl_xor_sync(kFull, hi[a], o));
+        }
+        if ((tid & 31) == 0) {
+            slo[a][tid >> 5] = lo[a];
+            shi[a][tid >> 5] = hi[a];
+        }
+    }
+    __syncthreads();
+    unsigned char *base = ws + (size_t)b * per_cloud;
+    int *start = reinterpret_cast<int *>(base + off_start), *fill = reinterpret_cast<int *>(base + off_fill);
+    for (int i = tid; i < kGridMaxCells + 1; i += 256) start[i] = 0;
+    for (int i = tid; i < kGridMaxCells; i += 256) fill[i] = 0;
+    if (tid == 0) {
+        float e[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            float l = slo[a][0], h = shi[a][0];
+            for (int w = 1; w < 8; ++w) {
+                l = fminf(l, slo[a][w]);
+                h = fmaxf(h, shi[a][w]);
+            }
+            lo[a] = l;
+            hi[a] = h;
+            e[a] = h - l;
+            if (!(e[a] >= 0.f) || !isfinite(e[a])) e[a] = 0.f;   // NaN / inf coordinates: everything lands in cell 0
+        }
+        // the two axes with the largest extent
+        int a0 = 0, a1 = 1, drop = 2;
+        if (e[0] <= e[1] && e[0] <= e[2]) drop = 0;
+        else if (e[1] <= e[0] && e[1] <= e[2]) drop = 1;
+        a0 = drop == 0 ? 1 : 0;
+        a1 = drop == 2 ? 1 : 2;
+        const float cells = fminf((float)kGridMaxCells, fmaxf(1.f, (float)N / kGridTargetPerCell));
+        float h = sqrtf(fmaxf(e[a0] * e[a1], 1e-30f) / cells);
+        if (!(h > 0.f) || !isfinite(h)) h = 1.f;
+        h = fmaxf(h, fmaxf(e[a0], e[a1]) * 1e-4f);     // at most 10^4 cells along an axis before the product is capped
+        int g0 = max(1, (int)ceilf(e[a0] / h)), g1 = max(1, (int)ceilf(e[a1] / h));
+        while ((long long)g0 * g1 > kGridMaxCells) {
+            h *= 1.1f;
+            g0 = max(1, (int)ceilf(e[a0] / h));
+            g1 = max(1, (int)ceilf(e[a1] / h));
+        }
+        KnnGrid gr;
+        gr.o0 = isfinite(lo[a0]) ? lo[a0] : 0.f;
+        gr.o1 = isfinite(lo[a1]) ? lo[a1] : 0.f;
+        gr.h = h;
+        gr.inv0 = gr.inv1 = 1.f / h;
+        gr.a0 = a0; gr.a1 = a1; gr.g0 = g0; gr.g1 = g1;
+        gr.pad0 = gr.pad1 = gr.pad2 = 0;
+        *reinterpret_cast<KnnGrid *>(base) = gr;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_grid_count(const float *__restrict__ ref, int N, unsigned char *__restrict__ ws, size_t per_cloud,
+                                                    size_t off_start) {
+    const int b = blockIdx.y, j = blockIdx.x * 256 + threadIdx.x;
+    if (j >= N) return;
+    unsigned char *base = ws + (size_t)b * per_cloud;
+    const KnnGrid gr = *reinterpret_cast<const KnnGrid *>(base);
+    const float *p = ref + ((size_t)b * N + j) * 3;
+    const int c = grid_cell_1d(__ldg(p + gr.a1), gr.o1, gr.inv1, gr.g1) * gr.g0 + grid_cell_1d(__ldg(p + gr.a0), gr.o0, gr.inv0, gr.g0);
+    atomicAdd(reinterpret_cast<int *>(base + off_start) + c, 1);
+}
+
+// counts -> exclusive prefix (start[cells] = N), one CTA of 1024 threads per cloud
+__global__ void __launch_bounds__(1024) k_grid_scan(unsigned char *__restrict__ ws, size_t per_cloud, size_t off_start) {
+    unsigned char *base = ws + (size_t)blockIdx.x * per_cloud;
+    int *start = reinterpret_cast<int *>(base + off_start);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int v[4], sum = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        v[i] = start[tid * 4 + i];
+        sum += v[i];
+    }
+    int inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(kFull, inc, o);
+        if (lane >= o) inc += t;
+    }
+    __shared__ int wtot[32];
+    if (lane == 31) wtot[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int w = wtot[lane], winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(kFull, winc, o);
+            if (lane >= o) winc += t;
+        }
+        wtot[lane] = winc - w;
+    }
+    __syncthreads();
+    int run = wtot[warp] + inc - sum;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        start[tid * 4 + i] = run;
+        run += v[i];
+    }
+    if (tid == 1023) start[kGridMaxCells] = run;
+}
+
+__global__ void __launch_bounds__(256) k_grid_fill(const float *__restrict__ ref, int N, unsigned char *__restrict__ ws, size_t per_cloud,
+                                                   size_t off_start, size_t off_fill, size_t off_sorted) {
+    const int b = blockIdx.y, j = blockIdx.x * 256 + threadIdx.x;
+    if (j >= N) return;
+    unsigned char *base = ws + (size_t)b * per_cloud;
+    const KnnGrid gr = *reinterpret_cast<const KnnGrid *>(base);
+    const float *p = ref + ((size_t)b * N + j) * 3;
+    const float x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
+    const float v0 = gr.a0 == 0 ? x : (gr.a0 == 1 ? y : z), v1 = gr.a1 == 1 ? y : (gr.a1 == 2 ? z : x);
+    const int c = grid_cell_1d(v1, gr.o1, gr.inv1, gr.g1) * gr.g0 + grid_cell_1d(v0, gr.o0, gr.inv0, gr.g0);
+    const int pos = reinterpret_cast<const int *>(base + off_start)[c] + atomicAdd(reinterpret_cast<int *>(base + off_fill) + c, 1);
+    reinterpret_cast<float4 *>(base + off_sorted)[pos] = make_float4(x, y, z, __int_as_float(j));
+}
+
+template <int KCAP>
+__global__ void __launch_bounds__(256) k_knn_grid(const float *__restrict__ query, const unsigned char *__restrict__ ws, size_t per_cloud,
+                                                  size_t off_start, size_t off_sorted, int S, int N, int k, int64_t *__restrict__ out) {
+    constexpr int T = (KCAP + kKnnBuf) <= 128 ? 128 : 256;
+    constexpr int E = T / 32;
+    __shared__ unsigned long long slist[8][KCAP];
+    __shared__ unsigned long long sbuf[8][kKnnBuf];
+    const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int s = blockIdx.x * 8 + warp;
+    if (s >= S) return;
+    const unsigned char *base = ws + (size_t)b * per_cloud;
+    const KnnGrid gr = *reinterpret_cast<const KnnGrid *>(base);
+    const int *start = reinterpret_cast<const int *>(base + off_start);
+    const float4 *sorted = reinterpret_cast<const float4 *>(base + off_sorted);
+    const float *qp = query + ((size_t)b * S + s) * 3;
+    const float qx = __ldg(qp), qy = __ldg(qp + 1), qz = __ldg(qp + 2);
+    const float q0 = gr.a0 == 0 ? qx : (gr.a0 == 1 ? qy : qz), q1 = gr.a1 == 1 ? qy : (gr.a1 == 2 ? qz : qx);
+    const int c0 = grid_cell_1d(q0, gr.o0, gr.inv0, gr.g0), c1 = grid_cell_1d(q1, gr.o1, gr.inv1, gr.g1);
+    unsigned long long *L = slist[warp], *Bf = sbuf[warp];
+    const unsigned long long kInf = ~0ull;
+    for (int i = lane; i < KCAP; i += 32) L[i] = kInf;
+    __syncwarp();
+    float tau = __int_as_float(0x7f800000);
+    int cnt = 0;
+    auto span = [&](int cell_lo, int cell_hi) {   // cells [cell_lo, cell_hi] of one grid row: contiguous in `sorted`
+        const int beg = start[cell_lo], end = start[cell_hi + 1];
+        for (int i0 = beg; i0 < end; i0 += 32) {
+            const int i = i0 + lane;
+            bool pass = false;
+            float dd = 0.f;
+            unsigned ridx = 0;
+            if (i < end) {
+                const float4 p = __ldg(sorted + i);
+                dd = sqdist3(qx, qy, qz, p.x, p.y, p.z);   // square_distance(new_xyz, xyz): src - dst, as k_knn
+                ridx = (unsigned)__float_as_int(p.w);
+                pass = dd <= tau;
+            }
+            const unsigned m = __ballot_sync(kFull, pass);
+            if (m) {
+                if (pass) Bf[cnt + __popc(m & ((1u << lane) - 1))] = ((unsigned long long)__float_as_uint(dd) << 32) | ridx;
+                cnt += __popc(m);
+                __syncwarp();
+                if (cnt > kKnnBuf - 32) knn_flush<KCAP, E>(L, Bf, cnt, tau, k, lane);
+            }
+        }
+    };
+    const int rmax = max(max(c0, gr.g0 - 1 - c0), max(c1, gr.g1 - 1 - c1));
+    for (int r = 0; r <= rmax; ++r) {
+        const int lo0 = c0 - r, hi0 = c0 + r, lo1 = c1 - r, hi1 = c1 + r;
+        const int x0 = max(lo0, 0), x1 = min(hi0, gr.g0 - 1);
+        for (int y = max(lo1, 0); y <= min(hi1, gr.g1 - 1); ++y) {
+            if (y == lo1 || y == hi1) {
+                span(y * gr.g0 + x0, y * gr.g0 + x1);
+            } else {
+                if (lo0 >= 0) span(y * gr.g0 + lo0, y * gr.g0 + lo0);
+                if (hi0 < gr.g0) span(y * gr.g0 + hi0, y * gr.g0 + hi0);
+            }
+        }
+        if (cnt > 0) knn_flush<KCAP, E>(L, Bf, cnt, tau, k, lane);
+        // distance from the query to the nearest face of the explored block that still has cells behind it
+        float lb = __int_as_float(0x7f800000);
+        if (lo0 > 0) lb = fminf(lb, q0 - (gr.o0 + lo0 * gr.h));
+        if (hi0 < gr.g0 - 1) lb = fminf(lb, (gr.o0 + (hi0 + 1) * gr.h) - q0);
+        if (lo1 > 0) lb = fminf(lb, q1 - (gr.o1 + lo1 * gr.h));
+        if (hi1 < gr.g1 - 1) lb = fminf(lb, (gr.o1 + (hi1 + 1) * gr.h) - q1);
+        lb -= 1e-3f * gr.h;                            // cell assignment and the faces are rounded: stay on the safe side
+        if (lb > 0.f && tau < lb * lb * (1.f - 1e-5f)) break;
+    }
+    int64_t *o = out + ((size_t)b * S + s) * k;
+    for (int i = lane; i < k; i += 32) o[i] = (int64_t)(unsigned)(L[i] & 0xffffffffull);
+}
+
+// query_ball_point on the same grid: only the cells that the ball's bounding square touches are read.  The hits are
+// the points with !(d > r2) exactly as in k_ball_query; of those the nsample SMALLEST INDICES are wanted, ascending
+// (pointnet_util.py:86-92) - the k-best machinery of the kNN with the index as the key.
+template <int KCAP>
+__global__ void __launch_bounds__(256) k_ball_grid(const float *__restrict__ query, const unsigned char *__restrict__ ws, size_t per_cloud,
+                                                   size_t off_start, size_t off_sorted, float r2, float radius, int nsample, int S, int N,
+                                                   int64_t *__restrict__ out) {
+    constexpr int T = (KCAP + kKnnBuf) <= 128 ? 128 : 256;
+    constexpr int E = T / 32;
+    __shared__ unsigned long long slist[8][KCAP];
+    __shared__ unsigned long long sbuf[8][kKnnBuf];
+    const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int s = blockIdx.x * 8 + warp;
+    if (s >= S) return;
+    const unsigned char *base = ws + (size_t)b * per_cloud;
+    const KnnGrid gr = *reinterpret_cast<const KnnGrid *>(base);
+    const int *start = reinterpret_cast<const int *>(base + off_start);
+    const float4 *sorted = reinterpret_cast<const float4 *>(base + off_sorted);
+    const float *qp = query + ((size_t)b * S + s) * 3;
+    const float qx = __ldg(qp), qy = __ldg(qp + 1), qz = __ldg(qp + 2);
+    const float q0 = gr.a0 == 0 ? qx : (gr.a0 == 1 ? qy : qz), q1 = gr.a1 == 1 ? qy : (gr.a1 == 2 ? qz : qx);
+    unsigned long long *L = slist[warp], *Bf = sbuf[warp];
+    const unsigned long long kInf = ~0ull;
+    for (int i = lane; i < KCAP; i += 32) L[i] = kInf;
+    __syncwarp();
+    float tau = __int_as_float(0x7f800000);   // knn_flush's threshold (a float view of the key's high word): unused here
+    unsigned long long kth = kInf;            // the nsample-th smallest index so far
+    int cnt = 0;
+    const float reach = radius * (1.f + 1e-5f) + 1e-3f * gr.h;   // cell assignment is rounded: stay on the safe side
+    const bool any = r2 >= 0.f || r2 != r2;                         // a negative r2 has no hits (NaN: every !(d > r2) is true)
+    if (any) {
+        const int x0 = grid_cell_1d(q0 - reach, gr.o0, gr.inv0, gr.g0), x1 = grid_cell_1d(q0 + reach, gr.o0, gr.inv0, gr.g0);
+        const int y0 = grid_cell_1d(q1 - reach, gr.o1, gr.inv1, gr.g1), y1 = grid_cell_1d(q1 + reach, gr.o1, gr.inv1, gr.g1);
+        for (int y = y0; y <= y1; ++y) {
+            const int beg = start[y * gr.g0 + x0], end = start[y * gr.g0 + x1 + 1];
+            for (int i0 = beg; i0 < end; i0 += 32) {
+                const int i = i0 + lane;
+                bool pass = false;
+                unsigned ridx = 0;
+                if (i < end) {
+                    const float4 p = __ldg(sorted + i);
+                    const float dd = sqdist3(qx, qy, qz, p.x, p.y, p.z);
+                    ridx = (unsigned)__float_as_int(p.w);
+                    pass = !(dd > r2) && (unsigned long long)ridx <= kth;                  // :88
+                }
+                const unsigned m = __ballot_sync(kFull, pass);
+                if (m) {
+                    if (pass) Bf[cnt + __popc(m & ((1u << lane) - 1))] = (unsigned long long)ridx;
+                    cnt += __popc(m);
+                    __syncwarp();
+                    if (cnt > kKnnBuf - 32) {
+                        knn_flush<KCAP, E>(L, Bf, cnt, tau, nsample, lane);
+                        kth = L[nsample - 1];
+                    }
+                }
+            }
+        }
+        if (cnt > 0) knn_flush<KCAP, E>(L, Bf, cnt, tau, nsample, lane);
+    }
+    __syncwarp();
+    const unsigned long long first = L[0];
+    int64_t *o = out + ((size_t)b * S + s) * nsample;
+    for (int i = lane; i < nsample; i += 32) {
+        const unsigned long long v = L[i];
+        o[i] = v != kInf ? (int64_t)v : (first != kInf ? (int64_t)first : (int64_t)N);       // :90-92
+    }
+}
+
 }  // namespace cmr

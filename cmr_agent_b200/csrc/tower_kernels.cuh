@@ -23,8 +23,9 @@
 //   * measured on a B200: bf16 pieces (16-17 bits) give 5e-6 typical but 1.2e-5 worst over 300 episodes -
 //     not enough; kind::f16 rejects an fp16 operand meeting a bf16 one (illegal instruction), so "bf16 hi, fp16 lo"
 //     is not available; fp16 pieces cost the same three passes.
-//   * range: fp16 holds |x| <= 65504; conversions saturate (no inf/NaN), hi + lo then still carries values up to
-//     131008 at reduced precision, and any |activation| > 65504 raises the sticky fault flag (cmr_take_fault() == 3).
+//   * range: fp16 holds |x| <= 65504.  A larger activation converts to inf, its low piece to -inf, their products
+//     to NaN, and every max on the way is NaN-propagating (max.NaN): the embedding comes out NaN and
+//     k_tower_finish raises the sticky fault word (cmr_take_fault() == 3) - loud, never silently wrong.
 //     The tower's inputs are coordinates in metres and 0/1 flags; CMR_TOWER_FMT=0 builds the bf16 variant.
 //
 // Orientation: M = 128 points (TMEM lanes), N = output channels (TMEM columns), K = input channels.
@@ -35,10 +36,12 @@
 // Features travel between the blocks as 16-bit planes [B][N][64] (hi, lo; a third plane lo2 after block 3, whose
 // consumer adds them back to an exact fp32 for the identity shortcut) - 4 bytes per value, as fp32 would be.
 //
-// Warp roles of k_tower_mma (384 threads): warp 0 = TMA producer, warp 1 = TMEM allocation + MMA issue (one
-// elected lane), warps 4-7 and 8-11 = two epilogue groups working on alternate tiles, each with its own TMEM
+// Warp roles of k_tower_mma (640 threads): warp 0 = TMA producer, warp 1 = TMEM allocation + MMA issue (one
+// elected lane), warps 4-11 and 12-19 = two epilogue groups working on alternate tiles, each with its own TMEM
 // accumulators (D1/H 128 columns + D2 64|128 columns), so that the tensor pipe works on tile t+1 while tile t is
-// in the epilogue.  A CTA owns a contiguous range of 128-point tiles; when the range crosses into the next
+// in the epilogue.  A group is 8 warps: two per TMEM lane quarter, each taking half of the accumulator's columns
+// (a warp's dependent instructions issue every ~5 cycles; two epilogue warps per scheduler left the issue slots
+// 65 % idle - ncu, profiles/r2_tower_ncu.txt - four fill them).  A CTA owns a contiguous range of 128-point tiles; when the range crosses into the next
 // episode the epilogue groups flush their running maxima, recompute the per-episode biases and go on.
 #pragma once
 #include <cuda_bf16.h>
@@ -50,7 +53,7 @@ namespace cmr {
 
 constexpr int kTowerF = 64;            // embed_dim (config/KittiConfig.py:63)
 constexpr int kTowerTile = 128;        // points per tile = UMMA M
-constexpr int kTowerThreads = 384;
+constexpr int kTowerThreads = 640;      // 4 service warps + 16 epilogue warps
 constexpr float kTowerSlope = 0.2f;    // LeakyReLU(negative_slope=0.2), PointNN.py:267,272
 #ifndef CMR_TOWER_PASSES
 #define CMR_TOWER_PASSES 3
@@ -60,7 +63,6 @@ constexpr float kTowerSlope = 0.2f;    // LeakyReLU(negative_slope=0.2), PointNN
 #endif
 constexpr int kTowerPasses = CMR_TOWER_PASSES;   // 3: hh + hl + lh;  4: + ll
 constexpr bool kTowerF16 = CMR_TOWER_FMT == 1;   // pieces are fp16 (1, default) or bf16 (0)
-constexpr float kTowerF16Max = 65504.f;
 
 // ---- packed weights: byte offsets inside the blob k_tower_pack writes (one blob per block) ------------------------
 // mid block (blocks 2, 3):   W1a hi|lo [128 x 64], W2 hi|lo [64 x 128] as two K-blocks, Wsa hi|lo [64 x 64]
@@ -93,19 +95,38 @@ struct TowerBlobFirst {
 
 // ---- order-preserving float <-> uint keys for atomicMax (0 = "no value yet") ---------------------------------------
 __device__ __forceinline__ unsigned f2key(float v) {
-    unsigned b = __float_as_uint(v);
-    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+    // in PTX on .b32 registers: written in C the compiler turns `bits | 0x80000000` into FADD(-|v|, -0), which
+    // canonicalises a NaN and drops the bit (measured: benchmarks/debug/nanmax_probe.cu) - and NaN must stay the
+    // LARGEST key so that it wins every atomicMax
+    unsigned k;
+    asm("{\n"
+        ".reg .b32 t, m;\n"
+        "mov.b32 t, %1;\n"
+        "shr.s32 m, t, 31;\n"
+        "or.b32 m, m, 0x80000000;\n"
+        "xor.b32 %0, t, m;\n"
+        "}\n"
+        : "=r"(k)
+        : "f"(v));
+    return k;
 }
 __device__ __forceinline__ float key2f(unsigned k) {
     return __uint_as_float((k & 0x80000000u) ? (k ^ 0x80000000u) : ~k);
 }
-__device__ __forceinline__ float lrelu(float v) { return fmaxf(v, __fmul_rn(kTowerSlope, v)); }
+// max that PROPAGATES NaN (fmaxf drops it): an activation beyond the fp16 range turns into inf - inf = NaN in the
+// split products and must reach the output instead of being silently dropped by a max
+__device__ __forceinline__ float max_nan(float a, float b) {
+    float r;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ float lrelu(float v) { return max_nan(v, __fmul_rn(kTowerSlope, v)); }
 
 // two neighbouring channels -> one packed 16-bit pair (even channel in the low half), and back to fp32
 __device__ __forceinline__ unsigned pack2(float even, float odd) {
     unsigned r;
     if (kTowerF16)
-        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(odd), "f"(even));
+        asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(odd), "f"(even));
     else
         asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(odd), "f"(even));
     return r;
@@ -114,11 +135,6 @@ __device__ __forceinline__ float2 unpack2(unsigned p) {
     if (kTowerF16) return __half22float2(*reinterpret_cast<const __half2 *>(&p));
     return make_float2(__uint_as_float(p << 16), __uint_as_float(p & 0xffff0000u));
 }
-// the sticky fault word of the library (common.cuh): 3 = an activation of the tower left the fp16 range
-__device__ __forceinline__ void tower_range_check(bool out_of_range) {
-    if (kTowerF16 && __any_sync(kFull, out_of_range) && (threadIdx.x & 31) == 0) atomicExch(&g_fault, 3);
-}
-
 // ---- tcgen05 / TMEM wrappers (inline PTX; SASS: UTCHMMA, LDTM/STTM, UTCBAR) -----------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t *smem_slot, uint32_t cols) {   // one full warp
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(cols) : "memory");
@@ -219,7 +235,7 @@ __device__ __forceinline__ float warp_transpose_max(float (&v)[32], int lane) {
         for (int i = 0; i < half; ++i) {
             const float send = upper ? v[i] : v[i + half];
             const float keep = upper ? v[i + half] : v[i];
-            v[i] = fmaxf(keep, __shfl_xor_sync(kFull, send, half));
+            v[i] = max_nan(keep, __shfl_xor_sync(kFull, send, half));
         }
     }
     return v[0];
@@ -302,7 +318,6 @@ __device__ __forceinline__ void tower_tile_range(int total, int cta, int nctas, 
 // 128B-swizzled planes (row p = 128 bytes; 16-byte chunk q of the row lives at position q ^ (p & 7))
 template <int kPlanes>
 __device__ __forceinline__ void tower_stage_chunk(unsigned char *planes, int plane_bytes, int p, int j, const float (&v)[32]) {
-    bool big = false;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         uint4 hi, lo, lo2;
@@ -310,7 +325,6 @@ __device__ __forceinline__ void tower_stage_chunk(unsigned char *planes, int pla
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const float a = v[q * 8 + 2 * e], b = v[q * 8 + 2 * e + 1];
-            big |= fabsf(a) > kTowerF16Max || fabsf(b) > kTowerF16Max;
             const unsigned h = pack2(a, b);
             const float2 hf = unpack2(h);
             const float ra = __fsub_rn(a, hf.x), rb = __fsub_rn(b, hf.y);
@@ -327,7 +341,6 @@ __device__ __forceinline__ void tower_stage_chunk(unsigned char *planes, int pla
         *reinterpret_cast<uint4 *>(planes + plane_bytes + off) = lo;
         if (kPlanes == 3) *reinterpret_cast<uint4 *>(planes + 2 * plane_bytes + off) = lo2;
     }
-    tower_range_check(big);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -399,7 +412,7 @@ __global__ void __launch_bounds__(128) k_tower_first(const float *__restrict__ o
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] = -INFINITY;
             }
-            mx[j] = fmaxf(mx[j], warp_transpose_max(v, lane));
+            mx[j] = max_nan(mx[j], warp_transpose_max(v, lane));
         }
         fence_async_proxy();
         __syncthreads();
@@ -469,13 +482,13 @@ k_tower_mma(const unsigned char *__restrict__ blob, int B, int N, int tiles_per_
         mbar_init(w_full, 1);
         for (int s = 0; s < Cfg::kStages; ++s) {
             mbar_init(x_full + s, 1);
-            mbar_init(x_empty + s, kLast ? 128 : 1);
+            mbar_init(x_empty + s, kLast ? 256 : 1);
         }
         for (int g = 0; g < 2; ++g) {
             mbar_init(d1_full + g, 1);
-            mbar_init(h_full + g, 128);
+            mbar_init(h_full + g, 256);
             mbar_init(d2_full + g, 1);
-            mbar_init(t_empty + g, 128);
+            mbar_init(t_empty + g, 256);
         }
         tma_prefetch_map(&in_hi);
         tma_prefetch_map(&in_lo);
@@ -573,32 +586,36 @@ k_tower_mma(const unsigned char *__restrict__ blob, int B, int N, int tiles_per_
         }
     } else if (warp >= 4) {
         // ============================== epilogue groups ==============================
-        const int g = (warp - 4) >> 2;                  // group 0: warps 4-7, group 1: warps 8-11 -> tiles i = g (mod 2)
+        const int ew = warp - 4;                        // 0..15
+        const int g = ew >> 3;                          // group 0: warps 4-11, group 1: warps 12-19 -> tiles i = g (mod 2)
+        const int half = (ew >> 2) & 1;                 // which half of the accumulators' columns this warp takes
         const int wq = warp & 3;                        // TMEM lane quarter this warp may touch
         const int p = wq * 32 + lane;                   // point of the tile = TMEM lane
-        const int etid = tid - 128;                     // 0..255 over both groups
+        const int etid = tid - 128;                     // 0..511 over both groups
         const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
         const uint32_t d1 = tmem_base + g * Cfg::kBufCols + lane_addr, d2 = d1 + 128;
-        constexpr int kChunks2 = Cfg::kN2 / 32;
-        float mx[kChunks2];
+        constexpr int kChunks2 = Cfg::kN2 / 32;         // 32-column chunks of D2 (2 | 4): half h takes [h, h + 1) * kChunks2 / 2
+        constexpr int kMine2 = kChunks2 / 2;
+        float mx[kMine2];
 #pragma unroll
-        for (int j = 0; j < kChunks2; ++j) mx[j] = -INFINITY;
+        for (int j = 0; j < kMine2; ++j) mx[j] = -INFINITY;
         int cur_ep = -1;
         pdl_wait();                                      // prev_keys are the previous kernel's output
 
         auto flush = [&]() {
             if (cur_ep >= 0) {
 #pragma unroll
-                for (int j = 0; j < kChunks2; ++j) atomicMax(max_keys + cur_ep * Cfg::kN2 + 32 * j + lane, f2key(mx[j]));
+                for (int j = 0; j < kMine2; ++j)
+                    atomicMax(max_keys + cur_ep * Cfg::kN2 + 32 * (half * kMine2 + j) + lane, f2key(mx[j]));
             }
 #pragma unroll
-            for (int j = 0; j < kChunks2; ++j) mx[j] = -INFINITY;
+            for (int j = 0; j < kMine2; ++j) mx[j] = -INFINITY;
         };
-        // per-episode biases (both groups together: 256 threads, named barrier 1)
+        // per-episode biases (both groups together: 512 threads, named barrier 1)
         auto setup_episode = [&](int e) {
-            named_bar_sync(1, 256);                      // everybody is done with the previous episode's biases
+            named_bar_sync(1, 512);                      // everybody is done with the previous episode's biases
             if (etid < 64) maxprev[etid] = key2f(prev_keys[e * 64 + etid]);
-            named_bar_sync(1, 256);
+            named_bar_sync(1, 512);
             if (etid < 128) {
                 const float *w = reinterpret_cast<const float *>(blob + Blob::w1bT);
                 float a = reinterpret_cast<const float *>(blob + Blob::b1)[etid];
@@ -614,12 +631,12 @@ k_tower_mma(const unsigned char *__restrict__ blob, int B, int N, int tiles_per_
                     for (int k = 0; k < 64; ++k) a = __fmaf_rn(__ldg(w + k * 64 + c), maxprev[k], a);
                     bias2[c] = a;
                 }
-            } else {
+            } else if (etid < 256) {
                 const int c = etid - 128;
                 const float b = reinterpret_cast<const float *>(blob + TowerBlobLast::b2)[c];
                 bias2[c] = c >= 64 ? __fadd_rn(b, maxprev[c - 64]) : b;
             }
-            named_bar_sync(1, 256);
+            named_bar_sync(1, 512);
         };
 
         // both groups walk the CTA's tile list in the same order so that they meet at episode boundaries
@@ -640,24 +657,23 @@ k_tower_mma(const unsigned char *__restrict__ blob, int B, int N, int tiles_per_
             mbar_wait(d1_full + g, par);
             tc_fence_after();
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int jj = 0; jj < 2; ++jj) {
+                const int j = 2 * half + jj;
                 uint32_t r[32];
                 tmem_ld32(d1 + 32 * j, r);
                 tc_wait_ld();
                 uint32_t hi[16], lo[16];
-                bool big = false;
 #pragma unroll
                 for (int q = 0; q < 16; ++q) {
                     const float2 bb = *reinterpret_cast<const float2 *>(bias1 + 32 * j + 2 * q);
                     const float a = lrelu(__fadd_rn(__uint_as_float(r[2 * q]), bb.x));
                     const float b = lrelu(__fadd_rn(__uint_as_float(r[2 * q + 1]), bb.y));
-                    big |= fabsf(a) > kTowerF16Max || fabsf(b) > kTowerF16Max;
-                    const unsigned h = pack2(a, b);
+                            const unsigned h = pack2(a, b);
                     const float2 hf = unpack2(h);
                     hi[q] = h;
                     lo[q] = pack2(__fsub_rn(a, hf.x), __fsub_rn(b, hf.y));
                 }
-                tower_range_check(big);
+
                 tmem_st16(d1 + 32 * j, hi);
                 tmem_st16(d1 + 32 * j + 16, lo);
             }
@@ -665,7 +681,8 @@ k_tower_mma(const unsigned char *__restrict__ blob, int B, int N, int tiles_per_
                 mbar_wait(x_full + s, (i / Cfg::kStages) & 1);   // observe the TMA's writes ourselves before reading them
                 // D2 starts as bias + identity shortcut: feat (exact: hi + lo + lo2) for c < 64, max_prev for c >= 64
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int jj = 0; jj < 2; ++jj) {
+                    const int j = 2 * half + jj;
                     uint32_t r[32];
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
@@ -702,29 +719,34 @@ k_tower_mma(const unsigned char *__restrict__ blob, int B, int N, int tiles_per_
             mbar_wait(d2_full + g, par);
             tc_fence_after();
 #pragma unroll
-            for (int j = 0; j < kChunks2; ++j) {
+            for (int jj = 0; jj < kMine2; ++jj) {
+                const int j = half * kMine2 + jj;
                 uint32_t r[32];
                 tmem_ld32(d2 + 32 * j, r);
                 tc_wait_ld();
                 float v[32];
 #pragma unroll
-                for (int q = 0; q < 32; ++q) {
-                    const float d = __uint_as_float(r[q]);
-                    v[q] = lrelu(kLast ? d : __fadd_rn(d, bias2[32 * j + q]));
+                for (int q = 0; q < 8; ++q) {
+                    float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (!kLast) bb = *reinterpret_cast<const float4 *>(bias2 + 32 * j + 4 * q);   // (last: bias is in D2 already)
+                    v[4 * q] = lrelu(__fadd_rn(__uint_as_float(r[4 * q]), bb.x));
+                    v[4 * q + 1] = lrelu(__fadd_rn(__uint_as_float(r[4 * q + 1]), bb.y));
+                    v[4 * q + 2] = lrelu(__fadd_rn(__uint_as_float(r[4 * q + 2]), bb.z));
+                    v[4 * q + 3] = lrelu(__fadd_rn(__uint_as_float(r[4 * q + 3]), bb.w));
                 }
                 if (!kLast) tower_stage_chunk<kPlanesOut>(stage, 16384, p, j, v);
                 if (!valid) {
 #pragma unroll
                     for (int q = 0; q < 32; ++q) v[q] = -INFINITY;
                 }
-                mx[j] = fmaxf(mx[j], warp_transpose_max(v, lane));
+                mx[jj] = max_nan(mx[jj], warp_transpose_max(v, lane));
             }
             tc_fence_before();
             mbar_arrive(t_empty + g);                    // D1/H and D2 of this group may be overwritten
             if (!kLast) {
                 fence_async_proxy();
-                named_bar_sync(2 + g, 128);
-                if ((tid & 127) == 0) {
+                named_bar_sync(2 + g, 256);
+                if ((ew & 7) == 0 && lane == 0) {
                     tma_store_3d(&out_hi, 0, n0, e, stage);
                     tma_store_3d(&out_lo, 0, n0, e, stage + 16384);
                     if (kPlanesOut == 3) tma_store_3d(&out_lo2, 0, n0, e, stage + 32768);
@@ -746,7 +768,11 @@ k_tower_mma(const unsigned char *__restrict__ blob, int B, int N, int tiles_per_
 __global__ void k_tower_finish(const unsigned *__restrict__ keys, float *__restrict__ out, int n) {
     pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = key2f(keys[i]);
+    if (i < n) {
+        const float v = key2f(keys[i]);
+        out[i] = v;
+        if (!isfinite(v)) atomicExch(&g_fault, 3);   // an activation left the fp16 range (or the input held inf/NaN)
+    }
 }
 
 }  // namespace cmr

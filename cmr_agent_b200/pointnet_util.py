@@ -139,8 +139,25 @@ def farthest_point_sample_from(xyz, npoint, start):
     return out
 
 
-def query_ball_point(radius, nsample, xyz, new_xyz):
-    """pointnet_util.py:73-93 -> group_idx [B,S,nsample] int64."""
+_knn_ws = {}          # (device, bytes) -> workspace tensor of the grid searches (reused: the build is part of the call)
+KNN_GRID_MIN_POINTS = 2048
+
+
+def _grid_workspace(B, N, device):
+    nbytes = _lib.load().cmr_knn_grid_workspace_bytes(B, N)
+    key = (device, nbytes)
+    ws = _knn_ws.get(key)
+    if ws is None:
+        if len(_knn_ws) > 4:
+            _knn_ws.clear()
+        ws = _knn_ws[key] = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    return ws
+
+
+def query_ball_point(radius, nsample, xyz, new_xyz, method="auto"):
+    """pointnet_util.py:73-93 -> group_idx [B,S,nsample] int64.
+    method: "scan" = every query against every point; "grid" = only the cells of a uniform grid that the ball touches
+    (same result); "auto" = grid from 2048 points on (nsample <= 128)."""
     xyz = _f32c(xyz, "xyz")
     new_xyz = _f32c(new_xyz, "new_xyz")
     B, N, _ = xyz.shape
@@ -149,15 +166,29 @@ def query_ball_point(radius, nsample, xyz, new_xyz):
     r2 = float(torch.tensor(radius ** 2, dtype=torch.float32))
     n_eff = min(nsample, N)   # sort()[..., :nsample] cannot return more than N columns
     out = torch.empty(B, S, n_eff, device=xyz.device, dtype=torch.int64)
-    if n_eff > 0 and S > 0:
+    if n_eff == 0 or S == 0:
+        return out
+    if method not in ("auto", "grid", "scan"):
+        raise ValueError(method)
+    grid_ok = n_eff <= 128 and radius >= 0
+    if grid_ok and (method == "grid" or (method == "auto" and N >= KNN_GRID_MIN_POINTS)):
+        ws = _grid_workspace(B, N, xyz.device)
+        _lib.call("cmr_query_ball_point_grid", _lib.ptr(new_xyz), _lib.ptr(xyz), ctypes.c_float(r2),
+                  ctypes.c_float(float(abs(radius))), n_eff, B, S, N, _lib.ptr(ws), _lib.ptr(out), _lib.stream())
+    else:
         _lib.call("cmr_query_ball_point", _lib.ptr(new_xyz), _lib.ptr(xyz), ctypes.c_float(r2), n_eff, B, S, N,
                   _lib.ptr(out), _lib.stream())
     return out
 
 
-def knn_point(k, xyz, new_xyz):
+
+
+def knn_point(k, xyz, new_xyz, method="auto"):
     """``square_distance(new_xyz, xyz).argsort()[:, :, :k]`` (pointnet_util.py:115-116) without the
-    [B,S,N] matrix, ties ordered by index -> [B,S,min(k,N)] int64."""
+    [B,S,N] matrix, ties ordered by index -> [B,S,min(k,N)] int64.
+
+    method: "brute" = every query against every point (cmr_knn); "grid" = uniform grid over the cloud, rings of cells
+    around the query (cmr_knn_grid; the same result bit for bit); "auto" = grid from 2048 points on."""
     xyz = _f32c(xyz, "xyz")
     new_xyz = _f32c(new_xyz, "new_xyz")
     B, N, _ = xyz.shape
@@ -166,7 +197,14 @@ def knn_point(k, xyz, new_xyz):
     if k_eff > 128:
         raise _lib.CmrError("knn_point supports k <= 128")
     out = torch.empty(B, S, k_eff, device=xyz.device, dtype=torch.int64)
-    if k_eff > 0 and S > 0:
+    if k_eff == 0 or S == 0:
+        return out
+    if method not in ("auto", "grid", "brute"):
+        raise ValueError(method)
+    if method == "grid" or (method == "auto" and N >= KNN_GRID_MIN_POINTS):
+        ws = _grid_workspace(B, N, xyz.device)
+        _lib.call("cmr_knn_grid", _lib.ptr(new_xyz), _lib.ptr(xyz), B, S, N, k_eff, _lib.ptr(ws), _lib.ptr(out), _lib.stream())
+    else:
         _lib.call("cmr_knn", _lib.ptr(new_xyz), _lib.ptr(xyz), B, S, N, k_eff, _lib.ptr(out), _lib.stream())
     return out
 

@@ -240,9 +240,23 @@ CMR_API int cmr_farthest_point_sample(const float *xyz, const int64_t *start, in
  * models/PointNN.py:215-216, with the stable order (distance, index).  out [B,S,k] i64. k <= 128. */
 CMR_API int cmr_knn(const float *query, const float *ref, int B, int S, int N, int k, int64_t *out, void *stream);
 
+/* The same kNN, result identical bit for bit, with a uniform grid over the reference cloud built on the fly
+ * (counting sort by cell, then one warp per query walks rings of cells until no unexplored point can enter the
+ * list): two orders of magnitude fewer distance evaluations on LiDAR-scale clouds.
+ * workspace: the size cmr_knn_grid_workspace_bytes reports for (B, N), 256-byte aligned. */
+CMR_API size_t cmr_knn_grid_workspace_bytes(int B, int N);
+CMR_API int cmr_knn_grid(const float *query, const float *ref, int B, int S, int N, int k, void *workspace, int64_t *out,
+                         void *stream);
+
 /* query_ball_point - pointnet_util.py:73-93.  radius2 = float32(radius**2). out [B,S,nsample] i64. */
 CMR_API int cmr_query_ball_point(const float *query, const float *ref, float radius2, int nsample, int B, int S, int N,
                          int64_t *out, void *stream);
+
+/* The same ball query on the uniform grid of cmr_knn_grid (workspace of the same size): only the cells the ball can
+ * touch are read.  Result identical to cmr_query_ball_point.  radius = the reference's python float as f32,
+ * radius2 = float32(radius**2) as above.  nsample <= 128. */
+CMR_API int cmr_query_ball_point_grid(const float *query, const float *ref, float radius2, float radius, int nsample, int B,
+                                      int S, int N, void *workspace, int64_t *out, void *stream);
 
 /* grouping tail of sample_and_group - pointnet_util.py:120-129 fused: out [B,S,K,3+D] f32 =
  * cat(xyz[idx] - new_xyz, points[idx]); points may be NULL (D = 0). */

@@ -189,3 +189,52 @@ def test_group_points_and_knn_grouping(cuda):
     n1, p1 = pn.sample_and_group_all(xyz_cpu.to(cuda), feats.to(cuda))
     n2, p2 = po.sample_and_group_all(xyz_cpu, feats)
     assert torch.equal(n1.cpu(), n2) and torch.equal(p1.cpu(), p2)
+
+
+def _lidar_like(B, N, seed, unique=None):
+    return synth.make_cloud_batch(B, num_pt=N, seed=seed, unique=unique)
+
+
+@pytest.mark.parametrize("case", ["kitti", "padded_duplicates", "uniform_cube", "one_point_repeated", "line", "tiny",
+                                  "k_equals_n", "queries_outside", "k128"])
+def test_grid_knn_equals_brute_force_bit_for_bit(cuda, case):
+    """cmr_knn_grid (uniform grid + ring search) must return exactly what cmr_knn returns - the stable
+    (distance, index) order - on clouds that stress the search: LiDAR slabs, duplicate-padded clouds (exact ties),
+    a cube (the third axis is not binned), degenerate extents, queries far outside the cloud."""
+    from cmr_agent_b200 import pointnet_util as pn
+    g = torch.Generator().manual_seed(123)
+    k, S = 16, 257
+    if case == "kitti":
+        xyz = _lidar_like(2, 40960, 7)
+        k, S = 64, 640
+    elif case == "padded_duplicates":
+        xyz = _lidar_like(2, 8192, 9, unique=(2600, 2700))
+    elif case == "uniform_cube":
+        xyz = torch.rand(2, 6000, 3, generator=g) * 50 - 25
+    elif case == "one_point_repeated":
+        xyz = torch.ones(1, 3000, 3) * 3.25
+    elif case == "line":
+        xyz = torch.zeros(2, 5000, 3)
+        xyz[:, :, 2] = torch.rand(2, 5000, generator=g) * 100
+    elif case == "tiny":
+        xyz = torch.rand(3, 40, 3, generator=g)
+        k, S = 7, 40
+    elif case == "k_equals_n":
+        xyz = torch.rand(1, 100, 3, generator=g) * 10
+        k, S = 100, 30
+    elif case == "queries_outside":
+        xyz = _lidar_like(1, 10000, 11)
+    else:
+        xyz = _lidar_like(1, 20000, 13)
+        k = 128
+    xyz = xyz.contiguous().to(cuda)
+    if case == "queries_outside":
+        q = (torch.rand(1, S, 3, generator=g) * 2000 - 1000).to(cuda)
+    else:
+        idx = torch.randint(0, xyz.shape[1], (xyz.shape[0], S), generator=g).to(cuda)
+        q = pn.index_points(xyz, idx) + (torch.rand(xyz.shape[0], S, 3, generator=g).to(cuda) - 0.5) * 0.5
+    a = pn.knn_point(k, xyz, q, method="brute")
+    b = pn.knn_point(k, xyz, q, method="grid")
+    torch.cuda.synchronize()
+    assert a.shape == b.shape
+    assert torch.equal(a, b), f"{case}: {(a != b).sum().item()} of {a.numel()} neighbour slots differ"

@@ -115,3 +115,21 @@ def test_accelerated_agent_matches_the_reference_agent(cuda):
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
     for a, b in zip(got, want):
         assert float((a - b).abs().max() / b.abs().max()) <= 1e-5
+
+
+def test_tower_reports_activations_beyond_the_fp16_range(cuda):
+    """The split pieces are fp16: an activation beyond 65504 must come out as NaN/inf AND raise the sticky fault word
+    (cmr_take_fault() == 3) - never a silently wrong finite number."""
+    from cmr_agent_b200 import _lib, agent_tower
+    states = _states(321)
+    obs3d = _obs3d(2, 2048, 5)
+    _lib.take_fault()
+    ok = agent_tower.Tower3D(states, cuda)(obs3d.to(cuda))
+    torch.cuda.synchronize()
+    assert torch.isfinite(ok).all() and _lib.take_fault() == 0
+    obs3d[1, :3] *= 1e5                                  # "coordinates" of 10^7 metres in the second episode
+    bad = agent_tower.Tower3D(states, cuda)(obs3d.to(cuda))
+    torch.cuda.synchronize()
+    assert torch.isfinite(bad[0]).all() and torch.equal(bad[0], ok[0])     # episodes are independent
+    assert not torch.isfinite(bad[1]).all()
+    assert _lib.take_fault() == 3
