@@ -71,6 +71,8 @@ def frontend(args):
     start = torch.randint(0, N, (B,), generator=g).to(dev)
     feats = torch.randn(B, N, 3, generator=g).to(dev)
     t_fps = time_cuda(lambda: pn.farthest_point_sample_from(xyz, S, start), reps=5)
+    t_fps_cluster = time_cuda(lambda: pn.farthest_point_sample_from(xyz, S, start, method="cluster"), reps=3)
+    t_knn_brute = time_cuda(lambda: pn.knn_point(K, xyz, pn.index_points(xyz, pn.farthest_point_sample_from(xyz, S, start)), method="brute"), reps=3)
     fps = pn.farthest_point_sample_from(xyz, S, start)
     new_xyz = pn.index_points(xyz, fps)
     t_knn = time_cuda(lambda: pn.knn_point(K, xyz, new_xyz), reps=5)
@@ -80,7 +82,7 @@ def frontend(args):
     t_idx = time_cuda(lambda: pn.index_points(xyz, idx), reps=5)
     out = {
         "bench": "frontend", "batch": B, "N": N, "npoint": S, "k": K,
-        "fps_ms": t_fps * 1e3, "fps_rounds_per_s": B * S / t_fps, "fps_clouds_per_s": B / t_fps,
+        "fps_ms": t_fps * 1e3, "fps_cluster_kernel_ms": t_fps_cluster * 1e3, "knn_brute_plus_fps_ms": t_knn_brute * 1e3, "fps_rounds_per_s": B * S / t_fps, "fps_clouds_per_s": B / t_fps,
         "fps_byte_floor_frac": (12.0 * N + 8 * S) * B / t_fps / 1e9 / PEAK,
         "knn_ms": t_knn * 1e3, "knn_queries_per_s": B * S / t_knn, "knn_pair_evals_per_s": B * S * N / t_knn,
         "knn_byte_floor_frac": (12.0 * (N + S) + 8 * S * K) * B / t_knn / 1e9 / PEAK,

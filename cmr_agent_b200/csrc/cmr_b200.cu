@@ -171,66 +171,12 @@ static int launch_gather(const WsLayout &L, const char *ws, const float *img_fea
     // x = episode, y = kHeavyCtas bucket CTAs interleaved with the first light CTAs (8 buckets each), then the rest
     const int light = std::max(ceil_div(L.buckets, kGatherWarps), kHeavyCtas);
     // four SUMMED channels after whole slabs (features + occupancy of a cost volume): no slab pass of their own
-    static const bool tail_slab = getenv("CMR_B200_TAIL") && !strcmp(getenv("CMR_B200_TAIL"), "slab");
-    const int tail = (!tail_slab && C > kSlab && C % kSlab == 4 && mean_channels <= C - 4) ? 4 : 0;
+    const int tail = (C > kSlab && C % kSlab == 4 && mean_channels <= C - 4) ? 4 : 0;
     int rc = allow_smem(k_tile_gather, kGatherSmem);
     if (rc) return rc;
     return launch_pdl(k_tile_gather, dim3(B, kHeavyCtas + light), dim3(kGatherThreads), kGatherSmem, st, bcnt, bbuf,
                       L.buckets, hq, pix, L.pix16 ? 1 : 0, M, featT, img_feat, N, L.ncap, C, P, copy_image, vec, tma, obs2d, map_proj,
                       share, (long long)out_rows * P, (long long)row0 * P, row0, mean_channels, img_tma, map_img, tail);
-}
-
-// who carries the image half of obs2d: 'g' k_tile_gather (default), 'p' k_project, 's' k_image_copy on a side stream
-static char image_mode() {
-    static const char mode = [] { const char *e = getenv("CMR_B200_IMG"); return (e && (e[0] == 'p' || e[0] == 's')) ? e[0] : 'g'; }();
-    return mode;
-}
-
-// CMR_B200_IMG=stream: the image half of obs2d does not depend on the pose, so it is copied by k_image_copy on a
-// stream of the library's own that forks from `st` here and is joined by image_copy_join() when the observation's
-// other kernels have been launched.  Returns false when the copy cannot go this way (nothing has been launched).
-struct SideStream {
-    cudaStream_t stream = nullptr;
-    cudaEvent_t fork = nullptr, join = nullptr;
-};
-static SideStream *side_stream() {
-    static SideStream per_device[64];
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-    SideStream &s = per_device[dev];
-    if (!s.stream) {
-        if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess ||
-            cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) {
-            s.stream = nullptr;
-            return nullptr;
-        }
-    }
-    return &s;
-}
-static bool image_copy_fork(const float *img_feat, float *obs2d, int B, int C, int P, cudaStream_t st) {
-    if (!(P % 4 == 0 && P >= kBucketPix && aligned(img_feat, 16) && aligned(obs2d, 16))) return false;
-    alignas(64) CUtensorMap map_img, map_out;
-    memset(&map_img, 0, sizeof(map_img));
-    memset(&map_out, 0, sizeof(map_out));
-    if (!make_map3d(&map_img, img_feat, P, (uint64_t)C, B, kBucketPix, kSlab, CU_TENSOR_MAP_SWIZZLE_128B) ||
-        !make_map3d(&map_out, obs2d, P, 2 * (uint64_t)C, B, kBucketPix, kSlab, CU_TENSOR_MAP_SWIZZLE_128B))
-        return false;
-    SideStream *s = side_stream();
-    const size_t smem = sizeof(float) * kTileFloats * kCopyStages;
-    if (!s || allow_smem(k_image_copy, smem) != CMR_OK) return false;
-    if (cudaEventRecord(s->fork, st) != cudaSuccess || cudaStreamWaitEvent(s->stream, s->fork, 0) != cudaSuccess) return false;
-    const int boxes_per_row = ceil_div(P, kBucketPix), slabs = ceil_div(C, kSlab), total = B * slabs * boxes_per_row;
-    const int grid = std::min(ceil_div(total, kCopyStages), 2 * sm_count());
-    k_image_copy<<<grid, 32, smem, s->stream>>>(map_img, map_out, boxes_per_row, slabs, total);
-    ++g_launches;
-    cudaEventRecord(s->join, s->stream);
-    return true;
-}
-static int image_copy_join(cudaStream_t st) {
-    SideStream *s = side_stream();
-    cudaError_t e = s ? cudaStreamWaitEvent(st, s->join, 0) : cudaErrorUnknown;
-    return e == cudaSuccess ? CMR_OK : (int)e;
 }
 
 // true when the image half of obs2d can travel as tiled TMA boxes inside k_project
@@ -331,10 +277,9 @@ static int launch_fps(const float *xyz, const int64_t *start, int B, int N, int 
 // rows of the predicted-overlap points, channel-major -> point-major: by TMA boxes when the tensor allows it
 static int launch_feat_compact(const uint8_t *overlap, const float *feat, int B, int N, int C, int groups, const int *seg,
                                float *featT, cudaStream_t st) {
-    static const bool use_tma = [] { const char *e = getenv("CMR_B200_COMPACT"); return !(e && e[0] == 'l'); }();
     alignas(64) CUtensorMap map_feat;
     memset(&map_feat, 0, sizeof(map_feat));
-    if (use_tma && N % 4 == 0 && N >= 32 && C >= 64 && aligned(feat, 16) &&
+    if (N % 4 == 0 && N >= 32 && C >= 64 && aligned(feat, 16) &&
         make_map3d(&map_feat, feat, N, (uint64_t)C, B, 32, 64, CU_TENSOR_MAP_SWIZZLE_128B)) {
         const size_t smem = sizeof(float) * 4 * 64 * 32;
         int rc = allow_smem(k_feat_compact_tma, smem);
@@ -472,11 +417,10 @@ static int project_impl(const float *pc, const uint8_t *overlap, const float *K,
     WsLayout L = ws_layout(B, N, C, H * W);
     char *ws = static_cast<char *>(workspace);
     alignas(64) CUtensorMap map_img, map_out;
-    // who carries the image half of obs2d: k_tile_gather (its light warps have an idle tile and idle time while
-    // they wait for k_project; CMR_B200_IMG=gather, the default when the bucket path is taken) or k_project
-    static const bool img_in_gather = image_mode() != 'p';
-    const bool img_tma = !(img_in_gather && bucket_path(L, C)) &&
-                         image_copy_by_tma(img_feat, obs2d, B, C, H * W, &map_img, &map_out);
+    // who carries the image half of obs2d: k_tile_gather when the bucket path is taken (its light warps have an idle
+    // tile and idle time while they wait for k_project); on grids too large for the bucket path k_project does, as
+    // tiled TMA traffic beside its arithmetic
+    const bool img_tma = !bucket_path(L, C) && image_copy_by_tma(img_feat, obs2d, B, C, H * W, &map_img, &map_out);
     if (!img_tma) {
         memset(&map_img, 0, sizeof(map_img));
         memset(&map_out, 0, sizeof(map_out));
@@ -525,20 +469,15 @@ int cmr_observe(const float *pc, const uint8_t *overlap, const float *img_feat, 
     int copied = 0;
     int rc = check_observe_dims(B, N, C, H, W);
     if (rc) return rc;
-    const bool forked = image_mode() == 's' && (C % kSlab) == 0 && image_copy_fork(img_feat, obs2d, B, C, H * W, S_(stream));
     rc = project_impl(pc, overlap, K, pose, mean, workspace, B, N, C, H, W, obs3d, pix_out, mvis_out, img_feat, obs2d,
                       &copied, false, stream);
     const bool projected = rc == CMR_OK;
-    if (!rc) rc = cmr_tile_scatter(img_feat, K, workspace, B, N, C, H, W, (copied || forked) ? 0 : 1, obs2d, stream);
+    if (!rc) rc = cmr_tile_scatter(img_feat, K, workspace, B, N, C, H, W, copied ? 0 : 1, obs2d, stream);
     if (rc && projected) {
         // k_project has filled the bucket counters and nobody will consume them: leave the workspace as the next
         // cmr_observe expects it (counters and queue header zero) instead of silently wrong results later
         WsLayout L = ws_layout(B, N, C, H * W);
         cudaMemsetAsync(static_cast<char *>(workspace) + L.off_bcnt, 0, L.bcnt_bytes, S_(stream));
-    }
-    if (forked) {   // joined whatever happened: a capturing stream must not be left forked
-        const int jrc = image_copy_join(S_(stream));
-        if (!rc) rc = jrc;
     }
     return rc;
 }
@@ -705,6 +644,25 @@ static int build_knn_grid(const float *ref, int B, int N, unsigned char *ws, con
     return after_launch();
 }
 
+// farthest_point_sample with cell pruning (k_fps_grid): same indices; one SM per cloud.
+int cmr_farthest_point_sample_grid(const float *xyz, const int64_t *start, int B, int N, int npoint, void *workspace, int64_t *out,
+                                   void *stream) {
+    CMR_REQUIRE(xyz && start && out && workspace && B > 0 && N > 0 && npoint > 0, CMR_EINVAL);
+    CMR_REQUIRE(aligned(workspace, 256), CMR_EALIGN);
+    const FpsGridSmem m = fps_grid_smem(N);
+    CMR_REQUIRE(m.total <= 220 * 1024, CMR_ERANGE);   // the running distances of one cloud live in one SM's shared memory
+    const KnnGridWs w = knn_grid_ws(N);
+    unsigned char *ws = static_cast<unsigned char *>(workspace);
+    cudaStream_t st = S_(stream);
+    int rc = build_knn_grid(xyz, B, N, ws, w, st);
+    if (rc) return rc;
+    rc = allow_smem(k_fps_grid, m.total);
+    if (rc) return rc;
+    k_fps_grid<<<B, kFpsGridThreads, m.total, st>>>(xyz, start, ws, w.per_cloud, w.off_start, w.off_sorted, N, npoint, m.off_cmax,
+                                                    m.off_cidx, m.off_list, out);
+    return after_launch();
+}
+
 size_t cmr_knn_grid_workspace_bytes(int B, int N) { return (B > 0 && N > 0) ? (size_t)B * knn_grid_ws(N).per_cloud : 0; }
 
 int cmr_knn_grid(const float *query, const float *ref, int B, int S, int N, int k, void *workspace, int64_t *out, void *stream) {
@@ -793,13 +751,9 @@ int cmr_cost_volume_warp(const float *pc, const uint8_t *mask, const float *Kmat
     CMR_REQUIRE(bucket_path(L, C), CMR_EUNSUPPORTED);   // grids of up to 12288 pixels
     char *ws = static_cast<char *>(workspace);
     const float *zero_mean = reinterpret_cast<const float *>(ws + L.off_zero);   // X = R p + t: nothing is subtracted
-    alignas(64) CUtensorMap none_a, none_b;
-    memset(&none_a, 0, sizeof(none_a));
-    memset(&none_b, 0, sizeof(none_b));
     cudaStream_t st = S_(stream);
-    // only the masked points are projected (k_project_masked); CMR_B200_CV_PROJECT=full: k_project over all N points
-    static const bool full_project = [] { const char *e = getenv("CMR_B200_CV_PROJECT"); return e && e[0] == 'f'; }();
-    if (!full_project) {
+    // only the masked points are projected (k_project_masked)
+    {
         const int *seg = reinterpret_cast<const int *>(ws + L.off_seg);
         int *bcnt = reinterpret_cast<int *>(ws + L.off_bcnt);
         unsigned *bbuf = reinterpret_cast<unsigned *>(ws + L.off_bbuf);
@@ -813,12 +767,7 @@ int cmr_cost_volume_warp(const float *pc, const uint8_t *mask, const float *Kmat
         else
             rc = launch_pdl(k_project_masked<int32_t>, grid, block, 0, st, pc, mask, Kmat, poses, zero_mean, seg, N, L.ncap,
                             L.groups, H, W, vec, reinterpret_cast<int32_t *>(ws + L.off_pix), bcnt, bbuf, L.buckets, hdr, hq, K);
-    } else if (L.pix16)
-        rc = launch_project<uint16_t>(L, ws, pc, mask, Kmat, poses, zero_mean, E, N, C, H, W, nullptr, nullptr, nullptr, false,
-                                      none_a, none_b, false, st, K);
-    else
-        rc = launch_project<int32_t>(L, ws, pc, mask, Kmat, poses, zero_mean, E, N, C, H, W, nullptr, nullptr, nullptr, false,
-                                     none_a, none_b, false, st, K);
+    }
     if (rc) return rc;
     return launch_gather(L, ws, nullptr, E, N, C, P, false, out, st, K, C, 0, mean_channels);
 }

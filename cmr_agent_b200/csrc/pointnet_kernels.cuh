@@ -724,4 +724,154 @@ __global__ void __launch_bounds__(256) k_ball_grid(const float *__restrict__ que
     }
 }
 
+// -------------------------------------------------------------------------------------------------
+// farthest_point_sample on the grid (same indices as k_fps, bit for bit).  After s samples only the points within
+// about one sample spacing of the newest centroid can still lower their distance; everything else is skipped CELL BY
+// CELL: a cell whose bounding square lies farther from the centroid than the largest running distance inside the
+// cell cannot change (d = min(d, dist) with dist >= d).  Work per round drops from N points to the centroid's
+// neighbourhood (N ln(npoint) point updates in total instead of N npoint), and one CTA - one SM - carries a whole
+// cloud, so 148 clouds run at once instead of 37 four-CTA clusters.
+//   shared memory: the running distances of all points in cell order (4N bytes), per cell {max distance bits, lowest
+//   original index attaining it}, the list of cells to update this round.
+//   round: (1) every thread tests its cells against the centroid, (2) a warp per listed cell updates the cell's
+//   points (coordinates from the cell-sorted copy in L2) and its record, (3) arg-max over the cell records.
+constexpr int kFpsGridThreads = 1024;
+struct FpsGridSmem {
+    size_t off_d, off_cmax, off_cidx, off_list, total;
+};
+inline FpsGridSmem fps_grid_smem(int N) {
+    FpsGridSmem m;
+    m.off_d = 0;
+    m.off_cmax = round_up(sizeof(float) * (size_t)N, 16);
+    m.off_cidx = m.off_cmax + sizeof(unsigned) * kGridMaxCells;
+    m.off_list = m.off_cidx + sizeof(unsigned) * kGridMaxCells;
+    m.total = m.off_list + sizeof(unsigned short) * kGridMaxCells;
+    return m;
+}
+
+__global__ void __launch_bounds__(kFpsGridThreads, 1)
+    k_fps_grid(const float *__restrict__ xyz, const int64_t *__restrict__ start, const unsigned char *__restrict__ ws, size_t per_cloud,
+               size_t off_start, size_t off_sorted, int N, int npoint, size_t off_cmax, size_t off_cidx, size_t off_list,
+               int64_t *__restrict__ out) {
+    extern __shared__ __align__(16) unsigned char fps_smem[];
+    float *sd = reinterpret_cast<float *>(fps_smem);
+    unsigned *cmax = reinterpret_cast<unsigned *>(fps_smem + off_cmax);
+    unsigned *cidx = reinterpret_cast<unsigned *>(fps_smem + off_cidx);
+    unsigned short *list = reinterpret_cast<unsigned short *>(fps_smem + off_list);
+    __shared__ int nlist;
+    __shared__ uint2 wrec[32];
+    __shared__ float cen[4];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned char *base = ws + (size_t)b * per_cloud;
+    const KnnGrid gr = *reinterpret_cast<const KnnGrid *>(base);
+    const int *cstart = reinterpret_cast<const int *>(base + off_start);
+    const float4 *sorted = reinterpret_cast<const float4 *>(base + off_sorted);
+    const float *cloud = xyz + (size_t)b * N * 3;
+    const int ncells = gr.g0 * gr.g1;
+    for (int i = tid; i < N; i += kFpsGridThreads) sd[i] = 1e10f;                    // :61
+    const unsigned kBig = __float_as_uint(1e10f);
+    for (int c = tid; c < ncells; c += kFpsGridThreads) {
+        const int n = cstart[c + 1] - cstart[c];
+        cmax[c] = n > 0 ? kBig : 0u;       // an empty cell never wins and never needs an update
+        cidx[c] = 0xffffffffu;             // (set by the first update: every non-empty cell is updated in round 0)
+    }
+    long long s0 = start[b];
+    if (s0 < 0) s0 += N;
+    unsigned cur = (unsigned)min(max(s0, 0ll), (long long)N - 1);
+    if (tid == 0) {
+        cen[0] = __ldg(cloud + (size_t)cur * 3);
+        cen[1] = __ldg(cloud + (size_t)cur * 3 + 1);
+        cen[2] = __ldg(cloud + (size_t)cur * 3 + 2);
+        nlist = 0;
+    }
+    __syncthreads();
+    int64_t *o = out + (size_t)b * npoint;
+    const float slack = 1e-3f * gr.h;
+    for (int it = 0; it < npoint; ++it) {
+        if (tid == 0) o[it] = (int64_t)cur;                                            // :65
+        if (it == npoint - 1) break;
+        const float cx = cen[0], cy = cen[1], cz = cen[2];
+        const float c0 = gr.a0 == 0 ? cx : (gr.a0 == 1 ? cy : cz), c1 = gr.a1 == 1 ? cy : (gr.a1 == 2 ? cz : cx);
+        // (1) which cells can still change
+        for (int c = tid; c < ncells; c += kFpsGridThreads) {
+            const unsigned m = cmax[c];
+            bool active = false;
+            if (m != 0u) {
+                const int i0 = c % gr.g0, i1 = c / gr.g0;
+                const float lo0 = gr.o0 + i0 * gr.h - slack, hi0 = gr.o0 + (i0 + 1) * gr.h + slack;
+                const float lo1 = gr.o1 + i1 * gr.h - slack, hi1 = gr.o1 + (i1 + 1) * gr.h + slack;
+                const float dx = fmaxf(fmaxf(lo0 - c0, c0 - hi0), 0.f), dy = fmaxf(fmaxf(lo1 - c1, c1 - hi1), 0.f);
+                const float lb2 = (dx * dx + dy * dy) * (1.f - 1e-5f);
+                active = !(lb2 > __uint_as_float(m));
+            }
+            const unsigned bal = __ballot_sync(__activemask(), active);
+            if (active) {
+                // warp-aggregated append (lanes of a warp scan consecutive cells)
+                const unsigned act = __activemask();
+                const int leader = __ffs(bal) - 1;
+                int basep = 0;
+                if (lane == leader) basep = atomicAdd(&nlist, __popc(bal));
+                basep = __shfl_sync(act, basep, leader);
+                list[basep + __popc(bal & ((1u << lane) - 1))] = (unsigned short)c;
+            }
+        }
+        __syncthreads();
+        // (2) a warp per listed cell
+        const int nl = nlist;
+        for (int li = warp; li < nl; li += kFpsGridThreads / 32) {
+            const int c = list[li];
+            const int beg = cstart[c], end = cstart[c + 1];
+            unsigned bm = 0u, bi = 0xffffffffu;
+            for (int i0 = beg; i0 < end; i0 += 32) {
+                const int i = i0 + lane;
+                unsigned bits = 0u, idx = 0xffffffffu;
+                if (i < end) {
+                    const float4 p = __ldg(sorted + i);
+                    const float dist = sqdist3(p.x, p.y, p.z, cx, cy, cz);              // :67
+                    const float d = fminf(sd[i], dist);                                 // :68
+                    sd[i] = d;
+                    bits = __float_as_uint(d);
+                    idx = (unsigned)__float_as_int(p.w);
+                }
+                const unsigned wm = __reduce_max_sync(kFull, bits);
+                const unsigned wi = __reduce_min_sync(kFull, bits == wm ? idx : 0xffffffffu);
+                if (wm > bm || (wm == bm && wi < bi)) {
+                    bm = wm;
+                    bi = wi;
+                }
+            }
+            if (lane == 0) {
+                cmax[c] = bm;
+                cidx[c] = bi;
+            }
+        }
+        __syncthreads();
+        // (3) arg-max over the cell records: the largest distance, the lowest original index among equals (:69)
+        unsigned bm = 0u, bi = 0xffffffffu;
+        for (int c = tid; c < ncells; c += kFpsGridThreads) {
+            const unsigned m = cmax[c], ix = cidx[c];
+            if (m > bm || (m == bm && ix < bi)) {
+                bm = m;
+                bi = ix;
+            }
+        }
+        const unsigned wm = __reduce_max_sync(kFull, bm);
+        const unsigned wi = __reduce_min_sync(kFull, bm == wm ? bi : 0xffffffffu);
+        if (lane == 0) wrec[warp] = make_uint2(wm, wi);
+        __syncthreads();
+        if (warp == 0) {
+            const uint2 r = wrec[lane];
+            const unsigned gm = __reduce_max_sync(kFull, r.x);
+            const unsigned gi = __reduce_min_sync(kFull, r.x == gm ? r.y : 0xffffffffu);
+            if (lane < 3) cen[lane] = __ldg(cloud + (size_t)gi * 3 + lane);
+            if (lane == 0) {
+                cen[3] = __uint_as_float(gi);
+                nlist = 0;
+            }
+        }
+        __syncthreads();
+        cur = __float_as_uint(cen[3]);
+    }
+}
+
 }  // namespace cmr

@@ -234,37 +234,6 @@ __device__ __forceinline__ void mean_pass(unsigned mask, int cnt_of_lane, const 
     }
 }
 
-// The image half of obs2d (obs2d[b, 0:C] = img_geo_feat[b], environment.py:83) as a kernel of its own, for a side
-// stream beside k_project (CMR_B200_IMG=stream): it depends on nothing but the output buffer.  One thread per CTA
-// moves boxes of [64 channels][32 pixels] global -> shared -> global with TMA, kCopyStages at a time.
-constexpr int kCopyStages = 4;
-__global__ void __launch_bounds__(32) k_image_copy(const __grid_constant__ CUtensorMap map_img,
-                                                   const __grid_constant__ CUtensorMap map_out, int boxes_per_row,
-                                                   int slabs, int total) {
-    extern __shared__ __align__(1024) float smem_c[];   // [kCopyStages][kTileFloats]
-    __shared__ __align__(8) uint64_t bar[kCopyStages];
-    if (threadIdx.x != 0) return;
-    for (int s = 0; s < kCopyStages; ++s) mbar_init(&bar[s], 1);
-    fence_async_proxy();
-    unsigned parity = 0;
-    for (int i0 = (int)blockIdx.x * kCopyStages; i0 < total; i0 += (int)gridDim.x * kCopyStages) {
-        const int ns = min(kCopyStages, total - i0);
-        for (int s = 0; s < ns; ++s) {
-            const int i = i0 + s, px = i % boxes_per_row, slab = (i / boxes_per_row) % slabs, b = i / (boxes_per_row * slabs);
-            mbar_arrive_expect_tx(&bar[s], (unsigned)(kTileFloats * sizeof(float)));
-            tma_load_3d(smem_c + s * kTileFloats, &map_img, px * kBucketPix, slab * kSlab, b, &bar[s]);
-        }
-        for (int s = 0; s < ns; ++s) {
-            const int i = i0 + s, px = i % boxes_per_row, slab = (i / boxes_per_row) % slabs, b = i / (boxes_per_row * slabs);
-            mbar_wait(&bar[s], parity);
-            tma_store_3d(&map_out, px * kBucketPix, slab * kSlab, b, smem_c + s * kTileFloats);
-            bulk_commit();
-        }
-        bulk_wait_read_all();   // the stages are free again
-        parity ^= 1u;
-    }
-}
-
 __global__ void __launch_bounds__(kGatherThreads, CMR_GATHER_MINB)
     k_tile_gather(int *bcnt, const unsigned *bbuf, int buckets, const int *hq, const void *pix, int pix16, const int *M,
                   const float *__restrict__ featT, const float *__restrict__ img_feat, int N, int ncap, int C, int P,

@@ -127,13 +127,26 @@ def farthest_point_sample(xyz, npoint):
     return farthest_point_sample_from(xyz, npoint, start)
 
 
-def farthest_point_sample_from(xyz, npoint, start):
-    """Same as ``farthest_point_sample`` with explicit start indices [B] int64 (extension)."""
+FPS_GRID_MAX_POINTS = 45000       # the pruned sampler keeps a cloud's running distances in one SM's shared memory
+
+
+def farthest_point_sample_from(xyz, npoint, start, method="auto"):
+    """Same as ``farthest_point_sample`` with explicit start indices [B] int64 (extension).
+    method: "cluster" = every point every round, one thread-block cluster per cloud; "grid" = cell pruning on a uniform
+    grid, one SM per cloud (same indices); "auto" = grid for 2048 <= N <= 45000."""
     xyz = _f32c(xyz, "xyz")
     B, N, _ = xyz.shape
     start = _i64c(start, "start")
     out = torch.empty(B, npoint, device=xyz.device, dtype=torch.int64)
-    if npoint > 0:
+    if npoint <= 0:
+        return out
+    if method not in ("auto", "grid", "cluster"):
+        raise ValueError(method)
+    if method == "grid" or (method == "auto" and KNN_GRID_MIN_POINTS <= N <= FPS_GRID_MAX_POINTS):
+        ws = _grid_workspace(B, N, xyz.device)
+        _lib.call("cmr_farthest_point_sample_grid", _lib.ptr(xyz), _lib.ptr(start), B, N, npoint, _lib.ptr(ws), _lib.ptr(out),
+                  _lib.stream())
+    else:
         _lib.call("cmr_farthest_point_sample", _lib.ptr(xyz), _lib.ptr(start), B, N, npoint, _lib.ptr(out),
                   _lib.stream())
     return out

@@ -236,6 +236,13 @@ CMR_API int cmr_index_points_backward(const float *grad_out, const int64_t *idx,
 CMR_API int cmr_farthest_point_sample(const float *xyz, const int64_t *start, int B, int N, int npoint, int64_t *out,
                               void *stream);
 
+/* The same sampling with cell pruning on the uniform grid of cmr_knn_grid (workspace of the same size): per round
+ * only the cells that the newest centroid can still affect are updated, one SM carries a whole cloud.  Indices
+ * identical to cmr_farthest_point_sample.  N up to about 45000 (the running distances live in shared memory;
+ * CMR_ERANGE beyond). */
+CMR_API int cmr_farthest_point_sample_grid(const float *xyz, const int64_t *start, int B, int N, int npoint, void *workspace,
+                                           int64_t *out, void *stream);
+
 /* kNN = square_distance(...).argsort()[:, :, :k] - pointnet_util.py:115-116,233-234,
  * models/PointNN.py:215-216, with the stable order (distance, index).  out [B,S,k] i64. k <= 128. */
 CMR_API int cmr_knn(const float *query, const float *ref, int B, int S, int N, int k, int64_t *out, void *stream);

@@ -238,3 +238,81 @@ def test_grid_knn_equals_brute_force_bit_for_bit(cuda, case):
     torch.cuda.synchronize()
     assert a.shape == b.shape
     assert torch.equal(a, b), f"{case}: {(a != b).sum().item()} of {a.numel()} neighbour slots differ"
+
+
+@pytest.mark.parametrize("case", ["kitti", "padded_duplicates", "cube", "zero_radius", "huge_radius", "nothing_in_radius", "tiny"])
+def test_grid_ball_query_equals_the_scan(cuda, case):
+    """cmr_query_ball_point_grid against cmr_query_ball_point (which the goldens pin): the first nsample indices in
+    ascending order, padded with the first hit, N where nothing lies within the radius."""
+    from cmr_agent_b200 import pointnet_util as pn
+    g = torch.Generator().manual_seed(77)
+    radius, nsample, S = 1.0, 32, 300
+    if case == "kitti":
+        xyz = _lidar_like(2, 40960, 17)
+        radius, nsample, S = 2.0, 64, 640
+    elif case == "padded_duplicates":
+        xyz = _lidar_like(2, 8192, 19, unique=(2600, 2700))
+        radius = 1.5
+    elif case == "cube":
+        xyz = torch.rand(2, 6000, 3, generator=g) * 20 - 10
+        radius, nsample = 2.5, 128
+    elif case == "zero_radius":
+        xyz = _lidar_like(1, 5000, 23)
+        radius = 0.0
+    elif case == "huge_radius":
+        xyz = _lidar_like(1, 5000, 29)
+        radius, nsample = 1e4, 48
+    elif case == "nothing_in_radius":
+        xyz = _lidar_like(1, 5000, 31)
+        radius = 1e-3
+    else:
+        xyz = torch.rand(2, 50, 3, generator=g)
+        radius, nsample, S = 0.4, 16, 50
+    xyz = xyz.contiguous().to(cuda)
+    idx = torch.randint(0, xyz.shape[1], (xyz.shape[0], S), generator=g).to(cuda)
+    q = pn.index_points(xyz, idx)
+    if case in ("nothing_in_radius",):
+        q = q + 500.0
+    elif case not in ("zero_radius",):
+        q = q + (torch.rand(xyz.shape[0], S, 3, generator=g).to(cuda) - 0.5) * 0.3
+    a = pn.query_ball_point(radius, nsample, xyz, q, method="scan")
+    b = pn.query_ball_point(radius, nsample, xyz, q, method="grid")
+    torch.cuda.synchronize()
+    assert torch.equal(a, b), f"{case}: {(a != b).sum().item()} of {a.numel()} slots differ"
+    if case == "nothing_in_radius":
+        assert bool((a == xyz.shape[1]).all())
+
+
+@pytest.mark.parametrize("case", ["kitti", "padded_duplicates", "cube", "one_point_repeated", "line", "small", "all_points"])
+def test_grid_fps_equals_the_cluster_kernel(cuda, case):
+    """cmr_farthest_point_sample_grid (cell pruning) against cmr_farthest_point_sample (pinned by the goldens): the
+    same indices in the same order, including ties (duplicate-padded clouds) and degenerate extents."""
+    from cmr_agent_b200 import pointnet_util as pn
+    g = torch.Generator().manual_seed(5)
+    npoint = 256
+    if case == "kitti":
+        xyz = _lidar_like(3, 40960, 41)
+        npoint = 1280
+    elif case == "padded_duplicates":
+        xyz = _lidar_like(2, 8192, 43, unique=(2600, 2700))
+        npoint = 3000                                   # more samples than unique points: zero distances, index ties
+    elif case == "cube":
+        xyz = torch.rand(2, 6000, 3, generator=g) * 50 - 25
+    elif case == "one_point_repeated":
+        xyz = torch.ones(1, 3000, 3) * 3.25
+        npoint = 64
+    elif case == "line":
+        xyz = torch.zeros(2, 5000, 3)
+        xyz[:, :, 2] = torch.rand(2, 5000, generator=g) * 100
+    elif case == "small":
+        xyz = torch.rand(4, 300, 3, generator=g) * 10
+        npoint = 128
+    else:
+        xyz = _lidar_like(1, 2500, 47)
+        npoint = 2500
+    xyz = xyz.contiguous().to(cuda)
+    start = torch.randint(0, xyz.shape[1], (xyz.shape[0],), generator=g).to(cuda)
+    a = pn.farthest_point_sample_from(xyz, npoint, start, method="cluster")
+    b = pn.farthest_point_sample_from(xyz, npoint, start, method="grid")
+    torch.cuda.synchronize()
+    assert torch.equal(a, b), f"{case}: first difference at column {int((a != b).any(dim=0).float().argmax())}"
