@@ -34,7 +34,12 @@ constexpr int kBucketPix = 32;      // pixels per scatter bucket (scatter_kernel
 constexpr int kBucketMaxBuckets = 384;  // buckets per episode the bucket path supports (H*W <= 12288)
 constexpr int kBucketStride = 384;      // ints per episode in bcnt
 constexpr int kBucketHdr = 64;          // ints after the counters: [0] heavy-queue length, [1] ticket of k_tile_gather
-constexpr int kLightMax = 64;           // a bucket that receives more visible points than this is queued as heavy
+constexpr int kLightMax = 64;           // capacity of the one-warp path of k_tile_gather: two keys per lane
+#ifndef CMR_LIGHT_LIMIT
+#define CMR_LIGHT_LIMIT 64
+#endif
+constexpr int kLightLimit = CMR_LIGHT_LIMIT;   // a bucket that receives more visible points than this is queued as heavy
+static_assert(kLightLimit >= 1 && kLightLimit <= kLightMax, "the one-warp path holds at most kLightMax entries");
 constexpr int kCountSeen = 1 << 24;     // added to a heavy bucket's counter by the first of its two readers
 constexpr int kBucketCap = 2048;    // entries a bucket's buffer holds; fuller buckets are re-read from the id list
 
@@ -498,8 +503,8 @@ __global__ void CMR_PROJ_BOUNDS k_project(const float *__restrict__ pc, const ui
                 const int slot = atomicAdd(bc + bucket, 1);
                 if (slot < kBucketCap)
                     bbuf[((size_t)b * buckets + bucket) * kBucketCap + slot] = ((unsigned)e.y << 7) | ((unsigned)e.x & 127u);
-                // exactly one point per bucket sees the counter cross kLightMax: it queues the bucket as heavy
-                if (slot == kLightMax) hq[atomicAdd(hdr, 1)] = (int)(((unsigned)b << 16) | (unsigned)bucket);
+                // exactly one point per bucket sees the counter cross kLightLimit: it queues the bucket as heavy
+                if (slot == kLightLimit) hq[atomicAdd(hdr, 1)] = (int)(((unsigned)b << 16) | (unsigned)bucket);
             }
         }
     }
@@ -587,7 +592,7 @@ __global__ void __launch_bounds__(32 * CMR_PROJ_WARPS)
                     const int slot = atomicAdd(bc + id / kBucketPix, 1);
                     if (slot < kBucketCap)
                         bbuf[((size_t)b * buckets + id / kBucketPix) * kBucketCap + slot] = ((unsigned)pos << 7) | ((unsigned)id & 127u);
-                    if (slot == kLightMax) hq[atomicAdd(hdr, 1)] = (int)(((unsigned)b << 16) | (unsigned)(id / kBucketPix));
+                    if (slot == kLightLimit) hq[atomicAdd(hdr, 1)] = (int)(((unsigned)b << 16) | (unsigned)(id / kBucketPix));
                 }
             }
         }

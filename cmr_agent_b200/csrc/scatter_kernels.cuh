@@ -290,10 +290,10 @@ __global__ void __launch_bounds__(kGatherThreads, CMR_GATHER_MINB)
             int *cb = bcnt + (size_t)b * kBucketStride + bk;
             const int n = ld_cg_s32(cb) & (kCountSeen - 1);
             if (lane == 0 && n != 0) {
-                if (n <= kLightMax) *cb = 0;   // this warp is the counter's only reader
+                if (n <= kLightLimit) *cb = 0;   // this warp is the counter's only reader
                 else if (atomicAdd(cb, kCountSeen) >= kCountSeen) *cb = 0;   // the bucket CTA has been here
             }
-            if (n > 0 && n <= kLightMax) {
+            if (n > 0 && n <= kLightLimit) {
                 // all the rows this unit will add: on their way to L2 before the first one is needed
                 if (lane < n)
                     for (int q = 0; q < C; q += 32) prefetch_l2(featT + ((size_t)bs * N + (e0 >> 7)) * C + q);
@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(kGatherThreads, CMR_GATHER_MINB)
                 } else {
                     store_zeros(C, p0, P, vec, proj, lane);
                 }
-            } else if (n > 0 && n <= kLightMax) {   // otherwise the bucket CTAs own the bucket
+            } else if (n > 0 && n <= kLightLimit) {   // otherwise the bucket CTAs own the bucket
                 // the tail channels of this unit's rows: on their way while the entries are ranked
                 float4 t0 = make_float4(0.f, 0.f, 0.f, 0.f), t1 = t0;
                 if (tail) {
