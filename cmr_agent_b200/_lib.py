@@ -86,7 +86,7 @@ def load():
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
-        if lib.cmr_abi_version() != 2:
+        if lib.cmr_abi_version() != 3:
             raise CmrError("libcmr_b200.so ABI version mismatch; rebuild it")
         _lib = lib
     return _lib

@@ -33,7 +33,7 @@ extern "C" {
 #define CMR_API
 #endif
 
-#define CMR_ABI_VERSION 2
+#define CMR_ABI_VERSION 3
 
 #define CMR_OK 0
 #define CMR_EINVAL (-1)      /* null pointer, non-positive size */
