@@ -659,7 +659,7 @@ int cmr_farthest_point_sample_grid(const float *xyz, const int64_t *start, int B
     rc = allow_smem(k_fps_grid, m.total);
     if (rc) return rc;
     k_fps_grid<<<B, kFpsGridThreads, m.total, st>>>(xyz, start, ws, w.per_cloud, w.off_start, w.off_sorted, N, npoint, m.off_cmax,
-                                                    m.off_cidx, m.off_list, out);
+                                                    m.off_cidx, m.off_list, m.off_cs, out);
     return after_launch();
 }
 

@@ -737,7 +737,7 @@ __global__ void __launch_bounds__(256) k_ball_grid(const float *__restrict__ que
 //   points (coordinates from the cell-sorted copy in L2) and its record, (3) arg-max over the cell records.
 constexpr int kFpsGridThreads = 1024;
 struct FpsGridSmem {
-    size_t off_d, off_cmax, off_cidx, off_list, total;
+    size_t off_d, off_cmax, off_cidx, off_list, off_cs, total;
 };
 inline FpsGridSmem fps_grid_smem(int N) {
     FpsGridSmem m;
@@ -745,22 +745,24 @@ inline FpsGridSmem fps_grid_smem(int N) {
     m.off_cmax = round_up(sizeof(float) * (size_t)N, 16);
     m.off_cidx = m.off_cmax + sizeof(unsigned) * kGridMaxCells;
     m.off_list = m.off_cidx + sizeof(unsigned) * kGridMaxCells;
-    m.total = m.off_list + sizeof(unsigned short) * kGridMaxCells;
+    m.off_cs = m.off_list + sizeof(unsigned short) * kGridMaxCells;        // cell start offsets, u16 pairs would not do: N > 65535 is allowed
+    m.total = m.off_cs + sizeof(int) * (kGridMaxCells + 4);
     return m;
 }
 
 __global__ void __launch_bounds__(kFpsGridThreads, 1)
     k_fps_grid(const float *__restrict__ xyz, const int64_t *__restrict__ start, const unsigned char *__restrict__ ws, size_t per_cloud,
                size_t off_start, size_t off_sorted, int N, int npoint, size_t off_cmax, size_t off_cidx, size_t off_list,
-               int64_t *__restrict__ out) {
+               size_t off_cs, int64_t *__restrict__ out) {
     extern __shared__ __align__(16) unsigned char fps_smem[];
     float *sd = reinterpret_cast<float *>(fps_smem);
     unsigned *cmax = reinterpret_cast<unsigned *>(fps_smem + off_cmax);
     unsigned *cidx = reinterpret_cast<unsigned *>(fps_smem + off_cidx);
     unsigned short *list = reinterpret_cast<unsigned short *>(fps_smem + off_list);
+    int *cs = reinterpret_cast<int *>(fps_smem + off_cs);                // the cells' start offsets, a copy in shared memory
     __shared__ int nlist;
     __shared__ uint2 wrec[32];
-    __shared__ float cen[4];
+    __shared__ float cen[3];
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned char *base = ws + (size_t)b * per_cloud;
     const KnnGrid gr = *reinterpret_cast<const KnnGrid *>(base);
@@ -770,10 +772,20 @@ __global__ void __launch_bounds__(kFpsGridThreads, 1)
     const int ncells = gr.g0 * gr.g1;
     for (int i = tid; i < N; i += kFpsGridThreads) sd[i] = 1e10f;                    // :61
     const unsigned kBig = __float_as_uint(1e10f);
-    for (int c = tid; c < ncells; c += kFpsGridThreads) {
-        const int n = cstart[c + 1] - cstart[c];
-        cmax[c] = n > 0 ? kBig : 0u;       // an empty cell never wins and never needs an update
-        cidx[c] = 0xffffffffu;             // (set by the first update: every non-empty cell is updated in round 0)
+    for (int c = tid; c <= ncells; c += kFpsGridThreads) cs[c] = cstart[c];
+    // this thread's cells (at most kGridMaxCells / threads of them) and the low corners of their squares, for all rounds
+    constexpr int kMyCells = kGridMaxCells / kFpsGridThreads;
+    float mylo0[kMyCells], mylo1[kMyCells];
+#pragma unroll
+    for (int j = 0; j < kMyCells; ++j) {
+        const int c = tid + j * kFpsGridThreads;
+        mylo0[j] = gr.o0 + (c % gr.g0) * gr.h;
+        mylo1[j] = gr.o1 + (c / gr.g0) * gr.h;
+        if (c < ncells) {
+            const int n = cstart[c + 1] - cstart[c];
+            cmax[c] = n > 0 ? kBig : 0u;   // an empty cell never wins and never needs an update
+            cidx[c] = 0xffffffffu;         // (set by the first update: every non-empty cell is updated in round 0)
+        }
     }
     long long s0 = start[b];
     if (s0 < 0) s0 += N;
@@ -787,31 +799,33 @@ __global__ void __launch_bounds__(kFpsGridThreads, 1)
     __syncthreads();
     int64_t *o = out + (size_t)b * npoint;
     const float slack = 1e-3f * gr.h;
+    float cx = cen[0], cy = cen[1], cz = cen[2];      // the newest centroid, in every thread's registers
     for (int it = 0; it < npoint; ++it) {
         if (tid == 0) o[it] = (int64_t)cur;                                            // :65
         if (it == npoint - 1) break;
-        const float cx = cen[0], cy = cen[1], cz = cen[2];
         const float c0 = gr.a0 == 0 ? cx : (gr.a0 == 1 ? cy : cz), c1 = gr.a1 == 1 ? cy : (gr.a1 == 2 ? cz : cx);
         // (1) which cells can still change
-        for (int c = tid; c < ncells; c += kFpsGridThreads) {
-            const unsigned m = cmax[c];
+#pragma unroll
+        for (int j = 0; j < kMyCells; ++j) {
+            const int c = tid + j * kFpsGridThreads;
             bool active = false;
-            if (m != 0u) {
-                const int i0 = c % gr.g0, i1 = c / gr.g0;
-                const float lo0 = gr.o0 + i0 * gr.h - slack, hi0 = gr.o0 + (i0 + 1) * gr.h + slack;
-                const float lo1 = gr.o1 + i1 * gr.h - slack, hi1 = gr.o1 + (i1 + 1) * gr.h + slack;
-                const float dx = fmaxf(fmaxf(lo0 - c0, c0 - hi0), 0.f), dy = fmaxf(fmaxf(lo1 - c1, c1 - hi1), 0.f);
-                const float lb2 = (dx * dx + dy * dy) * (1.f - 1e-5f);
-                active = !(lb2 > __uint_as_float(m));
+            if (c < ncells) {
+                const unsigned m = cmax[c];
+                if (m != 0u) {
+                    const float lo0 = mylo0[j] - slack, hi0 = mylo0[j] + gr.h + slack;
+                    const float lo1 = mylo1[j] - slack, hi1 = mylo1[j] + gr.h + slack;
+                    const float dx = fmaxf(fmaxf(lo0 - c0, c0 - hi0), 0.f), dy = fmaxf(fmaxf(lo1 - c1, c1 - hi1), 0.f);
+                    const float lb2 = (dx * dx + dy * dy) * (1.f - 1e-5f);
+                    active = !(lb2 > __uint_as_float(m));
+                }
             }
-            const unsigned bal = __ballot_sync(__activemask(), active);
+            const unsigned bal = __ballot_sync(kFull, active);   // (the loop is unrolled: all lanes are here)
             if (active) {
                 // warp-aggregated append (lanes of a warp scan consecutive cells)
-                const unsigned act = __activemask();
                 const int leader = __ffs(bal) - 1;
                 int basep = 0;
                 if (lane == leader) basep = atomicAdd(&nlist, __popc(bal));
-                basep = __shfl_sync(act, basep, leader);
+                basep = __shfl_sync(bal, basep, leader);
                 list[basep + __popc(bal & ((1u << lane) - 1))] = (unsigned short)c;
             }
         }
@@ -820,7 +834,7 @@ __global__ void __launch_bounds__(kFpsGridThreads, 1)
         const int nl = nlist;
         for (int li = warp; li < nl; li += kFpsGridThreads / 32) {
             const int c = list[li];
-            const int beg = cstart[c], end = cstart[c + 1];
+            const int beg = cs[c], end = cs[c + 1];
             unsigned bm = 0u, bi = 0xffffffffu;
             for (int i0 = beg; i0 < end; i0 += 32) {
                 const int i = i0 + lane;
@@ -858,19 +872,17 @@ __global__ void __launch_bounds__(kFpsGridThreads, 1)
         const unsigned wm = __reduce_max_sync(kFull, bm);
         const unsigned wi = __reduce_min_sync(kFull, bm == wm ? bi : 0xffffffffu);
         if (lane == 0) wrec[warp] = make_uint2(wm, wi);
+        if (tid == 0) nlist = 0;           // (everybody is past step (2))
         __syncthreads();
-        if (warp == 0) {
-            const uint2 r = wrec[lane];
-            const unsigned gm = __reduce_max_sync(kFull, r.x);
-            const unsigned gi = __reduce_min_sync(kFull, r.x == gm ? r.y : 0xffffffffu);
-            if (lane < 3) cen[lane] = __ldg(cloud + (size_t)gi * 3 + lane);
-            if (lane == 0) {
-                cen[3] = __uint_as_float(gi);
-                nlist = 0;
-            }
-        }
-        __syncthreads();
-        cur = __float_as_uint(cen[3]);
+        // every warp finishes the reduction itself: no second barrier, no broadcast through shared memory
+        const uint2 r = wrec[lane];
+        const unsigned gm = __reduce_max_sync(kFull, r.x);
+        const unsigned gi = __reduce_min_sync(kFull, r.x == gm ? r.y : 0xffffffffu);
+        const float cv = lane < 3 ? __ldg(cloud + (size_t)gi * 3 + lane) : 0.f;
+        cx = __shfl_sync(kFull, cv, 0);
+        cy = __shfl_sync(kFull, cv, 1);
+        cz = __shfl_sync(kFull, cv, 2);
+        cur = gi;
     }
 }
 

@@ -7,7 +7,7 @@
 //
 // Algebra (oracle/tower_oracle.py):  the input of blocks 2-4 is cat([feat (64), max_prev.repeat(N) (64)]), so the
 // half of every first-layer product that meets the repeated max is a PER-EPISODE BIAS  W[:, 64:] @ max_prev.
-//   block 1 (k_tower_first, fp32 FMA - K = 5 is no tensor-core shape):
+//   block 1 (k_tower_first, packed fp32 FFMA2 - K = 5 is no tensor-core shape):
 //       h = lrelu(W1 x + b1) (5 ch);  out = lrelu(W2 h + Ws x + (b2 + bs))              -> feat1 [64]
 //   blocks 2, 3 (k_tower_mma<false>):
 //       h = lrelu(W1a feat + bias1_e)           (128 ch;  bias1_e = b1 + W1b max_prev)
@@ -85,10 +85,11 @@ struct TowerBlobLast {
     static constexpr int b2 = b1 + 128 * 4;                 // [128]
     static constexpr int total = b2 + 128 * 4;
 };
-// block 1: fp32, per output channel 12 floats {W2 row (5), Ws row (5), b2 + bs, 0}, then W1 [5][5], b1 [5]
+// block 1: fp32, per PAIR of output channels (c, c+1) 24 floats: {W2[c][i], W2[c+1][i]} i<5, {Ws[c][i], Ws[c+1][i]} i<5,
+// {b2+bs of c, of c+1}, 2 x 0 - ready for packed FFMA2; then W1 [5][5], b1 [5]
 struct TowerBlobFirst {
-    static constexpr int rows = 0;                          // [64][12] f32
-    static constexpr int w1 = 64 * 12 * 4;                  // [5][5]
+    static constexpr int rows = 0;                          // [32][24] f32
+    static constexpr int w1 = 32 * 24 * 4;                  // [5][5]
     static constexpr int b1 = w1 + 25 * 4;                  // [5]
     static constexpr int total = ((b1 + 5 * 4 + 15) / 16) * 16;
 };
@@ -121,6 +122,32 @@ __device__ __forceinline__ float max_nan(float a, float b) {
     return r;
 }
 __device__ __forceinline__ float lrelu(float v) { return max_nan(v, __fmul_rn(kTowerSlope, v)); }
+// packed fp32 pairs (Blackwell FADD2 / FMUL2 / FFMA2): two IEEE round-to-nearest operations per instruction, the
+// same results as the scalar ones
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+    float2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<unsigned long long &>(r)) : "l"(reinterpret_cast<unsigned long long &>(a)), "l"(reinterpret_cast<unsigned long long &>(b)));
+    return r;
+}
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
+    float2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<unsigned long long &>(r)) : "l"(reinterpret_cast<unsigned long long &>(a)), "l"(reinterpret_cast<unsigned long long &>(b)));
+    return r;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+    float2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<unsigned long long &>(r)) : "l"(reinterpret_cast<unsigned long long &>(a)), "l"(reinterpret_cast<unsigned long long &>(b)));
+    return r;
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    float2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(reinterpret_cast<unsigned long long &>(r)) : "l"(reinterpret_cast<unsigned long long &>(a)), "l"(reinterpret_cast<unsigned long long &>(b)), "l"(reinterpret_cast<unsigned long long &>(c)));
+    return r;
+}
+__device__ __forceinline__ float2 lrelu2(float2 v) {
+    const float2 t = mul2(v, make_float2(kTowerSlope, kTowerSlope));
+    return make_float2(max_nan(v.x, t.x), max_nan(v.y, t.y));
+}
 
 // two neighbouring channels -> one packed 16-bit pair (even channel in the low half), and back to fp32
 __device__ __forceinline__ unsigned pack2(float even, float odd) {
@@ -150,6 +177,20 @@ __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sy
 // all tcgen05.mma issued so far by this thread have completed -> one arrival on `bar`
 __device__ __forceinline__ void tc_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// non-blocking probe: has the phase with this parity completed?
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -260,9 +301,9 @@ __global__ void k_tower_pack(int kind, const float *__restrict__ W1, const float
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     if (kind == 0) {
         float *rows = reinterpret_cast<float *>(blob + TowerBlobFirst::rows);
-        for (int i = tid; i < 64 * 12; i += nth) {
-            const int c = i / 12, j = i % 12;
-            rows[i] = j < 5 ? W2[c * 5 + j] : j < 10 ? Ws[c * 5 + j - 5] : j == 10 ? __fadd_rn(b2[c], bs[c]) : 0.f;
+        for (int i = tid; i < 32 * 24; i += nth) {
+            const int pr = i / 24, j = i % 24, c = 2 * pr + (j & 1), k = j >> 1;   // k: 0-4 W2, 5-9 Ws, 10 bias, 11 pad
+            rows[i] = k < 5 ? W2[c * 5 + k] : k < 10 ? Ws[c * 5 + k - 5] : k == 10 ? __fadd_rn(b2[c], bs[c]) : 0.f;
         }
         float *w1 = reinterpret_cast<float *>(blob + TowerBlobFirst::w1);
         for (int i = tid; i < 25; i += nth) w1[i] = W1[i];
@@ -324,16 +365,15 @@ __device__ __forceinline__ void tower_stage_chunk(unsigned char *planes, int pla
         unsigned *ph = &hi.x, *pl = &lo.x, *pl2 = &lo2.x;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            const float a = v[q * 8 + 2 * e], b = v[q * 8 + 2 * e + 1];
-            const unsigned h = pack2(a, b);
-            const float2 hf = unpack2(h);
-            const float ra = __fsub_rn(a, hf.x), rb = __fsub_rn(b, hf.y);
-            const unsigned l = pack2(ra, rb);
+            const float2 ab = make_float2(v[q * 8 + 2 * e], v[q * 8 + 2 * e + 1]);
+            const unsigned h = pack2(ab.x, ab.y);
+            const float2 res = sub2(ab, unpack2(h));
+            const unsigned l = pack2(res.x, res.y);
             ph[e] = h;
             pl[e] = l;
             if (kPlanes == 3) {
-                const float2 lf = unpack2(l);
-                pl2[e] = pack2(__fsub_rn(ra, lf.x), __fsub_rn(rb, lf.y));
+                const float2 res2 = sub2(res, unpack2(l));
+                pl2[e] = pack2(res2.x, res2.y);
             }
         }
         const int off = p * 128 + (((4 * j + q) ^ (p & 7)) << 4);
@@ -351,8 +391,8 @@ __global__ void __launch_bounds__(128) k_tower_first(const float *__restrict__ o
     extern __shared__ __align__(1024) unsigned char tower_smem[];
     unsigned char *const smem = tower_smem;
     unsigned char *planes = smem;                                  // 2 x 16 KB
-    float *wrow = reinterpret_cast<float *>(smem + 32768);         // [64][12]
-    float *w1 = wrow + 64 * 12;                                    // [25] + b1 [5]
+    float *wrow = reinterpret_cast<float *>(smem + 32768);         // [32 channel pairs][24]
+    float *w1 = wrow + 32 * 24;                                    // [25] + b1 [5]
     const int tid = threadIdx.x, lane = tid & 31;
     for (int i = tid; i < TowerBlobFirst::total / 4; i += 128) wrow[i] = reinterpret_cast<const float *>(blob)[i];
     if (tid == 0) {
@@ -363,16 +403,27 @@ __global__ void __launch_bounds__(128) k_tower_first(const float *__restrict__ o
     pdl_wait();        // obs3d is the previous kernel's output when the tower follows cmr_observe in a stream
     int t0, t1;
     tower_tile_range(B * tiles_per_ep, blockIdx.x, gridDim.x, t0, t1);
-    float mx[2] = {-INFINITY, -INFINITY};
+    // running maxima per point lane, in registers across the tiles of an episode; exchanged across the warp at a flush
+    float rmx[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) rmx[i] = -INFINITY;
     int cur_ep = -1;
+    auto flush = [&]() {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            float t[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) t[i] = rmx[32 * j + i];
+            const float m = warp_transpose_max(t, lane);
+            if (cur_ep >= 0) atomicMax(max_keys + cur_ep * 64 + 32 * j + lane, f2key(m));
+        }
+#pragma unroll
+        for (int i = 0; i < 64; ++i) rmx[i] = -INFINITY;
+    };
     for (int t = t0; t < t1; ++t) {
         const int e = t / tiles_per_ep, n0 = (t - e * tiles_per_ep) * kTowerTile;
         if (e != cur_ep) {
-            if (cur_ep >= 0) {
-                atomicMax(max_keys + cur_ep * 64 + lane, f2key(mx[0]));
-                atomicMax(max_keys + cur_ep * 64 + 32 + lane, f2key(mx[1]));
-            }
-            mx[0] = mx[1] = -INFINITY;
+            flush();
             cur_ep = e;
         }
         const int n = n0 + tid;
@@ -387,32 +438,39 @@ __global__ void __launch_bounds__(128) k_tower_first(const float *__restrict__ o
             for (int c = 0; c < 5; ++c) a = __fmaf_rn(w1[o * 5 + c], x[c], a);
             h[o] = lrelu(a);
         }
+        float2 in2[10];                                  // every input duplicated: one FFMA2 serves two output channels
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            in2[i] = make_float2(h[i], h[i]);
+            in2[5 + i] = make_float2(x[i], x[i]);
+        }
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             float v[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const float4 *r = reinterpret_cast<const float4 *>(wrow + (32 * j + i) * 12);
-                const float4 r0 = r[0], r1 = r[1], r2 = r[2];
-                float a = r2.z;
-                a = __fmaf_rn(r0.x, h[0], a);
-                a = __fmaf_rn(r0.y, h[1], a);
-                a = __fmaf_rn(r0.z, h[2], a);
-                a = __fmaf_rn(r0.w, h[3], a);
-                a = __fmaf_rn(r1.x, h[4], a);
-                a = __fmaf_rn(r1.y, x[0], a);
-                a = __fmaf_rn(r1.z, x[1], a);
-                a = __fmaf_rn(r1.w, x[2], a);
-                a = __fmaf_rn(r2.x, x[3], a);
-                a = __fmaf_rn(r2.y, x[4], a);
-                v[i] = lrelu(a);
+            for (int pr = 0; pr < 16; ++pr) {
+                const float4 *r = reinterpret_cast<const float4 *>(wrow + (16 * j + pr) * 24);
+                const float4 r0 = r[0], r1 = r[1], r2 = r[2], r3 = r[3], r4 = r[4], r5 = r[5];
+                float2 a = make_float2(r5.x, r5.y);      // (b2 + bs) of the two channels
+                a = fma2(make_float2(r0.x, r0.y), in2[0], a);
+                a = fma2(make_float2(r0.z, r0.w), in2[1], a);
+                a = fma2(make_float2(r1.x, r1.y), in2[2], a);
+                a = fma2(make_float2(r1.z, r1.w), in2[3], a);
+                a = fma2(make_float2(r2.x, r2.y), in2[4], a);
+                a = fma2(make_float2(r2.z, r2.w), in2[5], a);
+                a = fma2(make_float2(r3.x, r3.y), in2[6], a);
+                a = fma2(make_float2(r3.z, r3.w), in2[7], a);
+                a = fma2(make_float2(r4.x, r4.y), in2[8], a);
+                a = fma2(make_float2(r4.z, r4.w), in2[9], a);
+                a = lrelu2(a);
+                v[2 * pr] = a.x;
+                v[2 * pr + 1] = a.y;
             }
             tower_stage_chunk<2>(planes, 16384, tid, j, v);
-            if (!valid) {
+            if (valid) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = -INFINITY;
+                for (int i = 0; i < 32; ++i) rmx[32 * j + i] = max_nan(rmx[32 * j + i], v[i]);
             }
-            mx[j] = max_nan(mx[j], warp_transpose_max(v, lane));
         }
         fence_async_proxy();
         __syncthreads();
@@ -424,10 +482,7 @@ __global__ void __launch_bounds__(128) k_tower_first(const float *__restrict__ o
         }
         __syncthreads();
     }
-    if (cur_ep >= 0) {
-        atomicMax(max_keys + cur_ep * 64 + lane, f2key(mx[0]));
-        atomicMax(max_keys + cur_ep * 64 + 32 + lane, f2key(mx[1]));
-    }
+    flush();
     pdl_launch_dependents();
 }
 
@@ -530,10 +585,8 @@ k_tower_mma(const unsigned char *__restrict__ blob, int B, int N, int tiles_per_
             // second GEMM of tile i (its h is in TMEM): D2 (+)= H * W2^T, three passes over 8 K-chunks
             auto issue_c2 = [&](int i) {
                 const int g = i & 1;
-                mbar_wait(h_full + g, (i >> 1) & 1);
                 tc_fence_after();
                 const uint32_t d1 = tmem_base + g * Cfg::kBufCols, d2 = d1 + 128;
-                bool acc = true;      // D2 already holds the shortcut product (mid) or shortcut + bias (last)
 #pragma unroll
                 for (int pass = 0; pass < kTowerPasses; ++pass) {
                     const int a_lo = tower_pass_a(pass) ? 16 : 0;               // the lo pairs sit 16 columns after the hi pairs
@@ -544,21 +597,17 @@ k_tower_mma(const unsigned char *__restrict__ blob, int B, int N, int tiles_per_
                     for (int kk = 0; kk < 8; ++kk) {
                         const uint32_t a = d1 + 32 * (kk >> 1) + 8 * (kk & 1) + a_lo;
                         const uint64_t b = umma_desc_sw128(w + (kk >> 2) * (Cfg::kN2 * 128) + (kk & 3) * 32);
-                        mma_ts(d2, a, b, idesc, acc);
-                        acc = true;
+                        mma_ts(d2, a, b, idesc, true);   // D2 already holds the shortcut product (mid) or shortcut + bias (last)
                     }
                 }
                 tc_commit(d2_full + g);
             };
-            mbar_wait(w_full, 0);
-            for (int i = 0; i < ntiles; ++i) {
+            // first GEMM of tile i: D1 = X * W1a^T (N = 128); mid blocks also start D2 = X * Wsa^T (N = 64)
+            auto issue_c1 = [&](int i) {
                 const int s = i % Cfg::kStages, g = i & 1;
-                mbar_wait(x_full + s, (i / Cfg::kStages) & 1);
-                if (i >= 2) mbar_wait(t_empty + g, ((i >> 1) - 1) & 1);
                 tc_fence_after();
                 const uint32_t xs = sbase + Cfg::off_stage + s * Cfg::kStageBytes;
                 const uint32_t d1 = tmem_base + g * Cfg::kBufCols, d2 = d1 + 128;
-                // first GEMM: D1 = X * W1a^T (N = 128); mid blocks also start D2 = X * Wsa^T (N = 64)
 #pragma unroll
                 for (int pass = 0; pass < kTowerPasses; ++pass) {
                     const uint32_t xa = xs + (tower_pass_a(pass) ? 16384 : 0);
@@ -580,9 +629,30 @@ k_tower_mma(const unsigned char *__restrict__ blob, int B, int N, int tiles_per_
                     }
                 }
                 tc_commit(d1_full + g);
-                if (i >= 1) issue_c2(i - 1);
+            };
+            mbar_wait(w_full, 0);
+            // Issue whichever GEMM is READY, the second GEMM of an older tile first: with a fixed order (C1(i), C2(i-1), ...)
+            // C2(i-1) queued behind a C1(i) that was itself waiting for the OTHER epilogue group to free its accumulators,
+            // and the two groups ran one after the other instead of side by side (5600 cycles per tile, ncu).
+            int n1 = 0, n2 = 0;   // tiles whose first / second GEMM has been issued
+            while (n2 < ntiles) {
+                bool did = false;
+                if (n2 < n1 && mbar_test(h_full + (n2 & 1), (n2 >> 1) & 1)) {
+                    issue_c2(n2);
+                    ++n2;
+                    did = true;
+                }
+                if (!did && n1 < ntiles && n1 - n2 < 2) {
+                    const int i = n1;
+                    if (mbar_test(x_full + i % Cfg::kStages, (i / Cfg::kStages) & 1) &&
+                        (i < 2 || mbar_test(t_empty + (i & 1), ((i >> 1) - 1) & 1))) {
+                        issue_c1(i);
+                        ++n1;
+                        did = true;
+                    }
+                }
+                if (!did) __nanosleep(32);
             }
-            if (ntiles > 0) issue_c2(ntiles - 1);
         }
     } else if (warp >= 4) {
         // ============================== epilogue groups ==============================
@@ -599,14 +669,28 @@ k_tower_mma(const unsigned char *__restrict__ blob, int B, int N, int tiles_per_
         float mx[kMine2];
 #pragma unroll
         for (int j = 0; j < kMine2; ++j) mx[j] = -INFINITY;
+        // blocks 2, 3 (one 32-channel chunk per warp): the running maxima stay per POINT LANE in registers across the
+        // tiles of an episode - one max per value - and are exchanged across the warp once, when they are flushed
+        constexpr int kRegMax = kLast ? 1 : 32;
+        float rmx[kRegMax];
+#pragma unroll
+        for (int q = 0; q < kRegMax; ++q) rmx[q] = -INFINITY;
         int cur_ep = -1;
         pdl_wait();                                      // prev_keys are the previous kernel's output
 
         auto flush = [&]() {
+            if (!kLast) {
+                float t[32];
+#pragma unroll
+                for (int q = 0; q < 32; ++q) t[q] = rmx[q < kRegMax ? q : 0];
+                mx[0] = warp_transpose_max(t, lane);
+#pragma unroll
+                for (int q = 0; q < kRegMax; ++q) rmx[q] = -INFINITY;
+            }
             if (cur_ep >= 0) {
 #pragma unroll
                 for (int j = 0; j < kMine2; ++j)
-                    atomicMax(max_keys + cur_ep * Cfg::kN2 + 32 * (half * kMine2 + j) + lane, f2key(mx[j]));
+                    atomicMax(max_keys + cur_ep * Cfg::kN2 + 32 * (half * kMine2 + j) + lane, f2key(kLast ? lrelu(mx[j]) : mx[j]));
             }
 #pragma unroll
             for (int j = 0; j < kMine2; ++j) mx[j] = -INFINITY;
@@ -666,12 +750,11 @@ k_tower_mma(const unsigned char *__restrict__ blob, int B, int N, int tiles_per_
 #pragma unroll
                 for (int q = 0; q < 16; ++q) {
                     const float2 bb = *reinterpret_cast<const float2 *>(bias1 + 32 * j + 2 * q);
-                    const float a = lrelu(__fadd_rn(__uint_as_float(r[2 * q]), bb.x));
-                    const float b = lrelu(__fadd_rn(__uint_as_float(r[2 * q + 1]), bb.y));
-                            const unsigned h = pack2(a, b);
-                    const float2 hf = unpack2(h);
+                    const float2 ab = lrelu2(add2(make_float2(__uint_as_float(r[2 * q]), __uint_as_float(r[2 * q + 1])), bb));
+                    const unsigned h = pack2(ab.x, ab.y);
+                    const float2 res = sub2(ab, unpack2(h));
                     hi[q] = h;
-                    lo[q] = pack2(__fsub_rn(a, hf.x), __fsub_rn(b, hf.y));
+                    lo[q] = pack2(res.x, res.y);
                 }
 
                 tmem_st16(d1 + 32 * j, hi);
@@ -725,21 +808,36 @@ k_tower_mma(const unsigned char *__restrict__ blob, int B, int N, int tiles_per_
                 tmem_ld32(d2 + 32 * j, r);
                 tc_wait_ld();
                 float v[32];
+                if (kLast) {
+                    // only the max over the points leaves block 4, and LeakyReLU is monotonic: max(lrelu(v)) = lrelu(max(v))
+                    // - the activation is applied once per channel when the maxima are flushed (the bias is in D2 already)
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (!kLast) bb = *reinterpret_cast<const float4 *>(bias2 + 32 * j + 4 * q);   // (last: bias is in D2 already)
-                    v[4 * q] = lrelu(__fadd_rn(__uint_as_float(r[4 * q]), bb.x));
-                    v[4 * q + 1] = lrelu(__fadd_rn(__uint_as_float(r[4 * q + 1]), bb.y));
-                    v[4 * q + 2] = lrelu(__fadd_rn(__uint_as_float(r[4 * q + 2]), bb.z));
-                    v[4 * q + 3] = lrelu(__fadd_rn(__uint_as_float(r[4 * q + 3]), bb.w));
-                }
-                if (!kLast) tower_stage_chunk<kPlanesOut>(stage, 16384, p, j, v);
-                if (!valid) {
+                    for (int q = 0; q < 32; ++q) v[q] = __uint_as_float(r[q]);
+                } else {
 #pragma unroll
-                    for (int q = 0; q < 32; ++q) v[q] = -INFINITY;
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 bb = *reinterpret_cast<const float4 *>(bias2 + 32 * j + 4 * q);
+                        const float2 a = lrelu2(add2(make_float2(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1])), make_float2(bb.x, bb.y)));
+                        const float2 b = lrelu2(add2(make_float2(__uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3])), make_float2(bb.z, bb.w)));
+                        v[4 * q] = a.x;
+                        v[4 * q + 1] = a.y;
+                        v[4 * q + 2] = b.x;
+                        v[4 * q + 3] = b.y;
+                    }
                 }
-                mx[jj] = max_nan(mx[jj], warp_transpose_max(v, lane));
+                if (!kLast) {
+                    tower_stage_chunk<kPlanesOut>(stage, 16384, p, j, v);
+                    if (valid) {
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) rmx[q < kRegMax ? q : 0] = max_nan(rmx[q < kRegMax ? q : 0], v[q]);
+                    }
+                } else {
+                    if (!valid) {
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) v[q] = -INFINITY;
+                    }
+                    mx[jj] = max_nan(mx[jj], warp_transpose_max(v, lane));
+                }
             }
             tc_fence_before();
             mbar_arrive(t_empty + g);                    // D1/H and D2 of this group may be overwritten

@@ -489,6 +489,65 @@ def iterate(data, pose_source, action_r, action_t, config, prev_distance=None, w
     return pose_source, rew, dist, obs2d, obs3d
 
 
+class CapturedRollout:
+    """A whole rollout with GIVEN actions as one CUDA graph (see ``capture_rollout``)."""
+
+    def __init__(self, graph, pose, rewards, distances, obs2d, obs3d, keep):
+        self.graph, self.pose, self.rewards, self.distances = graph, pose, rewards, distances
+        self.observation_2d, self.observation_3d = obs2d, obs3d
+        self._keep = keep
+
+    def replay(self):
+        """Run the rollout again (same inputs, whatever they hold now); the result tensors are rewritten in place:
+        ``pose`` [B,4,4] final poses, ``rewards`` / ``distances`` [iters,B,1,1], ``observation_2d/3d`` of the last pose."""
+        self.graph.replay()
+        return self
+
+
+@torch.no_grad()
+def capture_rollout(data, config, actions_r, actions_t, with_reward=True):
+    """Extension for callers with scripted or precomputed actions: ``init`` + ``len(actions_r)`` iterations of
+    observe -> step -> reward (Test_Agent.py:150-170 with the agent's choices given) captured ONCE as a CUDA graph -
+    a replay costs one launch on the host instead of ~5 calls per iteration.  actions_r / actions_t:
+    [iters, B, 1|3] / [iters, B, 2|3] int64 on the device (their CONTENT may change between replays, like every input
+    tensor's).  The per-batch state of ``data`` is prepared before the capture."""
+    ep = _episode(data)
+    iters = int(actions_r.shape[0])
+    actions_r = _lib.require_cuda(actions_r, "actions_r", torch.int64).contiguous()
+    actions_t = _lib.require_cuda(actions_t, "actions_t", torch.int64).contiguous()
+    dev = ep.device
+    pose0, _ = init(data)
+    if with_reward:
+        reward(pose0, data, None)                               # per-batch reward state (and the memoised distance)
+    pose = pose0.clone()
+    rewards = torch.zeros(iters, ep.B, 1, 1, device=dev)
+    distances = torch.zeros(iters, ep.B, 1, 1, device=dev)
+    torch.cuda.synchronize(dev)
+
+    def body():
+        pose.copy_(pose0)
+        prev = None
+        o2 = o3 = None
+        for it in range(iters):
+            o2, o3 = observation_from_a_pose(data, pose)
+            step(actions_r[it], actions_t[it], pose, config)
+            if with_reward:
+                r, prev = reward(pose, data, prev)
+                rewards[it].copy_(r)
+                distances[it].copy_(prev)
+        return o2, o3
+
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        body()                                                  # warm-up outside the capture
+    torch.cuda.current_stream(dev).wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        o2, o3 = body()
+    return CapturedRollout(graph, pose, rewards, distances, o2, o3, (data, actions_r, actions_t, pose0))
+
+
 def expert(pose_source, targets, config, data=None):
     """environment.py:143-176.  Implemented on the device in
     cmr_expert; see cmr_agent_b200/expert.py."""

@@ -127,13 +127,13 @@ def farthest_point_sample(xyz, npoint):
     return farthest_point_sample_from(xyz, npoint, start)
 
 
-FPS_GRID_MAX_POINTS = 45000       # the pruned sampler keeps a cloud's running distances in one SM's shared memory
+FPS_GRID_MAX_POINTS = 41900       # the pruned sampler keeps a cloud's running distances in one SM's shared memory
 
 
 def farthest_point_sample_from(xyz, npoint, start, method="auto"):
     """Same as ``farthest_point_sample`` with explicit start indices [B] int64 (extension).
     method: "cluster" = every point every round, one thread-block cluster per cloud; "grid" = cell pruning on a uniform
-    grid, one SM per cloud (same indices); "auto" = grid for 2048 <= N <= 45000."""
+    grid, one SM per cloud (same indices); "auto" = grid for 2048 <= N <= 41900."""
     xyz = _f32c(xyz, "xyz")
     B, N, _ = xyz.shape
     start = _i64c(start, "start")

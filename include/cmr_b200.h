@@ -238,7 +238,7 @@ CMR_API int cmr_farthest_point_sample(const float *xyz, const int64_t *start, in
 
 /* The same sampling with cell pruning on the uniform grid of cmr_knn_grid (workspace of the same size): per round
  * only the cells that the newest centroid can still affect are updated, one SM carries a whole cloud.  Indices
- * identical to cmr_farthest_point_sample.  N up to about 45000 (the running distances live in shared memory;
+ * identical to cmr_farthest_point_sample.  N up to about 41900 (the running distances live in shared memory;
  * CMR_ERANGE beyond). */
 CMR_API int cmr_farthest_point_sample_grid(const float *xyz, const int64_t *start, int B, int N, int npoint, void *workspace,
                                            int64_t *out, void *stream);

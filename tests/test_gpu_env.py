@@ -548,3 +548,36 @@ def test_validation_mode_reports_device_faults(cuda):
         env.step(torch.tensor([[3], [4]], device=cuda), torch.tensor([[0, 0], [0, 0]], device=cuda), pose, cfg)
     finally:
         env.set_validation(False)
+
+
+def test_captured_rollout_equals_the_eager_loop(cuda):
+    """environment.capture_rollout: the rollout as one CUDA graph; replays follow changed inputs (new actions)."""
+    env = _env()
+    data_cpu = synth.make_batch(3, seed=51, num_pt=8192, img_h=160, img_w=512)
+    data = hp.to_device(data_cpu, cuda)
+    cfg = synth.StepConfig(device=cuda)
+    iters = 5
+    a_r, a_t = synth.make_actions(3, iters, seed=3)
+    a_r, a_t = a_r.to(cuda), a_t.to(cuda)
+
+    def eager(ar, at):
+        pose, _ = env.init(data)
+        prev, rews, dists = None, [], []
+        for it in range(iters):
+            o2, o3 = env.observation_from_a_pose(data, pose)
+            env.step(ar[it], at[it], pose, cfg)
+            r, prev = env.reward(pose, data, prev)
+            rews.append(r)
+            dists.append(prev)
+        return pose, torch.stack(rews), torch.stack(dists), o2, o3
+
+    roll = env.capture_rollout(data, cfg, a_r, a_t)
+    for trial in range(2):
+        roll.replay()
+        torch.cuda.synchronize()
+        want = eager(a_r, a_t)
+        assert torch.equal(roll.pose, want[0]) and torch.equal(roll.rewards, want[1]) and torch.equal(roll.distances, want[2])
+        assert torch.equal(roll.observation_2d, want[3]) and torch.equal(roll.observation_3d, want[4])
+        b_r, b_t = synth.make_actions(3, iters, seed=99)        # new actions written INTO the captured tensors
+        a_r.copy_(b_r.to(cuda))
+        a_t.copy_(b_t.to(cuda))
