@@ -61,6 +61,15 @@ constexpr float kTowerSlope = 0.2f;    // LeakyReLU(negative_slope=0.2), PointNN
 #ifndef CMR_TOWER_FMT
 #define CMR_TOWER_FMT 1
 #endif
+#ifndef CMR_TOWER_REGMAX
+#define CMR_TOWER_REGMAX 0
+#endif
+#ifndef CMR_TOWER_PACKED
+#define CMR_TOWER_PACKED 1
+#endif
+constexpr bool kTowerRegMax = CMR_TOWER_REGMAX != 0;   // running maxima per point lane in registers (measured SLOWER: 64 more
+                                                       // registers cost occupancy / spills - off); else: one 31-step exchange per tile
+constexpr bool kTowerPacked = CMR_TOWER_PACKED != 0;   // FADD2/FMUL2/FFMA2 in the epilogues
 constexpr int kTowerPasses = CMR_TOWER_PASSES;   // 3: hh + hl + lh;  4: + ll
 constexpr bool kTowerF16 = CMR_TOWER_FMT == 1;   // pieces are fp16 (1, default) or bf16 (0)
 
@@ -125,21 +134,25 @@ __device__ __forceinline__ float lrelu(float v) { return max_nan(v, __fmul_rn(kT
 // packed fp32 pairs (Blackwell FADD2 / FMUL2 / FFMA2): two IEEE round-to-nearest operations per instruction, the
 // same results as the scalar ones
 __device__ __forceinline__ float2 add2(float2 a, float2 b) {
+    if (!kTowerPacked) return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y));
     float2 r;
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<unsigned long long &>(r)) : "l"(reinterpret_cast<unsigned long long &>(a)), "l"(reinterpret_cast<unsigned long long &>(b)));
     return r;
 }
 __device__ __forceinline__ float2 sub2(float2 a, float2 b) {
+    if (!kTowerPacked) return make_float2(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y));
     float2 r;
     asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<unsigned long long &>(r)) : "l"(reinterpret_cast<unsigned long long &>(a)), "l"(reinterpret_cast<unsigned long long &>(b)));
     return r;
 }
 __device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+    if (!kTowerPacked) return make_float2(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y));
     float2 r;
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<unsigned long long &>(r)) : "l"(reinterpret_cast<unsigned long long &>(a)), "l"(reinterpret_cast<unsigned long long &>(b)));
     return r;
 }
 __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    if (!kTowerPacked) return make_float2(__fmaf_rn(a.x, b.x, c.x), __fmaf_rn(a.y, b.y, c.y));
     float2 r;
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(reinterpret_cast<unsigned long long &>(r)) : "l"(reinterpret_cast<unsigned long long &>(a)), "l"(reinterpret_cast<unsigned long long &>(b)), "l"(reinterpret_cast<unsigned long long &>(c)));
     return r;
@@ -404,21 +417,27 @@ __global__ void __launch_bounds__(128) k_tower_first(const float *__restrict__ o
     int t0, t1;
     tower_tile_range(B * tiles_per_ep, blockIdx.x, gridDim.x, t0, t1);
     // running maxima per point lane, in registers across the tiles of an episode; exchanged across the warp at a flush
-    float rmx[64];
+    constexpr int kR = kTowerRegMax ? 64 : 2;
+    float rmx[kR];                                       // kTowerRegMax: per value; else: per 32-channel chunk, lane = channel
 #pragma unroll
-    for (int i = 0; i < 64; ++i) rmx[i] = -INFINITY;
+    for (int i = 0; i < kR; ++i) rmx[i] = -INFINITY;
     int cur_ep = -1;
     auto flush = [&]() {
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-            float t[32];
+            float m;
+            if (kTowerRegMax) {
+                float t[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) t[i] = rmx[32 * j + i];
-            const float m = warp_transpose_max(t, lane);
+                for (int i = 0; i < 32; ++i) t[i] = rmx[(32 * j + i) % kR];
+                m = warp_transpose_max(t, lane);
+            } else {
+                m = rmx[j];
+            }
             if (cur_ep >= 0) atomicMax(max_keys + cur_ep * 64 + 32 * j + lane, f2key(m));
         }
 #pragma unroll
-        for (int i = 0; i < 64; ++i) rmx[i] = -INFINITY;
+        for (int i = 0; i < kR; ++i) rmx[i] = -INFINITY;
     };
     for (int t = t0; t < t1; ++t) {
         const int e = t / tiles_per_ep, n0 = (t - e * tiles_per_ep) * kTowerTile;
@@ -467,9 +486,17 @@ __global__ void __launch_bounds__(128) k_tower_first(const float *__restrict__ o
                 v[2 * pr + 1] = a.y;
             }
             tower_stage_chunk<2>(planes, 16384, tid, j, v);
-            if (valid) {
+            if (kTowerRegMax) {
+                if (valid) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) rmx[32 * j + i] = max_nan(rmx[32 * j + i], v[i]);
+                    for (int i = 0; i < 32; ++i) rmx[(32 * j + i) % kR] = max_nan(rmx[(32 * j + i) % kR], v[i]);
+                }
+            } else {
+                if (!valid) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = -INFINITY;
+                }
+                rmx[j] = max_nan(rmx[j], warp_transpose_max(v, lane));
             }
         }
         fence_async_proxy();
@@ -671,7 +698,8 @@ k_tower_mma(const unsigned char *__restrict__ blob, int B, int N, int tiles_per_
         for (int j = 0; j < kMine2; ++j) mx[j] = -INFINITY;
         // blocks 2, 3 (one 32-channel chunk per warp): the running maxima stay per POINT LANE in registers across the
         // tiles of an episode - one max per value - and are exchanged across the warp once, when they are flushed
-        constexpr int kRegMax = kLast ? 1 : 32;
+        constexpr bool kMidRegMax = !kLast && kTowerRegMax;
+        constexpr int kRegMax = kMidRegMax ? 32 : 1;
         float rmx[kRegMax];
 #pragma unroll
         for (int q = 0; q < kRegMax; ++q) rmx[q] = -INFINITY;
@@ -679,7 +707,7 @@ k_tower_mma(const unsigned char *__restrict__ blob, int B, int N, int tiles_per_
         pdl_wait();                                      // prev_keys are the previous kernel's output
 
         auto flush = [&]() {
-            if (!kLast) {
+            if (kMidRegMax) {
                 float t[32];
 #pragma unroll
                 for (int q = 0; q < 32; ++q) t[q] = rmx[q < kRegMax ? q : 0];
@@ -825,8 +853,8 @@ k_tower_mma(const unsigned char *__restrict__ blob, int B, int N, int tiles_per_
                         v[4 * q + 3] = b.y;
                     }
                 }
-                if (!kLast) {
-                    tower_stage_chunk<kPlanesOut>(stage, 16384, p, j, v);
+                if (!kLast) tower_stage_chunk<kPlanesOut>(stage, 16384, p, j, v);
+                if (kMidRegMax) {
                     if (valid) {
 #pragma unroll
                         for (int q = 0; q < 32; ++q) rmx[q < kRegMax ? q : 0] = max_nan(rmx[q < kRegMax ? q : 0], v[q]);
