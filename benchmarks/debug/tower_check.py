@@ -1,6 +1,6 @@
 """Block-by-block check of the tcgen05 tower against oracle/tower_oracle.py (debugging aid, GPU box).
 Reads the kernel's own intermediates back from the workspace: max keys of every block, feat2 (planes 2,3),
-feat3 (planes 0,1,4).   python benchmarks/debug/tower_check.py [B] [N]"""
+feat3 (planes 0,1).   python benchmarks/debug/tower_check.py [B] [N]"""
 import os
 import sys
 
@@ -43,7 +43,7 @@ def main():
     torch.cuda.synchronize()
     ws = tower._ws
     plane_bytes = (B * N * 128 + 1023) // 1024 * 1024
-    keys = ws[5 * plane_bytes: 5 * plane_bytes + B * 320 * 4].cpu().numpy().view(np.uint32)
+    keys = ws[4 * plane_bytes: 4 * plane_bytes + B * 320 * 4].cpu().numpy().view(np.uint32)
     k1, k2, k3 = (key2f(keys[i * B * 64:(i + 1) * B * 64]).reshape(B, 64) for i in range(3))
     k4 = key2f(keys[3 * B * 64:]).reshape(B, 128)
     # oracle, block by block
@@ -53,7 +53,7 @@ def main():
     f4 = to.block(states[3], f3, m3); m4 = f4.max(dim=2)[0]
     print("max1", scaled(k1, m1), "max2", scaled(k2, m2), "max3", scaled(k3, m3), "max4", scaled(k4, m4))
     feat2 = piece_plane(ws, 2, plane_bytes, B, N) + piece_plane(ws, 3, plane_bytes, B, N)
-    feat3 = piece_plane(ws, 0, plane_bytes, B, N) + piece_plane(ws, 1, plane_bytes, B, N) + piece_plane(ws, 4, plane_bytes, B, N)
+    feat3 = piece_plane(ws, 0, plane_bytes, B, N) + piece_plane(ws, 1, plane_bytes, B, N)
     print("feat2", scaled(feat2, f2.permute(0, 2, 1)), "feat3", scaled(feat3, f3.permute(0, 2, 1)))
     print("out", scaled(out.cpu(), m4), "finite", bool(torch.isfinite(out).all()))
     bad = (feat2 - f2.permute(0, 2, 1)).abs().max(dim=2)[0]

@@ -295,29 +295,29 @@ static int launch_feat_compact(const uint8_t *overlap, const float *feat, int B,
     return after_launch();
 }
 
-// workspace: five bf16 planes [B][N][64] + the max keys of the four blocks (64, 64, 64, 128 per episode)
+// workspace: four fp16 planes [B][N][64] (two (hi, lo) pairs, ping-pong between the blocks) + the max keys of the four blocks (64, 64, 64, 128 per episode)
 struct TowerWs {
     size_t plane, off_keys, keys_bytes, total;
 };
 static TowerWs tower_ws(int B, int N) {
     TowerWs w;
     w.plane = round_up((size_t)B * N * 128, 1024);
-    w.off_keys = 5 * w.plane;
+    w.off_keys = 4 * w.plane;
     w.keys_bytes = (size_t)B * (64 * 3 + 128) * sizeof(unsigned);
     w.total = w.off_keys + round_up(w.keys_bytes, 1024);
     return w;
 }
-template <bool kLast, int kPlanesOut>
+template <bool kLast>
 static int launch_tower_mma(const void *blob, int B, int N, int tiles_per_ep, int box_rows, const CUtensorMap &in_hi, const CUtensorMap &in_lo,
-                            const CUtensorMap &in_lo2, const CUtensorMap &out_hi, const CUtensorMap &out_lo,
-                            const CUtensorMap &out_lo2, const unsigned *prev_keys, unsigned *max_keys, cudaStream_t st) {
-    auto kern = k_tower_mma<kLast, kPlanesOut>;
+                            const CUtensorMap &out_hi, const CUtensorMap &out_lo, const unsigned *prev_keys, unsigned *max_keys,
+                            cudaStream_t st) {
+    auto kern = k_tower_mma<kLast>;
     const size_t smem = TowerCfg<kLast>::smem_bytes;
     int rc = allow_smem(kern, smem);
     if (rc) return rc;
     const int grid = std::min(B * tiles_per_ep, sm_count());
     return launch_pdl(kern, dim3(grid), dim3(kTowerThreads), smem, st, static_cast<const unsigned char *>(blob), B, N, tiles_per_ep, box_rows,
-                      in_hi, in_lo, in_lo2, out_hi, out_lo, out_lo2, prev_keys, max_keys);
+                      in_hi, in_lo, out_hi, out_lo, prev_keys, max_keys);
 }
 
 extern "C" {
@@ -1066,16 +1066,16 @@ int cmr_tower_forward(const float *obs3d, const void *blob1, const void *blob2, 
     cudaStream_t st = S_(stream);
     const TowerWs w = tower_ws(B, N);
     char *ws = static_cast<char *>(workspace);
-    char *plane[5];
-    for (int i = 0; i < 5; ++i) plane[i] = ws + i * w.plane;
+    char *plane[4];
+    for (int i = 0; i < 4; ++i) plane[i] = ws + i * w.plane;
     unsigned *keys1 = reinterpret_cast<unsigned *>(ws + w.off_keys), *keys2 = keys1 + (size_t)B * 64, *keys3 = keys2 + (size_t)B * 64,
              *keys4 = keys3 + (size_t)B * 64;
     cudaError_t e = cudaMemsetAsync(keys1, 0, w.keys_bytes, st);
     if (e != cudaSuccess) return (int)e;
     const int tiles_per_ep = ceil_div(N, kTowerTile);
     const uint32_t rows = (uint32_t)std::min(N, kTowerTile);
-    alignas(64) CUtensorMap m[5];
-    for (int i = 0; i < 5; ++i)
+    alignas(64) CUtensorMap m[4];
+    for (int i = 0; i < 4; ++i)
         if (!make_plane_map(&m[i], plane[i], (uint64_t)N, (uint64_t)B, rows)) return CMR_EUNSUPPORTED;
     // block 1 (fp32 pipes): obs3d -> planes 0,1
     {
@@ -1087,12 +1087,12 @@ int cmr_tower_forward(const float *obs3d, const void *blob1, const void *blob2, 
                         tiles_per_ep, m[0], m[1], keys1);
         if (rc) return rc;
     }
-    // block 2: planes 0,1 -> 2,3;  block 3: planes 2,3 -> 0,1,4;  block 4: planes 0,1,4 -> keys
-    int rc = launch_tower_mma<false, 2>(blob2, B, N, tiles_per_ep, (int)rows, m[0], m[1], m[1], m[2], m[3], m[3], keys1, keys2, st);
+    // block 2: planes 0,1 -> 2,3;  block 3: planes 2,3 -> 0,1;  block 4: planes 0,1 -> keys
+    int rc = launch_tower_mma<false>(blob2, B, N, tiles_per_ep, (int)rows, m[0], m[1], m[2], m[3], keys1, keys2, st);
     if (rc) return rc;
-    rc = launch_tower_mma<false, 3>(blob3, B, N, tiles_per_ep, (int)rows, m[2], m[3], m[3], m[0], m[1], m[4], keys2, keys3, st);
+    rc = launch_tower_mma<false>(blob3, B, N, tiles_per_ep, (int)rows, m[2], m[3], m[0], m[1], keys2, keys3, st);
     if (rc) return rc;
-    rc = launch_tower_mma<true, 2>(blob4, B, N, tiles_per_ep, (int)rows, m[0], m[1], m[4], m[0], m[1], m[4], keys3, keys4, st);
+    rc = launch_tower_mma<true>(blob4, B, N, tiles_per_ep, (int)rows, m[0], m[1], m[0], m[1], keys3, keys4, st);
     if (rc) return rc;
     return launch_pdl(k_tower_finish, dim3(ceil_div(B * 128, 256)), dim3(256), 0, st, (const unsigned *)keys4, embed, B * 128);
 }

@@ -74,12 +74,16 @@ constexpr int kTowerPasses = CMR_TOWER_PASSES;   // 3: hh + hl + lh;  4: + ll
 constexpr bool kTowerF16 = CMR_TOWER_FMT == 1;   // pieces are fp16 (1, default) or bf16 (0)
 
 // ---- packed weights: byte offsets inside the blob k_tower_pack writes (one blob per block) ------------------------
-// mid block (blocks 2, 3):   W1a hi|lo [128 x 64], W2 hi|lo [64 x 128] as two K-blocks, Wsa hi|lo [64 x 64]
+// mid block (blocks 2, 3):   {Wsa [64 x 64]; W1a [128 x 64]; Wsa again} hi, the same lo: rows 0-191 and rows 64-255 are each
+//                            ONE B operand (N = 192) for the first GEMM plus the shortcut product, with the shortcut's
+//                            columns before or after D1's (the two D2 buffers of an epilogue group sit either side
+//                            of its D1); W2 hi|lo [64 x 128] as two K-blocks
 // last block (block 4):      W1a hi|lo [128 x 64], W2 hi|lo [128 x 128] as two K-blocks
 // then fp32 side arrays (read from global memory when an episode's biases are set up)
 struct TowerBlobMid {
-    static constexpr int w1_hi = 0, w1_lo = 16384, w2_hi = 32768, w2_lo = 49152, ws_hi = 65536, ws_lo = 73728;
-    static constexpr int smem_bytes = 81920;
+    static constexpr int ws_hi = 0, w1_hi = 8192, ws2_hi = 24576, ws_lo = 32768, w1_lo = 40960, ws2_lo = 57344, w2_hi = 65536,
+                         w2_lo = 81920;
+    static constexpr int smem_bytes = 98304;
     static constexpr int w1bT = smem_bytes;                 // [64][128] f32: W1[:, 64+k] transposed
     static constexpr int b1 = w1bT + 64 * 128 * 4;          // [128]
     static constexpr int wsbT = b1 + 128 * 4;               // [64][64]: Ws[:, 64+k] transposed
@@ -187,9 +191,15 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-// all tcgen05.mma issued so far by this thread have completed -> one arrival on `bar`
+// all tcgen05.mma issued so far have completed -> one arrival on `bar` (whole converged warp, elected lane - as the MMAs)
 __device__ __forceinline__ void tc_commit(uint64_t *bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+    asm volatile(
+        "{\n"
+        ".reg .pred e;\n"
+        "elect.sync _|e, 0xffffffff;\n"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+        "}\n" ::"r"(smem_u32(bar))
+        : "memory");
 }
 // non-blocking probe: has the phase with this parity completed?
 __device__ __forceinline__ bool mbar_test(uint64_t *bar, unsigned parity) {
@@ -208,13 +218,18 @@ __device__ __forceinline__ bool mbar_test(uint64_t *bar, unsigned parity) {
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// D[tmem] (+)= A[smem desc] * B[smem desc]            (kind::f16: bf16 operands, fp32 accumulate)
+// The MMA wrappers are called by a whole CONVERGED warp and elect the issuing lane themselves (elect.sync): issued
+// from inside an `if (lane == 0)` region the compiler cannot tell that a single thread is active and wraps every
+// UTCHMMA in an elect / branch loop - ~95 cycles of issue per MMA, which made the issuing thread the tower's
+// bottleneck (48 MMAs x 95 = the 4550 cycles per tile ncu measured).
+// D[tmem] (+)= A[smem desc] * B[smem desc]            (kind::f16: 16-bit operands, fp32 accumulate)
 __device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
     asm volatile(
         "{\n"
-        ".reg .pred p;\n"
+        ".reg .pred p, e;\n"
+        "elect.sync _|e, 0xffffffff;\n"
         "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
         "}\n" ::"r"(d_tmem),
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
         : "memory");
@@ -223,9 +238,10 @@ __device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_
 __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, bool accumulate) {
     asm volatile(
         "{\n"
-        ".reg .pred p;\n"
+        ".reg .pred p, e;\n"
+        "elect.sync _|e, 0xffffffff;\n"
         "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
         "}\n" ::"r"(d_tmem),
         "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
         : "memory");
@@ -279,6 +295,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volati
 // 2-D tiled TMA through a 3-D tensor map [B][N][64] bf16 (boxes of [1][128][64], 128B swizzle; rows beyond N are
 // zero-filled on load and clipped on store)
 __device__ __forceinline__ void tma_store_3d_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_3d_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // per-channel max over the 32 points of a warp: lane l ends up with max_p v_p[l] (31 exchanges instead of 32 x 5)
 __device__ __forceinline__ float warp_transpose_max(float (&v)[32], int lane) {
@@ -329,7 +346,8 @@ __global__ void k_tower_pack(int kind, const float *__restrict__ W1, const float
     // conv1, feature half: W1[:, :64] -> B operand [128 rows][64 K]
     for (int i = tid; i < 128 * 64; i += nth) {
         const int n = i >> 6, k = i & 63;
-        pack_split(blob + TowerBlobMid::w1_hi, blob + TowerBlobMid::w1_lo, n, k, W1[n * 128 + k]);
+        pack_split(blob + (last ? TowerBlobLast::w1_hi : TowerBlobMid::w1_hi), blob + (last ? TowerBlobLast::w1_lo : TowerBlobMid::w1_lo), n, k,
+                   W1[n * 128 + k]);
     }
     // conv2: W2 [out2][128] -> two K-blocks of [out2 rows][64 K]
     const int w2_hi = last ? TowerBlobLast::w2_hi : TowerBlobMid::w2_hi, w2_lo = last ? TowerBlobLast::w2_lo : TowerBlobMid::w2_lo;
@@ -351,6 +369,7 @@ __global__ void k_tower_pack(int kind, const float *__restrict__ W1, const float
         for (int i = tid; i < 64 * 64; i += nth) {
             const int n = i >> 6, k = i & 63;
             pack_split(blob + TowerBlobMid::ws_hi, blob + TowerBlobMid::ws_lo, n, k, Ws[n * 128 + k]);
+            pack_split(blob + TowerBlobMid::ws2_hi, blob + TowerBlobMid::ws2_lo, n, k, Ws[n * 128 + k]);
         }
         float *wsbT = reinterpret_cast<float *>(blob + TowerBlobMid::wsbT);
         for (int i = tid; i < 64 * 64; i += nth) {
@@ -514,34 +533,45 @@ __global__ void __launch_bounds__(128) k_tower_first(const float *__restrict__ o
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// k_tower_mma<kLast, kPlanesOut>: blocks 2-4.
-//   kLast = false: in planes (hi, lo); out planes kPlanesOut (2 after block 2, 3 after block 3); 64 max keys / episode
-//   kLast = true : in planes (hi, lo, lo2); no feature output; 128 max keys / episode
+// k_tower_mma<kLast>: blocks 2-4.  Features travel as two fp16 planes (hi, lo): 22 significant bits.
+//   kLast = false: in planes (hi, lo) -> out planes (hi, lo); 64 max keys / episode
+//   kLast = true : in planes (hi, lo); no feature output; 128 max keys / episode
+// Shared memory: weights | input stages (TMA loads) | per-group output staging (mid blocks; TMA stores) | biases.
+// An input stage of a mid block is handed back by the tensor core itself (tcgen05.commit after the first GEMM), and
+// the outputs are staged in buffers of their own: while a stage doubled as the output staging area it stayed
+// occupied for a tile's whole life (~8 us), and three stages capped the kernel at ~2.7 us per tile.
 template <bool kLast>
 struct TowerCfg {
-    static constexpr int kInPlanes = kLast ? 3 : 2;
-    static constexpr int kStageBytes = 49152;                       // room for 3 planes of 16 KB (in, or staged out)
-    static constexpr int kStages = kLast ? 2 : 3;
+    static constexpr int kInPlanes = 2;
+    static constexpr int kStageBytes = 32768;                       // two planes of 16 KB
+    static constexpr int kStages = kLast ? 4 : 2;
+    static constexpr int kOutBytes = kLast ? 0 : 2 * 32768;         // one staging buffer per epilogue group
     static constexpr int kWeightBytes = kLast ? TowerBlobLast::smem_bytes : TowerBlobMid::smem_bytes;
     static constexpr int kN2 = kLast ? 128 : 64;                    // channels of the second GEMM
-    static constexpr int kBufCols = 128 + kN2;                      // TMEM columns per epilogue group: D1/H + D2
+    // TMEM columns per epilogue group: last block [D1/H 128][D2 128]; mid blocks [D2a 64][D1/H 128][D2b 64] - the
+    // tiles of a group alternate between D2a and D2b, so that the first GEMM of the group's NEXT tile (which also
+    // writes that tile's D2) runs while the epilogue still reads this tile's D2
+    static constexpr int kBufCols = 256;
+    static constexpr int kD1 = kLast ? 0 : 64;                      // column of D1 inside the group's block
     static constexpr int kTmemCols = 512;
     static constexpr int off_stage = kWeightBytes;
-    static constexpr int off_bias1 = off_stage + kStages * kStageBytes;   // [128] f32
+    static constexpr int off_out = off_stage + kStages * kStageBytes;
+    static constexpr int off_bias1 = off_out + kOutBytes;                  // [128] f32
     static constexpr int off_bias2 = off_bias1 + 512;                      // [128] f32
     static constexpr int off_maxprev = off_bias2 + 512;                    // [64] f32
     static constexpr int off_bars = off_maxprev + 256;                     // mbarriers
-    static constexpr int kNumBars = 1 + 2 * kStages + 8;
+    static constexpr int kNumBars = 1 + 2 * kStages + 6;
     static constexpr int off_tmem_slot = off_bars + kNumBars * 8;
     static constexpr int smem_bytes = off_tmem_slot + 16;
 };
+static_assert(TowerCfg<false>::smem_bytes <= 232448 && TowerCfg<true>::smem_bytes <= 232448, "tower kernels: shared memory over the 227 KB limit");
+static_assert(TowerCfg<false>::off_stage % 1024 == 0 && TowerCfg<true>::off_stage % 1024 == 0, "TMA stages need 1024-byte alignment (128B swizzle)");
 
-template <bool kLast, int kPlanesOut>
+template <bool kLast>
 __global__ void __launch_bounds__(kTowerThreads, 1)
 k_tower_mma(const unsigned char *__restrict__ blob, int B, int N, int tiles_per_ep, int box_rows, const __grid_constant__ CUtensorMap in_hi,
-            const __grid_constant__ CUtensorMap in_lo, const __grid_constant__ CUtensorMap in_lo2,
-            const __grid_constant__ CUtensorMap out_hi, const __grid_constant__ CUtensorMap out_lo,
-            const __grid_constant__ CUtensorMap out_lo2, const unsigned *__restrict__ prev_keys, unsigned *__restrict__ max_keys) {
+            const __grid_constant__ CUtensorMap in_lo, const __grid_constant__ CUtensorMap out_hi,
+            const __grid_constant__ CUtensorMap out_lo, const unsigned *__restrict__ prev_keys, unsigned *__restrict__ max_keys) {
     using Cfg = TowerCfg<kLast>;
     using Blob = typename std::conditional<kLast, TowerBlobLast, TowerBlobMid>::type;
     extern __shared__ __align__(1024) unsigned char tower_smem[];
@@ -552,7 +582,7 @@ k_tower_mma(const unsigned char *__restrict__ blob, int B, int N, int tiles_per_
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + Cfg::off_bars);
     uint64_t *w_full = bars;
     uint64_t *x_full = bars + 1, *x_empty = x_full + Cfg::kStages;
-    uint64_t *d1_full = x_empty + Cfg::kStages, *h_full = d1_full + 2, *d2_full = h_full + 2, *t_empty = d2_full + 2;
+    uint64_t *d1_full = x_empty + Cfg::kStages, *h_full = d1_full + 2, *d2_full = h_full + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + Cfg::off_tmem_slot);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -570,15 +600,12 @@ k_tower_mma(const unsigned char *__restrict__ blob, int B, int N, int tiles_per_
             mbar_init(d1_full + g, 1);
             mbar_init(h_full + g, 256);
             mbar_init(d2_full + g, 1);
-            mbar_init(t_empty + g, 256);
         }
         tma_prefetch_map(&in_hi);
         tma_prefetch_map(&in_lo);
-        if (kLast) tma_prefetch_map(&in_lo2);
         if (!kLast) {
             tma_prefetch_map(&out_hi);
             tma_prefetch_map(&out_lo);
-            if (kPlanesOut == 3) tma_prefetch_map(&out_lo2);
         }
     }
     if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
@@ -601,19 +628,19 @@ k_tower_mma(const unsigned char *__restrict__ blob, int B, int N, int tiles_per_
                 mbar_arrive_expect_tx(x_full + s, Cfg::kInPlanes * box_rows * 128);   // a box is min(N, 128) rows
                 tma_load_3d(st, &in_hi, 0, n0, e, x_full + s);
                 tma_load_3d(st + 16384, &in_lo, 0, n0, e, x_full + s);
-                if (kLast) tma_load_3d(st + 32768, &in_lo2, 0, n0, e, x_full + s);
             }
         }
     } else if (warp == 1) {
-        // ============================== MMA issuer ==============================
-        if (lane == 0) {
+        // ============================== MMA issuer (whole warp, converged; see mma_ss) ==============================
+        {
             const uint32_t sbase = smem_u32(smem);
 
             // second GEMM of tile i (its h is in TMEM): D2 (+)= H * W2^T, three passes over 8 K-chunks
             auto issue_c2 = [&](int i) {
                 const int g = i & 1;
                 tc_fence_after();
-                const uint32_t d1 = tmem_base + g * Cfg::kBufCols, d2 = d1 + 128;
+                const uint32_t d1 = tmem_base + g * Cfg::kBufCols + Cfg::kD1;
+                const uint32_t d2 = kLast ? d1 + 128 : (((i >> 1) & 1) ? d1 + 128 : d1 - 64);
 #pragma unroll
                 for (int pass = 0; pass < kTowerPasses; ++pass) {
                     const int a_lo = tower_pass_a(pass) ? 16 : 0;               // the lo pairs sit 16 columns after the hi pairs
@@ -634,51 +661,49 @@ k_tower_mma(const unsigned char *__restrict__ blob, int B, int N, int tiles_per_
                 const int s = i % Cfg::kStages, g = i & 1;
                 tc_fence_after();
                 const uint32_t xs = sbase + Cfg::off_stage + s * Cfg::kStageBytes;
-                const uint32_t d1 = tmem_base + g * Cfg::kBufCols, d2 = d1 + 128;
+                // mid blocks: Wsa and W1a are stacked into one 192-row B operand and D2's columns adjoin D1's, so one
+                // MMA per K-chunk produces both X * W1a^T (128 columns) and the shortcut product X * Wsa^T (64 columns):
+                // {D2a, D1} from rows {Wsa, W1a} for the group's even tiles, {D1, D2b} from rows {W1a, Wsa} for its odd ones
+                constexpr int n1 = kLast ? 128 : 192;
+                const bool second = ((i >> 1) & 1) != 0;
+                const uint32_t dst = tmem_base + g * Cfg::kBufCols + (kLast || second ? Cfg::kD1 : 0);
 #pragma unroll
                 for (int pass = 0; pass < kTowerPasses; ++pass) {
                     const uint32_t xa = xs + (tower_pass_a(pass) ? 16384 : 0);
-                    const uint32_t w1 = sbase + (tower_pass_b(pass) ? Blob::w1_lo : Blob::w1_hi);
-                    const uint32_t idesc = tower_idesc(128, pass);
+                    uint32_t w1 = sbase + (tower_pass_b(pass) ? Blob::w1_lo : Blob::w1_hi);
+                    if (!kLast && !second) w1 -= 8192;                       // start at the leading copy of Wsa
+                    const uint32_t idesc = tower_idesc(n1, pass);
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk)
-                        mma_ss(d1, umma_desc_sw128(xa + kk * 32), umma_desc_sw128(w1 + kk * 32), idesc, (pass | kk) != 0);
-                }
-                if (!kLast) {
-#pragma unroll
-                    for (int pass = 0; pass < kTowerPasses; ++pass) {
-                        const uint32_t xa = xs + (tower_pass_a(pass) ? 16384 : 0);
-                        const uint32_t ws = sbase + (tower_pass_b(pass) ? TowerBlobMid::ws_lo : TowerBlobMid::ws_hi);
-                        const uint32_t idesc = tower_idesc(64, pass);
-#pragma unroll
-                        for (int kk = 0; kk < 4; ++kk)
-                            mma_ss(d2, umma_desc_sw128(xa + kk * 32), umma_desc_sw128(ws + kk * 32), idesc, (pass | kk) != 0);
-                    }
+                        mma_ss(dst, umma_desc_sw128(xa + kk * 32), umma_desc_sw128(w1 + kk * 32), idesc, (pass | kk) != 0);
                 }
                 tc_commit(d1_full + g);
+                if (!kLast) tc_commit(x_empty + s);      // both products of x are done when this fires: refill the stage
             };
             mbar_wait(w_full, 0);
-            // Issue whichever GEMM is READY, the second GEMM of an older tile first: with a fixed order (C1(i), C2(i-1), ...)
-            // C2(i-1) queued behind a C1(i) that was itself waiting for the OTHER epilogue group to free its accumulators,
-            // and the two groups ran one after the other instead of side by side (5600 cycles per tile, ncu).
-            int n1 = 0, n2 = 0;   // tiles whose first / second GEMM has been issued
-            while (n2 < ntiles) {
-                bool did = false;
-                if (n2 < n1 && mbar_test(h_full + (n2 & 1), (n2 >> 1) & 1)) {
-                    issue_c2(n2);
-                    ++n2;
-                    did = true;
+            __syncwarp();
+            // Issue order: C1(0), C1(1), then for every tile i: C2(i), C1(i + 2).  The tensor pipe executes in issue
+            // order, so C1(i + 2) - which overwrites the D1/H columns C2(i) reads - needs no barrier of its own; its D2
+            // buffer (mid: the group's other one; last: written by the epilogue, not by C1) was released before the
+            // group arrived on h_full(i).  The first GEMM of a group's next tile therefore runs while the group is still
+            // in this tile's second epilogue: with C1(i + 2) held back until that epilogue had finished, each group
+            // sat through C1 + E1 + C2 + E2 in series (3500 cycles per tile, ncu).
+            auto wait_x = [&](int i) {
+                mbar_wait(x_full + i % Cfg::kStages, (i / Cfg::kStages) & 1);
+                __syncwarp();
+            };
+            for (int i = 0; i < 2 && i < ntiles; ++i) {
+                wait_x(i);
+                issue_c1(i);
+            }
+            for (int i = 0; i < ntiles; ++i) {
+                mbar_wait(h_full + (i & 1), (i >> 1) & 1);
+                __syncwarp();
+                issue_c2(i);
+                if (i + 2 < ntiles) {
+                    wait_x(i + 2);
+                    issue_c1(i + 2);
                 }
-                if (!did && n1 < ntiles && n1 - n2 < 2) {
-                    const int i = n1;
-                    if (mbar_test(x_full + i % Cfg::kStages, (i / Cfg::kStages) & 1) &&
-                        (i < 2 || mbar_test(t_empty + (i & 1), ((i >> 1) - 1) & 1))) {
-                        issue_c1(i);
-                        ++n1;
-                        did = true;
-                    }
-                }
-                if (!did) __nanosleep(32);
             }
         }
     } else if (warp >= 4) {
@@ -690,7 +715,7 @@ k_tower_mma(const unsigned char *__restrict__ blob, int B, int N, int tiles_per_
         const int p = wq * 32 + lane;                   // point of the tile = TMEM lane
         const int etid = tid - 128;                     // 0..511 over both groups
         const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
-        const uint32_t d1 = tmem_base + g * Cfg::kBufCols + lane_addr, d2 = d1 + 128;
+        const uint32_t d1 = tmem_base + g * Cfg::kBufCols + Cfg::kD1 + lane_addr;
         constexpr int kChunks2 = Cfg::kN2 / 32;         // 32-column chunks of D2 (2 | 4): half h takes [h, h + 1) * kChunks2 / 2
         constexpr int kMine2 = kChunks2 / 2;
         float mx[kMine2];
@@ -752,8 +777,13 @@ k_tower_mma(const unsigned char *__restrict__ blob, int B, int N, int tiles_per_
         };
 
         // both groups walk the CTA's tile list in the same order so that they meet at episode boundaries
+        int e = t0 / tiles_per_ep, n0 = (t0 - e * tiles_per_ep) * kTowerTile - kTowerTile;   // walked without a division per tile
         for (int i = 0; i < ntiles; ++i) {
-            const int t = t0 + i, e = t / tiles_per_ep, n0 = (t - e * tiles_per_ep) * kTowerTile;
+            n0 += kTowerTile;
+            if (n0 >= tiles_per_ep * kTowerTile) {
+                n0 = 0;
+                ++e;
+            }
             if (e != cur_ep) {
                 flush();
                 setup_episode(e);
@@ -762,8 +792,10 @@ k_tower_mma(const unsigned char *__restrict__ blob, int B, int N, int tiles_per_
             if ((i & 1) != g) continue;
             const int s = i % Cfg::kStages;
             const uint32_t par = (i >> 1) & 1;
+            const uint32_t d2 = kLast ? d1 + 128 : (par ? d1 + 128 : d1 - 64);   // mid: the group's D2 buffers alternate
             const bool valid = n0 + p < N;
-            unsigned char *stage = smem + Cfg::off_stage + s * Cfg::kStageBytes;
+            unsigned char *stage = smem + Cfg::off_stage + s * Cfg::kStageBytes;   // input planes (last block reads them)
+            unsigned char *ostage = smem + Cfg::off_out + g * 32768;               // this group's output staging (mid)
 
             // ---- E1: D1 -> h = lrelu(D1 + bias1) -> bf16 hi|lo pairs back into the same TMEM columns ----
             mbar_wait(d1_full + g, par);
@@ -790,7 +822,7 @@ k_tower_mma(const unsigned char *__restrict__ blob, int B, int N, int tiles_per_
             }
             if (kLast) {
                 mbar_wait(x_full + s, (i / Cfg::kStages) & 1);   // observe the TMA's writes ourselves before reading them
-                // D2 starts as bias + identity shortcut: feat (exact: hi + lo + lo2) for c < 64, max_prev for c >= 64
+                // D2 starts as bias + identity shortcut: feat (hi + lo) for c < 64, max_prev for c >= 64
 #pragma unroll
                 for (int jj = 0; jj < 2; ++jj) {
                     const int j = 2 * half + jj;
@@ -804,13 +836,12 @@ k_tower_mma(const unsigned char *__restrict__ blob, int B, int N, int tiles_per_
                             const int off = p * 128 + (((4 * j + q) ^ (p & 7)) << 4);
                             const uint4 xh = *reinterpret_cast<const uint4 *>(stage + off);
                             const uint4 xl = *reinterpret_cast<const uint4 *>(stage + 16384 + off);
-                            const uint4 xl2 = *reinterpret_cast<const uint4 *>(stage + 32768 + off);
-                            const unsigned *ph = &xh.x, *pl = &xl.x, *pl2 = &xl2.x;
+                            const unsigned *ph = &xh.x, *pl = &xl.x;
 #pragma unroll
                             for (int e2 = 0; e2 < 4; ++e2) {
-                                const float2 hf = unpack2(ph[e2]), lf = unpack2(pl[e2]), l2f = unpack2(pl2[e2]);
-                                const float x0 = __fadd_rn(__fadd_rn(hf.x, lf.x), l2f.x);
-                                const float x1 = __fadd_rn(__fadd_rn(hf.y, lf.y), l2f.y);
+                                const float2 hf = unpack2(ph[e2]), lf = unpack2(pl[e2]);
+                                const float x0 = __fadd_rn(hf.x, lf.x);
+                                const float x1 = __fadd_rn(hf.y, lf.y);
                                 o[2 * e2] = __fadd_rn(o[2 * e2], x0);
                                 o[2 * e2 + 1] = __fadd_rn(o[2 * e2 + 1], x1);
                             }
@@ -827,6 +858,11 @@ k_tower_mma(const unsigned char *__restrict__ blob, int B, int N, int tiles_per_
             if (kLast) mbar_arrive(x_empty + s);         // this thread's reads of the input stage are done
 
             // ---- E2: D2 -> out = lrelu(D2 [+ bias2]) -> running max (+ staged 16-bit planes -> TMA store) ----
+            if (!kLast) {
+                // the staging buffer is free again once the TMA store of this group's previous tile has read it
+                if ((ew & 7) == 0 && lane == 0) tma_store_3d_wait_read();
+                named_bar_sync(2 + g, 256);
+            }
             mbar_wait(d2_full + g, par);
             tc_fence_after();
 #pragma unroll
@@ -853,7 +889,7 @@ k_tower_mma(const unsigned char *__restrict__ blob, int B, int N, int tiles_per_
                         v[4 * q + 3] = b.y;
                     }
                 }
-                if (!kLast) tower_stage_chunk<kPlanesOut>(stage, 16384, p, j, v);
+                if (!kLast) tower_stage_chunk<2>(ostage, 16384, p, j, v);
                 if (kMidRegMax) {
                     if (valid) {
 #pragma unroll
@@ -867,22 +903,18 @@ k_tower_mma(const unsigned char *__restrict__ blob, int B, int N, int tiles_per_
                     mx[jj] = max_nan(mx[jj], warp_transpose_max(v, lane));
                 }
             }
-            tc_fence_before();
-            mbar_arrive(t_empty + g);                    // D1/H and D2 of this group may be overwritten
             if (!kLast) {
                 fence_async_proxy();
                 named_bar_sync(2 + g, 256);
                 if ((ew & 7) == 0 && lane == 0) {
-                    tma_store_3d(&out_hi, 0, n0, e, stage);
-                    tma_store_3d(&out_lo, 0, n0, e, stage + 16384);
-                    if (kPlanesOut == 3) tma_store_3d(&out_lo2, 0, n0, e, stage + 32768);
+                    tma_store_3d(&out_hi, 0, n0, e, ostage);
+                    tma_store_3d(&out_lo, 0, n0, e, ostage + 16384);
                     bulk_commit();
-                    tma_store_3d_wait_read();
-                    mbar_arrive(x_empty + s);            // the stage may be refilled
                 }
             }
         }
         flush();
+        if (!kLast && (ew & 7) == 0 && lane == 0) tma_store_3d_wait_all();   // the next block reads these planes
     }
     tc_fence_before();
     __syncthreads();
