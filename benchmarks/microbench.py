@@ -235,7 +235,7 @@ def tower_bench(args):
     res = {"bench": "tower", "B": B, "N": N, "tower_ms": t * 1e3, "points_per_s": B * N / t,
            "tflops_reference_count": 2.0 * macs_ref * B * N / t / 1e12, "tflops_executed_logical": 2.0 * macs_here * B * N / t / 1e12,
            "tensor_passes_per_product": 3, "tflops_tensor_pipe": 3 * 2.0 * (macs_here - 665) * B * N / t / 1e12,
-           "hbm_bytes_per_point": 20 + 256 * 2 + 256 + 256 + 384 + 384, }
+           "hbm_bytes_per_point": 20 + 256 * 6, }   # obs3d + three feature maps (two fp16 planes) written and read once
     res["hbm_gbs"] = res["hbm_bytes_per_point"] * B * N / t / 1e9
     res["hbm_frac"] = res["hbm_gbs"] / PEAK
     try:

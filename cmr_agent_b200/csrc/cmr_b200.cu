@@ -1082,7 +1082,7 @@ int cmr_tower_forward(const float *obs3d, const void *blob1, const void *blob2, 
         const size_t smem = 32768 + TowerBlobFirst::total;
         int rc = allow_smem(k_tower_first, smem);
         if (rc) return rc;
-        const int grid = std::min(B * tiles_per_ep, 4 * sm_count());
+        const int grid = std::min(B * tiles_per_ep, 6 * sm_count());   // 6 CTAs fit an SM (registers, shared memory)
         rc = launch_pdl(k_tower_first, dim3(grid), dim3(128), smem, st, obs3d, static_cast<const unsigned char *>(blob1), B, N,
                         tiles_per_ep, m[0], m[1], keys1);
         if (rc) return rc;

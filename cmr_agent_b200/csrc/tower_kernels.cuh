@@ -33,16 +33,28 @@
 //       128B swizzle: exactly the K-major UMMA layout), h is written BACK INTO TMEM by the epilogue as packed bf16
 //       pairs over the accumulator it was read from, and the second GEMM takes its A operand from TMEM.
 //   B operand = weights, pre-split and pre-swizzled once by k_tower_pack, resident in shared memory.
-// Features travel between the blocks as 16-bit planes [B][N][64] (hi, lo; a third plane lo2 after block 3, whose
-// consumer adds them back to an exact fp32 for the identity shortcut) - 4 bytes per value, as fp32 would be.
+// Features travel between the blocks as two fp16 planes [B][N][64] (hi, lo) - 4 bytes per value, as fp32 would be;
+// block 4 adds them back (hi + lo, 22 bits) for its identity shortcut.
 //
-// Warp roles of k_tower_mma (640 threads): warp 0 = TMA producer, warp 1 = TMEM allocation + MMA issue (one
-// elected lane), warps 4-11 and 12-19 = two epilogue groups working on alternate tiles, each with its own TMEM
-// accumulators (D1/H 128 columns + D2 64|128 columns), so that the tensor pipe works on tile t+1 while tile t is
-// in the epilogue.  A group is 8 warps: two per TMEM lane quarter, each taking half of the accumulator's columns
-// (a warp's dependent instructions issue every ~5 cycles; two epilogue warps per scheduler left the issue slots
-// 65 % idle - ncu, profiles/r2_tower_ncu.txt - four fill them).  A CTA owns a contiguous range of 128-point tiles; when the range crosses into the next
-// episode the epilogue groups flush their running maxima, recompute the per-episode biases and go on.
+// Warp roles of k_tower_mma (608 threads):
+//   warp 0       TMA loads: the weights once, then a ring of input stages (two 16 KB planes each)
+//   warp 1       TMEM allocation + MMA issue.  The whole warp runs converged and every tcgen05.mma elects its lane
+//                itself (see mma_ss).  Order: C1(0), C1(1), then per tile i: C2(i), C1(i + 2) - the tensor pipe
+//                executes in issue order, so the first GEMM of tile i + 2 needs no barrier against the second GEMM
+//                of tile i whose H columns it overwrites.  Mid blocks: one N = 192 MMA per K-chunk covers GEMM 1
+//                and the shortcut product, and tcgen05.commit hands the input stage back to the TMA warp.
+//   warps 2-17   epilogue, ONE software-pipelined group: warp = (TMEM lane quarter) x (column quarter).  Per tile
+//                they run E1(i + 1) (D1 -> h -> fp16 pairs back into TMEM) BEFORE E2(i) (D2 -> output, maxima), so
+//                the second GEMM of tile i has a whole E1 to complete.  TMEM holds two tiles (2 x 256 columns; mid
+//                blocks: [D2a 64][D1 128][D2b 64] with the D2 buffers alternating).  Running maxima stay per point
+//                lane in registers and cross the warp once per episode.
+//   warp 18      TMA stores (mid blocks): takes each staged output tile over through an mbarrier.
+// A CTA owns a contiguous range of 128-point tiles; when the range crosses into the next episode the epilogue
+// recomputes the per-episode biases (double-buffered by episode parity, E1 may be an episode ahead of E2).
+// How it got here (ncu, profiles/r2_tower_ncu.txt; cycles per 128-point tile of a mid block): 4550 with MMAs issued
+// from an `if (lane == 0)` region (the issuing thread was the bottleneck), 3500 with elected issue + N = 192,
+// 3400 with C1 issued behind C2, 3050 with the pipelined epilogue group, register maxima and the store warp.
+// The floors: tensor pipe 1920, HBM 2140, shared-memory traffic ~2060, issue slots ~1700 - all 60-65 % busy.
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -53,7 +65,7 @@ namespace cmr {
 
 constexpr int kTowerF = 64;            // embed_dim (config/KittiConfig.py:63)
 constexpr int kTowerTile = 128;        // points per tile = UMMA M
-constexpr int kTowerThreads = 640;      // 4 service warps + 16 epilogue warps
+constexpr int kTowerThreads = 608;      // TMA-load warp + MMA warp + 16 epilogue warps + TMA-store warp
 constexpr float kTowerSlope = 0.2f;    // LeakyReLU(negative_slope=0.2), PointNN.py:267,272
 #ifndef CMR_TOWER_PASSES
 #define CMR_TOWER_PASSES 3
@@ -273,6 +285,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr)
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
@@ -412,6 +431,26 @@ __device__ __forceinline__ void tower_stage_chunk(unsigned char *planes, int pla
         *reinterpret_cast<uint4 *>(planes + off) = hi;
         *reinterpret_cast<uint4 *>(planes + plane_bytes + off) = lo;
         if (kPlanes == 3) *reinterpret_cast<uint4 *>(planes + 2 * plane_bytes + off) = lo2;
+    }
+}
+
+// the same for 16 channels [16 * cq, 16 * cq + 16) of the row: two 16-byte chunks per plane
+__device__ __forceinline__ void tower_stage_cols16(unsigned char *planes, int plane_bytes, int p, int cq, const float (&v)[16]) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        uint4 hi, lo;
+        unsigned *ph = &hi.x, *pl = &lo.x;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 ab = make_float2(v[q * 8 + 2 * e], v[q * 8 + 2 * e + 1]);
+            const unsigned h = pack2(ab.x, ab.y);
+            const float2 res = sub2(ab, unpack2(h));
+            ph[e] = h;
+            pl[e] = pack2(res.x, res.y);
+        }
+        const int off = p * 128 + (((2 * cq + q) ^ (p & 7)) << 4);
+        *reinterpret_cast<uint4 *>(planes + off) = hi;
+        *reinterpret_cast<uint4 *>(planes + plane_bytes + off) = lo;
     }
 }
 
@@ -556,11 +595,11 @@ struct TowerCfg {
     static constexpr int kTmemCols = 512;
     static constexpr int off_stage = kWeightBytes;
     static constexpr int off_out = off_stage + kStages * kStageBytes;
-    static constexpr int off_bias1 = off_out + kOutBytes;                  // [128] f32
-    static constexpr int off_bias2 = off_bias1 + 512;                      // [128] f32
-    static constexpr int off_maxprev = off_bias2 + 512;                    // [64] f32
+    static constexpr int off_bias1 = off_out + kOutBytes;                  // [2][128] f32 (by episode parity)
+    static constexpr int off_bias2 = off_bias1 + 1024;                     // [2][128] f32
+    static constexpr int off_maxprev = off_bias2 + 1024;                   // [64] f32
     static constexpr int off_bars = off_maxprev + 256;                     // mbarriers
-    static constexpr int kNumBars = 1 + 2 * kStages + 6;
+    static constexpr int kNumBars = 1 + 2 * kStages + 6 + 4;
     static constexpr int off_tmem_slot = off_bars + kNumBars * 8;
     static constexpr int smem_bytes = off_tmem_slot + 16;
 };
@@ -583,6 +622,7 @@ k_tower_mma(const unsigned char *__restrict__ blob, int B, int N, int tiles_per_
     uint64_t *w_full = bars;
     uint64_t *x_full = bars + 1, *x_empty = x_full + Cfg::kStages;
     uint64_t *d1_full = x_empty + Cfg::kStages, *h_full = d1_full + 2, *d2_full = h_full + 2;
+    uint64_t *o_full = d2_full + 2, *o_free = o_full + 2;      // output staging buffers (mid blocks)
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + Cfg::off_tmem_slot);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -594,12 +634,14 @@ k_tower_mma(const unsigned char *__restrict__ blob, int B, int N, int tiles_per_
         mbar_init(w_full, 1);
         for (int s = 0; s < Cfg::kStages; ++s) {
             mbar_init(x_full + s, 1);
-            mbar_init(x_empty + s, kLast ? 256 : 1);
+            mbar_init(x_empty + s, kLast ? 512 : 1);
         }
         for (int g = 0; g < 2; ++g) {
             mbar_init(d1_full + g, 1);
-            mbar_init(h_full + g, 256);
+            mbar_init(h_full + g, 512);
             mbar_init(d2_full + g, 1);
+            mbar_init(o_full + g, 512);
+            mbar_init(o_free + g, 1);
         }
         tma_prefetch_map(&in_hi);
         tma_prefetch_map(&in_lo);
@@ -706,215 +748,245 @@ k_tower_mma(const unsigned char *__restrict__ blob, int B, int N, int tiles_per_
                 }
             }
         }
-    } else if (warp >= 4) {
-        // ============================== epilogue groups ==============================
-        const int ew = warp - 4;                        // 0..15
-        const int g = ew >> 3;                          // group 0: warps 4-11, group 1: warps 12-19 -> tiles i = g (mod 2)
-        const int half = (ew >> 2) & 1;                 // which half of the accumulators' columns this warp takes
+    } else if (warp == 18) {
+        // ============================== TMA-store warp (mid blocks) ==============================
+        // The epilogue warps hand a staged tile over through an mbarrier and go on; with a 512-thread bar.sync before
+        // the store every warp waited for the slowest one, once per tile (13 % of the epilogue's time, ncu).
+        if (!kLast && lane == 0) {
+            int e = t0 / tiles_per_ep, n0 = (t0 - e * tiles_per_ep) * kTowerTile - kTowerTile;
+            for (int i = 0; i < ntiles; ++i) {
+                n0 += kTowerTile;
+                if (n0 >= tiles_per_ep * kTowerTile) {
+                    n0 = 0;
+                    ++e;
+                }
+                const int b = i & 1;
+                unsigned char *ostage = smem + Cfg::off_out + b * 32768;
+                mbar_wait(o_full + b, (i >> 1) & 1);
+                tma_store_3d(&out_hi, 0, n0, e, ostage);
+                tma_store_3d(&out_lo, 0, n0, e, ostage + 16384);
+                bulk_commit();
+                tma_store_3d_wait_read();
+                mbar_arrive(o_free + b);
+            }
+            tma_store_3d_wait_all();                     // the next block reads these planes
+        }
+    } else {
+        // ============================== epilogue (16 warps, one software-pipelined group) ==============================
+        // Warp = (TMEM lane quarter wq = warp % 4) x (column quarter cq): it owns 32 of D1's 128 columns and a quarter
+        // of D2's.  Per tile i the warps run E1(i + 1) BEFORE E2(i): the second GEMM of tile i has the whole of
+        // E1(i + 1) to complete, so the wait for it is hidden (two alternating groups each sat in that wait 26 % of
+        // the time, ncu).  The running maxima stay per point lane in registers (16 | 32 per thread) and are exchanged
+        // across the warp only when an episode ends.
+        const int ew = warp - 2;                        // 0..15
+        const int cq = ew >> 2;                         // column quarter
         const int wq = warp & 3;                        // TMEM lane quarter this warp may touch
         const int p = wq * 32 + lane;                   // point of the tile = TMEM lane
-        const int etid = tid - 128;                     // 0..511 over both groups
+        const int etid = tid - 64;                      // 0..511
         const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
-        const uint32_t d1 = tmem_base + g * Cfg::kBufCols + Cfg::kD1 + lane_addr;
-        constexpr int kChunks2 = Cfg::kN2 / 32;         // 32-column chunks of D2 (2 | 4): half h takes [h, h + 1) * kChunks2 / 2
-        constexpr int kMine2 = kChunks2 / 2;
-        float mx[kMine2];
+        constexpr int kC2 = Cfg::kN2 / 4;               // D2 columns per warp: 16 (mid) | 32 (last)
+        float rmx[kC2];
 #pragma unroll
-        for (int j = 0; j < kMine2; ++j) mx[j] = -INFINITY;
-        // blocks 2, 3 (one 32-channel chunk per warp): the running maxima stay per POINT LANE in registers across the
-        // tiles of an episode - one max per value - and are exchanged across the warp once, when they are flushed
-        constexpr bool kMidRegMax = !kLast && kTowerRegMax;
-        constexpr int kRegMax = kMidRegMax ? 32 : 1;
-        float rmx[kRegMax];
-#pragma unroll
-        for (int q = 0; q < kRegMax; ++q) rmx[q] = -INFINITY;
-        int cur_ep = -1;
+        for (int q = 0; q < kC2; ++q) rmx[q] = -INFINITY;
+        const int e_first = t0 / tiles_per_ep;
         pdl_wait();                                      // prev_keys are the previous kernel's output
 
-        auto flush = [&]() {
-            if (kMidRegMax) {
-                float t[32];
-#pragma unroll
-                for (int q = 0; q < 32; ++q) t[q] = rmx[q < kRegMax ? q : 0];
-                mx[0] = warp_transpose_max(t, lane);
-#pragma unroll
-                for (int q = 0; q < kRegMax; ++q) rmx[q] = -INFINITY;
-            }
-            if (cur_ep >= 0) {
-#pragma unroll
-                for (int j = 0; j < kMine2; ++j)
-                    atomicMax(max_keys + cur_ep * Cfg::kN2 + 32 * (half * kMine2 + j) + lane, f2key(kLast ? lrelu(mx[j]) : mx[j]));
-            }
-#pragma unroll
-            for (int j = 0; j < kMine2; ++j) mx[j] = -INFINITY;
-        };
-        // per-episode biases (both groups together: 512 threads, named barrier 1)
+        // per-episode biases, double-buffered by episode parity (E1 may be one episode ahead of E2)
         auto setup_episode = [&](int e) {
-            named_bar_sync(1, 512);                      // everybody is done with the previous episode's biases
-            if (etid < 64) maxprev[etid] = key2f(prev_keys[e * 64 + etid]);
+            const int buf = (e - e_first) & 1;
+            float *b1 = bias1 + buf * 128, *b2 = bias2 + buf * 128;
+            // bias1[c] = b1[c] + sum_k W1[c][64 + k] * max_prev[k]: 8 channels per warp, the 64 terms in four slices of 16
+            // across the lanes; bias2[c] = (b2 + bs)[c] + sum_k Ws[c][64 + k] * max_prev[k] (mid): 4 channels per warp,
+            // eight slices of 8.  Every weight load is issued up front and is in flight together with the previous
+            // block's maxima (a 64-step loop per thread was a chain of L2 round trips: ~5 us per episode change, ncu).
+            const int c1 = 8 * ew + (lane & 7), ks1 = lane >> 3;
+            const int c2 = 4 * ew + (lane & 3), ks2 = lane >> 2;
+            float wv1[16], wv2[kLast ? 1 : 8];
+            {
+                const float *w = reinterpret_cast<const float *>(blob + Blob::w1bT) + (ks1 * 16) * 128 + c1;
+#pragma unroll
+                for (int k = 0; k < 16; ++k) wv1[k] = __ldg(w + k * 128);
+            }
+            if (!kLast) {
+                const float *w = reinterpret_cast<const float *>(blob + TowerBlobMid::wsbT) + (ks2 * 8) * 64 + c2;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) wv2[k < (kLast ? 1 : 8) ? k : 0] = __ldg(w + k * 64);
+            }
+            const float g1 = __ldg(reinterpret_cast<const float *>(blob + Blob::b1) + c1);
+            const float g2 = __ldg(reinterpret_cast<const float *>(blob + Blob::b2) + (kLast ? (etid & 127) : c2));
+            const float mp = etid < 64 ? key2f(prev_keys[e * 64 + etid]) : 0.f;
+            named_bar_sync(1, 512);                      // everybody is past the E2 of the tile before last: buf is free
+            if (etid < 64) maxprev[etid] = mp;
             named_bar_sync(1, 512);
-            if (etid < 128) {
-                const float *w = reinterpret_cast<const float *>(blob + Blob::w1bT);
-                float a = reinterpret_cast<const float *>(blob + Blob::b1)[etid];
-#pragma unroll 8
-                for (int k = 0; k < 64; ++k) a = __fmaf_rn(__ldg(w + k * 128 + etid), maxprev[k], a);
-                bias1[etid] = a;
-            } else if (!kLast) {
-                if (etid < 192) {
-                    const int c = etid - 128;
-                    const float *w = reinterpret_cast<const float *>(blob + TowerBlobMid::wsbT);
-                    float a = reinterpret_cast<const float *>(blob + TowerBlobMid::b2)[c];
-#pragma unroll 8
-                    for (int k = 0; k < 64; ++k) a = __fmaf_rn(__ldg(w + k * 64 + c), maxprev[k], a);
-                    bias2[c] = a;
-                }
-            } else if (etid < 256) {
-                const int c = etid - 128;
-                const float b = reinterpret_cast<const float *>(blob + TowerBlobLast::b2)[c];
-                bias2[c] = c >= 64 ? __fadd_rn(b, maxprev[c - 64]) : b;
+            {
+                float a = 0.f;
+#pragma unroll
+                for (int k = 0; k < 16; ++k) a = __fmaf_rn(wv1[k], maxprev[ks1 * 16 + k], a);
+                a = __fadd_rn(a, __shfl_xor_sync(kFull, a, 8));
+                a = __fadd_rn(a, __shfl_xor_sync(kFull, a, 16));
+                if (ks1 == 0) b1[c1] = __fadd_rn(a, g1);
+            }
+            if (!kLast) {
+                float a = 0.f;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) a = __fmaf_rn(wv2[k < (kLast ? 1 : 8) ? k : 0], maxprev[ks2 * 8 + k], a);
+                a = __fadd_rn(a, __shfl_xor_sync(kFull, a, 4));
+                a = __fadd_rn(a, __shfl_xor_sync(kFull, a, 8));
+                a = __fadd_rn(a, __shfl_xor_sync(kFull, a, 16));
+                if (ks2 == 0) b2[c2] = __fadd_rn(a, g2);
+            } else if (etid < 128) {
+                b2[etid] = etid >= 64 ? __fadd_rn(g2, maxprev[etid - 64]) : g2;
             }
             named_bar_sync(1, 512);
         };
+        // an episode's maxima leave the registers: lane l of the warp ends up with channel l of the warp's columns
+        auto flush = [&](int e) {
+            float t[32];
+#pragma unroll
+            for (int q = 0; q < 32; ++q) t[q] = q < kC2 ? rmx[q < kC2 ? q : 0] : -INFINITY;
+            const float m = warp_transpose_max(t, lane);
+            if (lane < kC2) atomicMax(max_keys + e * Cfg::kN2 + kC2 * cq + lane, f2key(kLast ? lrelu(m) : m));
+#pragma unroll
+            for (int q = 0; q < kC2; ++q) rmx[q] = -INFINITY;
+        };
 
-        // both groups walk the CTA's tile list in the same order so that they meet at episode boundaries
-        int e = t0 / tiles_per_ep, n0 = (t0 - e * tiles_per_ep) * kTowerTile - kTowerTile;   // walked without a division per tile
-        for (int i = 0; i < ntiles; ++i) {
-            n0 += kTowerTile;
-            if (n0 >= tiles_per_ep * kTowerTile) {
-                n0 = 0;
-                ++e;
+        // ---- E1(i): D1 -> h = lrelu(D1 + bias1) -> fp16 hi|lo pairs back into the same TMEM columns ----
+        int e1 = e_first, n1 = (t0 - e1 * tiles_per_ep) * kTowerTile - kTowerTile, ep1 = -1;   // walked without divisions
+        auto step_e1 = [&](int i) {
+            n1 += kTowerTile;
+            if (n1 >= tiles_per_ep * kTowerTile) {
+                n1 = 0;
+                ++e1;
             }
-            if (e != cur_ep) {
-                flush();
-                setup_episode(e);
-                cur_ep = e;
+            if (e1 != ep1) {
+                setup_episode(e1);
+                ep1 = e1;
             }
-            if ((i & 1) != g) continue;
-            const int s = i % Cfg::kStages;
+            const int g = i & 1;
             const uint32_t par = (i >> 1) & 1;
-            const uint32_t d2 = kLast ? d1 + 128 : (par ? d1 + 128 : d1 - 64);   // mid: the group's D2 buffers alternate
-            const bool valid = n0 + p < N;
-            unsigned char *stage = smem + Cfg::off_stage + s * Cfg::kStageBytes;   // input planes (last block reads them)
-            unsigned char *ostage = smem + Cfg::off_out + g * 32768;               // this group's output staging (mid)
-
-            // ---- E1: D1 -> h = lrelu(D1 + bias1) -> bf16 hi|lo pairs back into the same TMEM columns ----
+            const float *b1 = bias1 + ((e1 - e_first) & 1) * 128 + 32 * cq;
+            const uint32_t d1 = tmem_base + g * Cfg::kBufCols + Cfg::kD1 + lane_addr + 32 * cq;
             mbar_wait(d1_full + g, par);
             tc_fence_after();
-#pragma unroll
-            for (int jj = 0; jj < 2; ++jj) {
-                const int j = 2 * half + jj;
+            {
                 uint32_t r[32];
-                tmem_ld32(d1 + 32 * j, r);
+                tmem_ld32(d1, r);
                 tc_wait_ld();
                 uint32_t hi[16], lo[16];
 #pragma unroll
                 for (int q = 0; q < 16; ++q) {
-                    const float2 bb = *reinterpret_cast<const float2 *>(bias1 + 32 * j + 2 * q);
+                    const float2 bb = *reinterpret_cast<const float2 *>(b1 + 2 * q);
                     const float2 ab = lrelu2(add2(make_float2(__uint_as_float(r[2 * q]), __uint_as_float(r[2 * q + 1])), bb));
                     const unsigned h = pack2(ab.x, ab.y);
                     const float2 res = sub2(ab, unpack2(h));
                     hi[q] = h;
                     lo[q] = pack2(res.x, res.y);
                 }
-
-                tmem_st16(d1 + 32 * j, hi);
-                tmem_st16(d1 + 32 * j + 16, lo);
+                tmem_st16(d1, hi);
+                tmem_st16(d1 + 16, lo);
             }
             if (kLast) {
+                const int s = i % Cfg::kStages;
+                const unsigned char *stage = smem + Cfg::off_stage + s * Cfg::kStageBytes;
+                const float *b2 = bias2 + ((e1 - e_first) & 1) * 128 + 32 * cq;
                 mbar_wait(x_full + s, (i / Cfg::kStages) & 1);   // observe the TMA's writes ourselves before reading them
                 // D2 starts as bias + identity shortcut: feat (hi + lo) for c < 64, max_prev for c >= 64
+                uint32_t r[32];
 #pragma unroll
-                for (int jj = 0; jj < 2; ++jj) {
-                    const int j = 2 * half + jj;
-                    uint32_t r[32];
+                for (int q = 0; q < 4; ++q) {
+                    const float4 b0 = *reinterpret_cast<const float4 *>(b2 + 8 * q);
+                    const float4 b4 = *reinterpret_cast<const float4 *>(b2 + 8 * q + 4);
+                    float o[8] = {b0.x, b0.y, b0.z, b0.w, b4.x, b4.y, b4.z, b4.w};
+                    if (cq < 2) {
+                        const int off = p * 128 + (((4 * cq + q) ^ (p & 7)) << 4);
+                        const uint4 xh = *reinterpret_cast<const uint4 *>(stage + off);
+                        const uint4 xl = *reinterpret_cast<const uint4 *>(stage + 16384 + off);
+                        const unsigned *ph = &xh.x, *pl = &xl.x;
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float4 b0 = *reinterpret_cast<const float4 *>(bias2 + 32 * j + 8 * q);
-                        const float4 b1 = *reinterpret_cast<const float4 *>(bias2 + 32 * j + 8 * q + 4);
-                        float o[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-                        if (j < 2) {
-                            const int off = p * 128 + (((4 * j + q) ^ (p & 7)) << 4);
-                            const uint4 xh = *reinterpret_cast<const uint4 *>(stage + off);
-                            const uint4 xl = *reinterpret_cast<const uint4 *>(stage + 16384 + off);
-                            const unsigned *ph = &xh.x, *pl = &xl.x;
-#pragma unroll
-                            for (int e2 = 0; e2 < 4; ++e2) {
-                                const float2 hf = unpack2(ph[e2]), lf = unpack2(pl[e2]);
-                                const float x0 = __fadd_rn(hf.x, lf.x);
-                                const float x1 = __fadd_rn(hf.y, lf.y);
-                                o[2 * e2] = __fadd_rn(o[2 * e2], x0);
-                                o[2 * e2 + 1] = __fadd_rn(o[2 * e2 + 1], x1);
-                            }
+                        for (int e2 = 0; e2 < 4; ++e2) {
+                            const float2 x = add2(unpack2(ph[e2]), unpack2(pl[e2]));
+                            o[2 * e2] = __fadd_rn(o[2 * e2], x.x);
+                            o[2 * e2 + 1] = __fadd_rn(o[2 * e2 + 1], x.y);
                         }
-#pragma unroll
-                        for (int e2 = 0; e2 < 8; ++e2) r[8 * q + e2] = __float_as_uint(o[e2]);
                     }
-                    tmem_st32(d2 + 32 * j, r);
+#pragma unroll
+                    for (int e2 = 0; e2 < 8; ++e2) r[8 * q + e2] = __float_as_uint(o[e2]);
                 }
+                tmem_st32(d1 + 128, r);
+                tc_wait_st();
+                tc_fence_before();
+                mbar_arrive(h_full + g);
+                mbar_arrive(x_empty + s);                // this thread's reads of the input stage are done
+            } else {
+                tc_wait_st();
+                tc_fence_before();
+                mbar_arrive(h_full + g);
             }
-            tc_wait_st();
-            tc_fence_before();
-            mbar_arrive(h_full + g);
-            if (kLast) mbar_arrive(x_empty + s);         // this thread's reads of the input stage are done
+        };
 
-            // ---- E2: D2 -> out = lrelu(D2 [+ bias2]) -> running max (+ staged 16-bit planes -> TMA store) ----
-            if (!kLast) {
-                // the staging buffer is free again once the TMA store of this group's previous tile has read it
-                if ((ew & 7) == 0 && lane == 0) tma_store_3d_wait_read();
-                named_bar_sync(2 + g, 256);
+        // ---- E2(i): D2 -> out = lrelu(D2 + bias2) -> running max (+ staged 16-bit planes -> TMA store) ----
+        int e2 = e_first, n2 = n1, ep2 = -1;
+        auto step_e2 = [&](int i) {
+            n2 += kTowerTile;
+            if (n2 >= tiles_per_ep * kTowerTile) {
+                n2 = 0;
+                ++e2;
             }
+            if (e2 != ep2) {
+                if (ep2 >= 0) flush(ep2);
+                ep2 = e2;
+            }
+            const int g = i & 1;
+            const uint32_t par = (i >> 1) & 1;
+            const bool valid = n2 + p < N;
+            const uint32_t dg = tmem_base + g * Cfg::kBufCols + Cfg::kD1 + lane_addr;
+            const uint32_t d2 = (kLast ? dg + 128 : (par ? dg + 128 : dg - 64)) + kC2 * cq;   // mid: the D2 buffers alternate
             mbar_wait(d2_full + g, par);
             tc_fence_after();
-#pragma unroll
-            for (int jj = 0; jj < kMine2; ++jj) {
-                const int j = half * kMine2 + jj;
+            if (kLast) {
+                // only the max over the points leaves block 4, and LeakyReLU is monotonic: max(lrelu(v)) = lrelu(max(v))
+                // - the activation is applied once per channel when the maxima are flushed (the bias is in D2 already)
                 uint32_t r[32];
-                tmem_ld32(d2 + 32 * j, r);
+                tmem_ld32(d2, r);
                 tc_wait_ld();
-                float v[32];
-                if (kLast) {
-                    // only the max over the points leaves block 4, and LeakyReLU is monotonic: max(lrelu(v)) = lrelu(max(v))
-                    // - the activation is applied once per channel when the maxima are flushed (the bias is in D2 already)
+                if (valid) {
 #pragma unroll
-                    for (int q = 0; q < 32; ++q) v[q] = __uint_as_float(r[q]);
-                } else {
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const float4 bb = *reinterpret_cast<const float4 *>(bias2 + 32 * j + 4 * q);
-                        const float2 a = lrelu2(add2(make_float2(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1])), make_float2(bb.x, bb.y)));
-                        const float2 b = lrelu2(add2(make_float2(__uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3])), make_float2(bb.z, bb.w)));
-                        v[4 * q] = a.x;
-                        v[4 * q + 1] = a.y;
-                        v[4 * q + 2] = b.x;
-                        v[4 * q + 3] = b.y;
-                    }
+                    for (int q = 0; q < kC2; ++q) rmx[q] = max_nan(rmx[q], __uint_as_float(r[q < 32 ? q : 0]));
                 }
-                if (!kLast) tower_stage_chunk<2>(ostage, 16384, p, j, v);
-                if (kMidRegMax) {
-                    if (valid) {
+            } else {
+                unsigned char *ostage = smem + Cfg::off_out + (i & 1) * 32768;
+                if (i >= 2) mbar_wait(o_free + (i & 1), ((i >> 1) - 1) & 1);   // the store of tile i - 2 has read the buffer
+                const float *b2 = bias2 + ((e2 - e_first) & 1) * 128 + 16 * cq;
+                uint32_t r[16];
+                tmem_ld16(d2, r);
+                tc_wait_ld();
+                float v[16];
 #pragma unroll
-                        for (int q = 0; q < 32; ++q) rmx[q < kRegMax ? q : 0] = max_nan(rmx[q < kRegMax ? q : 0], v[q]);
-                    }
-                } else {
-                    if (!valid) {
-#pragma unroll
-                        for (int q = 0; q < 32; ++q) v[q] = -INFINITY;
-                    }
-                    mx[jj] = max_nan(mx[jj], warp_transpose_max(v, lane));
+                for (int q = 0; q < 4; ++q) {
+                    const float4 bb = *reinterpret_cast<const float4 *>(b2 + 4 * q);
+                    const float2 a = lrelu2(add2(make_float2(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1])), make_float2(bb.x, bb.y)));
+                    const float2 b = lrelu2(add2(make_float2(__uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3])), make_float2(bb.z, bb.w)));
+                    v[4 * q] = a.x;
+                    v[4 * q + 1] = a.y;
+                    v[4 * q + 2] = b.x;
+                    v[4 * q + 3] = b.y;
                 }
-            }
-            if (!kLast) {
+                tower_stage_cols16(ostage, 16384, p, cq, v);
+                if (valid) {
+#pragma unroll
+                    for (int q = 0; q < kC2; ++q) rmx[q] = max_nan(rmx[q], v[q < 16 ? q : 0]);
+                }
                 fence_async_proxy();
-                named_bar_sync(2 + g, 256);
-                if ((ew & 7) == 0 && lane == 0) {
-                    tma_store_3d(&out_hi, 0, n0, e, ostage);
-                    tma_store_3d(&out_lo, 0, n0, e, ostage + 16384);
-                    bulk_commit();
-                }
+                mbar_arrive(o_full + (i & 1));           // the store warp takes it from here
             }
+        };
+
+        step_e1(0);
+        for (int i = 0; i < ntiles; ++i) {
+            if (i + 1 < ntiles) step_e1(i + 1);
+            step_e2(i);
         }
-        flush();
-        if (!kLast && (ew & 7) == 0 && lane == 0) tma_store_3d_wait_all();   // the next block reads these planes
+        flush(ep2);
     }
     tc_fence_before();
     __syncthreads();
