@@ -148,7 +148,7 @@ static bool bucket_path(const WsLayout &L, int C) {
 // obs2d [B, 2C, P] (out_rows = 2C, row0 = C); a cost volume writes [E, C, P] (out_rows = C, row0 = 0).
 static int launch_gather(const WsLayout &L, const char *ws, const float *img_feat, int B, int N, int C, int P,
                          bool copy_image, float *obs2d, cudaStream_t st, int share = 1, int out_rows = 0, int row0 = -1,
-                         int mean_channels = 1 << 30) {
+                         int mean_channels = 1 << 30, int heavy_from = kLightLimit) {
     if (out_rows <= 0) out_rows = 2 * C;
     if (row0 < 0) row0 = C;
     int *bcnt = reinterpret_cast<int *>(const_cast<char *>(ws) + L.off_bcnt);
@@ -172,9 +172,17 @@ static int launch_gather(const WsLayout &L, const char *ws, const float *img_fea
     const int light = std::max(ceil_div(L.buckets, kGatherWarps), kHeavyCtas);
     // four SUMMED channels after whole slabs (features + occupancy of a cost volume): no slab pass of their own
     const int tail = (C > kSlab && C % kSlab == 4 && mean_channels <= C - 4) ? 4 : 0;
-    int rc = allow_smem(k_tile_gather, kGatherSmem);
+    if (heavy_from > kLightLimit) {   // a cost volume: its warps hold up to kMidMax keys
+        const size_t smem = std::max(kGatherSmem, gather_smem_light(kHeavyFrom));
+        int rc = allow_smem(k_tile_gather<true>, smem);
+        if (rc) return rc;
+        return launch_pdl(k_tile_gather<true>, dim3(B, kHeavyCtas + light), dim3(kGatherThreads), smem, st, bcnt, bbuf, L.buckets, hq, pix,
+                          L.pix16 ? 1 : 0, M, featT, img_feat, N, L.ncap, C, P, copy_image, vec, tma, obs2d, map_proj, share,
+                          (long long)out_rows * P, (long long)row0 * P, row0, mean_channels, img_tma, map_img, tail);
+    }
+    int rc = allow_smem(k_tile_gather<false>, kGatherSmem);
     if (rc) return rc;
-    return launch_pdl(k_tile_gather, dim3(B, kHeavyCtas + light), dim3(kGatherThreads), kGatherSmem, st, bcnt, bbuf,
+    return launch_pdl(k_tile_gather<false>, dim3(B, kHeavyCtas + light), dim3(kGatherThreads), kGatherSmem, st, bcnt, bbuf,
                       L.buckets, hq, pix, L.pix16 ? 1 : 0, M, featT, img_feat, N, L.ncap, C, P, copy_image, vec, tma, obs2d, map_proj,
                       share, (long long)out_rows * P, (long long)row0 * P, row0, mean_channels, img_tma, map_img, tail);
 }
@@ -769,7 +777,7 @@ int cmr_cost_volume_warp(const float *pc, const uint8_t *mask, const float *Kmat
                             L.groups, H, W, vec, reinterpret_cast<int32_t *>(ws + L.off_pix), bcnt, bbuf, L.buckets, hdr, hq, K);
     }
     if (rc) return rc;
-    return launch_gather(L, ws, nullptr, E, N, C, P, false, out, st, K, C, 0, mean_channels);
+    return launch_gather(L, ws, nullptr, E, N, C, P, false, out, st, K, C, 0, mean_channels, kHeavyFrom);
 }
 
 // ------------------------------------------------------------------------------ dataset side ----

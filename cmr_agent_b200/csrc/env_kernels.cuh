@@ -38,8 +38,19 @@ constexpr int kLightMax = 64;           // capacity of the one-warp path of k_ti
 #ifndef CMR_LIGHT_LIMIT
 #define CMR_LIGHT_LIMIT 64
 #endif
-constexpr int kLightLimit = CMR_LIGHT_LIMIT;   // a bucket that receives more visible points than this is queued as heavy
+constexpr int kLightLimit = CMR_LIGHT_LIMIT;   // buckets up to here take the warp's shuffle-ranked fast path
 static_assert(kLightLimit >= 1 && kLightLimit <= kLightMax, "the one-warp path holds at most kLightMax entries");
+#ifndef CMR_MID_MAX
+#define CMR_MID_MAX 256
+#endif
+// Cost volumes: a bucket with kLightLimit < n <= kMidMax entries is still done by ONE warp (binned by pixel in shared
+// memory, ranked inside its pixel).  729 poses of one cloud put most of their points into such buckets, and a
+// 256-thread bucket CTA with its CTA-wide barriers is built for a handful of horizon buckets (measured on a B200:
+// cost volume 1.03 -> 0.72 ms).  An observe is the opposite case - a grid of a few waves whose time is its slowest
+// unit - and keeps the threshold at kLightLimit (with 256 the B = 32 gather went from 33 to 52 us).
+constexpr int kMidMax = CMR_MID_MAX < kLightLimit ? kLightLimit : CMR_MID_MAX;
+static_assert(kMidMax % 32 == 0 || kMidMax == kLightLimit, "whole entries per lane");
+constexpr int kHeavyFrom = kMidMax;            // cost volumes: a bucket that receives more visible points than this is queued as heavy
 constexpr int kCountSeen = 1 << 24;     // added to a heavy bucket's counter by the first of its two readers
 constexpr int kBucketCap = 2048;    // entries a bucket's buffer holds; fuller buckets are re-read from the id list
 
@@ -592,7 +603,7 @@ __global__ void __launch_bounds__(32 * CMR_PROJ_WARPS)
                     const int slot = atomicAdd(bc + id / kBucketPix, 1);
                     if (slot < kBucketCap)
                         bbuf[((size_t)b * buckets + id / kBucketPix) * kBucketCap + slot] = ((unsigned)pos << 7) | ((unsigned)id & 127u);
-                    if (slot == kLightLimit) hq[atomicAdd(hdr, 1)] = (int)(((unsigned)b << 16) | (unsigned)(id / kBucketPix));
+                    if (slot == kHeavyFrom) hq[atomicAdd(hdr, 1)] = (int)(((unsigned)b << 16) | (unsigned)(id / kBucketPix));
                 }
             }
         }

@@ -65,9 +65,16 @@ constexpr int kRowBatch = 8;            // rows per batch; a warp keeps two batc
 constexpr unsigned kKeyFirst = 1u << 31, kKeyLast = 1u << 30;   // flags of a sorted key: pixel << 24 | point
 constexpr unsigned kPadKey = 0;   // no flags, point 0: loaded, added to a run that is never stored
 static_assert(kBucketPix == 32 && kLightMax == 64, "one lane per pixel / two keys per lane");
+static_assert(kMidMax * 16 + kMidMax * 4 <= kSlab * kBucketPix * 4, "a mid unit's tail rows and binned keys share the idle tile");
 static_assert(kBucketCap % kGatherThreads == 0, "whole entries per thread");
 
-constexpr size_t kGatherSmemLight = kGatherWarps * (sizeof(float) * kTileFloats + sizeof(unsigned) * (kLightMax + 32));
+// a warp's sorted keys + [32] points per pixel + [32] cursors: as many keys as the launch's heavy_from allows
+__host__ __device__ constexpr int warp_keys(int heavy_from) { return heavy_from > kLightMax ? heavy_from + 64 : kLightMax + 32; }
+constexpr int kMidPer = kMidMax / 32;   // entries per lane of a mid unit
+__host__ __device__ constexpr size_t gather_smem_light(int heavy_from) {
+    return kGatherWarps * (sizeof(float) * kTileFloats + sizeof(unsigned) * warp_keys(heavy_from));
+}
+constexpr size_t kGatherSmemLight = gather_smem_light(kLightMax);
 constexpr size_t kGatherSmemHeavy = sizeof(float) * kTileFloats + sizeof(unsigned) * 3 * kBucketCap + sizeof(int) * 128;
 constexpr size_t kGatherSmem = kGatherSmemLight > kGatherSmemHeavy ? kGatherSmemLight : kGatherSmemHeavy;
 // what a bucket CTA does not need of the light units' tiles stages feature rows (kSlab floats per row), together
@@ -234,12 +241,20 @@ __device__ __forceinline__ void mean_pass(unsigned mask, int cnt_of_lane, const 
     }
 }
 
+
+// kMid: the launch's warps also take buckets of kLightLimit < n <= kMidMax entries (cost volumes).  A template
+// parameter, not a branch: with the mid unit compiled into the observe's kernel its light units lost 6 % (register
+// allocation and scheduling of the shared code; measured: 33.5 -> 35.7 us at B = 32).
+template <bool kMid>
 __global__ void __launch_bounds__(kGatherThreads, CMR_GATHER_MINB)
     k_tile_gather(int *bcnt, const unsigned *bbuf, int buckets, const int *hq, const void *pix, int pix16, const int *M,
                   const float *__restrict__ featT, const float *__restrict__ img_feat, int N, int ncap, int C, int P,
                   bool copy_image, bool vec, bool tma, float *__restrict__ obs2d,
                   const __grid_constant__ CUtensorMap map_proj, int share, long long out_estride, long long proj_off,
                   int tma_y0, int mean_channels, bool img_tma, const __grid_constant__ CUtensorMap map_img, int tail) {
+    // heavy_from: buckets with more entries than this were queued for the bucket CTAs by the projecting kernel
+    // (kLightLimit for an observe, kMidMax for a cost volume); up to it a warp does the bucket alone.
+    constexpr int heavy_from = kMid ? kHeavyFrom : kLightLimit;
     // tail (0 or 4): the last four channels (a slab of their own, all of them SUMS) are not given a pass over the
     // rows by the light warps: a lane sums them for ITS pixel, in point order (the occupancy row of a cost volume).
     // share: consecutive episodes (poses) that look at the same cloud, i.e. the same feature rows.
@@ -278,8 +293,9 @@ __global__ void __launch_bounds__(kGatherThreads, CMR_GATHER_MINB)
         const int b = blockIdx.x;
         const int bk = role_idx * kGatherWarps + warp;
         float *tile = smem_g + warp * kTileFloats;
-        unsigned *sk = reinterpret_cast<unsigned *>(smem_g + kGatherWarps * kTileFloats) + warp * (kLightMax + 32);
-        int *pc = reinterpret_cast<int *>(sk + kLightMax);   // [32] points per pixel
+        constexpr int wkeys = warp_keys(heavy_from);
+        unsigned *sk = reinterpret_cast<unsigned *>(smem_g + kGatherWarps * kTileFloats) + warp * wkeys;
+        int *pc = reinterpret_cast<int *>(sk + (kMid ? wkeys - 64 : kLightMax));   // [32] points per pixel (mid: then [32] cursors)
         const int p0 = bk * kBucketPix;
         float *out = obs2d + (size_t)b * out_estride;
         float *proj = out + proj_off;
@@ -290,10 +306,10 @@ __global__ void __launch_bounds__(kGatherThreads, CMR_GATHER_MINB)
             int *cb = bcnt + (size_t)b * kBucketStride + bk;
             const int n = ld_cg_s32(cb) & (kCountSeen - 1);
             if (lane == 0 && n != 0) {
-                if (n <= kLightLimit) *cb = 0;   // this warp is the counter's only reader
+                if (n <= heavy_from) *cb = 0;   // this warp is the counter's only reader
                 else if (atomicAdd(cb, kCountSeen) >= kCountSeen) *cb = 0;   // the bucket CTA has been here
             }
-            if (n > 0 && n <= kLightLimit) {
+            if (n > 0 && n <= heavy_from) {
                 // all the rows this unit will add: on their way to L2 before the first one is needed
                 if (lane < n)
                     for (int q = 0; q < C; q += 32) prefetch_l2(featT + ((size_t)bs * N + (e0 >> 7)) * C + q);
@@ -419,6 +435,112 @@ __global__ void __launch_bounds__(kGatherThreads, CMR_GATHER_MINB)
                     add_rows<false>(sk, 0, n, rows, (unsigned)C, tl);
                     if (c0 < mean_channels) mean_pass(multi, my_cnt, tl);
                     DBG_MARK(3);
+                    if (tma) {
+                        fence_async_proxy();
+                        __syncwarp();
+                        if (lane == 0) store_tile_tma(tile, &map_proj, tma_y0 + c0, p0, b);
+                    } else {
+                        __syncwarp();
+                        store_tile<32>(tile, c0, C, p0, P, proj, lane);
+                    }
+                    __syncwarp();
+                }
+            } else if (kMid && n > kLightLimit && n <= heavy_from) {
+                // ---------------------------------------------------------- mid unit: up to kMidMax entries, still one warp
+                // Entries lane + 32 i.  The order (pixel, point) is established by binning: points per pixel (shared-
+                // memory atomics), an exclusive scan across the lanes, every entry dropped into its pixel's segment in
+                // arrival order, then ranked against the (few) entries of its own segment only.  The flags fall out of
+                // the rank.  The tile - idle until the first slab is zeroed - holds the binned keys and the tail rows.
+                unsigned key[kMidPer];
+                key[0] = ((e0 & 31u) << 24) | (e0 >> 7);
+                key[1] = lane + 32 < n ? ((e1 & 31u) << 24) | (e1 >> 7) : 0xffffffffu;
+#pragma unroll
+                for (int i = 2; i < kMidPer; ++i) {
+                    const unsigned e = lane + 32 * i < n ? ld_cg_u32(src + lane + 32 * i) : 0xffffffffu;
+                    key[i] = e == 0xffffffffu ? e : ((e & 31u) << 24) | (e >> 7);
+                }
+#pragma unroll
+                for (int i = 2; i < kMidPer; ++i)
+                    if (lane + 32 * i < n)
+                        for (int q = 0; q < C; q += 32) prefetch_l2(featT + ((size_t)bs * N + (key[i] & 0xffffffu)) * C + q);
+                int *cur = pc + 32;
+                unsigned *binned = reinterpret_cast<unsigned *>(tile) + kTileFloats - kMidMax;   // the tile's last kMidMax words
+                pc[lane] = 0;
+                cur[lane] = 0;
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < kMidPer; ++i)
+                    if (lane + 32 * i < n) atomicAdd(&pc[key[i] >> 24], 1);
+                __syncwarp();
+                const int my_cnt = pc[lane];
+                int incl = my_cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int up = __shfl_up_sync(kFull, incl, o);
+                    if (lane >= o) incl += up;
+                }
+                const int start = incl - my_cnt;
+                int seg[kMidPer];   // where the entry's pixel starts in the sorted list
+#pragma unroll
+                for (int i = 0; i < kMidPer; ++i) {
+                    const bool ok = lane + 32 * i < n;
+                    const int px = ok ? (int)(key[i] >> 24) : 0;
+                    seg[i] = __shfl_sync(kFull, start, px);
+                    if (ok) binned[seg[i] + atomicAdd(&cur[px], 1)] = key[i];
+                }
+                __syncwarp();
+                int pos[kMidPer];
+#pragma unroll
+                for (int i = 0; i < kMidPer; ++i) {
+                    const bool ok = lane + 32 * i < n;
+                    const int c = ok ? pc[key[i] >> 24] : 0;
+                    int r = 0;
+                    for (int j = 0; j < c; ++j) r += binned[seg[i] + j] < key[i];
+                    pos[i] = seg[i] + r;
+                    if (ok) sk[pos[i]] = key[i] | (r == 0 ? kKeyFirst : 0u) | (r == c - 1 ? kKeyLast : 0u);
+                }
+                __syncwarp();
+                const unsigned multi = __ballot_sync(kFull, my_cnt > 1);
+                const LaneRows tl = lane_rows(tile, lane);
+                if (tail) {
+                    // the four summed channels: every entry's values go to its sorted place, lane = pixel adds its own group
+                    float4 *tv = reinterpret_cast<float4 *>(tile);   // n * 16 bytes <= half of the tile (binned sits in its end)
+                    const float *tb = featT + (size_t)bs * N * C + (C - 4);
+#pragma unroll
+                    for (int h = 0; h < kMidPer; h += 4) {
+                        float4 t[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            if (lane + 32 * (h + i) < n) t[i] = ldg_f4(tb + (size_t)(key[h + i] & 0xffffffu) * C);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            if (lane + 32 * (h + i) < n) tv[pos[h + i]] = t[i];
+                    }
+                    __syncwarp();
+                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int i = 0; i < my_cnt; ++i) {
+                        const float4 v = tv[start + i];
+                        acc.x = __fadd_rn(acc.x, v.x);
+                        acc.y = __fadd_rn(acc.y, v.y);
+                        acc.z = __fadd_rn(acc.z, v.z);
+                        acc.w = __fadd_rn(acc.w, v.w);
+                    }
+                    __syncwarp();
+                    if (p0 + lane < P) {
+                        float *dst = proj + (size_t)(C - 4) * P + p0 + lane;
+                        dst[0] = acc.x;
+                        dst[(size_t)P] = acc.y;
+                        dst[2 * (size_t)P] = acc.z;
+                        dst[3 * (size_t)P] = acc.w;
+                    }
+                }
+                for (int slab = 0; slab < (tail ? slabs - 1 : slabs); ++slab) {
+                    const int c0 = kSlab * slab;
+                    const float *rows = featT + (size_t)bs * N * C + (c0 + 2 * lane < C ? c0 + 2 * lane : 0);
+                    zero_tile<32>(tile, lane);
+                    __syncwarp();
+                    add_rows<false>(sk, 0, n, rows, (unsigned)C, tl);
+                    if (c0 < mean_channels) mean_pass(multi, my_cnt, tl);
                     if (tma) {
                         fence_async_proxy();
                         __syncwarp();
