@@ -1,8 +1,9 @@
 """Round-2 summaries from the captures a gpurun call leaves in gpurun_out/ (tracked copies live here).
 
-    python profiles/make_r2.py <env.ncu-rep> <tower.ncu-rep> [launches.csv]
+    python profiles/make_r2.py <env.ncu-rep> <tower.ncu-rep> [cost_volume.ncu-rep] [bench_launches.csv]
 
-Outputs: r2_env_kernels_ncu.txt, r2_tower_ncu.txt, dram_traffic.json, r2_sass_evidence.txt (+ r2_bench_launches_summary.txt)
+Outputs: r2_env_kernels_ncu.txt, r2_tower_ncu.txt, r2_cost_volume_ncu.txt, dram_traffic.json, r2_sass_evidence.txt,
+r2_bench_launches.csv + r2_bench_launches_summary.txt
 """
 import collections
 import csv
@@ -82,6 +83,34 @@ def sass():
                 f.write(f"{short[:70]:70s} " + " ".join(f"{k}={v}" for k, v in sorted(c.items())) + "\n")
 
 
+def launches(path):
+    """ncu launch list of `bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline`: per-kernel launches, time and share."""
+    rows = [r for r in csv.reader(open(path, errors="replace")) if len(r) > 5]
+    hdr = next(r for r in rows if "Kernel Name" in r)
+    kn, mv = hdr.index("Kernel Name"), hdr.index("Metric Value")
+    per = collections.OrderedDict()
+    for r in rows[rows.index(hdr) + 1:]:
+        try:
+            t = float(r[mv].replace(",", ""))
+        except ValueError:
+            continue
+        name = r[kn].split("(")[0].replace("void ", "").replace("cmr::", "")
+        c = per.setdefault(name, [0, 0.0])
+        c[0] += 1
+        c[1] += t
+    total = sum(v[1] for v in per.values())
+    with open(path) as src, open(os.path.join(HERE, "r2_bench_launches.csv"), "w") as dst:
+        dst.write(src.read())
+    with open(os.path.join(HERE, "r2_bench_launches_summary.txt"), "w") as f:
+        f.write("# r2: ncu --metrics gpu__time_duration.sum --clock-control none -s 180 -c 200 --csv\n"
+                "#     python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline   (cold caches, serialised launches:\n"
+                "#     the SHARES are what compares with bench.py's live events, not the absolute times)\n")
+        f.write(f"{'kernel':44s} {'launches':>9s} {'total ns':>12s} {'avg ns':>10s} {'share':>7s}\n")
+        for k, (n, t) in sorted(per.items(), key=lambda kv: -kv[1][1]):
+            f.write(f"{k[:44]:44s} {n:9d} {t:12.0f} {t / n:10.0f} {t / total:7.1%}\n")
+    print(open(os.path.join(HERE, "r2_bench_launches_summary.txt")).read())
+
+
 if __name__ == "__main__":
     tr = {}
     if len(sys.argv) > 1 and os.path.exists(sys.argv[1]):
@@ -92,6 +121,13 @@ if __name__ == "__main__":
         tr.update(summarise(sys.argv[2], "r2_tower_ncu.txt",
                             '# r2: ncu --set full --clock-control none --import-source on -k regex:"k_tower" -s 20 -c 5\n'
                             "#     python benchmarks/microbench.py tower --batch 32   (B200, 32 x 40960 points)\n"))
+    if len(sys.argv) > 3 and os.path.exists(sys.argv[3]):
+        cv = summarise(sys.argv[3], "r2_cost_volume_ncu.txt",
+                       '# r2: ncu --set full --clock-control none --import-source on -k regex:"k_tile_gather|k_project_masked" -s 4 -c 2\n'
+                       "#     python benchmarks/microbench.py cost_volume   (B200, 729 poses of one KITTI cloud, 1.015 GB out)\n")
+        tr.update({k + " (cost volume)": v for k, v in cv.items()})
+    if len(sys.argv) > 4 and os.path.exists(sys.argv[4]):
+        launches(sys.argv[4])
     if tr:
         tr["note"] = ("dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full --clock-control none, round 2. "
                       "Below the algorithmic bytes where a kernel's output is still in the 126 MB L2 when it ends.")
