@@ -10,6 +10,7 @@
 #include "env_kernels.cuh"
 #include "pointnet_kernels.cuh"
 #include "scatter_kernels.cuh"
+#include "cost_volume_kernels.cuh"
 #include "dataset_kernels.cuh"
 #include "tower_kernels.cuh"
 #include "session.cuh"
@@ -326,6 +327,12 @@ static int launch_tower_mma(const void *blob, int B, int N, int tiles_per_ep, in
     const int grid = std::min(B * tiles_per_ep, sm_count());
     return launch_pdl(kern, dim3(grid), dim3(kTowerThreads), smem, st, static_cast<const unsigned char *>(blob), B, N, tiles_per_ep, box_rows,
                       in_hi, in_lo, out_hi, out_lo, prev_keys, max_keys);
+}
+
+// CMR_B200_CV=buckets: the cost volume takes the observation's bucket kernels whatever its shape (parity tests of that path)
+static bool cv_force_buckets() {
+    const char *e = getenv("CMR_B200_CV");
+    return e && strcmp(e, "buckets") == 0;
 }
 
 extern "C" {
@@ -760,7 +767,44 @@ int cmr_cost_volume_warp(const float *pc, const uint8_t *mask, const float *Kmat
     char *ws = static_cast<char *>(workspace);
     const float *zero_mean = reinterpret_cast<const float *>(ws + L.off_zero);   // X = R p + t: nothing is subtracted
     cudaStream_t st = S_(stream);
-    // only the masked points are projected (k_project_masked)
+    // The reference's shape (64 mean channels + the summed score, a grid of whole 32-pixel buckets that fits the
+    // shared-memory histogram): one CTA per pose does everything (cost_volume_kernels.cuh).  The bucket buffers are not
+    // used on this path; its scratch arrays (compacted coordinates, pixel ids, the sorted lists) live in their place.
+    {
+        const size_t need = round_up(sizeof(float4) * (size_t)B * L.ncap, 256) + 3 * round_up(sizeof(uint16_t) * (size_t)E * L.ncap, 256) +
+                            round_up(sizeof(uint16_t) * (size_t)E * (P + 2), 256);
+        const bool fused = C == kCvFeat + 4 && mean_channels == kCvFeat && P % 32 == 0 && P <= kCvMaxP && L.ncap <= 65535 &&
+                           need <= L.total - L.off_bbuf && !cv_force_buckets();
+        if (fused) {
+            char *o = ws + L.off_bbuf;
+            float4 *xyzc = reinterpret_cast<float4 *>(o);
+            o += round_up(sizeof(float4) * (size_t)B * L.ncap, 256);
+            uint16_t *pix16 = reinterpret_cast<uint16_t *>(o);
+            o += round_up(sizeof(uint16_t) * (size_t)E * L.ncap, 256);
+            uint16_t *tmp16 = reinterpret_cast<uint16_t *>(o);
+            o += round_up(sizeof(uint16_t) * (size_t)E * L.ncap, 256);
+            uint16_t *sorted16 = reinterpret_cast<uint16_t *>(o);
+            o += round_up(sizeof(uint16_t) * (size_t)E * L.ncap, 256);
+            uint16_t *gstart = reinterpret_cast<uint16_t *>(o);
+            const bool vec = (N % 4 == 0) && aligned(mask, 4);
+            k_xyz_compact<<<dim3(ceil_div(L.groups, 8), B), 256, 0, st>>>(pc, mask, reinterpret_cast<const int *>(ws + L.off_seg), N, L.ncap,
+                                                                         L.groups, vec, xyzc);
+            rc = after_launch();
+            if (rc) return rc;
+            rc = allow_smem(k_cost_volume_sort, kCvSmem);
+            if (rc) return rc;
+            k_cost_volume_sort<<<E, kCvSortThreads, kCvSmem, st>>>(xyzc, reinterpret_cast<const int *>(ws + L.off_m), Kmat, poses, zero_mean,
+                                                               L.ncap, H, W, K, N >= kBmmChainMinCols, pix16, tmp16, sorted16, gstart);
+            rc = after_launch();
+            if (rc) return rc;
+            rc = allow_smem(k_cost_volume_gather, kCvTileSmem);
+            if (rc) return rc;
+            return launch_pdl(k_cost_volume_gather, dim3(ceil_div(P / 32, kCvWarps * kCvPerWarp), E), dim3(kCvThreads), kCvTileSmem, st,
+                              reinterpret_cast<const float *>(ws + L.off_feat), N, L.ncap, C, P, K, (const uint16_t *)sorted16,
+                              (const uint16_t *)gstart, out);
+        }
+    }
+    // any other shape: only the masked points are projected (k_project_masked) into the observation's bucket buffers
     {
         const int *seg = reinterpret_cast<const int *>(ws + L.off_seg);
         int *bcnt = reinterpret_cast<int *>(ws + L.off_bcnt);

@@ -138,6 +138,41 @@ def test_gpu_matches_oracle(cuda, B, N, img_h, img_w, nlabel, dense):
     assert torch.equal(again_f, got_f) and torch.equal(again_o, got_o)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,N,img_h,img_w,nlabel,dense", [
+    (1, 40960, 160, 512, 3, False),
+    (2, 40960, 64, 64, 2, True),
+])
+def test_gpu_bucket_path_matches_oracle(cuda, monkeypatch, B, N, img_h, img_w, nlabel, dense):
+    """The reference's shape takes the one-CTA-per-pose kernel (cost_volume_kernels.cuh); every other shape - more
+    channels, a grid that is not whole 32-pixel buckets - takes the observation's bucket kernels.  CMR_B200_CV=buckets
+    sends the same cases down that path: the two must agree with the oracle, hence with each other, bit for bit."""
+    from cmr_agent_b200 import cost_volume
+    monkeypatch.setenv("CMR_B200_CV", "buckets")
+    data, mask, poses, scores = _case(B, N, img_h, img_w, nlabel, 3, dense)
+    H, W = img_h // 4, img_w // 4
+    want_f, want_o = cvo.warp(data["pc"], mask, poses, data["K"], data["pc_geo_feat"], scores, H, W)
+    got_f, got_o = cost_volume.warp(data["pc"].to(cuda), mask.to(cuda), poses.to(cuda), data["K"],
+                                    data["pc_geo_feat"].to(cuda), scores.to(cuda), H, W)
+    assert torch.equal(got_o.cpu(), want_o) and torch.equal(got_f.cpu(), want_f)
+
+
+@pytest.mark.gpu
+def test_gpu_cloud_collapsed_onto_few_pixels(cuda):
+    """A cloud seen from far away: tens of thousands of points on a handful of pixels (the bitmap ordering of
+    k_cost_volume_pose; a quadratic ranking would take seconds here)."""
+    from cmr_agent_b200 import cost_volume
+    data, mask, poses, scores = _case(1, 40960, 160, 512, 2, 5, True)
+    poses = poses.clone()
+    poses[:, :, 2, 3] += 4000.0          # push the cloud 4 km down the optical axis
+    H, W = 40, 128
+    want_f, want_o = cvo.warp(data["pc"], mask, poses, data["K"], data["pc_geo_feat"], scores, H, W)
+    assert int((want_o > 0).sum(dim=-1).max()) <= 64 and float(want_o.sum()) > 1000    # a few pixels hold everything
+    got_f, got_o = cost_volume.warp(data["pc"].to(cuda), mask.to(cuda), poses.to(cuda), data["K"],
+                                    data["pc_geo_feat"].to(cuda), scores.to(cuda), H, W)
+    assert torch.equal(got_o.cpu(), want_o) and torch.equal(got_f.cpu(), want_f)
+
+
 def test_cost_volume_rejects_cpu_tensors():
     from cmr_agent_b200 import _lib, cost_volume
     data, mask, poses, scores = _case(1, 256, 64, 64, 2, 1)
