@@ -1,22 +1,25 @@
-// cost_volume_kernels.cuh - the pose-sampling cost volume of models/IterModel.py:272-351 as ONE kernel per pose.
+// cost_volume_kernels.cuh - the pose-sampling cost volume of models/IterModel.py:272-351 for the reference's own shape
+// (64 mean channels + the summed score, a grid of whole 32-pixel buckets): one counting sort per pose, one gather.
 //
 // The observation's kernels (k_project_masked + k_tile_gather, env_kernels.cuh / scatter_kernels.cuh) hand points to
 // 32-pixel buckets through global atomics and per-bucket buffers and then restore the point order bucket by bucket.
 // That is built for a view in which a bucket holds a dozen points.  A cost volume is the other regime: hundreds of
 // candidate poses look at the SAME masked points (8956 of a KITTI cloud), two thirds of them land inside the image,
-// 4.3 per occupied pixel, and everything a pose needs - 36 KB of coordinates, its own ordering - fits one CTA.
-// Per pose (blockIdx.x), 256 threads:
-//   A1  project the cloud's masked points (compacted once per cloud by k_xyz_compact), pixel ids -> global (L2),
-//       points per pixel -> shared-memory histogram                                  (:281-304, :316-318)
-//   A2  exclusive scan over the H*W pixels -> where every pixel's points begin
-//   A3  counting-sort fill in arrival order, then every point is ranked against the (few) points of its own pixel:
-//       `sorted` = the visible points in (pixel, point) order - the order torch's CPU scatter adds them in
-//   B   warps take 32-pixel buckets from a shared counter; a feature row is a 256-byte warp load (two channels per
-//       lane, the score on lane 0), a pixel's rows are added in point order, a finished pixel leaves as its mean
-//       (scores: sum) into a pixel-major tile [32][64] (XOR-swizzled: conflict-free both ways), and the tile is
-//       written channel-major with 128-byte coalesced stores.                          (:341-343)
-// No global atomics, no bucket buffers, no second kernel; ~160 k warp instructions per pose instead of ~480 k.
+// 4.3 per occupied pixel, and everything a pose needs to order them fits one CTA's shared memory.
+//   k_xyz_compact         once per cloud: coordinates of the masked points, in index order
+//   k_cost_volume_sort    one CTA per pose.  Project (:281-304, :316-318), points per pixel -> shared-memory histogram,
+//                         exclusive scan over the H*W pixels, counting-sort fill in arrival order, then every point is
+//                         ranked against the (few) points of its own pixel: `sorted` = the visible points in (pixel,
+//                         point) order - the order torch's CPU scatter adds them in.  A pixel with more than 256
+//                         points is ordered through a bitmap of the cloud instead (rank = marked points before it).
+//   k_cost_volume_gather  one warp per 32-pixel bucket: its rows are a contiguous piece of `sorted`.  A feature row is a
+//                         256-byte warp load (two channels per lane, the score on lane 0); a pixel's rows are added in
+//                         point order; a finished pixel leaves as its mean (scores: sum) into a pixel-major tile
+//                         [32][64] (XOR-swizzled: conflict-free both ways), and the tile is written channel-major
+//                         as full 128-byte lines.  (:341-343)
+// No global atomics, no bucket buffers; 240 M warp instructions for the 729 poses of a KITTI cloud instead of 350 M.
 // Results are bit-identical to the bucket path (same projection code, same sequential sums, same division).
+// Measured on a B200: 1.03 ms (round 1) -> 0.73 ms (mid units in the bucket path) -> 0.48 ms.
 #pragma once
 #include "common.cuh"
 #include "env_kernels.cuh"

@@ -285,7 +285,11 @@ CMR_API int cmr_take_fault(void *stream);
  *                            -> out [B*K, C, H*W] f32: channel c < mean_channels = scatter-mean of feat[c] over the
  *                            masked points that land in the pixel (:341), channel c >= mean_channels = their SUM
  *                            (:343: pass the in-camera scores as an extra channel).  mean_channels is a multiple of
- *                            64 or >= C.  Sums run in point order.  B*K <= 65535, H*W <= 12288. */
+ *                            64 or >= C.  Sums run in point order.  B*K <= 65535, H*W <= 12288.
+ *                            The reference's shape (C = 68: 64 features + score + padding, mean_channels = 64, H*W a
+ *                            multiple of 32 up to 8192, N <= 65535) takes a dedicated pair of kernels (one counting
+ *                            sort per pose, csrc/cost_volume_kernels.cuh); every other shape takes the observation's
+ *                            bucket kernels.  Same bits either way (CMR_B200_CV=buckets forces the second path). */
 CMR_API size_t cmr_cost_volume_workspace_bytes(int B, int K, int N, int C, int P);
 CMR_API int cmr_cost_volume_prepare(const uint8_t *mask, const float *feat, int B, int K, int N, int C,
                                     void *workspace, void *stream);

@@ -123,7 +123,7 @@ if __name__ == "__main__":
                             "#     python benchmarks/microbench.py tower --batch 32   (B200, 32 x 40960 points)\n"))
     if len(sys.argv) > 3 and os.path.exists(sys.argv[3]):
         cv = summarise(sys.argv[3], "r2_cost_volume_ncu.txt",
-                       '# r2: ncu --set full --clock-control none --import-source on -k regex:"k_tile_gather|k_project_masked" -s 4 -c 2\n'
+                       '# r2: ncu --set full --clock-control none --import-source on -k regex:"k_cost_volume" -s 4 -c 2\n'
                        "#     python benchmarks/microbench.py cost_volume   (B200, 729 poses of one KITTI cloud, 1.015 GB out)\n")
         tr.update({k + " (cost volume)": v for k, v in cv.items()})
     if len(sys.argv) > 4 and os.path.exists(sys.argv[4]):
