@@ -8,6 +8,7 @@ warm-up, inputs resident in HBM.
   python benchmarks/microbench.py env [--batch 32]         per-kernel times of one rollout iteration
   python benchmarks/microbench.py cost_volume              IterModel's 729-pose warp of one KITTI cloud
   python benchmarks/microbench.py tower [--batch 32]       the agent's 3-D tower (tcgen05) vs the reference's modules on cuDNN
+  python benchmarks/microbench.py sample [--batch 32]      image features sampled bilinearly at the points' projections
 """
 import argparse
 import ctypes
@@ -217,6 +218,29 @@ def cost_volume_bench(args):
                       "cpu_threads": torch.get_num_threads()}), flush=True)
 
 
+def sample_bench(args):
+    """environment.sample_image_features (north_star's point-side bilinear gather; an extension) at KITTI
+    size, ground-truth pose (about 30 % of the points inside the frustum).  Bytes: 12N in, 4CN + N out per episode."""
+    from oracle import env_oracle as eo
+    dev = torch.device("cuda:0")
+    B, N, C = args.batch, 40960, 64
+    cpu = synth.make_batch(min(B, 8), seed=2023, num_pt=N, img_h=160, img_w=512)
+    rep = (B + cpu["pc"].shape[0] - 1) // cpu["pc"].shape[0]
+    data = {}
+    for k in ("pc", "pc_overlap_pred", "pc_geo_feat", "img_geo_feat", "K", "P"):
+        data[k] = cpu[k].repeat(rep, *([1] * (cpu[k].dim() - 1)))[:B].contiguous()
+    pose = eo.to_disentangled(data["P"].clone(), data["pc"]).contiguous().to(dev)
+    for k in ("pc", "pc_overlap_pred", "pc_geo_feat", "img_geo_feat"):
+        data[k] = data[k].to(dev)
+    data["img"] = torch.zeros(1, 1, 1, 1).expand(B, 3, 160, 512)
+    feats, cam = env.sample_image_features(data, pose)            # builds the pixel-major image once
+    t = time_cuda(lambda: env.sample_image_features(data, pose), warm=3, reps=20)
+    byts = (12.0 * N + 4.0 * C * N + N) * B
+    print(json.dumps({"bench": "sample", "batch": B, "N": N, "C": C, "in_frustum_frac": float(cam.float().mean()),
+                      "sample_us": t * 1e6, "points_per_s": B * N / t, "gbs": byts / t / 1e9, "frac_of_hbm": byts / t / 1e9 / PEAK}),
+          flush=True)
+
+
 def tower_bench(args):
     """models/CMRAgent.py:92-101 at KITTI size: cmr_tower_forward against the reference's own ConvBNReLURes1D modules
     (oracle/_ref, eager cuDNN/cuBLAS on the same GPU, TF32 on - torch's default - and off).
@@ -279,9 +303,9 @@ def tower_bench(args):
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("which", choices=["frontend", "sweep", "env", "cost_volume", "tower"])
+    ap.add_argument("which", choices=["frontend", "sweep", "env", "cost_volume", "tower", "sample"])
     ap.add_argument("--batch", type=int, default=None)
     a = ap.parse_args()
     if a.batch is None:
         a.batch = 128 if a.which == "frontend" else 32
-    {"frontend": frontend, "sweep": sweep, "env": env_kernels, "cost_volume": cost_volume_bench, "tower": tower_bench}[a.which](a)
+    {"frontend": frontend, "sweep": sweep, "env": env_kernels, "cost_volume": cost_volume_bench, "tower": tower_bench, "sample": sample_bench}[a.which](a)

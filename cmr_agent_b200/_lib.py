@@ -30,6 +30,9 @@ SIGNATURES = {
     "cmr_cost_volume_workspace_bytes": (ctypes.c_size_t, [_c_int] * 5),
     "cmr_cost_volume_prepare": (_c_int, [_c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp]),
     "cmr_cost_volume_warp": (_c_int, [_c_vp] * 5 + [_c_int] * 7 + [_c_vp, _c_vp]),
+    "cmr_sample_workspace_bytes": (ctypes.c_size_t, [_c_int] * 3),
+    "cmr_sample_prepare": (_c_int, [_c_vp, _c_int, _c_int, _c_int, _c_vp, _c_vp]),
+    "cmr_sample_image_features": (_c_int, [_c_vp] * 5 + [_c_int] * 5 + [_c_vp, _c_vp, _c_vp]),
     "cmr_fps_f64": (_c_int, [_c_vp, _c_vp, _c_int, _c_int, _c_int, _c_vp, _c_vp, _c_vp]),
     "cmr_nearest_f64": (_c_int, [_c_vp, _c_vp, _c_int, _c_int, _c_int, _c_vp, _c_vp]),
     "cmr_episode_scan": (_c_int, [_c_vp, _c_int, _c_int, _c_int, _c_vp, _c_vp]),

@@ -11,6 +11,7 @@
 #include "pointnet_kernels.cuh"
 #include "scatter_kernels.cuh"
 #include "cost_volume_kernels.cuh"
+#include "sample_kernels.cuh"
 #include "dataset_kernels.cuh"
 #include "tower_kernels.cuh"
 #include "session.cuh"
@@ -822,6 +823,35 @@ int cmr_cost_volume_warp(const float *pc, const uint8_t *mask, const float *Kmat
     }
     if (rc) return rc;
     return launch_gather(L, ws, nullptr, E, N, C, P, false, out, st, K, C, 0, mean_channels, kHeavyFrom);
+}
+
+// ------------------------------------------------------------------------------ bilinear sampling ----
+// image features at the points' projections (north_star; SURVEY.md D1: an extra operator, oracle F.grid_sample)
+
+size_t cmr_sample_workspace_bytes(int B, int C, int P) {
+    if (B <= 0 || C <= 0 || P <= 0) return 0;
+    return round_up(sizeof(float) * (size_t)B * C * P, 256);
+}
+
+int cmr_sample_prepare(const float *img_feat, int B, int C, int P, void *workspace, void *stream) {
+    CMR_REQUIRE(img_feat && workspace && B > 0 && C > 0 && P > 0, CMR_EINVAL);
+    CMR_REQUIRE(B <= 65535 && ceil_div(C, 32) <= 65535, CMR_ERANGE);
+    CMR_REQUIRE(aligned(workspace, 256), CMR_EALIGN);
+    k_image_transpose<<<dim3(ceil_div(P, 32), ceil_div(C, 32), B), 256, 0, S_(stream)>>>(img_feat, C, P, static_cast<float *>(workspace));
+    return after_launch();
+}
+
+int cmr_sample_image_features(const float *pc, const float *Kmat, const float *pose, const float *mean, const void *workspace,
+                              int B, int N, int C, int H, int W, float *out, uint8_t *in_cam, void *stream) {
+    CMR_REQUIRE(pc && Kmat && pose && mean && workspace && out && B > 0 && N > 0 && C > 0 && H > 0 && W > 0, CMR_EINVAL);
+    CMR_REQUIRE(B <= 65535 && (long long)H * W < (1LL << 31) / 4 && (C % 2) == 0, CMR_ERANGE);
+    CMR_REQUIRE(aligned(pose, 16) && aligned(workspace, 256), CMR_EALIGN);
+    int rc = allow_smem(k_bilinear_sample, kSmpSmem);
+    if (rc) return rc;
+    const bool vec = (N % 4 == 0) && aligned(out, 16);
+    k_bilinear_sample<<<dim3(ceil_div(N, 32 * kSmpWarps), B), kSmpThreads, kSmpSmem, S_(stream)>>>(
+        pc, Kmat, pose, mean, static_cast<const float *>(workspace), N, C, H, W, vec, out, in_cam);
+    return after_launch();
 }
 
 // ------------------------------------------------------------------------------ dataset side ----

@@ -170,6 +170,7 @@ class _Episode:
         _lib.call("cmr_episode_prepare", _lib.ptr(self.overlap), _lib.ptr(feat), B, N, C, _lib.ptr(self.ws),
                   _lib.stream())
         # everything cmr_observe needs that does not change between iterations, ready for ctypes
+        self.img_rows = None     # sample_image_features: the image features pixel-major, built on first use
         self.observe_head = (self.pc.data_ptr(), self.overlap.data_ptr(), self.img_feat.data_ptr(), self.K.data_ptr())
         self.observe_mid = (self.mean.data_ptr(), self.ws.data_ptr(), B, N, C, H, W)
         self.obs2d_shape = (B, 2 * C, H, W)
@@ -223,6 +224,34 @@ def observation_from_a_pose(data, RT, return_pixels=False):
     if return_pixels:
         return obs2d, obs3d, pix, mvis
     return obs2d, obs3d
+
+
+@torch.no_grad()
+def sample_image_features(data, RT):
+    """Image features sampled bilinearly at every point's projection (BASELINE.json north_star: "bilinearly sample
+    image features onto visible points").  An EXTENSION - the reference has no point-side gather; the
+    operator is ``F.grid_sample(img_geo_feat, uv, mode="bilinear", padding_mode="zeros", align_corners=True)`` at
+    the pixel coordinates of environment.py:54-59, zero for points outside the frustum of :61-65
+    (oracle/sample_oracle.py).
+
+    -> (features [B,C,N] f32 - the layout of data["pc_geo_feat"] -, in_cam [B,N] bool)."""
+    ep = _episode(data)
+    if not (RT.is_cuda and RT.dtype is torch.float32 and RT.is_contiguous()):
+        RT = _dev_f32(RT, "RT")
+    if tuple(RT.shape) != ep.pose_shape:
+        raise _lib.CmrError(f"RT must be {list(ep.pose_shape)}")
+    if ep.C % 2:
+        raise _lib.CmrError("sample_image_features: an even number of channels is required")
+    st = _lib.stream()
+    if ep.img_rows is None:      # [B, H*W, C]: a pixel's channels as one row; does not depend on the pose
+        nbytes = _lib.load().cmr_sample_workspace_bytes(ep.B, ep.C, ep.H * ep.W)
+        ep.img_rows = torch.empty(nbytes, dtype=torch.uint8, device=ep.device)
+        _lib.call("cmr_sample_prepare", _lib.ptr(ep.img_feat), ep.B, ep.C, ep.H * ep.W, _lib.ptr(ep.img_rows), st)
+    feats = torch.empty(ep.B, ep.C, ep.N, device=ep.device, dtype=torch.float32)
+    in_cam = torch.empty(ep.B, ep.N, device=ep.device, dtype=torch.uint8)
+    _lib.call("cmr_sample_image_features", _lib.ptr(ep.pc), _lib.ptr(ep.K), _lib.ptr(RT), _lib.ptr(ep.mean),
+              _lib.ptr(ep.img_rows), ep.B, ep.N, ep.C, ep.H, ep.W, _lib.ptr(feats), _lib.ptr(in_cam), st)
+    return feats, in_cam.view(torch.bool)
 
 
 def init(data):

@@ -297,6 +297,24 @@ CMR_API int cmr_cost_volume_warp(const float *pc, const uint8_t *mask, const flo
                                  void *workspace, int B, int K, int N, int C, int H, int W, int mean_channels,
                                  float *out, void *stream);
 
+/* ------------------------------------------------------------------ bilinear sampling ---- */
+
+/* Image features sampled bilinearly at the points' projections ("bilinearly sample image features onto visible points",
+ * BASELINE.json north_star).  An EXTRA operator: the reference has no point-side gather - its
+ * observation is the reverse scatter of environment/environment.py:67-83, cmr_observe above - so this one is
+ * specified by F.grid_sample(mode="bilinear", padding_mode="zeros", align_corners=True) evaluated at the pixel
+ * coordinates of environment.py:54-59, times the frustum mask of :61-65 (oracle/sample_oracle.py).
+ *   cmr_sample_prepare         once per batch of images: img_feat [B,C,P] f32 -> workspace ([B,P,C], a pixel = one row)
+ *   cmr_sample_image_features  pc [B,3,N], Kmat [B,3,3], pose [B,4,4] (16-byte aligned), mean [B,3] (the clouds' means,
+ *                              cmr_episode_prepare) -> out [B,C,N] f32 (zero where the point is outside the frustum),
+ *                              in_cam [B,N] u8 (may be NULL).  C even.  The four weighted neighbours are summed left to
+ *                              right, every operation rounded: bit-identical to the CPU restatement. */
+CMR_API size_t cmr_sample_workspace_bytes(int B, int C, int P);
+CMR_API int cmr_sample_prepare(const float *img_feat, int B, int C, int P, void *workspace, void *stream);
+CMR_API int cmr_sample_image_features(const float *pc, const float *Kmat, const float *pose, const float *mean,
+                                      const void *workspace, int B, int N, int C, int H, int W, float *out,
+                                      uint8_t *in_cam, void *stream);
+
 /* ------------------------------------------------------------------ agent: 3-D tower ---- */
 
 /* The 3-D state tower of the agent - models/CMRAgent.py:25-29 (state_3d_embed: four ConvBNReLURes1D blocks,

@@ -1,6 +1,6 @@
 """Round-2 summaries from the captures a gpurun call leaves in gpurun_out/ (tracked copies live here).
 
-    python profiles/make_r2.py <env.ncu-rep> <tower.ncu-rep> [cost_volume.ncu-rep] [bench_launches.csv]
+    python profiles/make_r2.py <env.ncu-rep> <tower.ncu-rep> [cost_volume.ncu-rep] [bench_launches.csv] [sample.ncu-rep]
 
 Outputs: r2_env_kernels_ncu.txt, r2_tower_ncu.txt, r2_cost_volume_ncu.txt, dram_traffic.json, r2_sass_evidence.txt,
 r2_bench_launches.csv + r2_bench_launches_summary.txt
@@ -128,6 +128,11 @@ if __name__ == "__main__":
         tr.update({k + " (cost volume)": v for k, v in cv.items()})
     if len(sys.argv) > 4 and os.path.exists(sys.argv[4]):
         launches(sys.argv[4])
+    if len(sys.argv) > 5 and os.path.exists(sys.argv[5]):
+        sm = summarise(sys.argv[5], "r2_sample_ncu.txt",
+                       '# r2: ncu --set full --clock-control none --import-source on -k regex:"k_bilinear_sample" -s 3 -c 1\n'
+                       "#     python benchmarks/microbench.py sample   (B200, 32 KITTI episodes at the ground-truth pose)\n")
+        tr.update(sm)
     if tr:
         tr["note"] = ("dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full --clock-control none, round 2. "
                       "Below the algorithmic bytes where a kernel's output is still in the 126 MB L2 when it ends.")
