@@ -29,6 +29,7 @@ data-path collective ("weak" scaling: 32 episodes per GPU).
 import argparse
 import ctypes
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -701,6 +702,64 @@ def tower_bench(dev, B, N, bf16_peak):
             "frac_of_bf16_sustained": tensor_tf / bf16_peak, "passes": "3 x fp16 (split operands), fp32 accumulate in TMEM"}
 
 
+def _median_ms(fn, dev, warm=2, reps=5):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize(dev)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for a, b in ev:
+        a.record()
+        fn()
+        b.record()
+    torch.cuda.synchronize(dev)
+    return statistics.median(a.elapsed_time(b) for a, b in ev)
+
+
+def cost_volume_bench(dev, peak, nlabel=9):
+    """IterModel's cost-volume warp (models/IterModel.py:272-351) at the reference's sizes - one KITTI cloud,
+    nlabel^3 = 729 candidate poses around the ground truth, 68 x 5120 floats out per pose.  The whole call (prepare + warp)."""
+    from cmr_agent_b200 import cost_volume
+    data = synth.make_batch(1, seed=SEED + 3, **SHAPE)
+    g = torch.Generator().manual_seed(SEED + 4)
+    scores = torch.rand(1, SHAPE["num_pt"], generator=g)
+    base = torch.linspace(-(nlabel - 1) / 2, (nlabel - 1) / 2, nlabel)
+    gt = data["P"][0, 0:3, :]
+    poses = []
+    for ry in base * (0.3 / (nlabel - 1)):
+        c, s_ = math.cos(float(ry)), math.sin(float(ry))
+        R = torch.tensor([[c, 0.0, s_], [0.0, 1.0, 0.0], [-s_, 0.0, c]])
+        for tx in base * (4.0 / (nlabel - 1)):
+            for tz in base * (4.0 / (nlabel - 1)):
+                poses.append(torch.cat([R @ gt[:, 0:3], R @ gt[:, 3:4] + torch.tensor([[float(tx)], [0.0], [float(tz)]])], dim=1))
+    poses = torch.stack(poses).unsqueeze(0).contiguous()
+    H, W = SHAPE["img_h"] // 4, SHAPE["img_w"] // 4
+    dargs = (data["pc"].to(dev), data["pc_overlap_pred"][0].to(dev), poses.to(dev), data["K"], data["pc_geo_feat"].to(dev),
+             scores.to(dev), H, W)
+    ms = _median_ms(lambda: cost_volume.warp(*dargs), dev)
+    wf, occ = cost_volume.warp(*dargs)
+    out_bytes = poses.shape[1] * 68.0 * H * W * 4
+    return {"poses": int(poses.shape[1]), "masked_points": int(data["pc_overlap_pred"][0].sum()),
+            "occupied_pixels_per_pose": float((occ > 0).sum()) / poses.shape[1], "ms": ms, "output_gbs": out_bytes / ms / 1e6,
+            "output_frac_of_hbm": out_bytes / ms / 1e6 / peak}
+
+
+def sample_bench(dev, peak, cpu, B):
+    """environment.sample_image_features (north_star's point-side bilinear gather, an extension - SURVEY D1) on this rank's
+    episodes at the ground-truth pose.  Bytes per episode: 12N in, 4CN + N out (the feature map stays in L2)."""
+    from cmr_agent_b200 import environment as env
+    data = dict(cpu)
+    for k in ("pc", "pc_overlap_pred", "pc_geo_feat", "img_geo_feat"):
+        data[k] = cpu[k].to(dev)
+    pose = cpu["P"].to(dev).clone()
+    env.to_disentangled(pose, data["pc"])
+    feats, cam = env.sample_image_features(data, pose)
+    ms = _median_ms(lambda: env.sample_image_features(data, pose), dev, warm=3, reps=10)
+    N, C = SHAPE["num_pt"], 64
+    byts = (12.0 * N + 4.0 * C * N + N) * B
+    return {"batch": B, "in_frustum_frac": float(cam.float().mean()), "us": ms * 1e3, "gbs": byts / ms / 1e6,
+            "frac_of_hbm": byts / ms / 1e6 / peak}
+
+
 def secondary_block(args, rank, world, local, dev, peak, bf16_peak, cpu, a_r, a_t):
     from cmr_agent_b200 import _lib
     sec = {}
@@ -764,6 +823,10 @@ def secondary_block(args, rank, world, local, dev, peak, bf16_peak, cpu, a_r, a_
         sec["frontend_b128"] = frontend_bench(dev, 128, with_cpu=not args.no_cpu_baseline)
         # ---- the agent's 3-D tower
         sec["tower3d"] = tower_bench(dev, args.batch, SHAPE["num_pt"], bf16_peak)
+        # ---- the cost-volume warp and the point-side bilinear gather (north_star)
+        sec["cost_volume_729_poses"] = cost_volume_bench(dev, peak)
+        sec["sample_image_features"] = sample_bench(dev, peak, cpu, args.batch)
+        torch.cuda.empty_cache()
         # ---- the reference's own environment.py on CUDA tensors
         sec["gpu_torch_baseline"] = gpu_torch_baseline(dev, cpu, a_r, a_t, iters)
     return sec
