@@ -158,11 +158,12 @@ def test_gpu_bucket_path_matches_oracle(cuda, monkeypatch, B, N, img_h, img_w, n
 
 
 @pytest.mark.gpu
-def test_gpu_cloud_collapsed_onto_few_pixels(cuda):
-    """A cloud seen from far away: tens of thousands of points on a handful of pixels (the bitmap ordering of
-    k_cost_volume_pose; a quadratic ranking would take seconds here)."""
+@pytest.mark.parametrize("N", [40960, 8192])     # lists in global memory / in shared memory
+def test_gpu_cloud_collapsed_onto_few_pixels(cuda, N):
+    """A cloud seen from far away: thousands of points on a handful of pixels (the bitmap ordering of
+    k_cost_volume_sort; a quadratic ranking would take seconds here)."""
     from cmr_agent_b200 import cost_volume
-    data, mask, poses, scores = _case(1, 40960, 160, 512, 2, 5, True)
+    data, mask, poses, scores = _case(1, N, 160, 512, 2, 5, True)
     poses = poses.clone()
     poses[:, :, 2, 3] += 4000.0          # push the cloud 4 km down the optical axis
     H, W = 40, 128
