@@ -1159,13 +1159,13 @@ int cmr_tower_forward(const float *obs3d, const void *blob1, const void *blob2, 
     alignas(64) CUtensorMap m[4];
     for (int i = 0; i < 4; ++i)
         if (!make_plane_map(&m[i], plane[i], (uint64_t)N, (uint64_t)B, rows)) return CMR_EUNSUPPORTED;
-    // block 1 (fp32 pipes): obs3d -> planes 0,1
+    // block 1 (five hidden channels on the fp32 pipes, the 64 outputs as one K = 16 GEMM): obs3d -> planes 0,1
     {
-        const size_t smem = 32768 + TowerBlobFirst::total;
+        const size_t smem = FirstCfg::smem_bytes;
         int rc = allow_smem(k_tower_first, smem);
         if (rc) return rc;
-        const int grid = std::min(B * tiles_per_ep, 6 * sm_count());   // 6 CTAs fit an SM (registers, shared memory)
-        rc = launch_pdl(k_tower_first, dim3(grid), dim3(128), smem, st, obs3d, static_cast<const unsigned char *>(blob1), B, N,
+        const int grid = std::min(B * tiles_per_ep, sm_count());
+        rc = launch_pdl(k_tower_first, dim3(grid), dim3(kFirstThreads), smem, st, obs3d, static_cast<const unsigned char *>(blob1), B, N,
                         tiles_per_ep, m[0], m[1], keys1);
         if (rc) return rc;
     }

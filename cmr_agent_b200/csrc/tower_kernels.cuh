@@ -7,7 +7,7 @@
 //
 // Algebra (oracle/tower_oracle.py):  the input of blocks 2-4 is cat([feat (64), max_prev.repeat(N) (64)]), so the
 // half of every first-layer product that meets the repeated max is a PER-EPISODE BIAS  W[:, 64:] @ max_prev.
-//   block 1 (k_tower_first, packed fp32 FFMA2 - K = 5 is no tensor-core shape):
+//   block 1 (k_tower_first: h on the fp32 pipes, the 64 outputs as ONE K = 16 tensor-core GEMM over (x, h, 1)):
 //       h = lrelu(W1 x + b1) (5 ch);  out = lrelu(W2 h + Ws x + (b2 + bs))              -> feat1 [64]
 //   blocks 2, 3 (k_tower_mma<false>):
 //       h = lrelu(W1a feat + bias1_e)           (128 ch;  bias1_e = b1 + W1b max_prev)
@@ -110,13 +110,15 @@ struct TowerBlobLast {
     static constexpr int b2 = b1 + 128 * 4;                 // [128]
     static constexpr int total = b2 + 128 * 4;
 };
-// block 1: fp32, per PAIR of output channels (c, c+1) 24 floats: {W2[c][i], W2[c+1][i]} i<5, {Ws[c][i], Ws[c+1][i]} i<5,
-// {b2+bs of c, of c+1}, 2 x 0 - ready for packed FFMA2; then W1 [5][5], b1 [5]
+// block 1: W1 [5][5] and b1 [5] in fp32 (the five hidden channels are computed on the fp32 pipes), then the B operand of
+// its one GEMM, hi | lo: [64 rows][K = 16] in rows of 128 bytes (the swizzled K-major layout of the other blocks; only
+// the first two 16-byte chunks of a row are used).  K slots: 0-4 the point's inputs x (weights Ws), 5-9 the hidden
+// channels h (weights W2), 10 the constant 1 (weight b2 + bs), 11-15 zero.
 struct TowerBlobFirst {
-    static constexpr int rows = 0;                          // [32][24] f32
-    static constexpr int w1 = 32 * 24 * 4;                  // [5][5]
-    static constexpr int b1 = w1 + 25 * 4;                  // [5]
-    static constexpr int total = ((b1 + 5 * 4 + 15) / 16) * 16;
+    static constexpr int w1 = 0;                            // [5][5] f32
+    static constexpr int b1 = 25 * 4;                       // [5] f32
+    static constexpr int w_hi = 128, w_lo = 128 + 8192;     // [64][64] 16-bit each
+    static constexpr int total = 128 + 2 * 8192;
 };
 
 // ---- order-preserving float <-> uint keys for atomicMax (0 = "no value yet") ---------------------------------------
@@ -349,10 +351,10 @@ __global__ void k_tower_pack(int kind, const float *__restrict__ W1, const float
                              unsigned char *__restrict__ blob) {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     if (kind == 0) {
-        float *rows = reinterpret_cast<float *>(blob + TowerBlobFirst::rows);
-        for (int i = tid; i < 32 * 24; i += nth) {
-            const int pr = i / 24, j = i % 24, c = 2 * pr + (j & 1), k = j >> 1;   // k: 0-4 W2, 5-9 Ws, 10 bias, 11 pad
-            rows[i] = k < 5 ? W2[c * 5 + k] : k < 10 ? Ws[c * 5 + k - 5] : k == 10 ? __fadd_rn(b2[c], bs[c]) : 0.f;
+        for (int i = tid; i < 64 * 16; i += nth) {
+            const int c = i >> 4, k = i & 15;
+            const float w = k < 5 ? Ws[c * 5 + k] : k < 10 ? W2[c * 5 + k - 5] : k == 10 ? __fadd_rn(b2[c], bs[c]) : 0.f;
+            pack_split(blob + TowerBlobFirst::w_hi, blob + TowerBlobFirst::w_lo, c, k, w);
         }
         float *w1 = reinterpret_cast<float *>(blob + TowerBlobFirst::w1);
         for (int i = tid; i < 25; i += nth) w1[i] = W1[i];
@@ -455,119 +457,239 @@ __device__ __forceinline__ void tower_stage_cols16(unsigned char *planes, int pl
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// k_tower_first: block 1 on the fp32 pipes.  thread = point; obs3d [B][5][N] -> feat1 planes (hi, lo) + max keys.
-__global__ void __launch_bounds__(128) k_tower_first(const float *__restrict__ obs3d, const unsigned char *__restrict__ blob, int B, int N,
-                                                     int tiles_per_ep, const __grid_constant__ CUtensorMap map_hi,
-                                                     const __grid_constant__ CUtensorMap map_lo, unsigned *__restrict__ max_keys) {
+// k_tower_first: block 1.  obs3d [B][5][N] -> feat1 planes (hi, lo) + max keys.
+//   h = lrelu(W1 x + b1)             five channels, on the fp32 pipes (25 FMAs per point)
+//   out = lrelu(W2 h + Ws x + b)     64 channels: ONE K = 16 GEMM per 128-point tile on the tensor core - the A row of a
+//                                    point is (x, h, 1, 0...), the B operand (Ws | W2 | b2 + bs | 0), three fp16 passes
+//                                    (the constant 1 has no low piece: the bias arrives exactly split)
+// Until this version the 64 channels were 320 packed FFMA2 per point: 99 us for the KITTI batch, as much as a whole
+// 128-to-64-channel block on the tensor core.
+// Warps (480 threads, one CTA per SM, a contiguous range of tiles each):
+//   0      the weights (one bulk copy)             1      TMEM allocation (2 x 64 columns) + MMA issue (converged, elected)
+//   2-5    builders: thread = point; x (the next tile's already on its way), h, the A row's two 16-byte chunks per
+//          piece into the stage (two stages)
+//   6-13   epilogue: warp = (TMEM lane quarter) x (32 of the 64 columns, 16 at a time): lrelu, fp16 hi|lo pieces into
+//          the output staging (two buffers), running maxima per point lane in registers
+//   14     TMA stores of the staged tiles
+// 86 us for 32 x 40960 points = 4.2 TB/s, 64 % of the HBM peak (276 bytes per point).  Measured and dropped: a second
+// epilogue group on alternate tiles (86 us) and a second builder group as well (864 threads, spills: 102 us).
+constexpr int kFirstThreads = 480;
+struct FirstCfg {
+    static constexpr int off_w = 0;                               // B operand: hi 8 KB | lo 8 KB
+    static constexpr int off_a = 16384;                           // 2 stages x (hi 16 KB | lo 16 KB): [128 rows][128 B], first 32 B used
+    static constexpr int off_out = off_a + 2 * 32768;             // 2 x (hi 16 KB | lo 16 KB): the output planes of a tile
+    static constexpr int off_bars = off_out + 2 * 32768;
+    static constexpr int kNumBars = 1 + 6 * 2;
+    static constexpr int off_tmem_slot = off_bars + kNumBars * 8;
+    static constexpr int smem_bytes = off_tmem_slot + 16;
+};
+
+__global__ void __launch_bounds__(kFirstThreads, 1)
+    k_tower_first(const float *__restrict__ obs3d, const unsigned char *__restrict__ blob, int B, int N, int tiles_per_ep,
+                  const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, unsigned *__restrict__ max_keys) {
     extern __shared__ __align__(1024) unsigned char tower_smem[];
     unsigned char *const smem = tower_smem;
-    unsigned char *planes = smem;                                  // 2 x 16 KB
-    float *wrow = reinterpret_cast<float *>(smem + 32768);         // [32 channel pairs][24]
-    float *w1 = wrow + 32 * 24;                                    // [25] + b1 [5]
-    const int tid = threadIdx.x, lane = tid & 31;
-    for (int i = tid; i < TowerBlobFirst::total / 4; i += 128) wrow[i] = reinterpret_cast<const float *>(blob)[i];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + FirstCfg::off_bars);
+    uint64_t *w_full = bars, *a_full = bars + 1, *a_empty = a_full + 2, *d_full = a_empty + 2, *d_empty = d_full + 2, *o_full = d_empty + 2,
+             *o_free = o_full + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + FirstCfg::off_tmem_slot);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    int t0, t1;
+    tower_tile_range(B * tiles_per_ep, blockIdx.x, gridDim.x, t0, t1);
+    const int ntiles = t1 - t0;
     if (tid == 0) {
+        mbar_init(w_full, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(a_full + s, 128);
+            mbar_init(a_empty + s, 1);
+            mbar_init(d_full + s, 1);
+            mbar_init(d_empty + s, 256);
+            mbar_init(o_full + s, 256);
+            mbar_init(o_free + s, 1);
+        }
         tma_prefetch_map(&map_hi);
         tma_prefetch_map(&map_lo);
     }
+    if (warp == 1) tmem_alloc(tmem_slot, 128);
+    tc_fence_before();
     __syncthreads();
-    pdl_wait();        // obs3d is the previous kernel's output when the tower follows cmr_observe in a stream
-    int t0, t1;
-    tower_tile_range(B * tiles_per_ep, blockIdx.x, gridDim.x, t0, t1);
-    // running maxima per point lane, in registers across the tiles of an episode; exchanged across the warp at a flush
-    constexpr int kR = kTowerRegMax ? 64 : 2;
-    float rmx[kR];                                       // kTowerRegMax: per value; else: per 32-channel chunk, lane = channel
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    // walks the CTA's tiles without a division per tile
+    int e = t0 / tiles_per_ep, n0 = (t0 - e * tiles_per_ep) * kTowerTile - kTowerTile;
+    auto next_tile = [&]() {
+        n0 += kTowerTile;
+        if (n0 >= tiles_per_ep * kTowerTile) {
+            n0 = 0;
+            ++e;
+        }
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {   // the weights do not depend on the previous kernel
+            mbar_arrive_expect_tx(w_full, 16384);
+            bulk_g2s(smem + FirstCfg::off_w, blob + TowerBlobFirst::w_hi, 16384, w_full);
+        }
+    } else if (warp == 1) {
+        // ============================== MMA issuer (whole warp, converged; see mma_ss) ==============================
+        const uint32_t sbase = smem_u32(smem);
+        mbar_wait(w_full, 0);
+        __syncwarp();
+        for (int i = 0; i < ntiles; ++i) {
+            const int s = i & 1;
+            mbar_wait(a_full + s, (i >> 1) & 1);
+            if (i >= 2) mbar_wait(d_empty + s, ((i >> 1) - 1) & 1);
+            __syncwarp();
+            tc_fence_after();
+            const uint32_t a = sbase + FirstCfg::off_a + s * 32768, d = tmem_base + s * 64;
 #pragma unroll
-    for (int i = 0; i < kR; ++i) rmx[i] = -INFINITY;
-    int cur_ep = -1;
-    auto flush = [&]() {
+            for (int pass = 0; pass < kTowerPasses; ++pass)
+                mma_ss(d, umma_desc_sw128(a + (tower_pass_a(pass) ? 16384 : 0)),
+                       umma_desc_sw128(sbase + FirstCfg::off_w + (tower_pass_b(pass) ? 8192 : 0)), tower_idesc(64, pass), pass != 0);
+            tc_commit(d_full + s);
+            tc_commit(a_empty + s);
+        }
+    } else if (warp < 6) {
+        // ============================== builders: thread = point ==============================
+        const int p = tid - 64;
+        float w1[25], b1[5];
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            float m;
-            if (kTowerRegMax) {
+        for (int i = 0; i < 25; ++i) w1[i] = __ldg(reinterpret_cast<const float *>(blob + TowerBlobFirst::w1) + i);
+#pragma unroll
+        for (int i = 0; i < 5; ++i) b1[i] = __ldg(reinterpret_cast<const float *>(blob + TowerBlobFirst::b1) + i);
+        pdl_wait();   // obs3d comes from the kernel before
+        // the next tile's inputs are loaded while this tile is built (a builder that waited for its own loads set the
+        // kernel's pace: one DRAM round trip per tile)
+        auto load_x = [&](float (&xx)[5]) {
+            const int n = n0 + p;
+#pragma unroll
+            for (int c = 0; c < 5; ++c) xx[c] = n < N ? __ldg(obs3d + ((size_t)e * 5 + c) * N + n) : 0.f;
+        };
+        float xn[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+        if (ntiles > 0) {
+            next_tile();
+            load_x(xn);
+        }
+        for (int i = 0; i < ntiles; ++i) {
+            const int s = i & 1;
+            float x[5], h[5];
+#pragma unroll
+            for (int c = 0; c < 5; ++c) x[c] = xn[c];
+            if (i + 1 < ntiles) {
+                next_tile();
+                load_x(xn);
+            }
+#pragma unroll
+            for (int o = 0; o < 5; ++o) {
+                float a = b1[o];
+#pragma unroll
+                for (int c = 0; c < 5; ++c) a = __fmaf_rn(w1[o * 5 + c], x[c], a);
+                h[o] = lrelu(a);
+            }
+            // the A row: K slots (x0..x4, h0..h4, 1, 0 x 5) as fp16 pairs, hi and lo pieces
+            const float in[16] = {x[0], x[1], x[2], x[3], x[4], h[0], h[1], h[2], h[3], h[4], 1.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            uint4 hi[2], lo[2];
+            unsigned *ph = &hi[0].x, *pl = &lo[0].x;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float2 ab = make_float2(in[2 * q], in[2 * q + 1]);
+                const unsigned hh = pack2(ab.x, ab.y);
+                const float2 res = sub2(ab, unpack2(hh));
+                ph[q] = hh;
+                pl[q] = pack2(res.x, res.y);
+            }
+            if (i >= 2) mbar_wait(a_empty + s, ((i >> 1) - 1) & 1);   // the MMAs that read this stage are done
+            unsigned char *st = smem + FirstCfg::off_a + s * 32768 + p * 128;
+            *reinterpret_cast<uint4 *>(st + ((0 ^ (p & 7)) << 4)) = hi[0];
+            *reinterpret_cast<uint4 *>(st + ((1 ^ (p & 7)) << 4)) = hi[1];
+            *reinterpret_cast<uint4 *>(st + 16384 + ((0 ^ (p & 7)) << 4)) = lo[0];
+            *reinterpret_cast<uint4 *>(st + 16384 + ((1 ^ (p & 7)) << 4)) = lo[1];
+            fence_async_proxy();   // generic-proxy writes, read by the tensor core through the async proxy
+            mbar_arrive(a_full + s);
+        }
+    } else if (warp < 14) {
+        // ============================== epilogue ==============================
+        const int ew = warp - 6;
+        const int half = ew >> 2;                       // which 32 of the 64 columns
+        const int wq = warp & 3;                        // TMEM lane quarter this warp may touch
+        const int p = wq * 32 + lane;                   // point of the tile = TMEM lane
+        const uint32_t d0 = tmem_base + ((uint32_t)(wq * 32) << 16) + 32 * half;
+        float rmx[32];
+#pragma unroll
+        for (int q = 0; q < 32; ++q) rmx[q] = -INFINITY;
+        int cur_ep = -1;
+        auto flush = [&]() {
+            if (cur_ep >= 0) {
                 float t[32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) t[i] = rmx[(32 * j + i) % kR];
-                m = warp_transpose_max(t, lane);
-            } else {
-                m = rmx[j];
+                for (int q = 0; q < 32; ++q) t[q] = rmx[q];
+                const float m = warp_transpose_max(t, lane);
+                atomicMax(max_keys + cur_ep * 64 + 32 * half + lane, f2key(m));
             }
-            if (cur_ep >= 0) atomicMax(max_keys + cur_ep * 64 + 32 * j + lane, f2key(m));
-        }
 #pragma unroll
-        for (int i = 0; i < kR; ++i) rmx[i] = -INFINITY;
-    };
-    for (int t = t0; t < t1; ++t) {
-        const int e = t / tiles_per_ep, n0 = (t - e * tiles_per_ep) * kTowerTile;
-        if (e != cur_ep) {
-            flush();
-            cur_ep = e;
-        }
-        const int n = n0 + tid;
-        const bool valid = n < N;
-        float x[5], h[5];
-#pragma unroll
-        for (int c = 0; c < 5; ++c) x[c] = valid ? __ldg(obs3d + ((size_t)e * 5 + c) * N + n) : 0.f;
-#pragma unroll
-        for (int o = 0; o < 5; ++o) {
-            float a = w1[25 + o];
-#pragma unroll
-            for (int c = 0; c < 5; ++c) a = __fmaf_rn(w1[o * 5 + c], x[c], a);
-            h[o] = lrelu(a);
-        }
-        float2 in2[10];                                  // every input duplicated: one FFMA2 serves two output channels
-#pragma unroll
-        for (int i = 0; i < 5; ++i) {
-            in2[i] = make_float2(h[i], h[i]);
-            in2[5 + i] = make_float2(x[i], x[i]);
-        }
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            float v[32];
-#pragma unroll
-            for (int pr = 0; pr < 16; ++pr) {
-                const float4 *r = reinterpret_cast<const float4 *>(wrow + (16 * j + pr) * 24);
-                const float4 r0 = r[0], r1 = r[1], r2 = r[2], r3 = r[3], r4 = r[4], r5 = r[5];
-                float2 a = make_float2(r5.x, r5.y);      // (b2 + bs) of the two channels
-                a = fma2(make_float2(r0.x, r0.y), in2[0], a);
-                a = fma2(make_float2(r0.z, r0.w), in2[1], a);
-                a = fma2(make_float2(r1.x, r1.y), in2[2], a);
-                a = fma2(make_float2(r1.z, r1.w), in2[3], a);
-                a = fma2(make_float2(r2.x, r2.y), in2[4], a);
-                a = fma2(make_float2(r2.z, r2.w), in2[5], a);
-                a = fma2(make_float2(r3.x, r3.y), in2[6], a);
-                a = fma2(make_float2(r3.z, r3.w), in2[7], a);
-                a = fma2(make_float2(r4.x, r4.y), in2[8], a);
-                a = fma2(make_float2(r4.z, r4.w), in2[9], a);
-                a = lrelu2(a);
-                v[2 * pr] = a.x;
-                v[2 * pr + 1] = a.y;
+            for (int q = 0; q < 32; ++q) rmx[q] = -INFINITY;
+        };
+        pdl_wait();   // the keys were cleared before this kernel
+        for (int i = 0; i < ntiles; ++i) {
+            next_tile();
+            if (e != cur_ep) {
+                flush();
+                cur_ep = e;
             }
-            tower_stage_chunk<2>(planes, 16384, tid, j, v);
-            if (kTowerRegMax) {
+            const int grp = i & 1;                       // accumulator and staging buffer of this tile
+            const uint32_t d = d0 + grp * 64;
+            unsigned char *ostage = smem + FirstCfg::off_out + grp * 32768;
+            const uint32_t par = (i >> 1) & 1;
+            const bool valid = n0 + p < N;
+            mbar_wait(d_full + grp, par);
+            tc_fence_after();
+            uint32_t r0[16], r1[16];
+            tmem_ld16(d, r0);
+            tmem_ld16(d + 16, r1);
+            tc_wait_ld();
+            tc_fence_before();
+            mbar_arrive(d_empty + grp);                  // the accumulator may be overwritten
+            if (i >= 2) mbar_wait(o_free + grp, par ^ 1);   // the store of tile i - 2 has read the staging buffer
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                float v[16];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const uint32_t a0 = hh ? r1[2 * q] : r0[2 * q], a1 = hh ? r1[2 * q + 1] : r0[2 * q + 1];
+                    const float2 a = lrelu2(make_float2(__uint_as_float(a0), __uint_as_float(a1)));
+                    v[2 * q] = a.x;
+                    v[2 * q + 1] = a.y;
+                }
+                tower_stage_cols16(ostage, 16384, p, 2 * half + hh, v);
                 if (valid) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) rmx[(32 * j + i) % kR] = max_nan(rmx[(32 * j + i) % kR], v[i]);
+                    for (int q = 0; q < 16; ++q) rmx[16 * hh + q] = max_nan(rmx[16 * hh + q], v[q]);
                 }
-            } else {
-                if (!valid) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = -INFINITY;
-                }
-                rmx[j] = max_nan(rmx[j], warp_transpose_max(v, lane));
             }
+            fence_async_proxy();
+            mbar_arrive(o_full + grp);
         }
-        fence_async_proxy();
-        __syncthreads();
-        if (tid == 0) {
-            tma_store_3d(&map_hi, 0, n0, e, planes);
-            tma_store_3d(&map_lo, 0, n0, e, planes + 16384);
-            bulk_commit();
-            tma_store_3d_wait_read();
+        flush();
+    } else {
+        // ============================== TMA-store warp ==============================
+        if (lane == 0) {
+            for (int i = 0; i < ntiles; ++i) {
+                next_tile();
+                const int s = i & 1;
+                unsigned char *ostage = smem + FirstCfg::off_out + s * 32768;
+                mbar_wait(o_full + s, (i >> 1) & 1);
+                tma_store_3d(&map_hi, 0, n0, e, ostage);
+                tma_store_3d(&map_lo, 0, n0, e, ostage + 16384);
+                bulk_commit();
+                tma_store_3d_wait_read();
+                mbar_arrive(o_free + s);
+            }
+            tma_store_3d_wait_all();                     // the next block reads these planes
         }
-        __syncthreads();
     }
-    flush();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 128);
     pdl_launch_dependents();
 }
 
