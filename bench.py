@@ -679,6 +679,96 @@ def gpu_torch_baseline(dev, cpu, a_r, a_t, iters):
             "(torch " + torch.__version__ + ", torch_scatter shim), features resident, 2 rollouts"}
 
 
+def agent_loop_bench(dev, batches=(1, 8, 32), iters=10, reps=3):
+    """BASELINE configs[0] / SURVEY 8d: the reference's own Test_Agent.py:150-170 loop - observation, the UNCHANGED
+    random-init CMRAgent (eval), deterministic actions, step - timed per iteration (wall clock, synchronised at both
+    ends; the loop's host work is part of what a user waits for) three ways: the reference's environment.py on CUDA
+    tensors, the drop-in environment, the drop-in environment with the agent's 3-D tower on tcgen05
+    (agent_tower.accelerate_agent).  Inputs resident on the device, as after the reference's feature networks."""
+    from oracle import reference_loader as rl
+    if not rl.available():
+        return {"unavailable": "oracle/_ref not staged (run oracle/make_ref.py where /root/reference exists)"}
+    import cmr_agent_b200
+    from cmr_agent_b200 import agent_tower, environment as drop_env
+    rl.put_on_path()
+    cmr_agent_b200.install()
+    out = {"loop": "Test_Agent.py:150-170, %d iterations, median of %d" % (iters, reps), "batches": []}
+    try:
+        from config import KittiConfiguration
+        from models import CMRAgent
+        ref_env = rl.environment()
+        old_device = ref_env.DEVICE
+        ref_env.DEVICE = dev
+        config = KittiConfiguration()
+        config.action_num = iters
+
+        def loop(env, agent, data):
+            pose_source, pose_target = env.init(data)
+            pose_target = env.to_disentangled(pose_target, data["pc"])
+            for _ in range(config.action_num):
+                s2, s3 = env.observation_from_a_pose(data, pose_source)
+                lr, lt, _ = agent(s2, s3)
+                a_r, a_t = agent.action_from_logits(lr, lt, deterministic=True)
+                pose_source = env.step(a_r, a_t, pose_source, config)
+            return pose_source
+
+        def timed_loop(env, agent, data):
+            with torch.no_grad():
+                loop(env, agent, data)
+                ts = []
+                for _ in range(reps):
+                    torch.cuda.synchronize(dev)
+                    t0 = time.perf_counter()
+                    loop(env, agent, data)
+                    torch.cuda.synchronize(dev)
+                    ts.append(time.perf_counter() - t0)
+            return statistics.median(ts) / iters * 1e3
+
+        try:
+            for B in batches:
+                cpu = synth.make_batch(B, first_episode=3, seed=SEED, **SHAPE)
+                data = dict(cpu)
+                for k in ("pc", "pc_overlap_pred", "pc_geo_feat", "img_geo_feat"):
+                    data[k] = cpu[k].to(dev)
+                torch.manual_seed(SEED)
+                agent = CMRAgent(config).to(dev).eval()
+                rec = {"batch": B, "reference_ms_per_iteration": timed_loop(ref_env, agent, data),
+                       "drop_in_env_ms_per_iteration": timed_loop(drop_env, agent, data)}
+                agent_tower.accelerate_agent(agent)
+                rec["drop_in_env_and_tower_ms_per_iteration"] = timed_loop(drop_env, agent, data)
+                # the same loop captured once as a CUDA graph (environment.capture_rollout with the agent as policy)
+                torch.distributions.Distribution.set_default_validate_args(False)   # its check reads the host
+                try:
+                    with torch.no_grad():
+                        roll = drop_env.capture_rollout(
+                            data, config, with_reward=False, iters=iters,
+                            policy=lambda s2, s3: agent.action_from_logits(*agent(s2, s3)[:2], deterministic=True))
+                        roll.replay()
+                        ts = []
+                        for _ in range(reps):
+                            torch.cuda.synchronize(dev)
+                            t0 = time.perf_counter()
+                            roll.replay()
+                            torch.cuda.synchronize(dev)
+                            ts.append(time.perf_counter() - t0)
+                    rec["captured_ms_per_iteration"] = statistics.median(ts) / iters * 1e3
+                    del roll
+                finally:
+                    torch.distributions.Distribution.set_default_validate_args(True)
+                best = min(rec["drop_in_env_and_tower_ms_per_iteration"], rec["captured_ms_per_iteration"])
+                rec["speedup"] = rec["reference_ms_per_iteration"] / best
+                rec["steps_per_s"] = B / best * 1e3
+                rec["reference_steps_per_s"] = B / rec["reference_ms_per_iteration"] * 1e3
+                out["batches"].append(rec)
+                del agent, data
+                torch.cuda.empty_cache()
+        finally:
+            ref_env.DEVICE = old_device
+    finally:
+        cmr_agent_b200.uninstall()
+    return out
+
+
 def tower_bench(dev, B, N, bf16_peak):
     from cmr_agent_b200 import agent_tower
     from oracle import tower_oracle as to
@@ -829,6 +919,8 @@ def secondary_block(args, rank, world, local, dev, peak, bf16_peak, cpu, a_r, a_
         torch.cuda.empty_cache()
         # ---- the reference's own environment.py on CUDA tensors
         sec["gpu_torch_baseline"] = gpu_torch_baseline(dev, cpu, a_r, a_t, iters)
+        # ---- configs[0]: the reference's Test_Agent loop with its unchanged CMRAgent in it
+        sec["test_agent_loop"] = agent_loop_bench(dev, iters=iters)
     return sec
 
 

@@ -519,32 +519,49 @@ def iterate(data, pose_source, action_r, action_t, config, prev_distance=None, w
 
 
 class CapturedRollout:
-    """A whole rollout with GIVEN actions as one CUDA graph (see ``capture_rollout``)."""
+    """A whole rollout as one CUDA graph (see ``capture_rollout``)."""
 
-    def __init__(self, graph, pose, rewards, distances, obs2d, obs3d, keep):
+    def __init__(self, graph, pose, rewards, distances, obs2d, obs3d, keep, actions_r=None, actions_t=None):
         self.graph, self.pose, self.rewards, self.distances = graph, pose, rewards, distances
         self.observation_2d, self.observation_3d = obs2d, obs3d
+        self.actions_r, self.actions_t = actions_r, actions_t
         self._keep = keep
 
     def replay(self):
         """Run the rollout again (same inputs, whatever they hold now); the result tensors are rewritten in place:
-        ``pose`` [B,4,4] final poses, ``rewards`` / ``distances`` [iters,B,1,1], ``observation_2d/3d`` of the last pose."""
+        ``pose`` [B,4,4] final poses, ``rewards`` / ``distances`` [iters,B,1,1], ``observation_2d/3d`` of the last pose
+        observed, ``actions_r`` / ``actions_t`` [iters,B,*] the actions taken."""
         self.graph.replay()
         return self
 
 
 @torch.no_grad()
-def capture_rollout(data, config, actions_r, actions_t, with_reward=True):
-    """Extension for callers with scripted or precomputed actions: ``init`` + ``len(actions_r)`` iterations of
-    observe -> step -> reward (Test_Agent.py:150-170 with the agent's choices given) captured ONCE as a CUDA graph -
-    a replay costs one launch on the host instead of ~5 calls per iteration.  actions_r / actions_t:
-    [iters, B, 1|3] / [iters, B, 2|3] int64 on the device (their CONTENT may change between replays, like every input
-    tensor's).  The per-batch state of ``data`` is prepared before the capture."""
+def capture_rollout(data, config, actions_r=None, actions_t=None, with_reward=True, policy=None, iters=None):
+    """Extension: ``init`` + iterations of observe -> (policy) -> step -> reward (Test_Agent.py:150-170) captured ONCE
+    as a CUDA graph - a replay costs one launch on the host instead of every call of every iteration.  Either
+
+    * ``actions_r`` / ``actions_t``: scripted actions, [iters, B, 1|3] / [iters, B, 2|3] int64 on the device (their
+      CONTENT may change between replays, like every input tensor's), or
+    * ``policy(observation_2d, observation_3d) -> (action_r, action_t)``: an on-device policy, e.g. the reference's
+      agent in eval mode (``lambda s2, s3: agent.action_from_logits(*agent(s2, s3)[:2], deterministic=True)``), run
+      inside the capture ``iters`` (default ``config.action_num``) times.  It must not synchronise with the host
+      (``torch.distributions`` validates its arguments with a host read unless
+      ``Distribution.set_default_validate_args(False)``).
+
+    The per-batch state of ``data`` (cloud mean, compacted features, intrinsics) is prepared before the capture and is
+    NOT rebuilt by a replay: capture again when the clouds or features change."""
     ep = _episode(data)
-    iters = int(actions_r.shape[0])
-    actions_r = _lib.require_cuda(actions_r, "actions_r", torch.int64).contiguous()
-    actions_t = _lib.require_cuda(actions_t, "actions_t", torch.int64).contiguous()
     dev = ep.device
+    if (policy is None) == (actions_r is None or actions_t is None):
+        raise ValueError("capture_rollout: give either actions_r and actions_t or a policy")
+    if policy is None:
+        iters = int(actions_r.shape[0])
+        actions_r = _lib.require_cuda(actions_r, "actions_r", torch.int64).contiguous()
+        actions_t = _lib.require_cuda(actions_t, "actions_t", torch.int64).contiguous()
+        taken_r, taken_t = actions_r, actions_t
+    else:
+        iters = int(config.action_num if iters is None else iters)
+        taken_r = taken_t = None
     pose0, _ = init(data)
     if with_reward:
         reward(pose0, data, None)                               # per-batch reward state (and the memoised distance)
@@ -554,12 +571,22 @@ def capture_rollout(data, config, actions_r, actions_t, with_reward=True):
     torch.cuda.synchronize(dev)
 
     def body():
+        nonlocal taken_r, taken_t
         pose.copy_(pose0)
         prev = None
         o2 = o3 = None
         for it in range(iters):
             o2, o3 = observation_from_a_pose(data, pose)
-            step(actions_r[it], actions_t[it], pose, config)
+            if policy is None:
+                a_r, a_t = actions_r[it], actions_t[it]
+            else:
+                a_r, a_t = policy(o2, o3)
+                if taken_r is None:                             # shapes are the policy's: allocated on the first pass
+                    taken_r = torch.zeros((iters,) + tuple(a_r.shape), dtype=a_r.dtype, device=dev)
+                    taken_t = torch.zeros((iters,) + tuple(a_t.shape), dtype=a_t.dtype, device=dev)
+                taken_r[it].copy_(a_r)
+                taken_t[it].copy_(a_t)
+            step(a_r, a_t, pose, config)
             if with_reward:
                 r, prev = reward(pose, data, prev)
                 rewards[it].copy_(r)
@@ -569,12 +596,14 @@ def capture_rollout(data, config, actions_r, actions_t, with_reward=True):
     side = torch.cuda.Stream(dev)
     side.wait_stream(torch.cuda.current_stream(dev))
     with torch.cuda.stream(side):
-        body()                                                  # warm-up outside the capture
+        for _ in range(3 if policy is not None else 1):         # warm-up outside the capture (cuDNN picks its kernels)
+            body()
     torch.cuda.current_stream(dev).wait_stream(side)
     graph = torch.cuda.CUDAGraph()
     with torch.cuda.graph(graph):
         o2, o3 = body()
-    return CapturedRollout(graph, pose, rewards, distances, o2, o3, (data, actions_r, actions_t, pose0))
+    return CapturedRollout(graph, pose, rewards, distances, o2, o3, (data, actions_r, actions_t, pose0, policy),
+                           taken_r, taken_t)
 
 
 def expert(pose_source, targets, config, data=None):

@@ -130,6 +130,42 @@ def test_test_agent_loop_on_the_drop_in_matches_the_reference_environment_on_cud
     assert float((target_ref - target_ours).abs().max()) <= 1e-4
 
 
+@pytest.mark.parametrize("B", [1, 4])
+def test_test_agent_loop_captured_as_one_graph_takes_the_eager_loop_s_actions(world, B):
+    """environment.capture_rollout(policy=...): the Test_Agent.py:150-170 loop with the reference's unchanged agent as
+    the on-device policy, captured once as a CUDA graph; every replay takes the eager loop's actions and ends at its
+    pose."""
+    from cmr_agent_b200 import agent_tower
+    w = world
+    config = w["cfg_cls"]()
+    agent = agent_tower.accelerate_agent(_agent(w, config))
+    data = _batch(B, w["dev"], first=11)
+    taken = []
+
+    def record(step, pose, s2, s3, rl_, tl_, ar, at):
+        taken.append((ar.clone(), at.clone()))
+        return ar, at
+
+    torch.distributions.Distribution.set_default_validate_args(False)   # the check synchronises with the host
+    try:
+        with torch.no_grad():
+            roll = w["env"].capture_rollout(
+                data, config, with_reward=False,
+                policy=lambda s2, s3: agent.action_from_logits(*agent(s2, s3)[:2], deterministic=True))
+            pose_eager, _ = _inference_loop(w["env"], agent, data, config, record)
+            for _ in range(2):
+                roll.replay()
+                torch.cuda.synchronize()
+                assert roll.actions_r.shape[0] == config.action_num == len(taken)
+                for it, (ar, at) in enumerate(taken):
+                    assert torch.equal(roll.actions_r[it], ar) and torch.equal(roll.actions_t[it], at), it
+                assert float((roll.pose - pose_eager).abs().max()) <= 1e-6
+        with pytest.raises(ValueError):
+            w["env"].capture_rollout(data, config)
+    finally:
+        torch.distributions.Distribution.set_default_validate_args(True)
+
+
 def test_train_agent_trajectory_buffer_and_update_run_unchanged(world):
     """Train_Agent.py:216-300 on the drop-in: expert, stochastic actions, reward, the reference's Buffer (which keeps
     every observation by reference), returns/advantages, one BC+PPO update through the unchanged CMRAgent."""
