@@ -27,6 +27,7 @@ data-path collective ("weak" scaling: 32 episodes per GPU).
            the reference's environment.py on CUDA tensors, the scalar all-reduce on NCCL).
 """
 import argparse
+import contextlib
 import ctypes
 import json
 import math
@@ -741,7 +742,7 @@ def agent_loop_bench(dev, batches=(1, 8, 32), iters=10, reps=3):
                 try:
                     with torch.no_grad():
                         roll = drop_env.capture_rollout(
-                            data, config, with_reward=False, iters=iters,
+                            data, config, with_reward=False, iters=iters, reusable=True,   # the per-batch preparation is in the graph
                             policy=lambda s2, s3: agent.action_from_logits(*agent(s2, s3)[:2], deterministic=True))
                         roll.replay()
                         ts = []
@@ -920,7 +921,8 @@ def secondary_block(args, rank, world, local, dev, peak, bf16_peak, cpu, a_r, a_
         # ---- the reference's own environment.py on CUDA tensors
         sec["gpu_torch_baseline"] = gpu_torch_baseline(dev, cpu, a_r, a_t, iters)
         # ---- configs[0]: the reference's Test_Agent loop with its unchanged CMRAgent in it
-        sec["test_agent_loop"] = agent_loop_bench(dev, iters=iters)
+        with contextlib.redirect_stdout(sys.stderr):     # the reference's config class prints a banner: not on OUR stdout
+            sec["test_agent_loop"] = agent_loop_bench(dev, iters=iters)
     return sec
 
 

@@ -155,7 +155,7 @@ class _Episode:
         self.src = tuple((data[k], data[k]._version) for k in _EP_KEYS)
         self.extra = (tuple(img.shape), _mean_provider, id(data.get("_cmr_b200_mean_override")))
         self.B, self.N, self.C, self.H, self.W = B, N, C, H, W
-        self.pc, self.img_feat = pc, img_feat
+        self.pc, self.img_feat, self.feat = pc, img_feat, feat
         self.overlap = overlap.view(torch.uint8)
         self.K = data["K"].to(device=pc.device, dtype=torch.float32, non_blocking=True).contiguous()  # :26, once
         self.mean = data.get("_cmr_b200_mean_override")
@@ -518,14 +518,40 @@ def iterate(data, pose_source, action_r, action_t, config, prev_distance=None, w
     return pose_source, rew, dist, obs2d, obs3d
 
 
+def _refresh_in_place(ep):
+    """The per-batch state of ``ep`` recomputed from the tensors it already points at, into the buffers it already owns
+    (no allocation, no host read: this is what a reusable captured rollout replays before its first observation)."""
+    if _mean_provider == "torch":
+        ep.mean.copy_(ep.pc.mean(dim=2))
+    else:
+        _lib.call("cmr_cloud_mean", _lib.ptr(ep.pc), ep.B, ep.N, _lib.ptr(ep.mean), _lib.stream())
+    _lib.call("cmr_episode_prepare", _lib.ptr(ep.overlap), _lib.ptr(ep.feat), ep.B, ep.N, ep.C, _lib.ptr(ep.ws), _lib.stream())
+
+
 class CapturedRollout:
     """A whole rollout as one CUDA graph (see ``capture_rollout``)."""
 
-    def __init__(self, graph, pose, rewards, distances, obs2d, obs3d, keep, actions_r=None, actions_t=None):
+    def __init__(self, graph, pose, rewards, distances, obs2d, obs3d, keep, actions_r=None, actions_t=None, reusable=None):
         self.graph, self.pose, self.rewards, self.distances = graph, pose, rewards, distances
         self.observation_2d, self.observation_3d = obs2d, obs3d
         self.actions_r, self.actions_t = actions_r, actions_t
         self._keep = keep
+        self._reusable = reusable          # (data, episode state) of a capture made with reusable=True
+
+    def load(self, batch):
+        """Another batch of the same shapes (a ``data`` dict as the reference's loader yields it) copied into the
+        tensors the graph was captured on; the next ``replay`` prepares and registers it.  Only for captures made
+        with ``reusable=True``."""
+        if self._reusable is None:
+            raise _lib.CmrError("CapturedRollout.load needs a capture made with reusable=True")
+        data, ep = self._reusable
+        for k in ("pc", "pc_overlap_pred", "pc_geo_feat", "img_geo_feat"):
+            if batch[k] is not data[k]:
+                data[k].copy_(batch[k], non_blocking=True)
+        ep.K.copy_(batch["K"].to(torch.float32), non_blocking=True)
+        if torch.is_tensor(data.get("K")) and batch["K"] is not data["K"]:
+            data["K"].copy_(batch["K"])
+        return self
 
     def replay(self):
         """Run the rollout again (same inputs, whatever they hold now); the result tensors are rewritten in place:
@@ -536,7 +562,8 @@ class CapturedRollout:
 
 
 @torch.no_grad()
-def capture_rollout(data, config, actions_r=None, actions_t=None, with_reward=True, policy=None, iters=None):
+def capture_rollout(data, config, actions_r=None, actions_t=None, with_reward=True, policy=None, iters=None,
+                    reusable=False):
     """Extension: ``init`` + iterations of observe -> (policy) -> step -> reward (Test_Agent.py:150-170) captured ONCE
     as a CUDA graph - a replay costs one launch on the host instead of every call of every iteration.  Either
 
@@ -549,9 +576,21 @@ def capture_rollout(data, config, actions_r=None, actions_t=None, with_reward=Tr
       ``Distribution.set_default_validate_args(False)``).
 
     The per-batch state of ``data`` (cloud mean, compacted features, intrinsics) is prepared before the capture and is
-    NOT rebuilt by a replay: capture again when the clouds or features change."""
+    NOT rebuilt by a replay - unless ``reusable=True``: then the graph itself begins with that preparation, and
+    ``CapturedRollout.load(batch)`` copies the next batch (same shapes) into the captured tensors - one capture serves
+    every batch of a run.  ``reusable`` needs the inputs in the layout the kernels read (float32 contiguous CUDA
+    tensors, a bool mask) and ``with_reward=False`` (the inference loop has no reward)."""
     ep = _episode(data)
     dev = ep.device
+    if reusable:
+        if with_reward:
+            raise ValueError("capture_rollout: reusable=True needs with_reward=False")
+        same = (ep.pc.data_ptr() == data["pc"].data_ptr() and ep.feat.data_ptr() == data["pc_geo_feat"].data_ptr() and
+                ep.img_feat.data_ptr() == data["img_geo_feat"].data_ptr() and
+                ep.overlap.data_ptr() == data["pc_overlap_pred"].data_ptr())
+        if not same or data.get("_cmr_b200_mean_override") is not None:
+            raise _lib.CmrError("capture_rollout(reusable=True): inputs must be float32 contiguous CUDA tensors and a bool "
+                                "mask, without a mean override (the graph reads them in place)")
     if (policy is None) == (actions_r is None or actions_t is None):
         raise ValueError("capture_rollout: give either actions_r and actions_t or a policy")
     if policy is None:
@@ -572,6 +611,8 @@ def capture_rollout(data, config, actions_r=None, actions_t=None, with_reward=Tr
 
     def body():
         nonlocal taken_r, taken_t
+        if reusable:
+            _refresh_in_place(ep)
         pose.copy_(pose0)
         prev = None
         o2 = o3 = None
@@ -602,8 +643,8 @@ def capture_rollout(data, config, actions_r=None, actions_t=None, with_reward=Tr
     graph = torch.cuda.CUDAGraph()
     with torch.cuda.graph(graph):
         o2, o3 = body()
-    return CapturedRollout(graph, pose, rewards, distances, o2, o3, (data, actions_r, actions_t, pose0, policy),
-                           taken_r, taken_t)
+    return CapturedRollout(graph, pose, rewards, distances, o2, o3, (data, actions_r, actions_t, pose0, policy, ep),
+                           taken_r, taken_t, (data, ep) if reusable else None)
 
 
 def expert(pose_source, targets, config, data=None):

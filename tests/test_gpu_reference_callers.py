@@ -150,18 +150,24 @@ def test_test_agent_loop_captured_as_one_graph_takes_the_eager_loop_s_actions(wo
     try:
         with torch.no_grad():
             roll = w["env"].capture_rollout(
-                data, config, with_reward=False,
+                data, config, with_reward=False, reusable=True,
                 policy=lambda s2, s3: agent.action_from_logits(*agent(s2, s3)[:2], deterministic=True))
-            pose_eager, _ = _inference_loop(w["env"], agent, data, config, record)
-            for _ in range(2):
-                roll.replay()
+            # the capture serves every batch of the run: the eager loop on a batch, then the same batch loaded into
+            # the captured tensors and replayed
+            for first in (11, 40, 11):
+                batch = _batch(B, w["dev"], first=first)
+                del taken[:]
+                pose_eager, _ = _inference_loop(w["env"], agent, batch, config, record)
+                roll.load(batch).replay()
                 torch.cuda.synchronize()
                 assert roll.actions_r.shape[0] == config.action_num == len(taken)
                 for it, (ar, at) in enumerate(taken):
-                    assert torch.equal(roll.actions_r[it], ar) and torch.equal(roll.actions_t[it], at), it
+                    assert torch.equal(roll.actions_r[it], ar) and torch.equal(roll.actions_t[it], at), (first, it)
                 assert float((roll.pose - pose_eager).abs().max()) <= 1e-6
         with pytest.raises(ValueError):
             w["env"].capture_rollout(data, config)
+        with pytest.raises(ValueError):
+            w["env"].capture_rollout(data, config, policy=lambda a, b: None, reusable=True)
     finally:
         torch.distributions.Distribution.set_default_validate_args(True)
 
