@@ -7,7 +7,10 @@ drop-ins and the following run exactly as the reference wrote them:
   * `models.CMRAgent` (random init, seed fixed, eval) in the `Test_Agent.py:150-170` inference loop,
   * `environment.buffer.Buffer` + `agent.action_logprob_and_entropy` + the PPO/BC update of `Train_Agent.py:216-300`,
   * `models.PointNN.KnnPointTransformer` (`models/PointNN.py:188-232`) forward and backward,
-  * `models.pointnet_util.PointNetSetAbstraction` (the module's own class, reaching the drop-ins through its globals).
+  * `models.pointnet_util.PointNetSetAbstraction` (the module's own class, reaching the drop-ins through its globals),
+  * the two driver scripts THEMSELVES - `Test_Agent.py` and `Train_Agent.py`, executed with runpy as `__main__` - with
+    stand-ins only for what lies outside the path (the dataset on disk, the feature network and its checkpoints,
+    tensorboardX) and, for training, one epoch instead of 64.
 
 The comparator is the reference's `environment/environment.py` / `models/pointnet_util.py` themselves on CUDA tensors
 (what a CMR-Agent user runs today), loaded under private module names.  On the GPU the reference is not bit-stable
@@ -302,3 +305,153 @@ def test_set_abstraction_class_of_the_reference_module_reaches_the_drop_ins(worl
     assert torch.equal(a[0], b[0])                   # same centroids: FPS indices are bit-exact
     assert torch.allclose(a[1], b[1], rtol=1e-4, atol=1e-6)
     assert torch.allclose(a[2], b[2], rtol=1e-3, atol=1e-7)
+
+
+# ---- the driver script itself ----------------------------------------------------------------------------------------
+class _SynthKitti(torch.utils.data.Dataset):
+    """Stand-in for dataset/KittiDataset.py (files on disk): what its loader yields per sample, from the synthetic
+    generator.  The feature network's outputs ride along under private names for `_FeatureNetStandIn`."""
+    first, count = 200, 3
+    counts = {"test": 3, "train": 32, "val": 8}
+
+    def __init__(self, config, mode="test"):
+        self.config = config
+        self.count = self.counts[mode]
+        self.first = {"test": 200, "train": 300, "val": 400}[mode]
+
+    def __len__(self):
+        return self.count
+
+    def __getitem__(self, i):
+        b = synth.make_batch(1, first_episode=self.first + i, seed=hp.SEED)
+        item = {k: v[0].clone() for k, v in b.items() if k != "img"}
+        item["img"] = torch.zeros(3, b["img"].shape[2], b["img"].shape[3])
+        for k in ("pc_overlap_pred", "pc_geo_feat", "img_geo_feat"):
+            item["_net_" + k] = item.pop(k)
+        return item
+
+
+class _FeatureNetStandIn(torch.nn.Module):
+    """Stand-in for models.MultiHeadModel (ViT + point transformer + checkpoint, outside the path): leaves on the
+    device what the real network leaves there."""
+
+    def __init__(self, config):
+        super().__init__()
+
+    def load_state_dict(self, state_dict, strict=True):
+        return None
+
+    def forward(self, data):
+        data["pc"] = data["pc"].cuda()
+        for k in ("pc_overlap_pred", "pc_geo_feat", "img_geo_feat"):
+            data[k] = data.pop("_net_" + k).cuda()
+        return data
+
+
+def test_the_reference_s_test_agent_script_runs_unchanged_on_the_drop_in(world, tmp_path, monkeypatch, capsys):
+    """`python Test_Agent.py --dataset kitti` (the file itself, through runpy, not a restatement of its loop) with
+    `environment.environment` = the drop-in: its imports, its loop (:150-170), its error metrics (:98-105,181-206).
+    Outside the path and replaced by stand-ins: the dataset on disk, the feature network, the two checkpoint files.
+    The errors it prints equal the same loop run here, sample by sample."""
+    import os
+    import runpy
+    import sys
+    import numpy as np
+    import dataset as ref_dataset
+    import models as ref_models
+    w = world
+    config = w["cfg_cls"]()
+    torch.manual_seed(99)
+    weights = w["CMRAgent"](config).state_dict()
+    monkeypatch.setattr(ref_dataset, "KittiDataset", _SynthKitti)
+    monkeypatch.setattr(ref_models, "MultiHeadModel", _FeatureNetStandIn)
+    monkeypatch.setattr(torch, "load", lambda path, *a, **k: weights if "agent" in str(path) else {})
+    monkeypatch.setattr(sys, "argv", ["Test_Agent.py", "--dataset", "kitti"])
+    monkeypatch.setenv("CUDA_VISIBLE_DEVICES", os.environ.get("CUDA_VISIBLE_DEVICES", "0"))
+    monkeypatch.chdir(tmp_path)
+    script = os.path.join(rl.put_on_path(), "Test_Agent.py")
+    with np.errstate(all="ignore"):
+        ns = runpy.run_path(script, run_name="__main__")
+    out = capsys.readouterr().out
+    assert ns["env"] is w["env"], "the script's `env` is not the drop-in"
+    assert "Registration Recall:" in out and "RRE Std:" in out
+    printed = [tuple(float(x) for x in ln.split()) for ln in out.splitlines()
+               if len(ln.split()) == 2 and ln.split()[0][0].isdigit()]
+    assert len(printed) == _SynthKitti.count, out
+    # the same samples through the loop as restated in this file, with the script's own metric
+    agent = w["CMRAgent"](config)
+    agent.load_state_dict(weights)
+    agent = agent.to(w["dev"]).eval()
+    torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark = False, False   # the script's set_seed set them
+    with torch.no_grad():
+        for i, (t_script, r_script) in enumerate(printed):
+            data = hp.to_device(synth.make_batch(1, first_episode=_SynthKitti.first + i, seed=hp.SEED), w["dev"])
+            pose, target = _inference_loop(w["env"], agent, data, config)
+            t_here, r_here = ns["get_P_diff"](pose[0].cpu().numpy(), target[0].cpu().numpy())
+            assert abs(t_here - t_script) <= 1e-3 * max(1.0, abs(t_here)), (i, t_here, t_script)
+            assert abs(r_here - r_script) <= 1e-3 * max(1.0, abs(r_here)), (i, r_here, r_script)
+
+
+def test_the_reference_s_train_agent_script_runs_unchanged_on_the_drop_in(world, tmp_path, monkeypatch, capsys):
+    """`python Train_Agent.py --dataset kitti` (the file itself, through runpy) on the drop-in: its validation pass
+    (:160-213), the trajectory loop with expert / stochastic actions / reward / Buffer (:216-248), the BC + PPO update
+    (:252-312), checkpointing and logging.  Stand-ins for what is outside the path: the dataset on disk, the feature
+    network and its checkpoint, tensorboardX; the configuration is the reference's class with ONE epoch (its 64 would
+    run for days) - 4 global steps of 8 episodes = one full buffer = one update."""
+    import os
+    import runpy
+    import sys
+    import time
+    import numpy as np
+    import config as ref_config
+    import dataset as ref_dataset
+    import models as ref_models
+    import tensorboardX
+    w = world
+    scalars = []
+
+    class OneEpoch(w["cfg_cls"]):
+        def __init__(self):
+            super().__init__()
+            self.epoch = 1
+            self.num_workers = 4
+
+    class Writer:
+        def __init__(self, *a, **k):
+            pass
+
+        def add_scalar(self, tag, value, global_step=None):
+            scalars.append((tag, float(value), global_step))
+
+    monkeypatch.setattr(ref_config, "KittiConfiguration", OneEpoch)
+    monkeypatch.setattr(ref_dataset, "KittiDataset", _SynthKitti)
+    monkeypatch.setattr(ref_models, "MultiHeadModel", _FeatureNetStandIn)
+    monkeypatch.setattr(tensorboardX, "SummaryWriter", Writer)
+    monkeypatch.setattr(torch, "load", lambda path, *a, **k: {})
+    monkeypatch.setattr(time, "sleep", lambda s: None)
+    if not hasattr(np, "Inf"):
+        monkeypatch.setattr(np, "Inf", np.inf, raising=False)      # Train_Agent.py:157-158 predates numpy 2
+    monkeypatch.setattr(sys, "argv", ["Train_Agent.py", "--dataset", "kitti"])
+    monkeypatch.setenv("CUDA_VISIBLE_DEVICES", os.environ.get("CUDA_VISIBLE_DEVICES", "0"))
+    monkeypatch.chdir(tmp_path)
+    script = os.path.join(rl.put_on_path(), "Train_Agent.py")
+    before = {k: v.clone() for k, v in w["CMRAgent"](OneEpoch()).state_dict().items()}   # shapes only
+    try:
+        ns = runpy.run_path(script, run_name="__main__")
+    finally:
+        torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark = False, False
+    out = capsys.readouterr().out
+    assert ns["env"] is w["env"], "the script's `env` is not the drop-in"
+    assert ns["Buffer"] is w["Buffer"]
+    assert "New Training!" in out and "0-th epoch end." in out
+    assert ns["global_step"] == _SynthKitti.counts["train"] // ns["config"].train_batch_size == 4
+    tags = [t for t, _, _ in scalars]
+    assert tags.count("val_error/error_r") == 1 and tags.count("train_loss/BC_Loss") == 1, tags
+    for tag, value, _ in scalars:
+        assert np.isfinite(value), (tag, value)
+    saved = [f for _, _, fs in os.walk(tmp_path / "checkpoint") for f in fs if f.endswith(".pth")]
+    assert len(saved) == 1, saved
+    after = ns["agent"].state_dict()
+    assert set(after) == set(before)
+    moved = sum(float((after[k].float().cpu() - before[k].float()).abs().sum()) for k in before)
+    assert moved > 0 and all(torch.isfinite(v.float()).all() for v in after.values())
