@@ -67,6 +67,8 @@ SIGNATURES = {
     "cmr_tower_pack": (_c_int, [_c_int] + [_c_vp] * 8),
     "cmr_tower_workspace_bytes": (_c_sz, [_c_int, _c_int]),
     "cmr_tower_forward": (_c_int, [_c_vp] * 6 + [_c_int, _c_int, _c_vp, _c_vp]),
+    "cmr_grouped_linear": (_c_int, [_c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_f, _c_int, _c_vp, _c_int,
+                                    _c_vp]),
 }
 
 _lib = None
@@ -89,7 +91,7 @@ def load():
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
-        if lib.cmr_abi_version() != 3:
+        if lib.cmr_abi_version() != 4:
             raise CmrError("libcmr_b200.so ABI version mismatch; rebuild it")
         _lib = lib
     return _lib

@@ -11,6 +11,7 @@ own modules - ``accelerate_agent`` only takes over ``forward`` while the module 
     tower = Tower3D.from_agent(agent)          # agent: the reference's CMRAgent, weights loaded
     embed_3d = tower(observation_3d)           # [B, 5, N] -> [B, 128]  (CMRAgent.py:101)
     accelerate_agent(agent)                    # agent(state_2d, state_3d) now uses it in eval/no_grad
+                                               # (and ``Heads``: the actor-critic heads, CMRAgent.py:70-86,106-113)
 """
 import torch
 
@@ -93,16 +94,77 @@ class Tower3D:
         return out
 
 
+class Heads:
+    """The actor-critic heads (models/CMRAgent.py:70-86: ``policy_r``, ``policy_t``, ``value`` - each
+    Linear, LeakyReLU, Linear, LeakyReLU, Linear) as three launches of ``cmr_grouped_linear``: layer l of ALL heads at
+    once, every head reading its own slice of the previous layer's output.  fp32, deterministic."""
+
+    MAX_K = 256
+
+    def __init__(self, heads):
+        import ctypes
+        import numpy as np
+        lin = [[m for m in h if isinstance(m, torch.nn.Linear)] for h in heads]
+        act = [[m for m in h if isinstance(m, torch.nn.LeakyReLU)] for h in heads]
+        depth = len(lin[0])
+        ok = depth >= 1 and all(len(l) == depth and len(a) == depth - 1 and len(list(h)) == 2 * depth - 1
+                                for l, a, h in zip(lin, act, heads))
+        slopes = {a.negative_slope for al in act for a in al}
+        if not ok or len(slopes) > 1 or len(heads) > 8:
+            raise _lib.CmrError("Heads: every head must be Linear (LeakyReLU Linear)* of one depth and one slope")
+        if any(m.in_features > self.MAX_K or m.bias is None for l in lin for m in l):
+            raise _lib.CmrError("Heads: layers wider than 256 inputs, or without a bias, stay on torch")
+        if len({l[0].in_features for l in lin}) != 1:
+            raise _lib.CmrError("Heads: the heads read the same embedding")
+        self.slope = slopes.pop() if slopes else 0.0
+        self.device = lin[0][0].weight.device
+        self.in_features = lin[0][0].in_features
+        self.layers = []
+        for l in range(depth):
+            mods = [h[l] for h in lin]
+            W = torch.cat([m.weight.detach().float().reshape(-1) for m in mods]).contiguous()
+            b = torch.cat([m.bias.detach().float() for m in mods]).contiguous()
+            desc, n0, w_off, in_off = [], 0, 0, 0
+            for m in mods:
+                desc += [0 if l == 0 else in_off, m.in_features, n0, n0 + m.out_features, w_off]
+                n0 += m.out_features
+                w_off += m.weight.numel()
+                in_off += m.in_features
+            d = np.asarray(desc, dtype=np.int64)
+            in_stride = self.in_features if l == 0 else in_off
+            self.layers.append(dict(W=W, b=b, desc=d, dptr=d.ctypes.data_as(ctypes.c_void_p), groups=len(mods), N=n0,
+                                    in_stride=in_stride, act=1 if l < depth - 1 else 0))
+        self.splits = [m.out_features for m in (h[-1] for h in lin)]
+
+    @torch.no_grad()
+    def __call__(self, embedding):
+        x = _lib.require_cuda(embedding, "state_embedding", torch.float32)
+        x = x if x.is_contiguous() else x.contiguous()
+        if x.dim() != 2 or x.shape[1] != self.in_features:
+            raise _lib.CmrError(f"state_embedding must be [B,{self.in_features}]")
+        B = x.shape[0]
+        for L in self.layers:
+            out = torch.empty(B, L["N"], device=x.device, dtype=torch.float32)
+            _lib.call("cmr_grouped_linear", _lib.ptr(x), L["in_stride"], _lib.ptr(L["W"]), _lib.ptr(L["b"]), L["dptr"],
+                      L["groups"], B, L["N"], float(self.slope), L["act"], _lib.ptr(out), L["N"], _lib.stream())
+            x = out
+        return torch.split(x, self.splits, dim=1)
+
+
 def accelerate_agent(agent):
     """Route the 3-D half of ``CMRAgent.forward`` (models/CMRAgent.py:92-101) through ``Tower3D`` whenever the module
     is in eval mode and autograd is off; otherwise the reference's own forward runs untouched.  The packed weights
     are rebuilt when any parameter or buffer of ``state_3d_embed`` has changed (``_version``)."""
     reference_forward = agent.forward
-    state = {"tower": None, "sig": None}
+    state = {"tower": None, "sig": None, "heads": None, "hsig": None}
+    head_modules = [agent.policy_r, agent.policy_t, agent.value]
 
     def _sig():
         return tuple((t.data_ptr(), t._version) for t in list(agent.state_3d_embed.parameters()) +
                      list(agent.state_3d_embed.buffers()))
+
+    def _hsig():
+        return tuple((t.data_ptr(), t._version) for m in head_modules for t in m.parameters())
 
     def forward(state_2d, state_3d):
         if agent.training or torch.is_grad_enabled() or not state_3d.is_cuda:
@@ -114,12 +176,13 @@ def accelerate_agent(agent):
         embed_2d = embed_2d.view(embed_2d.shape[0], -1)
         embed_3d = state["tower"](state_3d)                                         # :92-101
         state_embedding = torch.cat([embed_2d, embed_3d], dim=1)                    # :103
-        action_r_logits = agent.policy_r(state_embedding)                           # :106-110
-        action_t_logits = agent.policy_t(state_embedding)
-        action_r_logits = action_r_logits.view(action_r_logits.shape[0], agent.degree_r, agent.config.num_steps)
-        action_t_logits = action_t_logits.view(action_t_logits.shape[0], agent.degree_t, agent.config.num_steps)
-        value = agent.value(state_embedding).unsqueeze(-1)                          # :112-113
-        return action_r_logits, action_t_logits, value
+        hsig = _hsig()
+        if state["hsig"] != hsig:
+            state["heads"], state["hsig"] = Heads(head_modules), hsig
+        action_r_logits, action_t_logits, value = state["heads"](state_embedding)    # :106-113, three launches
+        action_r_logits = action_r_logits.reshape(action_r_logits.shape[0], agent.degree_r, agent.config.num_steps)
+        action_t_logits = action_t_logits.reshape(action_t_logits.shape[0], agent.degree_t, agent.config.num_steps)
+        return action_r_logits, action_t_logits, value.unsqueeze(-1)
 
     agent.forward = forward
     agent._cmr_b200_reference_forward = reference_forward

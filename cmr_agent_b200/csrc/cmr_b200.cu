@@ -8,6 +8,7 @@
 #include <cstring>
 
 #include "env_kernels.cuh"
+#include "heads_kernels.cuh"
 #include "pointnet_kernels.cuh"
 #include "scatter_kernels.cuh"
 #include "cost_volume_kernels.cuh"
@@ -566,6 +567,28 @@ int cmr_iteration(const cmr_iteration_args *a, float *pose, const int64_t *actio
                          obs3d, nullptr, nullptr, stream);
     }
     return rc;
+}
+
+// ---------------------------------------------------------------------------- agent: heads ----
+
+int cmr_grouped_linear(const float *in, int in_stride, const float *W, const float *bias, const int64_t *desc, int groups,
+                       int B, int N, float negative_slope, int activate, float *out, int out_stride, void *stream) {
+    CMR_REQUIRE(in && W && bias && desc && out && B > 0 && N > 0 && groups > 0, CMR_EINVAL);
+    CMR_REQUIRE(groups <= kLinMaxGroups, CMR_ERANGE);
+    LinGroups G{};
+    G.count = groups;
+    int next = 0;
+    for (int i = 0; i < groups; ++i) {
+        const int64_t *d = desc + 5 * i;
+        CMR_REQUIRE(d[1] > 0 && d[1] <= kLinMaxK, CMR_ERANGE);
+        // the groups tile [0, N) in order; their inputs lie inside a row of `in`
+        CMR_REQUIRE(d[2] == next && d[3] > d[2] && d[3] <= N && d[0] >= 0 && d[0] + d[1] <= in_stride && d[4] >= 0, CMR_EINVAL);
+        G.g[i] = LinGroup{(int)d[0], (int)d[1], (int)d[2], (int)d[3], (long long)d[4]};
+        next = (int)d[3];
+    }
+    CMR_REQUIRE(next == N && out_stride >= N, CMR_EINVAL);
+    return launch_pdl(k_grouped_linear, dim3(ceil_div(N, 8)), dim3(256), 0, S_(stream), in, in_stride, W, bias, G, B, N,
+                      negative_slope, activate ? 1 : 0, out, out_stride);
 }
 
 // ---------------------------------------------------------------------------- pointnet_util ----

@@ -33,7 +33,7 @@ extern "C" {
 #define CMR_API
 #endif
 
-#define CMR_ABI_VERSION 3
+#define CMR_ABI_VERSION 4
 
 #define CMR_OK 0
 #define CMR_EINVAL (-1)      /* null pointer, non-positive size */
@@ -314,6 +314,18 @@ CMR_API int cmr_sample_prepare(const float *img_feat, int B, int C, int P, void 
 CMR_API int cmr_sample_image_features(const float *pc, const float *Kmat, const float *pose, const float *mean,
                                       const void *workspace, int B, int N, int C, int H, int W, float *out,
                                       uint8_t *in_cam, void *stream);
+
+/* ------------------------------------------------------------------ agent: heads ---- */
+
+/* The actor-critic heads of the agent - models/CMRAgent.py:70-86 (policy_r, policy_t, value: Linear - LeakyReLU -
+ * Linear - LeakyReLU - Linear each) as applied at :106-113.  One call = layer l of ALL heads: a GROUPED linear layer
+ *     out[b, n] = act(bias[n] + sum_k in[b, in_off_g + k] * W[w_off_g + (n - n0_g) * K_g + k]),  n in [n0_g, n1_g)
+ * desc (HOST): `groups` x {in_off, K, n0, n1, w_off} int64; the groups tile [0, N) in order; K <= 256.
+ * in [B, in_stride], out [B, out_stride] f32 on the device; activate != 0 applies LeakyReLU(negative_slope).
+ * fp32, explicit fused multiply-adds in a fixed order: deterministic, a row's result does not depend on B. */
+CMR_API int cmr_grouped_linear(const float *in, int in_stride, const float *W, const float *bias, const int64_t *desc,
+                               int groups, int B, int N, float negative_slope, int activate, float *out, int out_stride,
+                               void *stream);
 
 /* ------------------------------------------------------------------ agent: 3-D tower ---- */
 

@@ -133,3 +133,39 @@ def test_tower_reports_activations_beyond_the_fp16_range(cuda):
     assert torch.isfinite(bad[0]).all() and torch.equal(bad[0], ok[0])     # episodes are independent
     assert not torch.isfinite(bad[1]).all()
     assert _lib.take_fault() == 3
+
+
+@pytest.mark.parametrize("dof6", [False, True])
+def test_heads_match_the_reference_s_modules(cuda, dof6):
+    """agent_tower.Heads (cmr_grouped_linear: layer l of policy_r, policy_t and value in ONE launch) against the
+    reference's own nn.Sequential heads (models/CMRAgent.py:70-86) in fp32: 1e-5 of the output's scale; a row's result
+    does not depend on the batch it sits in (bit-identical at B = 1 and inside B = 33)."""
+    if not rl.available():
+        pytest.skip("no reference tree (oracle/_ref)")
+    rl.put_on_path()
+    from config import KittiConfiguration
+    from models import CMRAgent
+    from cmr_agent_b200 import agent_tower
+    config = KittiConfiguration()
+    config.is_6_DoF = dof6
+    torch.manual_seed(11)
+    agent = CMRAgent(config).to(cuda).eval()
+    heads = agent_tower.Heads([agent.policy_r, agent.policy_t, agent.value])
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            for B in (1, 5, 33):
+                emb = torch.randn(B, 256, device=cuda) * 3.0
+                got = heads(emb)
+                want = (agent.policy_r(emb), agent.policy_t(emb), agent.value(emb))
+                for g, w_ in zip(got, want):
+                    assert g.shape == w_.shape
+                    assert float((g - w_).abs().max()) <= 1e-5 * float(w_.abs().max().clamp_min(1e-3)), (B, g.shape)
+                one = heads(emb[B - 1:].contiguous())
+                for g, o in zip(got, one):
+                    assert torch.equal(g[B - 1:], o)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    with pytest.raises(Exception):
+        agent_tower.Heads([torch.nn.Sequential(torch.nn.Linear(300, 4).to(cuda))])
