@@ -156,15 +156,34 @@ def accelerate_agent(agent):
     is in eval mode and autograd is off; otherwise the reference's own forward runs untouched.  The packed weights
     are rebuilt when any parameter or buffer of ``state_3d_embed`` has changed (``_version``)."""
     reference_forward = agent.forward
-    state = {"tower": None, "sig": None, "heads": None, "hsig": None}
+    state = {"tower": None, "sig": None, "heads": None, "hsig": None, "tail": None}
     head_modules = [agent.policy_r, agent.policy_t, agent.value]
 
     def _sig():
         return tuple((t.data_ptr(), t._version) for t in list(agent.state_3d_embed.parameters()) +
                      list(agent.state_3d_embed.buffers()))
 
+    # the 1x1 tail of the 2-D head (CMRAgent.py:59-61: AvgPool2d over the whole map, then Conv2d 1x1 - LeakyReLU -
+    # Conv2d 1x1 on a [B, 2f, 1, 1] tensor) is a two-layer MLP: it goes through the same grouped-linear launches
+    # instead of two cuDNN convolutions with their layout conversions.  Anything shaped differently stays on torch.
+    mods_2d = list(agent.state_2d_embed)
+    pools = [i for i, m in enumerate(mods_2d) if isinstance(m, torch.nn.AvgPool2d)]
+    cut = pools[-1] + 1 if pools else len(mods_2d)
+    tail_2d = mods_2d[cut:]
+    is_1x1 = lambda m: (isinstance(m, torch.nn.Conv2d) and tuple(m.kernel_size) == (1, 1) and tuple(m.stride) == (1, 1) and  # noqa: E731
+                        tuple(m.padding) == (0, 0) and m.groups == 1 and m.bias is not None and m.in_channels <= Heads.MAX_K)
+    tail_ok = (len(tail_2d) >= 1 and len(tail_2d) % 2 == 1 and
+               all(is_1x1(m) if i % 2 == 0 else isinstance(m, torch.nn.LeakyReLU) for i, m in enumerate(tail_2d)))
+    body_2d = torch.nn.Sequential(*mods_2d[:cut]) if tail_ok else agent.state_2d_embed
+
+    def _as_linear(conv):
+        lin = torch.nn.Linear(conv.in_channels, conv.out_channels, device=conv.weight.device)
+        lin.weight = torch.nn.Parameter(conv.weight.detach().reshape(conv.out_channels, conv.in_channels), requires_grad=False)
+        lin.bias = torch.nn.Parameter(conv.bias.detach(), requires_grad=False)
+        return lin
+
     def _hsig():
-        return tuple((t.data_ptr(), t._version) for m in head_modules for t in m.parameters())
+        return tuple((t.data_ptr(), t._version) for m in head_modules + (tail_2d if tail_ok else []) for t in m.parameters())
 
     def forward(state_2d, state_3d):
         if agent.training or torch.is_grad_enabled() or not state_3d.is_cuda:
@@ -172,13 +191,20 @@ def accelerate_agent(agent):
         sig = _sig()
         if state["sig"] != sig:
             state["tower"], state["sig"] = Tower3D.from_agent(agent), sig
-        embed_2d = agent.state_2d_embed(state_2d)                                   # CMRAgent.py:89-90
-        embed_2d = embed_2d.view(embed_2d.shape[0], -1)
-        embed_3d = state["tower"](state_3d)                                         # :92-101
-        state_embedding = torch.cat([embed_2d, embed_3d], dim=1)                    # :103
         hsig = _hsig()
         if state["hsig"] != hsig:
             state["heads"], state["hsig"] = Heads(head_modules), hsig
+            state["tail"] = Heads([torch.nn.Sequential(*[_as_linear(m) if i % 2 == 0 else m
+                                                         for i, m in enumerate(tail_2d)])]) if tail_ok else None
+        embed_2d = body_2d(state_2d)                                                # CMRAgent.py:89-90
+        if state["tail"] is not None and embed_2d.shape[2:] == (1, 1):
+            embed_2d = state["tail"](embed_2d.reshape(embed_2d.shape[0], -1))[0]
+        else:
+            for m in (tail_2d if tail_ok else []):
+                embed_2d = m(embed_2d)
+            embed_2d = embed_2d.reshape(embed_2d.shape[0], -1)
+        embed_3d = state["tower"](state_3d)                                         # :92-101
+        state_embedding = torch.cat([embed_2d, embed_3d], dim=1)                    # :103
         action_r_logits, action_t_logits, value = state["heads"](state_embedding)    # :106-113, three launches
         action_r_logits = action_r_logits.reshape(action_r_logits.shape[0], agent.degree_r, agent.config.num_steps)
         action_t_logits = action_t_logits.reshape(action_t_logits.shape[0], agent.degree_t, agent.config.num_steps)
