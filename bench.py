@@ -908,6 +908,14 @@ def secondary_block(args, rank, world, local, dev, peak, bf16_peak, cpu, a_r, a_
         sec["metric_all_reduce"] = {"backend": "nccl" if world > 1 else "none (1 rank)", "episodes": s["episodes"],
                                     "recall": s["recall"]}
     if rank == 0 and world == 1:
+        def comparator(name, fn):
+            """The two entries that run the REFERENCE's code (its environment / its agent from oracle/_ref) beside ours:
+            informational, and not allowed to take the bench line down with them."""
+            try:
+                with contextlib.redirect_stdout(sys.stderr):     # the reference's config class prints a banner
+                    sec[name] = fn()
+            except Exception as e:                               # noqa: BLE001
+                sec[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
         # ---- config 1 / training batch: latency through the Python API at the reference's own batch sizes
         sec["api_latency"] = [api_latency(dev, b) for b in (1, 8, 32)]
         # ---- config 4
@@ -919,10 +927,9 @@ def secondary_block(args, rank, world, local, dev, peak, bf16_peak, cpu, a_r, a_
         sec["sample_image_features"] = sample_bench(dev, peak, cpu, args.batch)
         torch.cuda.empty_cache()
         # ---- the reference's own environment.py on CUDA tensors
-        sec["gpu_torch_baseline"] = gpu_torch_baseline(dev, cpu, a_r, a_t, iters)
+        comparator("gpu_torch_baseline", lambda: gpu_torch_baseline(dev, cpu, a_r, a_t, iters))
         # ---- configs[0]: the reference's Test_Agent loop with its unchanged CMRAgent in it
-        with contextlib.redirect_stdout(sys.stderr):     # the reference's config class prints a banner: not on OUR stdout
-            sec["test_agent_loop"] = agent_loop_bench(dev, iters=iters)
+        comparator("test_agent_loop", lambda: agent_loop_bench(dev, iters=iters))
     return sec
 
 

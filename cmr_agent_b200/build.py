@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcmr_b200.so")
 SOURCES = ["cmr_b200.cu"]
-HEADERS = ["common.cuh", "env_kernels.cuh", "pointnet_kernels.cuh", "scatter_kernels.cuh", "dataset_kernels.cuh", "tower_kernels.cuh", "session.cuh", os.path.join("..", "..", "include", "cmr_b200.h")]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith(".cuh")) + [os.path.join("..", "..", "include", "cmr_b200.h")]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17",
