@@ -151,6 +151,104 @@ class Heads:
         return torch.split(x, self.splits, dim=1)
 
 
+class Head2D:
+    """The convolutional part of the agent's 2-D head (models/CMRAgent.py:34-58: eight ``Conv2d 3x3 [BatchNorm2d]
+    LeakyReLU [AvgPool2d]`` stages), EVAL MODE.  The convolutions stay cuDNN's (``F.conv2d`` without the bias); what
+    follows each of them - bias add, BatchNorm2d, LeakyReLU, AvgPool2d: up to four elementwise launches over the whole
+    feature map - is ONE launch of ``cmr_conv_epilogue`` with bias and BatchNorm folded into a per-channel scale/shift.
+    ``modules``: the leading part of ``state_2d_embed`` up to and including its last AvgPool2d."""
+
+    def __init__(self, modules):
+        nn = torch.nn
+        self.stages = []
+        mods = list(modules)
+        i = 0
+        while i < len(mods):
+            conv = mods[i]
+            if not (isinstance(conv, nn.Conv2d) and conv.groups == 1 and tuple(conv.stride) == (1, 1) and
+                    tuple(conv.dilation) == (1, 1) and conv.padding_mode == "zeros"):
+                raise _lib.CmrError("Head2D: expected a plain Conv2d")
+            i += 1
+            bn = None
+            if i < len(mods) and isinstance(mods[i], nn.BatchNorm2d):
+                bn = mods[i]
+                if not bn.track_running_stats or bn.running_mean is None:
+                    raise _lib.CmrError("Head2D: BatchNorm2d without running statistics")
+                i += 1
+            if not (i < len(mods) and isinstance(mods[i], nn.LeakyReLU)):
+                raise _lib.CmrError("Head2D: expected LeakyReLU after the convolution")
+            slope = float(mods[i].negative_slope)
+            i += 1
+            pool = None
+            if i < len(mods) and isinstance(mods[i], nn.AvgPool2d):
+                pool = mods[i]
+                if pool.padding not in (0, (0, 0)) or pool.ceil_mode or pool.divisor_override is not None:
+                    raise _lib.CmrError("Head2D: unsupported AvgPool2d")
+                i += 1
+            self.stages.append(dict(conv=conv, bn=bn, slope=slope, pool=pool, scale=None, shift=None))
+        self._sig = None
+
+    def _signature(self):
+        ts = []
+        for st in self.stages:
+            ts += [st["conv"].bias] if st["conv"].bias is not None else []
+            if st["bn"] is not None:
+                ts += [t for t in (st["bn"].weight, st["bn"].bias, st["bn"].running_mean, st["bn"].running_var) if t is not None]
+        return tuple((t.data_ptr(), t._version) for t in ts)
+
+    def _fold(self):
+        for st in self.stages:
+            conv, bn = st["conv"], st["bn"]
+            dev = conv.weight.device
+            bias = conv.bias.detach().float() if conv.bias is not None else torch.zeros(conv.out_channels, device=dev)
+            if bn is None:
+                scale, shift = torch.ones(conv.out_channels, device=dev), bias
+            else:
+                g = bn.weight.detach().float() if bn.weight is not None else torch.ones(conv.out_channels, device=dev)
+                beta = bn.bias.detach().float() if bn.bias is not None else torch.zeros(conv.out_channels, device=dev)
+                scale = g / torch.sqrt(bn.running_var.float() + bn.eps)
+                shift = (bias - bn.running_mean.float()) * scale + beta
+            st["scale"], st["shift"] = scale.contiguous(), shift.contiguous()
+
+    @staticmethod
+    def _pool_mode(pool, H, W):
+        if pool is None:
+            return 0
+        k = pool.kernel_size if isinstance(pool.kernel_size, tuple) else (pool.kernel_size, pool.kernel_size)
+        s_ = pool.stride if isinstance(pool.stride, tuple) else (pool.stride, pool.stride)
+        if tuple(k) == (2, 2) and tuple(s_) == (2, 2) and H % 2 == 0 and W % 4 == 0:
+            return 1
+        if tuple(k) == (H, W):
+            return 2
+        return -1
+
+    @torch.no_grad()
+    def __call__(self, x):
+        sig = self._signature()
+        if sig != self._sig:
+            self._fold()
+            self._sig = sig
+        x = _lib.require_cuda(x, "state_2d", torch.float32)
+        for st in self.stages:
+            conv = st["conv"]
+            x = torch.nn.functional.conv2d(x, conv.weight, None, conv.stride, conv.padding, conv.dilation, 1)
+            x = x if x.is_contiguous() else x.contiguous()
+            B, C, H, W = x.shape
+            mode = self._pool_mode(st["pool"], H, W)
+            fused = mode if mode >= 0 and (mode != 0 or (H * W) % 4 == 0) else 0
+            if fused == 0 and (H * W) % 4 != 0:          # odd maps: torch's own elementwise ops on the folded form
+                x = torch.nn.functional.leaky_relu(x * st["scale"].view(1, -1, 1, 1) + st["shift"].view(1, -1, 1, 1), st["slope"])
+            else:
+                shape = (B, C, H, W) if fused == 0 else ((B, C, H // 2, W // 2) if fused == 1 else (B, C, 1, 1))
+                y = x if fused == 0 else torch.empty(shape, device=x.device, dtype=torch.float32)
+                _lib.call("cmr_conv_epilogue", _lib.ptr(x), _lib.ptr(st["scale"]), _lib.ptr(st["shift"]), st["slope"], fused,
+                          B, C, H, W, _lib.ptr(y), _lib.stream())
+                x = y
+            if st["pool"] is not None and fused == 0:    # a pooling shape the kernel does not cover
+                x = st["pool"](x)
+        return x
+
+
 def accelerate_agent(agent):
     """Route the 3-D half of ``CMRAgent.forward`` (models/CMRAgent.py:92-101) through ``Tower3D`` whenever the module
     is in eval mode and autograd is off; otherwise the reference's own forward runs untouched.  The packed weights
@@ -175,6 +273,10 @@ def accelerate_agent(agent):
     tail_ok = (len(tail_2d) >= 1 and len(tail_2d) % 2 == 1 and
                all(is_1x1(m) if i % 2 == 0 else isinstance(m, torch.nn.LeakyReLU) for i, m in enumerate(tail_2d)))
     body_2d = torch.nn.Sequential(*mods_2d[:cut]) if tail_ok else agent.state_2d_embed
+    try:                                  # the convolutional stages with fused epilogues; any other structure stays on torch
+        body_2d = Head2D(mods_2d[:cut] if tail_ok else mods_2d)
+    except _lib.CmrError:
+        pass
 
     def _as_linear(conv):
         lin = torch.nn.Linear(conv.in_channels, conv.out_channels, device=conv.weight.device)

@@ -79,3 +79,77 @@ __global__ void __launch_bounds__(256) k_grouped_linear(const float *__restrict_
 }
 
 }  // namespace cmr
+
+// ---- epilogue of a convolution layer of the agent's 2-D head (models/CMRAgent.py:34-61), eval mode ---------------------
+// After every 3x3 convolution the reference runs up to four elementwise launches over the whole feature map: the bias
+// add, BatchNorm2d, LeakyReLU, AvgPool2d.  Folded (scale = g / sqrt(var + eps), shift = (bias - mean) * scale + beta;
+// scale = 1, shift = bias without a BatchNorm) they are ONE pass:  y = pool(lrelu(x * scale[c] + shift[c])).
+namespace cmr {
+
+__device__ __forceinline__ float lrelu_affine(float x, float sc, float sh, float slope) {
+    const float t = __fmaf_rn(x, sc, sh);
+    return t < 0.f ? __fmul_rn(t, slope) : t;
+}
+
+// pool = 0.  One float4 per thread and step; HW % 4 == 0, so a float4 never crosses a channel plane.
+__global__ void __launch_bounds__(256) k_conv_epilogue(const float *__restrict__ x, const float *__restrict__ scale,
+                                                       const float *__restrict__ shift, float slope, long long n4, int HW4,
+                                                       int C, float *__restrict__ y) {
+    pdl_launch_dependents();
+    pdl_wait();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)((i / HW4) % C);
+        const float sc = __ldg(scale + c), sh = __ldg(shift + c);
+        float4 v = *reinterpret_cast<const float4 *>(x + 4 * i);
+        v.x = lrelu_affine(v.x, sc, sh, slope);
+        v.y = lrelu_affine(v.y, sc, sh, slope);
+        v.z = lrelu_affine(v.z, sc, sh, slope);
+        v.w = lrelu_affine(v.w, sc, sh, slope);
+        *reinterpret_cast<float4 *>(y + 4 * i) = v;
+    }
+}
+
+// pool = 1: AvgPool2d(2, 2).  A thread reads four pixels of two rows and writes two outputs; W % 4 == 0, H % 2 == 0.
+__global__ void __launch_bounds__(256) k_conv_epilogue_pool2(const float *__restrict__ x, const float *__restrict__ scale,
+                                                             const float *__restrict__ shift, float slope, long long n2, int H,
+                                                             int W, int C, float *__restrict__ y) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int Wo2 = W >> 2, Ho = H >> 1;   // output pairs per row, output rows
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
+        const int wq = (int)(i % Wo2);
+        const long long r = i / Wo2;
+        const int ho = (int)(r % Ho);
+        const long long plane = r / Ho;          // b * C + c
+        const int c = (int)(plane % C);
+        const float sc = __ldg(scale + c), sh = __ldg(shift + c);
+        const float *p = x + (plane * H + 2 * ho) * W + 4 * wq;
+        const float4 a = *reinterpret_cast<const float4 *>(p), b = *reinterpret_cast<const float4 *>(p + W);
+        // torch's avg_pool2d: the window's values added row by row, then divided by its area
+        const float s0 = __fadd_rn(__fadd_rn(__fadd_rn(lrelu_affine(a.x, sc, sh, slope), lrelu_affine(a.y, sc, sh, slope)),
+                                             lrelu_affine(b.x, sc, sh, slope)), lrelu_affine(b.y, sc, sh, slope));
+        const float s1 = __fadd_rn(__fadd_rn(__fadd_rn(lrelu_affine(a.z, sc, sh, slope), lrelu_affine(a.w, sc, sh, slope)),
+                                             lrelu_affine(b.z, sc, sh, slope)), lrelu_affine(b.w, sc, sh, slope));
+        *reinterpret_cast<float2 *>(y + (plane * Ho + ho) * (W >> 1) + 2 * wq) = make_float2(__fmul_rn(s0, 0.25f), __fmul_rn(s1, 0.25f));
+    }
+}
+
+// pool = 2: AvgPool2d((H, W)) - one warp per (episode, channel) plane
+__global__ void __launch_bounds__(256) k_conv_epilogue_global(const float *__restrict__ x, const float *__restrict__ scale,
+                                                              const float *__restrict__ shift, float slope, int planes, int HW,
+                                                              int C, float *__restrict__ y) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int lane = threadIdx.x & 31;
+    const int plane = (int)blockIdx.x * (int)(blockDim.x >> 5) + (int)(threadIdx.x >> 5);
+    if (plane >= planes) return;
+    const int c = plane % C;
+    const float sc = __ldg(scale + c), sh = __ldg(shift + c);
+    float s = 0.f;
+    for (int i = lane; i < HW; i += 32) s = __fadd_rn(s, lrelu_affine(x[(size_t)plane * HW + i], sc, sh, slope));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s = __fadd_rn(s, __shfl_xor_sync(kFull, s, o));
+    if (lane == 0) y[plane] = __fdiv_rn(s, (float)HW);
+}
+
+}  // namespace cmr

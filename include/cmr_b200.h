@@ -327,6 +327,16 @@ CMR_API int cmr_grouped_linear(const float *in, int in_stride, const float *W, c
                                int groups, int B, int N, float negative_slope, int activate, float *out, int out_stride,
                                void *stream);
 
+/* Epilogue of one convolution layer of the agent's 2-D head - models/CMRAgent.py:34-61 (state_2d_embed: Conv2d 3x3,
+ * [BatchNorm2d], LeakyReLU, [AvgPool2d]), EVAL MODE: the caller runs the convolution WITHOUT its bias and folds bias
+ * and BatchNorm2d into per-channel scale / shift (scale = g / sqrt(var + eps), shift = (bias - mean) * scale + beta;
+ * 1 and bias without a BatchNorm).  One pass instead of up to four elementwise launches:
+ *     y = pool(LeakyReLU(x * scale[c] + shift[c]))
+ * x [B,C,H,W] f32 NCHW contiguous, 16-byte aligned.  pool 0: none, y [B,C,H,W] (may be x itself; H*W % 4 == 0);
+ * 1: AvgPool2d(2,2), y [B,C,H/2,W/2] (H even, W % 4 == 0);  2: AvgPool2d((H,W)), y [B,C,1,1]. */
+CMR_API int cmr_conv_epilogue(const float *x, const float *scale, const float *shift, float negative_slope, int pool, int B,
+                              int C, int H, int W, float *y, void *stream);
+
 /* ------------------------------------------------------------------ agent: 3-D tower ---- */
 
 /* The 3-D state tower of the agent - models/CMRAgent.py:25-29 (state_3d_embed: four ConvBNReLURes1D blocks,

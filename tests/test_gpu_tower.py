@@ -90,8 +90,8 @@ def test_accelerated_agent_matches_the_reference_agent(cuda):
     agent = CMRAgent(config).to(cuda).eval()
     # give the BatchNorms non-trivial running statistics
     with torch.no_grad():
-        for m in agent.state_3d_embed.modules():
-            if isinstance(m, torch.nn.BatchNorm1d):
+        for m in list(agent.state_3d_embed.modules()) + list(agent.state_2d_embed.modules()):
+            if isinstance(m, (torch.nn.BatchNorm1d, torch.nn.BatchNorm2d)):
                 m.running_mean.normal_(0, 0.2)
                 m.running_var.uniform_(0.5, 1.5)
                 m.weight.normal_(1.0, 0.2)
@@ -169,3 +169,24 @@ def test_heads_match_the_reference_s_modules(cuda, dof6):
         torch.backends.cuda.matmul.allow_tf32 = old
     with pytest.raises(Exception):
         agent_tower.Heads([torch.nn.Sequential(torch.nn.Linear(300, 4).to(cuda))])
+
+
+@pytest.mark.parametrize("shape,pool", [((2, 8, 6, 16), 0), ((3, 5, 4, 8), 1), ((2, 7, 5, 16), 2), ((1, 128, 40, 128), 1)])
+def test_conv_epilogue_matches_torch(cuda, shape, pool):
+    """cmr_conv_epilogue = pool(LeakyReLU(x * scale[c] + shift[c])) against torch's own ops on the folded form."""
+    from cmr_agent_b200 import _lib
+    B, C, H, W = shape
+    g = torch.Generator().manual_seed(B * 100 + C)
+    x = torch.randn(shape, generator=g).to(cuda)
+    scale = (torch.rand(C, generator=g) + 0.5).to(cuda)
+    shift = torch.randn(C, generator=g).to(cuda)
+    want = torch.nn.functional.leaky_relu(x * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1), 0.01)
+    if pool == 1:
+        want = torch.nn.functional.avg_pool2d(want, 2, 2)
+    elif pool == 2:
+        want = torch.nn.functional.avg_pool2d(want, (H, W), 1)
+    got = torch.empty_like(want)
+    _lib.call("cmr_conv_epilogue", _lib.ptr(x), _lib.ptr(scale), _lib.ptr(shift), 0.01, pool, B, C, H, W, _lib.ptr(got), _lib.stream())
+    torch.cuda.synchronize()
+    assert got.shape == want.shape
+    assert float((got - want).abs().max()) <= 2e-6 * float(want.abs().max())
