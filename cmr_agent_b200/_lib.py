@@ -67,7 +67,7 @@ SIGNATURES = {
     "cmr_tower_pack": (_c_int, [_c_int] + [_c_vp] * 8),
     "cmr_tower_workspace_bytes": (_c_sz, [_c_int, _c_int]),
     "cmr_tower_forward": (_c_int, [_c_vp] * 6 + [_c_int, _c_int, _c_vp, _c_vp]),
-    "cmr_conv_epilogue": (_c_int, [_c_vp, _c_vp, _c_vp, _c_f, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp]),
+    "cmr_conv_epilogue": (_c_int, [_c_vp, _c_vp, _c_vp, _c_f, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp]),
     "cmr_grouped_linear": (_c_int, [_c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_f, _c_int, _c_vp, _c_int,
                                     _c_vp]),
 }

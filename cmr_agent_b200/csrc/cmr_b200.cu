@@ -591,27 +591,42 @@ int cmr_grouped_linear(const float *in, int in_stride, const float *W, const flo
                       negative_slope, activate ? 1 : 0, out, out_stride);
 }
 
-int cmr_conv_epilogue(const float *x, const float *scale, const float *shift, float negative_slope, int pool, int B, int C,
-                      int H, int W, float *y, void *stream) {
+int cmr_conv_epilogue(const float *x, const float *scale, const float *shift, float negative_slope, int pool,
+                      int channels_last, int B, int C, int H, int W, float *y, void *stream) {
     CMR_REQUIRE(x && scale && shift && y && B > 0 && C > 0 && H > 0 && W > 0, CMR_EINVAL);
     CMR_REQUIRE(pool >= 0 && pool <= 2, CMR_EINVAL);
     CMR_REQUIRE(aligned(x, 16) && aligned(y, 8), CMR_EALIGN);
     const long long planes = (long long)B * C, HW = (long long)H * W;
     CMR_REQUIRE(planes < (1ll << 31) && HW < (1ll << 31), CMR_ERANGE);
     const int max_blocks = 8 * sm_count();
+    auto blocks = [&](long long n) { return dim3((unsigned)std::min<long long>((n + 255) / 256, max_blocks)); };
+    cudaStream_t st = S_(stream);
+    if (channels_last) {   // memory [B][H][W][C]
+        CMR_REQUIRE(C % 4 == 0 && aligned(scale, 16) && aligned(shift, 16) && aligned(y, 16), CMR_EUNSUPPORTED);
+        if (pool == 0) {
+            const long long n4 = planes * HW / 4;
+            return launch_pdl(k_conv_epilogue_nhwc, blocks(n4), dim3(256), 0, st, x, scale, shift, negative_slope, n4, C / 4, y);
+        }
+        if (pool == 1) {
+            CMR_REQUIRE(W % 2 == 0 && H % 2 == 0, CMR_EUNSUPPORTED);
+            const long long n4 = planes / 4 * (H / 2) * (W / 2);
+            return launch_pdl(k_conv_epilogue_pool2_nhwc, blocks(n4), dim3(256), 0, st, x, scale, shift, negative_slope, n4, H, W,
+                              C / 4, y);
+        }
+        return launch_pdl(k_conv_epilogue_global_nhwc, dim3((unsigned)((planes + 127) / 128)), dim3(128), 0, st, x, scale, shift,
+                          negative_slope, B, (int)HW, C, y);
+    }
     if (pool == 0) {
         CMR_REQUIRE(HW % 4 == 0 && aligned(y, 16), CMR_EUNSUPPORTED);
         const long long n4 = planes * HW / 4;
-        return launch_pdl(k_conv_epilogue, dim3((unsigned)std::min<long long>((n4 + 255) / 256, max_blocks)), dim3(256), 0,
-                          S_(stream), x, scale, shift, negative_slope, n4, (int)(HW / 4), C, y);
+        return launch_pdl(k_conv_epilogue, blocks(n4), dim3(256), 0, st, x, scale, shift, negative_slope, n4, (int)(HW / 4), C, y);
     }
     if (pool == 1) {
         CMR_REQUIRE(W % 4 == 0 && H % 2 == 0, CMR_EUNSUPPORTED);
         const long long n2 = planes * (H / 2) * (W / 4);
-        return launch_pdl(k_conv_epilogue_pool2, dim3((unsigned)std::min<long long>((n2 + 255) / 256, max_blocks)), dim3(256), 0,
-                          S_(stream), x, scale, shift, negative_slope, n2, H, W, C, y);
+        return launch_pdl(k_conv_epilogue_pool2, blocks(n2), dim3(256), 0, st, x, scale, shift, negative_slope, n2, H, W, C, y);
     }
-    return launch_pdl(k_conv_epilogue_global, dim3((unsigned)((planes + 7) / 8)), dim3(256), 0, S_(stream), x, scale, shift,
+    return launch_pdl(k_conv_epilogue_global, dim3((unsigned)((planes + 7) / 8)), dim3(256), 0, st, x, scale, shift,
                       negative_slope, (int)planes, (int)HW, C, y);
 }
 

@@ -153,3 +153,71 @@ __global__ void __launch_bounds__(256) k_conv_epilogue_global(const float *__res
 }
 
 }  // namespace cmr
+
+// ---- the same epilogues on channels-last data ([B][H][W][C] in memory): cuDNN's tensor-core convolutions are NHWC
+// kernels - handed NCHW tensors they convert input and output of every layer (16 layout launches per forward, half of
+// the convolutions' time at every batch size).  With the epilogue ours, the whole head can stay channels-last.
+namespace cmr {
+
+__device__ __forceinline__ float4 lrelu_affine4(float4 v, float4 sc, float4 sh, float slope) {
+    return make_float4(lrelu_affine(v.x, sc.x, sh.x, slope), lrelu_affine(v.y, sc.y, sh.y, slope),
+                       lrelu_affine(v.z, sc.z, sh.z, slope), lrelu_affine(v.w, sc.w, sh.w, slope));
+}
+
+__global__ void __launch_bounds__(256) k_conv_epilogue_nhwc(const float *__restrict__ x, const float *__restrict__ scale,
+                                                            const float *__restrict__ shift, float slope, long long n4, int C4,
+                                                            float *__restrict__ y) {
+    pdl_launch_dependents();
+    pdl_wait();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const int c4 = (int)(i % C4);
+        const float4 sc = __ldg(reinterpret_cast<const float4 *>(scale) + c4), sh = __ldg(reinterpret_cast<const float4 *>(shift) + c4);
+        reinterpret_cast<float4 *>(y)[i] = lrelu_affine4(reinterpret_cast<const float4 *>(x)[i], sc, sh, slope);
+    }
+}
+
+// AvgPool2d(2, 2): a thread = four channels of one output pixel
+__global__ void __launch_bounds__(256) k_conv_epilogue_pool2_nhwc(const float *__restrict__ x, const float *__restrict__ scale,
+                                                                  const float *__restrict__ shift, float slope, long long n4,
+                                                                  int H, int W, int C4, float *__restrict__ y) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int Ho = H >> 1, Wo = W >> 1;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const int c4 = (int)(i % C4);
+        long long r = i / C4;
+        const int wo = (int)(r % Wo);
+        r /= Wo;
+        const int ho = (int)(r % Ho);
+        const long long b = r / Ho;
+        const float4 sc = __ldg(reinterpret_cast<const float4 *>(scale) + c4), sh = __ldg(reinterpret_cast<const float4 *>(shift) + c4);
+        const float4 *p = reinterpret_cast<const float4 *>(x) + ((b * H + 2 * ho) * W + 2 * wo) * C4 + c4;
+        const float4 a = lrelu_affine4(p[0], sc, sh, slope), bq = lrelu_affine4(p[C4], sc, sh, slope);
+        const float4 c = lrelu_affine4(p[(long long)W * C4], sc, sh, slope), d = lrelu_affine4(p[(long long)W * C4 + C4], sc, sh, slope);
+        float4 o;   // the window's values added row by row, then divided by its area (torch's avg_pool2d)
+        o.x = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(a.x, bq.x), c.x), d.x), 0.25f);
+        o.y = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(a.y, bq.y), c.y), d.y), 0.25f);
+        o.z = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(a.z, bq.z), c.z), d.z), 0.25f);
+        o.w = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(a.w, bq.w), c.w), d.w), 0.25f);
+        reinterpret_cast<float4 *>(y)[i] = o;
+    }
+}
+
+// AvgPool2d((H, W)): a thread = one channel of one episode, walking the pixels (coalesced across the channels)
+__global__ void __launch_bounds__(128) k_conv_epilogue_global_nhwc(const float *__restrict__ x, const float *__restrict__ scale,
+                                                                   const float *__restrict__ shift, float slope, int B, int HW,
+                                                                   int C, float *__restrict__ y) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int i = (int)blockIdx.x * (int)blockDim.x + (int)threadIdx.x;
+    if (i >= B * C) return;
+    const int c = i % C, b = i / C;
+    const float sc = __ldg(scale + c), sh = __ldg(shift + c);
+    const float *p = x + (size_t)b * HW * C + c;
+    float s = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < HW; ++k) s = __fadd_rn(s, lrelu_affine(p[(size_t)k * C], sc, sh, slope));
+    y[i] = __fdiv_rn(s, (float)HW);
+}
+
+}  // namespace cmr

@@ -332,10 +332,12 @@ CMR_API int cmr_grouped_linear(const float *in, int in_stride, const float *W, c
  * and BatchNorm2d into per-channel scale / shift (scale = g / sqrt(var + eps), shift = (bias - mean) * scale + beta;
  * 1 and bias without a BatchNorm).  One pass instead of up to four elementwise launches:
  *     y = pool(LeakyReLU(x * scale[c] + shift[c]))
- * x [B,C,H,W] f32 NCHW contiguous, 16-byte aligned.  pool 0: none, y [B,C,H,W] (may be x itself; H*W % 4 == 0);
- * 1: AvgPool2d(2,2), y [B,C,H/2,W/2] (H even, W % 4 == 0);  2: AvgPool2d((H,W)), y [B,C,1,1]. */
-CMR_API int cmr_conv_epilogue(const float *x, const float *scale, const float *shift, float negative_slope, int pool, int B,
-                              int C, int H, int W, float *y, void *stream);
+ * x [B,C,H,W] f32, 16-byte aligned; channels_last = 0: NCHW contiguous, 1: torch's channels_last ([B][H][W][C] in
+ * memory, C % 4 == 0) - cuDNN's tensor-core convolutions are NHWC kernels and convert every layer's input and output when
+ * handed NCHW (half of their time); y has the layout of x.  pool 0: none, y [B,C,H,W] (may be x itself; NCHW:
+ * H*W % 4 == 0);  1: AvgPool2d(2,2), y [B,C,H/2,W/2] (H, W even; NCHW: W % 4 == 0);  2: AvgPool2d((H,W)), y [B,C,1,1]. */
+CMR_API int cmr_conv_epilogue(const float *x, const float *scale, const float *shift, float negative_slope, int pool,
+                              int channels_last, int B, int C, int H, int W, float *y, void *stream);
 
 /* ------------------------------------------------------------------ agent: 3-D tower ---- */
 

@@ -171,13 +171,16 @@ def test_heads_match_the_reference_s_modules(cuda, dof6):
         agent_tower.Heads([torch.nn.Sequential(torch.nn.Linear(300, 4).to(cuda))])
 
 
-@pytest.mark.parametrize("shape,pool", [((2, 8, 6, 16), 0), ((3, 5, 4, 8), 1), ((2, 7, 5, 16), 2), ((1, 128, 40, 128), 1)])
-def test_conv_epilogue_matches_torch(cuda, shape, pool):
-    """cmr_conv_epilogue = pool(LeakyReLU(x * scale[c] + shift[c])) against torch's own ops on the folded form."""
+@pytest.mark.parametrize("channels_last", [False, True])
+@pytest.mark.parametrize("shape,pool", [((2, 8, 6, 16), 0), ((3, 12, 4, 8), 1), ((2, 8, 5, 16), 2), ((1, 128, 40, 128), 1)])
+def test_conv_epilogue_matches_torch(cuda, shape, pool, channels_last):
+    """cmr_conv_epilogue = pool(LeakyReLU(x * scale[c] + shift[c])) against torch's own ops on the folded form, on NCHW
+    and on channels_last data."""
     from cmr_agent_b200 import _lib
     B, C, H, W = shape
+    fmt = torch.channels_last if channels_last else torch.contiguous_format
     g = torch.Generator().manual_seed(B * 100 + C)
-    x = torch.randn(shape, generator=g).to(cuda)
+    x = torch.randn(shape, generator=g).to(cuda).contiguous(memory_format=fmt)
     scale = (torch.rand(C, generator=g) + 0.5).to(cuda)
     shift = torch.randn(C, generator=g).to(cuda)
     want = torch.nn.functional.leaky_relu(x * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1), 0.01)
@@ -185,8 +188,9 @@ def test_conv_epilogue_matches_torch(cuda, shape, pool):
         want = torch.nn.functional.avg_pool2d(want, 2, 2)
     elif pool == 2:
         want = torch.nn.functional.avg_pool2d(want, (H, W), 1)
-    got = torch.empty_like(want)
-    _lib.call("cmr_conv_epilogue", _lib.ptr(x), _lib.ptr(scale), _lib.ptr(shift), 0.01, pool, B, C, H, W, _lib.ptr(got), _lib.stream())
+    got = torch.empty(want.shape, device=cuda, memory_format=fmt)
+    _lib.call("cmr_conv_epilogue", _lib.ptr(x), _lib.ptr(scale), _lib.ptr(shift), 0.01, pool, 1 if channels_last else 0,
+              B, C, H, W, _lib.ptr(got), _lib.stream())
     torch.cuda.synchronize()
     assert got.shape == want.shape
     assert float((got - want).abs().max()) <= 2e-6 * float(want.abs().max())
