@@ -68,6 +68,7 @@ SIGNATURES = {
     "cmr_tower_workspace_bytes": (_c_sz, [_c_int, _c_int]),
     "cmr_tower_forward": (_c_int, [_c_vp] * 6 + [_c_int, _c_int, _c_vp, _c_vp]),
     "cmr_conv_epilogue": (_c_int, [_c_vp, _c_vp, _c_vp, _c_f, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp]),
+    "cmr_to_channels_last": (_c_int, [_c_vp, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp]),
     "cmr_grouped_linear": (_c_int, [_c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_f, _c_int, _c_vp, _c_int,
                                     _c_vp]),
 }
@@ -92,7 +93,7 @@ def load():
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
-        if lib.cmr_abi_version() != 4:
+        if lib.cmr_abi_version() != 5:
             raise CmrError("libcmr_b200.so ABI version mismatch; rebuild it")
         _lib = lib
     return _lib

@@ -237,9 +237,14 @@ class Head2D:
         x = _lib.require_cuda(x, "state_2d", torch.float32)
         nhwc = self.channels_last and all(st["conv"].out_channels % 4 == 0 for st in self.stages)
         fmt = torch.channels_last if nhwc else torch.contiguous_format
+        if nhwc and x.dim() == 4 and x.is_contiguous() and not x.is_contiguous(memory_format=torch.channels_last):
+            # the observation arrives NCHW (environment.py:126): one transposing copy instead of torch's strided one
+            y = torch.empty(x.shape, device=x.device, dtype=torch.float32, memory_format=torch.channels_last)
+            _lib.call("cmr_to_channels_last", _lib.ptr(x), x.shape[0], x.shape[1], x.shape[2], x.shape[3], _lib.ptr(y), _lib.stream())
+            x = y
         for st in self.stages:
             conv = st["conv"]
-            x = x.contiguous(memory_format=fmt)            # (the observation: once; afterwards a no-op)
+            x = x.contiguous(memory_format=fmt)            # (a no-op on the converted observation and between the stages)
             x = torch.nn.functional.conv2d(x, st["weight"] if nhwc else conv.weight, None, conv.stride, conv.padding,
                                            conv.dilation, 1)
             x = x.contiguous(memory_format=fmt)

@@ -630,6 +630,18 @@ int cmr_conv_epilogue(const float *x, const float *scale, const float *shift, fl
                       negative_slope, (int)planes, (int)HW, C, y);
 }
 
+int cmr_to_channels_last(const float *x, int B, int C, int H, int W, float *y, void *stream) {
+    CMR_REQUIRE(x && y && x != y && B > 0 && C > 0 && H > 0 && W > 0, CMR_EINVAL);
+    const long long P = (long long)H * W;
+    CMR_REQUIRE(B <= 65535 && P < (1ll << 31) && (long long)C * P < (1ll << 40), CMR_ERANGE);
+    if (C % 4 == 0 && P % 4 == 0 && aligned(x, 16) && aligned(y, 16))
+        return launch_pdl(k_to_channels_last, dim3((unsigned)ceil_div((int)P, 128), (unsigned)ceil_div(C, 32), (unsigned)B), dim3(256),
+                          0, S_(stream), x, C, (int)P, y);
+    CMR_REQUIRE(ceil_div(C, 32) <= 65535, CMR_ERANGE);
+    k_image_transpose<<<dim3((unsigned)ceil_div((int)P, 32), (unsigned)ceil_div(C, 32), (unsigned)B), 256, 0, S_(stream)>>>(x, C, (int)P, y);
+    return after_launch();
+}
+
 // ---------------------------------------------------------------------------- pointnet_util ----
 
 int cmr_square_distance(const float *src, const int64_t src_stride[3], const float *dst, const int64_t dst_stride[3],

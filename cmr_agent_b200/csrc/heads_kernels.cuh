@@ -203,6 +203,36 @@ __global__ void __launch_bounds__(256) k_conv_epilogue_pool2_nhwc(const float *_
     }
 }
 
+// [B][C][P] -> [B][P][C] (NCHW -> torch's channels_last), P = H*W: what the head's first convolution wants of the
+// observation.  A CTA turns a [32 channels][128 pixels] tile round through shared memory: 16-byte loads along the
+// pixels, 16-byte stores along the channels (a pixel's 32 channels = one 128-byte line); the tile's row stride of 129
+// words keeps both the scalar tile writes and the transposed reads free of bank conflicts.  Requires C % 4 == 0 and
+// P % 4 == 0 (the launcher falls back to k_image_transpose otherwise).
+__global__ void __launch_bounds__(256) k_to_channels_last(const float *__restrict__ x, int C, int P, float *__restrict__ y) {
+    __shared__ float t[32][129];
+    pdl_launch_dependents();
+    pdl_wait();
+    const int b = blockIdx.z, p0 = blockIdx.x * 128, c0 = blockIdx.y * 32;
+    const float *src = x + (size_t)b * C * P;
+    float *dst = y + (size_t)b * C * P;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int i = threadIdx.x + 256 * k, r = i >> 5, q = i & 31;   // channel row r, pixel quad q
+        if (c0 + r < C && p0 + 4 * q < P) {
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(src + (size_t)(c0 + r) * P + p0) + q);
+            t[r][4 * q + 0] = v.x, t[r][4 * q + 1] = v.y, t[r][4 * q + 2] = v.z, t[r][4 * q + 3] = v.w;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int i = threadIdx.x + 256 * k, p = i >> 3, cq = i & 7;   // pixel p, channel quad cq
+        if (p0 + p < P && c0 + 4 * cq < C)
+            *reinterpret_cast<float4 *>(dst + (size_t)(p0 + p) * C + c0 + 4 * cq) =
+                make_float4(t[4 * cq + 0][p], t[4 * cq + 1][p], t[4 * cq + 2][p], t[4 * cq + 3][p]);
+    }
+}
+
 // AvgPool2d((H, W)): a thread = one channel of one episode, walking the pixels (coalesced across the channels)
 __global__ void __launch_bounds__(128) k_conv_epilogue_global_nhwc(const float *__restrict__ x, const float *__restrict__ scale,
                                                                    const float *__restrict__ shift, float slope, int B, int HW,

@@ -33,7 +33,7 @@ extern "C" {
 #define CMR_API
 #endif
 
-#define CMR_ABI_VERSION 4
+#define CMR_ABI_VERSION 5
 
 #define CMR_OK 0
 #define CMR_EINVAL (-1)      /* null pointer, non-positive size */
@@ -338,6 +338,12 @@ CMR_API int cmr_grouped_linear(const float *in, int in_stride, const float *W, c
  * H*W % 4 == 0);  1: AvgPool2d(2,2), y [B,C,H/2,W/2] (H, W even; NCHW: W % 4 == 0);  2: AvgPool2d((H,W)), y [B,C,1,1]. */
 CMR_API int cmr_conv_epilogue(const float *x, const float *scale, const float *shift, float negative_slope, int pool,
                               int channels_last, int B, int C, int H, int W, float *y, void *stream);
+
+/* The observation handed to the agent's 2-D head in the layout its convolutions run in - models/CMRAgent.py:89
+ * (`self.state_2d_embed(state_2d)`: the first Conv2d reads obs2d [B,2C,H/4,W/4] as environment.py:126 returns it, NCHW):
+ * x [B,C,H,W] f32 contiguous -> y the same values as torch's channels_last ([B][H][W][C] in memory), a pure copy
+ * (what `x.contiguous(memory_format=torch.channels_last)` returns, 2.3x faster at the reference's shape).  x != y. */
+CMR_API int cmr_to_channels_last(const float *x, int B, int C, int H, int W, float *y, void *stream);
 
 /* ------------------------------------------------------------------ agent: 3-D tower ---- */
 

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared_symbols():
         assert hasattr(lib, name), f"{name} declared in cmr_b200.h but not exported"
-    assert lib.cmr_abi_version() == 4
+    assert lib.cmr_abi_version() == 5
 
 
 def test_ctypes_table_matches_header():

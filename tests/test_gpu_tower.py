@@ -194,3 +194,20 @@ def test_conv_epilogue_matches_torch(cuda, shape, pool, channels_last):
     torch.cuda.synchronize()
     assert got.shape == want.shape
     assert float((got - want).abs().max()) <= 2e-6 * float(want.abs().max())
+
+
+@pytest.mark.parametrize("shape", [(1, 128, 40, 128), (3, 128, 40, 80), (2, 36, 6, 10), (2, 8, 5, 7), (1, 3, 4, 4)])
+def test_to_channels_last_is_torchs_copy(cuda, shape):
+    """cmr_to_channels_last = x.contiguous(memory_format=torch.channels_last) bit for bit (the observation handed to the
+    2-D head, models/CMRAgent.py:89), on the reference's shapes, on partial tiles and on shapes that take the scalar kernel."""
+    from cmr_agent_b200 import _lib
+    B, C, H, W = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(shape, generator=g).to(cuda)
+    want = x.contiguous(memory_format=torch.channels_last)
+    got = torch.full(shape, float("nan"), device=cuda).contiguous(memory_format=torch.channels_last)
+    _lib.call("cmr_to_channels_last", _lib.ptr(x), B, C, H, W, _lib.ptr(got), _lib.stream())
+    torch.cuda.synchronize()
+    assert got.is_contiguous(memory_format=torch.channels_last) or C == 1
+    assert torch.equal(got, want)
+    assert torch.equal(got.permute(0, 2, 3, 1).contiguous().view(-1), want.permute(0, 2, 3, 1).contiguous().view(-1))
