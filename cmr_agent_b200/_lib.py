@@ -16,6 +16,7 @@ _c_int = ctypes.c_int
 _c_vp = ctypes.c_void_p
 _c_f = ctypes.c_float
 _c_sz = ctypes.c_size_t
+_c_i64 = ctypes.c_int64
 
 # name -> (restype, argtypes); mirrors include/cmr_b200.h one to one
 SIGNATURES = {
@@ -69,6 +70,7 @@ SIGNATURES = {
     "cmr_tower_forward": (_c_int, [_c_vp] * 6 + [_c_int, _c_int, _c_vp, _c_vp]),
     "cmr_conv_epilogue": (_c_int, [_c_vp, _c_vp, _c_vp, _c_f, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp]),
     "cmr_to_channels_last": (_c_int, [_c_vp, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp]),
+    "cmr_deterministic_action": (_c_int, [_c_vp, _c_int, _c_i64, _c_vp, _c_int, _c_i64, _c_int, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp]),
     "cmr_grouped_linear": (_c_int, [_c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_f, _c_int, _c_vp, _c_int,
                                     _c_vp]),
 }

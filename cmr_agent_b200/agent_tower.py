@@ -329,6 +329,27 @@ def accelerate_agent(agent):
         action_t_logits = action_t_logits.reshape(action_t_logits.shape[0], agent.degree_t, agent.config.num_steps)
         return action_r_logits, action_t_logits, value.unsqueeze(-1)
 
+    reference_action = agent.action_from_logits              # the class's static method (models/CMRAgent.py:117-128)
+
+    def action_from_logits(r_logits, t_logits, deterministic=False):
+        """``deterministic=True`` on CUDA logits without autograd: one launch of ``cmr_deterministic_action`` (torch's
+        probabilities bit for bit, the first index of the largest); anything else is the reference's own function."""
+        ok = (deterministic and not torch.is_grad_enabled() and
+              all(t.is_cuda and t.dtype == torch.float32 and t.dim() == 3 and t.shape[0] == r_logits.shape[0] and
+                  t.stride(2) == 1 and t.stride(1) == t.shape[2] and t.stride(0) >= t.shape[1] * t.shape[2] and
+                  t.data_ptr() % 4 == 0 for t in (r_logits, t_logits)) and
+              r_logits.shape[2] == t_logits.shape[2] and 9 <= r_logits.shape[2] <= 16 and r_logits.shape[0] > 0)
+        if not ok:
+            return reference_action(r_logits, t_logits, deterministic)
+        B, S = r_logits.shape[0], r_logits.shape[2]
+        action_r = torch.empty(r_logits.shape[:2], device=r_logits.device, dtype=torch.int64)
+        action_t = torch.empty(t_logits.shape[:2], device=t_logits.device, dtype=torch.int64)
+        _lib.call("cmr_deterministic_action", _lib.ptr(r_logits), r_logits.shape[1], r_logits.stride(0), _lib.ptr(t_logits),
+                  t_logits.shape[1], t_logits.stride(0), B, S, _lib.ptr(action_r), _lib.ptr(action_t), None, None, _lib.stream())
+        return action_r, action_t
+
     agent.forward = forward
+    agent.action_from_logits = action_from_logits
     agent._cmr_b200_reference_forward = reference_forward
+    agent._cmr_b200_reference_action = reference_action
     return agent

@@ -630,6 +630,19 @@ int cmr_conv_epilogue(const float *x, const float *scale, const float *shift, fl
                       negative_slope, (int)planes, (int)HW, C, y);
 }
 
+int cmr_deterministic_action(const float *r_logits, int degree_r, int64_t r_batch_stride, const float *t_logits, int degree_t,
+                             int64_t t_batch_stride, int B, int steps, int64_t *action_r, int64_t *action_t, float *probs_r,
+                             float *probs_t, void *stream) {
+    CMR_REQUIRE(r_logits && t_logits && action_r && action_t && B > 0 && degree_r > 0 && degree_t > 0, CMR_EINVAL);
+    CMR_REQUIRE(steps >= 9 && steps <= 16, CMR_EUNSUPPORTED);   // the shapes whose summation order the kernel reproduces
+    CMR_REQUIRE(r_batch_stride >= (int64_t)degree_r * steps && t_batch_stride >= (int64_t)degree_t * steps, CMR_EINVAL);
+    CMR_REQUIRE((long long)B * (degree_r + degree_t) < (1ll << 30), CMR_ERANGE);
+    const int rows = B * (degree_r + degree_t);
+    return launch_pdl(k_deterministic_action, dim3((unsigned)ceil_div(rows, 8)), dim3(128), 0, S_(stream), r_logits, degree_r,
+                      (long long)r_batch_stride, t_logits, degree_t, (long long)t_batch_stride, B, steps,
+                      reinterpret_cast<long long *>(action_r), reinterpret_cast<long long *>(action_t), probs_r, probs_t);
+}
+
 int cmr_to_channels_last(const float *x, int B, int C, int H, int W, float *y, void *stream) {
     CMR_REQUIRE(x && y && x != y && B > 0 && C > 0 && H > 0 && W > 0, CMR_EINVAL);
     const long long P = (long long)H * W;

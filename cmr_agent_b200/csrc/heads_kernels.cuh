@@ -203,6 +203,65 @@ __global__ void __launch_bounds__(256) k_conv_epilogue_pool2_nhwc(const float *_
     }
 }
 
+// The deterministic action of models/CMRAgent.py:118-124: argmax over Categorical(logits=x).probs, for the rotation and
+// the translation logits in ONE launch (torch: 2 x 11 launches - amax, abs, eq, masked_fill, sub, exp, sum, log, add, sub,
+// softmax, argmax).  A half-warp per row of S logits, 9 <= S <= 16 (the reference: 11).  probs must be torch's bit for
+// bit - two different logits may round to the same probability, and argmax then takes the smaller index - so every
+// operation and the ORDER of both sums are torch's:
+//   Categorical.__init__:  n = x - logsumexp(x)     logsumexp = log(sum(exp(x - m))) + (|m| == inf ? 0 : m), m = max x
+//       the sum (ATen reduce_kernel, 9..16 inputs per output: 16 lanes along the row, halving offsets 8, 4, 2, 1; measured
+//       against five other orders, benchmarks/debug/action_diag/diag.py):  a_j = x[j] + x[j + 8], b_j = a_j + a_{j+4}, ...
+//   .probs = softmax(n)  (ATen softmax_warp_forward, 16 lanes per row): e = exp(n - max n), the sum by the same xor
+//       butterfly 8, 4, 2, 1 (the same value in every lane, floating-point addition being commutative), p = e / sum
+//   argmax: the FIRST index of the largest probability.
+// tests/test_gpu_tower.py compares probs and actions with torch's own on random and near-tied rows.
+__global__ void __launch_bounds__(128) k_deterministic_action(const float *__restrict__ xr, int Dr, long long sr,
+                                                              const float *__restrict__ xt, int Dt, long long st_, int B, int S,
+                                                              long long *__restrict__ ar, long long *__restrict__ at,
+                                                              float *__restrict__ pr, float *__restrict__ pt) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int lane = threadIdx.x & 31, l = lane & 15, half = lane & 16;
+    const int row = ((int)blockIdx.x * (int)(blockDim.x >> 5) + (int)(threadIdx.x >> 5)) * 2 + (half >> 4);
+    const int rows_r = B * Dr, rows = rows_r + B * Dt;
+    const bool live = row < rows;                       // (a dead half-warp walks along: the shuffles are warp-wide)
+    const bool is_r = row < rows_r;
+    const int k = is_r ? row : row - rows_r, D = is_r ? Dr : Dt;
+    const float *x = live ? (is_r ? xr + (long long)(k / D) * sr : xt + (long long)(k / D) * st_) + (long long)(k % D) * S : nullptr;
+    const float ninf = __int_as_float(0xff800000);
+    const float v = (live && l < S) ? __ldg(x + l) : ninf;
+    float m = v;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(kFull, m, o));
+    const float mm = (fabsf(m) == __int_as_float(0x7f800000)) ? 0.f : m;
+    const float e = (l < S) ? expf(__fsub_rn(v, m)) : 0.f;
+    float t = e;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) t = __fadd_rn(t, __shfl_xor_sync(kFull, t, o));
+    const float lse = __fadd_rn(logf(t), mm);
+    const float n = (l < S) ? __fsub_rn(v, lse) : ninf;
+    float M = n;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) M = fmaxf(M, __shfl_xor_sync(kFull, M, o));
+    const float E = (l < S) ? expf(__fsub_rn(n, M)) : 0.f;
+    float sum = E;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) sum = __fadd_rn(sum, __shfl_xor_sync(kFull, sum, o));
+    const float p = __fdiv_rn(E, sum);
+    float best = (l < S) ? p : ninf;
+    int arg = l;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(kFull, best, o);
+        const int oa = __shfl_xor_sync(kFull, arg, o);
+        if (ob > best || (ob == best && oa < arg)) best = ob, arg = oa;
+    }
+    if (!live) return;
+    float *probs = is_r ? pr : pt;
+    if (probs && l < S) probs[(long long)k * S + l] = p;
+    if (l == 0) (is_r ? ar : at)[k] = arg;
+}
+
 // [B][C][P] -> [B][P][C] (NCHW -> torch's channels_last), P = H*W: what the head's first convolution wants of the
 // observation.  A CTA turns a [32 channels][128 pixels] tile round through shared memory: 16-byte loads along the
 // pixels, 16-byte stores along the channels (a pixel's 32 channels = one 128-byte line); the tile's row stride of 129

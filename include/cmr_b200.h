@@ -339,6 +339,19 @@ CMR_API int cmr_grouped_linear(const float *in, int in_stride, const float *W, c
 CMR_API int cmr_conv_epilogue(const float *x, const float *scale, const float *shift, float negative_slope, int pool,
                               int channels_last, int B, int C, int H, int W, float *y, void *stream);
 
+/* The deterministic action - models/CMRAgent.py:118-124 (`action_from_logits(..., deterministic=True)`:
+ * `argmax(Categorical(logits=x).probs, dim=-1)` for the rotation and the translation logits), Test_Agent.py:166.
+ * One launch instead of torch's 22.  r_logits [B,degree_r,steps], t_logits [B,degree_t,steps] f32, innermost two
+ * dimensions dense, *_batch_stride in elements (the heads' logits are column blocks of one wider matrix);
+ * action_r [B,degree_r], action_t [B,degree_t] int64; probs_r / probs_t: NULL, or [B,degree,steps] f32 receiving
+ * the probabilities (tests).  9 <= steps <= 16 (the reference: 11): within that range the kernel reproduces torch's
+ * logsumexp and softmax operation by operation, INCLUDING the order of their sums, so that the probabilities are
+ * torch's bit for bit and ties between rounded probabilities resolve to the same (first) index; other step counts
+ * return CMR_EUNSUPPORTED and the caller keeps the reference's own function. */
+CMR_API int cmr_deterministic_action(const float *r_logits, int degree_r, int64_t r_batch_stride, const float *t_logits,
+                                     int degree_t, int64_t t_batch_stride, int B, int steps, int64_t *action_r,
+                                     int64_t *action_t, float *probs_r, float *probs_t, void *stream);
+
 /* The observation handed to the agent's 2-D head in the layout its convolutions run in - models/CMRAgent.py:89
  * (`self.state_2d_embed(state_2d)`: the first Conv2d reads obs2d [B,2C,H/4,W/4] as environment.py:126 returns it, NCHW):
  * x [B,C,H,W] f32 contiguous -> y the same values as torch's channels_last ([B][H][W][C] in memory), a pure copy

@@ -211,3 +211,80 @@ def test_to_channels_last_is_torchs_copy(cuda, shape):
     assert got.is_contiguous(memory_format=torch.channels_last) or C == 1
     assert torch.equal(got, want)
     assert torch.equal(got.permute(0, 2, 3, 1).contiguous().view(-1), want.permute(0, 2, 3, 1).contiguous().view(-1))
+
+
+def _action_rows(S, seed):
+    """Rows of logits that stress the tie-breaking: plain random rows at several scales, exact duplicates of the
+    maximum, and maxima one or two ulps apart (their probabilities usually round to the same float)."""
+    g = torch.Generator().manual_seed(seed)
+    rows = [torch.randn(6000, S, generator=g) * s for s in (1.0, 0.01, 10.0, 1e-4, 50.0)]
+    base = torch.randn(6000, S, generator=g)
+    top = base.max(dim=1, keepdim=True).values
+    j = torch.randint(0, S, (6000, 1), generator=g)
+    dup = base.clone().scatter_(1, j, top)                                    # a second copy of the maximum
+    up = base.clone().scatter_(1, j, torch.nextafter(top, top + 1))           # one ulp above the old maximum
+    up2 = torch.nextafter(up, up + 1).where(torch.zeros_like(up, dtype=torch.bool).scatter_(1, j, True), up)
+    down = base.clone().scatter_(1, j, torch.nextafter(top, top - 1))         # one ulp below
+    return torch.cat(rows + [dup, up, up2, down, base * 0.0, base * 0.0 + 3.5])
+
+
+@pytest.mark.parametrize("S", [11, 9, 16, 13])
+def test_deterministic_action_is_torchs_argmax_of_probs(cuda, S):
+    """cmr_deterministic_action against models/CMRAgent.py:118-124 on the same GPU: the probabilities of
+    Categorical(logits=x) bit for bit (every operation and the order of both sums are torch's), hence the same argmax -
+    including rows whose two largest probabilities round to the same float."""
+    from cmr_agent_b200 import _lib
+    x = _action_rows(S, 100 + S)
+    B = x.shape[0] // 6 * 2
+    r = x[:B * 3].reshape(B, 3, S).to(cuda)
+    wide = torch.zeros(B, 3 * S + 5, device=cuda)                             # the translation logits: a column block
+    wide[:, 2:2 + 3 * S] = x[-B * 3:].reshape(B, 3 * S).to(cuda)
+    t = wide[:, 2:2 + 3 * S].reshape(B, 3, S)
+    assert t.stride() == (3 * S + 5, S, 1)
+    a_r = torch.empty(B, 3, device=cuda, dtype=torch.int64)
+    a_t = torch.empty(B, 3, device=cuda, dtype=torch.int64)
+    p_r = torch.empty(B, 3, S, device=cuda)
+    p_t = torch.empty(B, 3, S, device=cuda)
+    _lib.call("cmr_deterministic_action", _lib.ptr(r), 3, r.stride(0), _lib.ptr(t), 3, t.stride(0), B, S, _lib.ptr(a_r),
+              _lib.ptr(a_t), _lib.ptr(p_r), _lib.ptr(p_t), _lib.stream())
+    torch.cuda.synchronize()
+    for logits, probs, act in ((r, p_r, a_r), (t, p_t, a_t)):
+        want = torch.distributions.Categorical(logits=logits).probs
+        assert torch.equal(probs, want), f"{int((probs != want).sum())} of {want.numel()} probabilities differ"
+        assert torch.equal(act, torch.argmax(want, dim=-1))
+    ties = (p_r == p_r.max(dim=-1, keepdim=True).values).sum(-1) > 1
+    assert int(ties.sum()) > 100                                               # the tie-breaking was exercised
+
+
+def test_accelerated_agent_takes_the_reference_s_deterministic_actions(cuda):
+    """accelerate_agent's action_from_logits: the reference's static method (models/CMRAgent.py:117-128) on the same
+    logits gives the same actions; sampling (deterministic=False) and autograd stay the reference's."""
+    if not rl.available():
+        pytest.skip("no reference tree (oracle/_ref is staged by oracle/make_ref.py in the build container)")
+    from cmr_agent_b200 import agent_tower
+    rl.put_on_path()
+    from config import KittiConfiguration
+    from models import CMRAgent
+    config = KittiConfiguration()
+    torch.manual_seed(5)
+    agent = agent_tower.accelerate_agent(CMRAgent(config).to(cuda).eval())
+    r = torch.randn(8, agent.degree_r, config.num_steps, device=cuda)
+    t = torch.randn(8, agent.degree_t, config.num_steps, device=cuda)
+    with torch.no_grad():
+        n0 = _lib_launches()
+        got = agent.action_from_logits(r, t, deterministic=True)
+        assert _lib_launches() == n0 + 1
+        want = CMRAgent.action_from_logits(r, t, deterministic=True)
+        assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
+        assert got[0].dtype == want[0].dtype and got[0].shape == want[0].shape
+        n0 = _lib_launches()
+        agent.action_from_logits(r, t, deterministic=False)
+        assert _lib_launches() == n0
+    n0 = _lib_launches()
+    agent.action_from_logits(r, t, deterministic=True)                        # autograd on: the reference's function
+    assert _lib_launches() == n0
+
+
+def _lib_launches():
+    from cmr_agent_b200 import _lib
+    return _lib.launch_count()
