@@ -85,6 +85,11 @@ emu = E / butterfly16(P16).unsqueeze(-1)
 print("kernel probs vs the emulation with butterfly16 (elements):", frac(p_r, emu))
 
 # elementwise functions of this build against torch's kernels
+if not os.path.exists(os.path.join(HERE, "libelem.so")):          # this library's flags (cmr_agent_b200/build.py)
+    import subprocess
+    subprocess.run(["nvcc", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "--fmad=false", "--prec-div=true",
+                    "--prec-sqrt=true", "--ftz=false", "-Xcompiler", "-fPIC", "-shared", "-cudart", "static", "-o",
+                    os.path.join(HERE, "libelem.so"), os.path.join(HERE, "elem.cu")], check=True)
 lib = ctypes.CDLL(os.path.join(HERE, "libelem.so"))
 a = (torch.rand(1 << 20, device=dev) * -20.0)
 b = torch.rand(1 << 20, device=dev) * 10 + 1e-3
