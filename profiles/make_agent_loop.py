@@ -20,8 +20,8 @@ GROUPS = [
     ("environment (this library)", ("k_project", "k_tile_gather", "k_tile_scatter", "k_step", "k_reward", "k_feat_compact",
                                     "k_cloud_mean", "k_overlap_scan", "k_to_disentangled", "k_mean", "k_scan")),
     ("3-D tower (this library, tcgen05)", ("k_tower",)),
-    ("heads + 1x1 tail (this library)", ("k_grouped_linear",)),
-    ("2-D head epilogues (this library)", ("k_conv_epilogue",)),
+    ("heads + 1x1 tail + action (this library)", ("k_grouped_linear", "k_deterministic_action")),
+    ("2-D head epilogues + layout (this library)", ("k_conv_epilogue", "k_to_channels_last")),
     ("2-D head convolutions (cuDNN / CUTLASS)", ("cudnn", "cutlass", "sm100_", "sm90_", "sm80_", "xmma", "implicit_convolve",
                                                  "conv", "nchwToNhwc", "nhwcToNchw", "gemm", "wgrad", "fprop")),
 ]
