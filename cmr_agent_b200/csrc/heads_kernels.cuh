@@ -304,8 +304,22 @@ __global__ void __launch_bounds__(128) k_conv_epilogue_global_nhwc(const float *
     const float sc = __ldg(scale + c), sh = __ldg(shift + c);
     const float *p = x + (size_t)b * HW * C + c;
     float s = 0.f;
-#pragma unroll 8
-    for (int k = 0; k < HW; ++k) s = __fadd_rn(s, lrelu_affine(p[(size_t)k * C], sc, sh, slope));
+    int k = 0;
+    for (; k + 32 <= HW; k += 32) {    // 32 loads in flight, then the additions in pixel order (torch's avg_pool2d order)
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = p[(size_t)(k + j) * C];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) s = __fadd_rn(s, lrelu_affine(v[j], sc, sh, slope));
+    }
+    for (; k + 8 <= HW; k += 8) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = p[(size_t)(k + j) * C];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s = __fadd_rn(s, lrelu_affine(v[j], sc, sh, slope));
+    }
+    for (; k < HW; ++k) s = __fadd_rn(s, lrelu_affine(p[(size_t)k * C], sc, sh, slope));
     y[i] = __fdiv_rn(s, (float)HW);
 }
 
