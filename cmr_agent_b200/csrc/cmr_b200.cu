@@ -613,7 +613,8 @@ int cmr_conv_epilogue(const float *x, const float *scale, const float *shift, fl
             return launch_pdl(k_conv_epilogue_pool2_nhwc, blocks(n4), dim3(256), 0, st, x, scale, shift, negative_slope, n4, H, W,
                               C / 4, y);
         }
-        return launch_pdl(k_conv_epilogue_global_nhwc, dim3((unsigned)((planes + 127) / 128)), dim3(128), 0, st, x, scale, shift,
+        CMR_REQUIRE(B <= 65535, CMR_ERANGE);
+        return launch_pdl(k_conv_epilogue_global_nhwc, dim3((unsigned)ceil_div(C, 128), (unsigned)B), dim3(512), 0, st, x, scale, shift,
                           negative_slope, B, (int)HW, C, y);
     }
     if (pool == 0) {

@@ -292,35 +292,38 @@ __global__ void __launch_bounds__(256) k_to_channels_last(const float *__restric
     }
 }
 
-// AvgPool2d((H, W)): a thread = one channel of one episode, walking the pixels (coalesced across the channels)
-__global__ void __launch_bounds__(128) k_conv_epilogue_global_nhwc(const float *__restrict__ x, const float *__restrict__ scale,
+// AvgPool2d((H, W)): a CTA = 128 channels of one episode.  The additions of a channel must run in pixel order (torch's
+// avg_pool2d adds the window row by row), so one thread owns a channel's sum - but the LOADS need not wait for it: four
+// threads per channel bring 64 pixels at a time into shared memory (16 independent loads each, already activated), then
+// the channel's thread adds the 64 values in order.  One DRAM round trip per 64 pixels instead of one per 13.
+__global__ void __launch_bounds__(512) k_conv_epilogue_global_nhwc(const float *__restrict__ x, const float *__restrict__ scale,
                                                                    const float *__restrict__ shift, float slope, int B, int HW,
                                                                    int C, float *__restrict__ y) {
+    __shared__ float t[64][128];
     pdl_launch_dependents();
     pdl_wait();
-    const int i = (int)blockIdx.x * (int)blockDim.x + (int)threadIdx.x;
-    if (i >= B * C) return;
-    const int c = i % C, b = i / C;
-    const float sc = __ldg(scale + c), sh = __ldg(shift + c);
-    const float *p = x + (size_t)b * HW * C + c;
+    const int b = blockIdx.y, c = (int)blockIdx.x * 128 + (int)(threadIdx.x & 127), q = threadIdx.x >> 7;
+    const bool live = c < C;
+    const float sc = live ? __ldg(scale + c) : 0.f, sh = live ? __ldg(shift + c) : 0.f;
+    const float *p = x + (size_t)b * HW * C + (live ? c : 0);
     float s = 0.f;
-    int k = 0;
-    for (; k + 32 <= HW; k += 32) {    // 32 loads in flight, then the additions in pixel order (torch's avg_pool2d order)
-        float v[32];
+    for (int k0 = 0; k0 < HW; k0 += 64) {
+        float v[16];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = p[(size_t)(k + j) * C];
+        for (int jj = 0; jj < 16; ++jj) {
+            const int k = k0 + q + 4 * jj;
+            v[jj] = (live && k < HW) ? p[(size_t)k * C] : 0.f;
+        }
 #pragma unroll
-        for (int j = 0; j < 32; ++j) s = __fadd_rn(s, lrelu_affine(v[j], sc, sh, slope));
+        for (int jj = 0; jj < 16; ++jj) t[q + 4 * jj][threadIdx.x & 127] = lrelu_affine(v[jj], sc, sh, slope);
+        __syncthreads();
+        if (q == 0) {
+            const int n = min(64, HW - k0);
+            for (int k = 0; k < n; ++k) s = __fadd_rn(s, t[k][threadIdx.x]);
+        }
+        __syncthreads();
     }
-    for (; k + 8 <= HW; k += 8) {
-        float v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = p[(size_t)(k + j) * C];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) s = __fadd_rn(s, lrelu_affine(v[j], sc, sh, slope));
-    }
-    for (; k < HW; ++k) s = __fadd_rn(s, lrelu_affine(p[(size_t)k * C], sc, sh, slope));
-    y[i] = __fdiv_rn(s, (float)HW);
+    if (q == 0 && live) y[(size_t)b * C + c] = __fdiv_rn(s, (float)HW);
 }
 
 }  // namespace cmr

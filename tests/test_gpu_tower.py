@@ -172,7 +172,8 @@ def test_heads_match_the_reference_s_modules(cuda, dof6):
 
 
 @pytest.mark.parametrize("channels_last", [False, True])
-@pytest.mark.parametrize("shape,pool", [((2, 8, 6, 16), 0), ((3, 12, 4, 8), 1), ((2, 8, 5, 16), 2), ((1, 128, 40, 128), 1)])
+@pytest.mark.parametrize("shape,pool", [((2, 8, 6, 16), 0), ((3, 12, 4, 8), 1), ((2, 8, 5, 16), 2), ((1, 128, 40, 128), 1),
+                                        ((2, 256, 5, 16), 2), ((1, 132, 5, 7), 2), ((3, 128, 9, 15), 2)])
 def test_conv_epilogue_matches_torch(cuda, shape, pool, channels_last):
     """cmr_conv_epilogue = pool(LeakyReLU(x * scale[c] + shift[c])) against torch's own ops on the folded form, on NCHW
     and on channels_last data."""
