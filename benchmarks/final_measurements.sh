@@ -12,3 +12,5 @@ python benchmarks/microbench.py env > /dev/null 2>&1 && ncu --set full --clock-c
 python benchmarks/microbench.py tower > /dev/null 2>&1 && ncu --set full --clock-control none --import-source on -k regex:k_tower -s 10 -c 5 -o gpurun_out/r2f_tower -f python benchmarks/microbench.py tower > gpurun_out/r2f_ncu3.log 2>&1; echo "tower ncu exit $?"
 python benchmarks/microbench.py cost_volume > /dev/null 2>&1 && ncu --set full --clock-control none --import-source on -k regex:"k_cost_volume" -s 4 -c 2 -o gpurun_out/r2f_cv -f python benchmarks/microbench.py cost_volume > gpurun_out/r2f_ncu4.log 2>&1; echo "cv ncu exit $?"
 python benchmarks/microbench.py sample > /dev/null 2>&1 && ncu --set full --clock-control none --import-source on -k regex:k_bilinear_sample -s 3 -c 1 -o gpurun_out/r2f_sample -f python benchmarks/microbench.py sample > gpurun_out/r2f_ncu5.log 2>&1; echo "sample ncu exit $?"
+bash benchmarks/agent_loop_profile.sh; echo "agent loop profile exit $?"   # then python profiles/make_agent_loop.py
+python benchmarks/debug/to_channels_last.py > gpurun_out/r2f_to_channels_last.txt 2>&1; echo "transposer exit $?"
