@@ -107,6 +107,41 @@ def test_install_before_the_reference_imports_keeps_its_packages_whole():
     """ % (ROOT, ref, ref))
 
 
+def test_accelerated_agent_keeps_the_reference_s_paths_where_the_kernels_do_not_apply():
+    """accelerate_agent on a CPU agent: forward and action_from_logits are wrapped, and on CPU tensors, in training mode
+    or with sampling they are the reference's own functions (models/CMRAgent.py:88-128) - same results, no library call."""
+    _needs_reference()
+    _run("""
+        import sys
+        sys.path.insert(0, %r)
+        import torch
+        from oracle import reference_loader as rl
+        rl.put_on_path()
+        from cmr_agent_b200 import agent_tower
+        from config import KittiConfiguration
+        from models import CMRAgent
+        config = KittiConfiguration()
+        torch.manual_seed(3)
+        agent = CMRAgent(config).eval()
+        reference_forward = agent.forward
+        agent = agent_tower.accelerate_agent(agent)
+        assert agent._cmr_b200_reference_action is CMRAgent.action_from_logits
+        r = torch.randn(4, agent.degree_r, config.num_steps)
+        t = torch.randn(4, agent.degree_t, config.num_steps)
+        with torch.no_grad():
+            got = agent.action_from_logits(r, t, deterministic=True)          # CPU logits: the reference's function
+            want = CMRAgent.action_from_logits(r, t, deterministic=True)
+            assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
+            torch.manual_seed(9); a = agent.action_from_logits(r, t, deterministic=False)
+            torch.manual_seed(9); b = CMRAgent.action_from_logits(r, t, deterministic=False)
+            assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+            s2, s3 = torch.randn(1, 128, 40, 128), torch.randn(1, 5, 256)
+            out, ref = agent(s2, s3), reference_forward(s2, s3)               # CPU state: the reference's forward
+            assert all(torch.equal(x, y) for x, y in zip(out, ref))
+        print("ok")
+    """ % ROOT)
+
+
 def test_install_after_the_reference_imports_repoints_bound_names():
     ref = _needs_reference()
     _run("""
